@@ -1,0 +1,276 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200 visualDet3D hot path (contract: see the task brief / DESIGN.md).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--batch 8]
+    torchrun --nproc-per-node N bench.py --gpus N ...        (one rank per GPU, NCCL)
+
+A "step" = one YOLOStereo3D forward (backbone -> cost volumes -> neck -> head -> decode -> NMS) over a batch of
+`--batch` synthetic 384x1280 stereo pairs per GPU (BASELINE.json configs[1]); ranks hold disjoint pairs (weak scaling)
+and exchange only one all-gather of detection records.  Prints ONE JSON line on rank 0.
+
+  value     : whole-job stereo pairs/s, inputs resident in HBM, timed with CUDA events, max over ranks
+  e2e       : same metric through the public detector API with HOST (pinned) inputs: H2D copies, forward, D2H of results
+  roofline  : scale-4 PSMCosine kernel (dominant cost-volume kernel): algorithmic bytes / CUDA-event time vs measured HBM peak
+  cpu_baseline : the CPU oracle port (oracle/torch_port.py, the reference's algorithm in fp32 PyTorch ops) on this host's cores
+  --impl reference : times that CPU implementation alone (the reference itself is Python and cannot travel to the GPU box)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "synthetic_384x1280_stereo_pairs_per_sec"
+UNIT = "pairs/s"
+H, W = 384, 1280
+PSM4_BYTES_PER_PAIR = 4 * (H // 4) * (W // 4) * (2 * 64 + 24)   # 18,677,760 B
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi sampling of SM clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_forward_rate(pairs: int, iters: int, threads: int):
+    """Oracle port on the host cores: `iters` forwards of `pairs` pairs at 384x1280 -> (pairs/s, seconds per forward)."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import torch_port as tp
+    from visualdet3d_b200 import synth
+    from visualdet3d_b200.detectors import build_synthetic_stereo3d
+    torch.set_num_threads(threads)
+    det, sd, cfg, (pm, ps) = build_synthetic_stereo3d(seed=0)
+    left, right, P2, P3 = synth.synth_stereo_inputs(pairs, H, W, seed=1)
+    tp.stereo3d_forward(sd, left, right, P2, cfg, pm, ps)          # warm-up (oneDNN primitive creation)
+    ts = []
+    for _ in range(iters):
+        t0 = time.perf_counter()
+        tp.stereo3d_forward(sd, left, right, P2, cfg, pm, ps)
+        ts.append(time.perf_counter() - t0)
+    med = statistics.median(ts)
+    return pairs / med, med
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; kind "port")."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    pairs = 1
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import torch_port as tp
+    from visualdet3d_b200 import synth
+    from visualdet3d_b200.detectors import build_synthetic_stereo3d
+    torch.set_num_threads(cores)
+    det, sd, cfg, (pm, ps) = build_synthetic_stereo3d(seed=0)
+    left, right, P2, P3 = synth.synth_stereo_inputs(pairs, H, W, seed=1)
+    for _ in range(max(1, min(args.warmup, 2))):
+        tp.stereo3d_forward(sd, left, right, P2, cfg, pm, ps)
+    steps = max(1, min(args.steps, 20))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        tp.stereo3d_forward(sd, left, right, P2, cfg, pm, ps)
+    dt = time.perf_counter() - t0
+    v = pairs * steps / dt
+    sample = f"{steps} forwards of {pairs} pair(s) 384x1280 (bounded sample of the batch-{args.batch} workload)"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": f"YOLOStereo3D forward, stereo 384x1280, ResNet-34 (CPU, {sample})"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=8, help="stereo pairs per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from visualdet3d_b200 import _lib, synth, parallel
+    from visualdet3d_b200.detectors import build_synthetic_stereo3d
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the B200 path has no CPU fallback; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    args.warmup = max(args.warmup, 3)
+    B = args.batch
+    kmax = 256
+
+    det, sd, cfg, _ = build_synthetic_stereo3d(seed=0)
+    det = det.to(dev).eval()
+    # every rank owns its own B pairs of the global batch (weak scaling): different seeds per rank
+    left, right, P2, P3 = synth.synth_stereo_inputs(B, H, W, seed=1 + rank)
+    hl, hr, hp = left.pin_memory(), right.pin_memory(), P2.pin_memory()
+    dl, dr, dp = hl.to(dev), hr.to(dev), hp.to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        dec = det.launch(dl, dr, dp)
+        return dec
+
+    def step_e2e():
+        l = hl.to(dev, non_blocking=True)
+        r = hr.to(dev, non_blocking=True)
+        p = hp.to(dev, non_blocking=True)
+        res = det.forward_batch(l, r, p)
+        allres = parallel.all_gather_detections(res, kmax, dev)
+        host = [(s.cpu(), b.cpu(), c.cpu()) for (s, b, c) in allres] if rank == 0 else None
+        return res, host
+
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            step_device()
+            res, _h = step_e2e()
+        # ---------------- device-resident timing ----------------------------------------------------------------
+        barrier()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        det.profile_events = []
+        _lib.launch_count_reset()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            dec = step_device()
+            # the all-gather belongs to the step: results -> record block -> NCCL
+            parallel.all_gather_detections(dec.results(), kmax, dev) if world > 1 else None
+        e1.record()
+        barrier()
+        launches = _lib.launch_count()
+        ms_dev = e0.elapsed_time(e1)
+        psm_ms = [a.elapsed_time(b) for a, b in det.profile_events]
+        det.profile_events = None
+        clocks = sampler.stop() if rank == 0 else None
+        # ---------------- end-to-end timing (host inputs) -----------------------------------------------------------
+        barrier()
+        t0 = time.perf_counter()
+        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e2.record()
+        for _ in range(args.steps):
+            res, host = step_e2e()
+        e3.record()
+        barrier()
+        ms_e2e = max(e2.elapsed_time(e3), 1e3 * (time.perf_counter() - t0) * 0.0)
+    t = torch.tensor([ms_dev, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_dev, ms_e2e = t.tolist()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pairs_total = B * world * args.steps
+    value = pairs_total / (ms_dev / 1e3)
+    e2e_v = pairs_total / (ms_e2e / 1e3)
+    peak, peak_kind = measured_peaks()
+    psm_avg_ms = statistics.mean(psm_ms) if psm_ms else None
+    achieved = (PSM4_BYTES_PER_PAIR * B / 1e9) / (psm_avg_ms / 1e3) if psm_avg_ms else None
+    ndet = sum(len(r[0]) for r in res)
+    h2d = int(hl.numel() * 4 + hr.numel() * 4 + hp.numel() * 4)
+    d2h = int(B * 4 + sum(len(s) * (4 + 44 + 8) for (s, _, _) in (host or [])))
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"YOLOStereo3D forward, batch {B} stereo 384x1280 per GPU, ResNet-34, random-init seeded weights",
+                   "global_batch": B * world, "parallelism": f"dp{world}", "l2": "inputs+weights (524 MB/step) exceed the 126 MB L2; no explicit flush",
+                   "conv_engine": os.environ.get("VD3D_CONV_ENGINE", "default"), "detections_per_step": ndet},
+        "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"kernel": "psm_cosine_nhwc_kernel<64> (scale-4 PSMCosine)", "bound": "hbm", "achieved": achieved, "peak": peak,
+                     "peak_kind": peak_kind, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
+                     "avg_launch_ms": psm_avg_ms, "algorithmic_bytes_per_launch": PSM4_BYTES_PER_PAIR * B, "traffic": None},
+    }
+    if not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        v, sec = cpu_forward_rate(1, 3, cores)
+        out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                               "sample": f"3 forwards of 1 pair 384x1280 (median {sec:.2f} s), oracle/torch_port.py on {cores} threads"}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,115 @@
+/*
+ * vd3d_b200.h — C ABI of libvd3d_b200.so: hand-written sm_100a kernels for visualDet3D's inference hot path.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; `stream` is a cudaStream_t passed as void*.
+ *   - activations are fp32, "NHWC" = [B][H][W][C] with an explicit channel pitch (`*_cs`, floats between two
+ *     pixels) and channel offset (`*_co`) so a kernel can read / write a channel slice of a wider tensor
+ *     (this is how every torch.cat on the path is fused away).
+ *   - every entry returns 0 on success, a negative VD3D_E* code otherwise; it never exits the process
+ *     (the reference's iou3d.cpp:13-21 CHECK_ERROR calls exit()).  vd3d_last_error() gives the message.
+ *   - all launches are asynchronous on `stream`; no entry synchronises unless documented.
+ *
+ * Reference interfaces replaced (R/ = visualDet3D/networks in the reference tree) are cited per entry.
+ */
+#ifndef VD3D_B200_H
+#define VD3D_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VD3D_OK 0
+#define VD3D_EINVAL -1   /* bad argument (shape / alignment / unsupported configuration) */
+#define VD3D_ECUDA -2    /* CUDA runtime / launch error */
+#define VD3D_ECAP -3     /* fixed-capacity buffer overflow (reported through a device flag, see decode) */
+
+const char* vd3d_last_error(void);
+int vd3d_version(void);
+/* number of kernel launches issued through this library since the last reset (bench.py's gpu_launches) */
+long long vd3d_launch_count(void);
+void vd3d_launch_count_reset(void);
+
+/* ---- layout helpers -------------------------------------------------------------------------------------- */
+/* [B][C][H][W] -> [B][H][W][out_cs] (+out_co).  Input side of the detectors (testers.py:24-25,39 hand NCHW). */
+int vd3d_nchw_to_nhwc(const float* in, float* out, int B, int C, int H, int W, int out_cs, int out_co, void* stream);
+/* [B][H][W][in_cs](+in_co) -> [B][C][H][W].  Used by the NCHW-facing op mirrors and the tests. */
+int vd3d_nhwc_to_nchw(const float* in, float* out, int B, int C, int H, int W, int in_cs, int in_co, void* stream);
+
+/* ---- dense convolution (SIMT fp32 implicit GEMM) ----------------------------------------------------------
+ * Replaces nn.Conv2d + folded eval-mode BatchNorm2d (+ReLU) (+residual add) as used by
+ * R/backbones/resnet.py:23-91,184-198, R/lib/ghost_module.py:27-31, R/lib/blocks.py:24-43,
+ * R/heads/detection_3d_head.py:47-82,500-533.
+ *   in   : NHWC [B][H][W] pitch in_cs, channels [in_co, in_co+Cin)
+ *   wgt  : [KH*KW*Cin][Cout]  (k = (kh*KW + kw)*Cin + ci), BN scale already folded in
+ *   bias : [Cout] (folded BN shift + conv bias) or NULL
+ *   res  : optional residual NHWC (same spatial size as out), added before the ReLU
+ *   out  : NHWC [B][Ho][Wo] pitch out_cs, channels [out_co, out_co+Cout)
+ *   Ho = (H + 2*pad - dil*(KH-1) - 1)/stride + 1 (same for Wo).  Requires Cout % 4 == 0, pitches/offsets % 4 == 0.
+ */
+int vd3d_conv2d_nhwc(const float* in, int B, int H, int W, int Cin, int in_cs, int in_co,
+                     const float* wgt, const float* bias, int KH, int KW, int stride, int pad, int dil,
+                     const float* res, int res_cs, int res_co,
+                     float* out, int Cout, int out_cs, int out_co, int relu, void* stream);
+
+/* depthwise 3x3 (stride 1, pad 1) + folded BN + ReLU: GhostModule.cheap_operation (R/lib/ghost_module.py:33-38).
+ * wgt [9][C] (tap-major), bias [C]. */
+int vd3d_dwconv3x3_nhwc(const float* in, int B, int H, int W, int C, int in_cs, int in_co,
+                        const float* wgt, const float* bias, float* out, int out_cs, int out_co, int relu, void* stream);
+
+/* nn.MaxPool2d(3, stride 2, pad 1) (R/backbones/resnet.py:123,190). */
+int vd3d_maxpool3x3s2_nhwc(const float* in, int B, int H, int W, int C, int in_cs, int in_co,
+                           float* out, int out_cs, int out_co, void* stream);
+/* nn.AvgPool2d(2) (R/detectors/yolostereo3d_core.py:25,34). H, W even. */
+int vd3d_avgpool2_nhwc(const float* in, int B, int H, int W, int C, int in_cs, int in_co,
+                       float* out, int out_cs, int out_co, void* stream);
+/* channel-slice copy (the torch.cat legs that cannot be fused into a producer). */
+int vd3d_copy_channels_nhwc(const float* in, int npix, int C, int in_cs, int in_co, float* out, int out_cs, int out_co, void* stream);
+
+/* ---- stereo cost volumes ---------------------------------------------------------------------------------
+ * PSMCosineModule.forward (R/lib/PSM_cost_volume.py:76-91):
+ *   out[b,h,w,i] = (1/C) * sum_c L[b,h,w,c] * R[b,h,w-i,c]   if w >= i else 0,   i in [0, D)
+ * L, R NHWC (pitch lr_cs, offset lr_co), out NHWC slice.  Algorithmic HBM bytes: 4*B*H*W*(2C + D). */
+int vd3d_psm_cosine_nhwc(const float* L, const float* R, int B, int H, int W, int C, int lr_cs, int lr_co,
+                         int D, float* out, int out_cs, int out_co, void* stream);
+/* Same op on the reference's own layout: left/right [B][C][H][W] -> cost [B][D][H][W] (op-level mirror). */
+int vd3d_psm_cosine_nchw(const float* L, const float* R, int B, int C, int H, int W, int D, float* out, void* stream);
+
+/* CostVolume.forward after the 1x1 down_sample (R/lib/PSM_cost_volume.py:44-63): concat volume
+ *   vol[b, c, i, h, w] = lf[b,h,w,c] (c < F) | rf[b,h,w-i,c-F] (c >= F)  if w >= i else 0
+ * gathered on the fly (never materialised) into Conv3d(2F->F,3,pad 1)+BN3d+ReLU; then Conv3d(F->F)+BN3d+ReLU.
+ *   lf, rf : NHWC [B][H][W][F] dense;  w1 [27][2F][F], b1 [F];  w2 [27][F][F], b2 [F]  (BN folded, tap = (kd*3+kh)*3+kw)
+ *   mid    : scratch [B][D][H][W][F]
+ *   out    : NHWC slice, channel = f*D + i  (the reshape at PSM_cost_volume.py:62)
+ * F must be 8. */
+int vd3d_concat_volume_conv3d(const float* lf, const float* rf, int B, int H, int W, int F, int D,
+                              const float* w1, const float* b1, const float* w2, const float* b2,
+                              float* mid, float* out, int out_cs, int out_co, void* stream);
+
+/* ---- anchors / decode / NMS ------------------------------------------------------------------------------
+ * Anchors.forward useful-mask (R/heads/anchors.py:93-111): mask[b,n] = any_t(-0.5 < y3d < 1.8 && |x3d| < 40).
+ *   anchors [N][4] f32, means_z [T][N] f32 (prior z mean per type), P2 [B][3][4] f32 -> mask [B][N] u8 */
+int vd3d_anchor_mask(const float* anchors, const float* means_z, const float* P2, int B, int N, int T,
+                     float y_min, float y_max, float x_thr, uint8_t* mask, void* stream);
+
+/* AnchorBasedDetection3DHead.get_bboxes (R/heads/detection_3d_head.py:341-400) + _decode (:218-263) +
+ * ClipBoxes (R/utils/utils.py:181-196) + torchvision.ops.nms (class-agnostic, IoU > thr suppresses), batched.
+ *   cls [B][N][ncls+1], reg [B][N][12], anchors [N][4], mean_std [N][T][6][2], mask [B][N] u8
+ *   workspace: ws, at least vd3d_decode_nms_workspace(B, cap) bytes
+ *   outputs (fixed capacity `cap` rows per image, rows >= count are undefined):
+ *     out_scores [B][cap] f32 (descending), out_boxes [B][cap][11] f32, out_cls [B][cap] i64,
+ *     out_anchor [B][cap] i32 (anchor index n of every kept row), out_count [B] i32 (kept rows),
+ *     out_ncand [B] i32 (candidates before NMS; > cap means overflow: count is then -1 for that image)
+ */
+long long vd3d_decode_nms_workspace(int B, int cap);
+int vd3d_decode_nms(const float* cls, const float* reg, const float* anchors, const float* mean_std,
+                    const uint8_t* mask, int B, int N, int ncls, int T, float score_thr, double iou_thr,
+                    float img_w, float img_h, int cap, void* ws,
+                    float* out_scores, float* out_boxes, int64_t* out_cls, int32_t* out_anchor,
+                    int32_t* out_count, int32_t* out_ncand, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

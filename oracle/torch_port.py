@@ -1,0 +1,337 @@
+"""ORACLE (test infrastructure, NOT product code).
+
+A CPU restatement, in plain fp32 PyTorch functional ops, of the visualDet3D inference forward named by
+BASELINE.json's north_star.  Every function cites the reference file:line it follows
+(R/ = /root/reference/visualDet3D/networks).  It operates on a reference-format ``state_dict`` so the same
+weights drive the reference, this port and the CUDA path.
+
+Parity status: PINNED.  ``tests/golden/make_golden.py`` imports the unmodified reference in the build
+container, runs it on seeded inputs/weights and commits the outputs under ``tests/golden/*.npz``;
+``tests/test_oracle_golden.py`` checks this port against those fixtures.  Arithmetic that lives in third-party
+code (oneDNN convs, torchvision.ops.nms, F.grid_sample) is called through the same torch/torchvision entry
+points the reference calls, so "same inputs -> same outputs" holds on one machine.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this file.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+SD = Dict[str, torch.Tensor]
+
+
+# --------------------------------------------------------------------------------------------------------
+# building blocks
+# --------------------------------------------------------------------------------------------------------
+def bn(sd: SD, p: str, x: torch.Tensor) -> torch.Tensor:
+    """nn.BatchNorm{2,3}d in eval mode (running stats), eps = 1e-5 (torch default; the reference never changes it)."""
+    return F.batch_norm(x, sd[p + ".running_mean"], sd[p + ".running_var"], sd[p + ".weight"], sd[p + ".bias"],
+                        training=False, eps=1e-5)
+
+
+def conv(sd: SD, p: str, x: torch.Tensor, stride=1, padding=0, dilation=1, groups=1) -> torch.Tensor:
+    return F.conv2d(x, sd[p + ".weight"], sd.get(p + ".bias"), stride=stride, padding=padding,
+                    dilation=dilation, groups=groups)
+
+
+def basic_block(sd: SD, p: str, x: torch.Tensor, stride: int = 1, dilation: int = 1) -> torch.Tensor:
+    """R/backbones/resnet.py:23-52 (BasicBlock.forward)."""
+    out = F.relu(bn(sd, p + ".bn1", conv(sd, p + ".conv1", x, stride=stride, padding=1)))
+    out = bn(sd, p + ".bn2", conv(sd, p + ".conv2", out, padding=dilation, dilation=dilation))
+    if (p + ".downsample.0.weight") in sd:
+        x = bn(sd, p + ".downsample.1", conv(sd, p + ".downsample.0", x, stride=stride))
+    return F.relu(out + x)
+
+
+def bottleneck(sd: SD, p: str, x: torch.Tensor, stride: int = 1, dilation: int = 1) -> torch.Tensor:
+    """R/backbones/resnet.py:55-91 (Bottleneck.forward)."""
+    out = F.relu(bn(sd, p + ".bn1", conv(sd, p + ".conv1", x)))
+    out = F.relu(bn(sd, p + ".bn2", conv(sd, p + ".conv2", out, stride=stride, padding=dilation, dilation=dilation)))
+    out = bn(sd, p + ".bn3", conv(sd, p + ".conv3", out))
+    if (p + ".downsample.0.weight") in sd:
+        x = bn(sd, p + ".downsample.1", conv(sd, p + ".downsample.0", x, stride=stride))
+    return F.relu(out + x)
+
+
+RESNET_LAYERS = {18: ("basic", [2, 2, 2, 2]), 34: ("basic", [3, 4, 6, 3]), 50: ("bottle", [3, 4, 6, 3]),
+                 101: ("bottle", [3, 4, 23, 3]), 152: ("bottle", [3, 8, 36, 3])}
+
+
+def resnet(sd: SD, p: str, img: torch.Tensor, depth: int, num_stages: int = 4, out_indices=(-1, 0, 1, 2, 3),
+           strides=(1, 2, 2, 2), dilations=(1, 1, 1, 1)) -> List[torch.Tensor]:
+    """R/backbones/resnet.py:184-198 (ResNet.forward); stage layout `_make_layer` :140-152.
+    Note `_make_layer` gives the FIRST block of a stage the stride and dilation=1, later blocks dilation."""
+    kind, layers = RESNET_LAYERS[depth]
+    block = basic_block if kind == "basic" else bottleneck
+    outs = []
+    x = F.relu(bn(sd, p + ".bn1", conv(sd, p + ".conv1", img, stride=2, padding=3)))
+    if -1 in out_indices:
+        outs.append(x)
+    x = F.max_pool2d(x, kernel_size=3, stride=2, padding=1)
+    for i in range(num_stages):
+        for j in range(layers[i]):
+            x = block(sd, f"{p}.layer{i + 1}.{j}", x, stride=strides[i] if j == 0 else 1,
+                      dilation=1 if j == 0 else dilations[i])
+        if i in out_indices:
+            outs.append(x)
+    return outs
+
+
+def res_ghost(sd: SD, p: str, x: torch.Tensor, oup: int) -> torch.Tensor:
+    """R/lib/ghost_module.py:46-64 (ResGhostModule.forward, stride 1): out = cat[x, x1, x2][:, :oup]."""
+    x1 = F.relu(bn(sd, p + ".primary_conv.2", conv(sd, p + ".primary_conv.1", x, padding=sd[p + ".primary_conv.1.weight"].shape[-1] // 2)))
+    w2 = sd[p + ".cheap_operation.0.weight"]
+    x2 = F.relu(bn(sd, p + ".cheap_operation.1",
+                   F.conv2d(x1, w2, None, stride=1, padding=w2.shape[-1] // 2, groups=x1.shape[1])))
+    return torch.cat([x, x1, x2], dim=1)[:, :oup]
+
+
+# --------------------------------------------------------------------------------------------------------
+# cost volumes  (R/lib/PSM_cost_volume.py)
+# --------------------------------------------------------------------------------------------------------
+def psm_cosine(left: torch.Tensor, right: torch.Tensor, max_disp: int, downsample_scale: int) -> torch.Tensor:
+    """R/lib/PSM_cost_volume.py:76-91: cost[b,i,h,w] = mean_c L[b,c,h,w] * R[b,c,h,w-i] for w >= i else 0."""
+    D = int(max_disp / downsample_scale)
+    B, C, H, W = left.shape
+    cost = torch.zeros(B, D, H, W, dtype=left.dtype)
+    for i in range(D):
+        if i > 0:
+            if i < W:
+                cost[:, i, :, i:] = (left[:, :, :, i:] * right[:, :, :, :-i]).mean(dim=1)
+        else:
+            cost[:, i] = (left * right).mean(dim=1)
+    return cost
+
+
+def concat_volume(lf: torch.Tensor, rf: torch.Tensor, D: int) -> torch.Tensor:
+    """R/lib/PSM_cost_volume.py:44-60: [B, 2F, D, H, W]; plane i holds L' (w>=i) and R' shifted by i."""
+    B, Fc, H, W = lf.shape
+    cost = torch.zeros(B, 2 * Fc, D, H, W, dtype=lf.dtype)
+    for i in range(D):
+        if i > 0:
+            if i < W:
+                cost[:, :Fc, i, :, i:] = lf[:, :, :, i:]
+                cost[:, Fc:, i, :, i:] = rf[:, :, :, :-i]
+        else:
+            cost[:, :Fc, i] = lf
+            cost[:, Fc:, i] = rf
+    return cost
+
+
+def cost_volume(sd: SD, p: str, left: torch.Tensor, right: torch.Tensor, max_disp: int, downsample_scale: int) -> torch.Tensor:
+    """R/lib/PSM_cost_volume.py:40-63 (CostVolume.forward)."""
+    D = int(max_disp / downsample_scale)
+    B, _, H, W = left.shape
+    lf = F.relu(bn(sd, p + ".down_sample.1", conv(sd, p + ".down_sample.0", left)))
+    rf = F.relu(bn(sd, p + ".down_sample.1", conv(sd, p + ".down_sample.0", right)))
+    cost = concat_volume(lf, rf, D)
+    cost = F.relu(bn(sd, p + ".conv3d.1", F.conv3d(cost, sd[p + ".conv3d.0.weight"], sd[p + ".conv3d.0.bias"], padding=1)))
+    cost = F.relu(bn(sd, p + ".conv3d.4", F.conv3d(cost, sd[p + ".conv3d.3.weight"], sd[p + ".conv3d.3.bias"], padding=1)))
+    return cost.reshape(B, -1, H, W).contiguous()
+
+
+def cost_volume_pyramid(sd: SD, p: str, v4: torch.Tensor, v8: torch.Tensor, v16: torch.Tensor) -> torch.Tensor:
+    """R/detectors/yolostereo3d_core.py:63-71 (CostVolumePyramid.forward, eval branch)."""
+    c4 = v4.shape[1]
+    x = res_ghost(sd, p + ".four_to_eight.0", v4, 3 * c4)
+    x = F.avg_pool2d(x, 2)
+    x = basic_block(sd, p + ".four_to_eight.2", x)
+    v8 = torch.cat([x, v8], dim=1)
+    x = res_ghost(sd, p + ".eight_to_sixteen.0", v8, 3 * v8.shape[1])
+    x = F.avg_pool2d(x, 2)
+    x = basic_block(sd, p + ".eight_to_sixteen.2", x)
+    v16 = torch.cat([x, v16], dim=1)
+    x = res_ghost(sd, p + ".depth_reason.0", v16, 3 * v16.shape[1])
+    x = basic_block(sd, p + ".depth_reason.1", x)
+    return x
+
+
+def stereo_core(sd: SD, left: torch.Tensor, right: torch.Tensor, depth: int = 34, stages: dict | None = None) -> torch.Tensor:
+    """R/detectors/yolostereo3d_core.py:110-126 + StereoMerging.forward :88-94. Returns features [B,1408,H/16,W/16]."""
+    B = left.shape[0]
+    feats = resnet(sd, "core.backbone", torch.cat([left, right], dim=0), depth, num_stages=3, out_indices=(0, 1, 2))
+    lf = [f[:B] for f in feats]
+    rf = [f[B:] for f in feats]
+    v0 = psm_cosine(lf[0], rf[0], 96, 4)
+    v1 = psm_cosine(lf[1], rf[1], 192, 8)
+    v2 = cost_volume(sd, "core.neck.cost_volume_2", lf[2], rf[2], 192, 16)
+    psv = cost_volume_pyramid(sd, "core.neck.depth_reasoning", v0, v1, v2)
+    features = torch.cat([lf[2], psv], dim=1)
+    if stages is not None:
+        stages.update(feat4=feats[0], feat8=feats[1], feat16=feats[2], vol4=v0, vol8=v1, vol16=v2, psv=psv, features=features)
+    return features
+
+
+def anchor_flatten(x: torch.Tensor, c: int) -> torch.Tensor:
+    """R/lib/blocks.py:117-136."""
+    return x.permute(0, 2, 3, 1).contiguous().view(x.shape[0], -1, c)
+
+
+def stereo_head(sd: SD, features: torch.Tensor, num_cls_output: int, num_reg_output: int = 12) -> Tuple[torch.Tensor, torch.Tensor]:
+    """R/heads/detection_3d_head.py:500-533 (StereoHead.init_layers) + :84-88 (forward); Dropout2d is identity in eval."""
+    p = "bbox_head.cls_feature_extraction"
+    x = F.relu(conv(sd, p + ".0", features, padding=1))
+    x = F.relu(conv(sd, p + ".3", x, padding=1))
+    cls = anchor_flatten(conv(sd, p + ".6", x, padding=1), num_cls_output)
+    p = "bbox_head.reg_feature_extraction"
+    x = F.relu(bn(sd, p + ".0.sequence.1", conv(sd, p + ".0.sequence.0", features, padding=1)))  # ConvBnReLU (blocks.py:24-43)
+    x = F.relu(basic_block(sd, p + ".1", x))
+    reg = anchor_flatten(conv(sd, p + ".3", x, padding=1), num_reg_output)
+    return cls, reg
+
+
+# --------------------------------------------------------------------------------------------------------
+# anchors  (R/heads/anchors.py)
+# --------------------------------------------------------------------------------------------------------
+def generate_anchors(base_size: float, ratios: np.ndarray, scales: np.ndarray) -> np.ndarray:
+    """R/heads/anchors.py:152-183: float64, per-cell order a = ratio_idx * n_scales + scale_idx."""
+    ratios = np.asarray(ratios, dtype=np.float64)
+    scales = np.asarray(scales, dtype=np.float64)
+    rr = np.repeat(ratios, len(scales))
+    ss = np.tile(scales, len(ratios))
+    side = base_size * ss
+    areas = side * side
+    w = np.sqrt(areas / rr)
+    h = w * rr
+    out = np.zeros((len(rr), 4))
+    out[:, 0] = 0 - w * 0.5
+    out[:, 1] = 0 - h * 0.5
+    out[:, 2] = w - w * 0.5
+    out[:, 3] = h - h * 0.5
+    return out
+
+
+def shift_anchors(shape_hw: Sequence[int], stride: float, anchors: np.ndarray) -> np.ndarray:
+    """R/heads/anchors.py:219-239: n = (y*W + x)*A + a."""
+    sx = (np.arange(0, shape_hw[1]) + 0.5) * stride
+    sy = (np.arange(0, shape_hw[0]) + 0.5) * stride
+    sx, sy = np.meshgrid(sx, sy)
+    shifts = np.stack([sx.ravel(), sy.ravel(), sx.ravel(), sy.ravel()], axis=1)
+    return (anchors[None, :, :] + shifts[:, None, :]).reshape(-1, 4)
+
+
+def build_anchors(image_hw: Sequence[int], acfg: dict, prior_mean: np.ndarray, prior_std: np.ndarray):
+    """R/heads/anchors.py:59-91. prior_* : [types, n_scales*levels, n_ratios, 6] float64.
+    Returns anchors f32 [N,4], anchor_mean_std f32 [N, types, 6, 2], and float64 -> f32 prior means [types, N, 6]."""
+    levels, strides, sizes = acfg["pyramid_levels"], acfg["strides"], acfg["sizes"]
+    ratios, scales = np.asarray(acfg["ratios"], dtype=np.float64), np.asarray(acfg["scales"], dtype=np.float64)
+    image_shape = np.array(image_hw)
+    all_anchors = np.zeros((0, 4)).astype(np.float32)
+    for idx, lv in enumerate(levels):
+        shp = (image_shape + 2 ** lv - 1) // (2 ** lv)
+        all_anchors = np.append(all_anchors, shift_anchors(shp, strides[idx], generate_anchors(sizes[idx], ratios, scales)), axis=0)
+    # anchors2indexes :45-57 (float64)
+    sz = np.sqrt((all_anchors[:, 2] - all_anchors[:, 0]) * (all_anchors[:, 3] - all_anchors[:, 1]))
+    sizes_int = np.argmin(np.abs(sz - (np.array(sizes) * scales)[:, None]), axis=0)
+    rt = (all_anchors[:, 3] - all_anchors[:, 1]) / (all_anchors[:, 2] - all_anchors[:, 0])
+    ratio_int = np.argmin(np.abs(rt - ratios[:, None]), axis=0)
+    means = torch.tensor(prior_mean[:, sizes_int, ratio_int], dtype=torch.float32)  # [types, N, 6]   (image.new(float64 ndarray) casts to f32)
+    stds = torch.tensor(prior_std[:, sizes_int, ratio_int], dtype=torch.float32)
+    mean_std = torch.stack([means, stds], dim=-1).permute(1, 0, 2, 3).contiguous()  # [N, types, 6, 2]
+    anchors = torch.tensor(all_anchors.astype(np.float32))
+    return anchors, mean_std, means
+
+
+def useful_mask(anchors: torch.Tensor, means: torch.Tensor, P2: torch.Tensor,
+                y_min_max=(-0.5, 1.8), x_thr=40.0) -> torch.Tensor:
+    """R/heads/anchors.py:93-111. anchors [N,4] f32, means [types,N,6] f32, P2 [B,3,4] -> bool [B,N]."""
+    xc = anchors[:, 0:4:2].mean(dim=1)
+    yc = anchors[:, 1:4:2].mean(dim=1)
+    fy = P2[:, 1:2, 1:2]
+    cy = P2[:, 1:2, 2:3]
+    cx = P2[:, 0:1, 2:3]
+    z = means[:, :, 0]
+    x3d = (xc * z - cx * z) / fy
+    y3d = (yc * z - cy * z) / fy
+    return torch.any((y3d > y_min_max[0]) * (y3d < y_min_max[1]) * (x3d.abs() < x_thr), dim=1)
+
+
+# --------------------------------------------------------------------------------------------------------
+# decode + NMS  (R/heads/detection_3d_head.py:218-263, 341-400)
+# --------------------------------------------------------------------------------------------------------
+def decode(boxes, deltas, mean_std, label, alpha_score):
+    """R/heads/detection_3d_head.py:218-263 (_decode)."""
+    std = torch.tensor([0.1, 0.1, 0.2, 0.2, 0.1, 0.1, 1, 1, 1, 1, 1, 1], dtype=torch.float32)
+    widths = boxes[..., 2] - boxes[..., 0]
+    heights = boxes[..., 3] - boxes[..., 1]
+    ctr_x = boxes[..., 0] + 0.5 * widths
+    ctr_y = boxes[..., 1] + 0.5 * heights
+    dx, dy = deltas[..., 0] * std[0], deltas[..., 1] * std[1]
+    dw, dh = deltas[..., 2] * std[2], deltas[..., 3] * std[3]
+    pcx = ctr_x + dx * widths
+    pcy = ctr_y + dy * heights
+    pw = torch.exp(dw) * widths
+    ph = torch.exp(dh) * heights
+    x1, y1, x2, y2 = pcx - 0.5 * pw, pcy - 0.5 * ph, pcx + 0.5 * pw, pcy + 0.5 * ph
+    sel = mean_std[torch.arange(len(label)), label]  # == anchors_3d_mean_std[one_hot_mask]
+    mask = sel[:, 0, 0] > 0
+    cx1 = ctr_x + deltas[..., 4] * std[4] * widths
+    cy1 = ctr_y + deltas[..., 5] * std[5] * heights
+    z = deltas[..., 6] * sel[:, 0, 1] + sel[:, 0, 0]
+    sn = deltas[..., 7] * sel[:, 1, 1] + sel[:, 1, 0]
+    cs = deltas[..., 8] * sel[:, 2, 1] + sel[:, 2, 0]
+    alpha = torch.atan2(sn, cs) / 2.0
+    w3 = deltas[..., 9] * sel[:, 3, 1] + sel[:, 3, 0]
+    h3 = deltas[..., 10] * sel[:, 4, 1] + sel[:, 4, 0]
+    l3 = deltas[..., 11] * sel[:, 5, 1] + sel[:, 5, 0]
+    out = torch.stack([x1, y1, x2, y2, cx1, cy1, z, w3, h3, l3, alpha], dim=1)
+    out[alpha_score[:, 0] < 0.5, -1] += np.pi
+    return out, mask
+
+
+def get_bboxes(cls_preds, reg_preds, anchors, mean_std, mask, image_hw, num_classes, score_thr, nms_iou_thr,
+               stages: dict | None = None):
+    """R/heads/detection_3d_head.py:341-400 for ONE image (cls_preds [N,C+1], reg_preds [N,12], mask [N] bool).
+    Class-agnostic NMS always (typo `cls_agnositc` at :381)."""
+    from torchvision.ops import nms
+    p = cls_preds.sigmoid()
+    cls_score = p[..., 0:num_classes][mask]
+    alpha_score = p[..., num_classes:num_classes + 1][mask]
+    reg = reg_preds[mask]
+    anc = anchors[mask]
+    ms = mean_std[mask]
+    idx0 = torch.nonzero(mask)[:, 0]
+    max_score, label = cls_score.max(dim=-1)
+    hs = max_score > score_thr
+    anc, ms, alpha_score, reg, max_score, label, idx0 = anc[hs], ms[hs], alpha_score[hs], reg[hs], max_score[hs], label[hs], idx0[hs]
+    boxes, valid = decode(anc, reg, ms, label, alpha_score)
+    H, W = image_hw
+    boxes[:, 0] = torch.clamp(boxes[:, 0], min=0)   # R/utils/utils.py:181-196 ClipBoxes
+    boxes[:, 1] = torch.clamp(boxes[:, 1], min=0)
+    boxes[:, 2] = torch.clamp(boxes[:, 2], max=W)
+    boxes[:, 3] = torch.clamp(boxes[:, 3], max=H)
+    max_score, boxes, label, idx0 = max_score[valid], boxes[valid], label[valid], idx0[valid]
+    keep = nms(boxes[:, :4], max_score, nms_iou_thr)
+    if stages is not None:
+        stages.update(cand_anchor_idx=idx0.clone(), cand_scores=max_score.clone(), cand_boxes=boxes.clone(),
+                      cand_labels=label.clone(), keep=keep.clone())
+    return max_score[keep], boxes[keep], label[keep], idx0[keep]
+
+
+# --------------------------------------------------------------------------------------------------------
+# detectors
+# --------------------------------------------------------------------------------------------------------
+def stereo3d_forward(sd: SD, left, right, P2, cfg: dict, prior_mean, prior_std, stages: dict | None = None):
+    """R/detectors/yolostereo3d_detector.py:77-96 (Stereo3D.test_forward), looped per image for B > 1
+    (the reference asserts B == 1; core + head are batch-invariant in eval mode)."""
+    with torch.no_grad():
+        feats = stereo_core(sd, left, right, cfg["backbone"]["depth"], stages)
+        ncls = cfg["head"]["num_classes"]
+        cls_preds, reg_preds = stereo_head(sd, feats, ncls + 1)
+        anchors, mean_std, means = build_anchors(left.shape[2:], cfg["head"]["anchors_cfg"], prior_mean, prior_std)
+        mask = useful_mask(anchors, means, P2)
+        if stages is not None:
+            stages.update(cls_preds=cls_preds, reg_preds=reg_preds, anchors=anchors, mean_std=mean_std, mask=mask)
+        outs = []
+        for b in range(left.shape[0]):
+            st = {} if stages is not None else None
+            outs.append(get_bboxes(cls_preds[b], reg_preds[b], anchors, mean_std, mask[b], left.shape[2:], ncls,
+                                   cfg["head"]["test_cfg"]["score_thr"], cfg["head"]["test_cfg"]["nms_iou_thr"], st))
+            if stages is not None:
+                stages.setdefault("per_image", []).append(st)
+        return outs

@@ -1,0 +1,144 @@
+"""Golden-vector generator: runs the UNMODIFIED reference (imported from /root/reference, CPU, fp32) on the seeded
+synthetic weights/inputs of visualdet3d_b200.synth and writes small fixtures next to this file.
+
+    python tests/golden/make_golden.py [stereo3d] [yolo3d] [gac] [monoflex] [km3d]
+
+Run in the build container only (the reference mount does not exist on the GPU box).  The fixtures pin
+oracle/torch_port.py (tests/test_oracle_golden.py) and are compared against the CUDA path directly
+(tests/test_*_gpu.py).  Large stage tensors are stored as a strided subsample plus two checksums.
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+import tempfile
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+import refload  # noqa: E402
+from visualdet3d_b200 import synth  # noqa: E402
+
+MAX_SAMPLES = 2048
+
+
+def subsample(t: torch.Tensor) -> dict:
+    """Fixture form of a stage tensor: strided samples + sum + abs-sum (float64)."""
+    f = t.detach().reshape(-1).to(torch.float64)
+    stride = max(1, f.numel() // MAX_SAMPLES)
+    return dict(shape=np.array(t.shape, dtype=np.int64), stride=np.int64(stride),
+                samples=f[::stride].to(torch.float32).numpy(), sum=np.float64(f.sum().item()),
+                abssum=np.float64(f.abs().sum().item()))
+
+
+def flatten_fixture(d: dict) -> dict:
+    out = {}
+    for k, v in d.items():
+        if isinstance(v, dict):
+            for kk, vv in v.items():
+                out[f"{k}/{kk}"] = vv
+        else:
+            out[k] = v
+    return out
+
+
+def to_edict(d):
+    from easydict import EasyDict
+    if isinstance(d, dict):
+        return EasyDict({k: to_edict(v) for k, v in d.items()})
+    return d
+
+
+def gen_stereo3d(H=96, W=320, B=2, seed=0, tag="stereo3d_96x320"):
+    refload.load_reference()
+    from visualDet3D.networks.utils.registry import DETECTOR_DICT
+    obj_types = ["Car", "Pedestrian"]
+    pm, ps = synth.synth_priors(16, 3, obj_types)
+    tmp = tempfile.mkdtemp()
+    synth.write_priors(tmp, pm, ps, obj_types)
+    cfg = synth.stereo3d_cfg(tmp, obj_types)
+    model = DETECTOR_DICT["Stereo3D"](to_edict(cfg))
+    shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    with open(os.path.join(HERE, "stereo3d_keys.json"), "w") as f:
+        json.dump({k: list(v) for k, v in shapes.items()}, f, indent=0)
+    sd = synth.synth_state_dict(shapes, seed)
+    missing = model.load_state_dict(sd, strict=False)
+    print("missing (training-only buffers expected):", missing.missing_keys, "unexpected:", missing.unexpected_keys)
+    model.eval()
+    left, right, P2, P3 = synth.synth_stereo_inputs(B, H, W, seed=1)
+
+    stages = {}
+    hooks = []
+
+    def cap(name):
+        def fn(mod, inp, out):
+            stages.setdefault(name, []).append(out.detach().clone() if torch.is_tensor(out) else out)
+        return fn
+
+    neck = model.core.neck
+    hooks.append(neck.cost_volume_0.register_forward_hook(cap("vol4")))
+    hooks.append(neck.cost_volume_1.register_forward_hook(cap("vol8")))
+    hooks.append(neck.cost_volume_2.register_forward_hook(cap("vol16")))
+    hooks.append(model.core.backbone.register_forward_hook(cap("backbone")))
+    hooks.append(model.core.register_forward_hook(cap("core")))
+    hooks.append(model.bbox_head.register_forward_hook(cap("head")))
+
+    fix = {}
+    outs = []
+    with torch.no_grad():
+        for b in range(B):  # reference asserts batch 1 (yolostereo3d_detector.py:78)
+            s, bb, ci = model([left[b:b + 1], right[b:b + 1], P2[b:b + 1], P3[b:b + 1]])
+            outs.append((s, bb, ci))
+            # the anchors/mask the reference used for this image
+            fix[f"mask_{b}"] = np.packbits(model.bbox_head.anchors.useful_mask[0].numpy())
+    for h in hooks:
+        h.remove()
+    for b in range(B):
+        s, bb, ci = outs[b]
+        fix[f"scores_{b}"] = s.numpy()
+        fix[f"bboxes_{b}"] = bb.numpy()
+        fix[f"cls_{b}"] = ci.numpy()
+        print(f"image {b}: {len(s)} detections; mask true = {int(model.bbox_head.anchors.useful_mask.sum())}")
+    fix["anchors"] = subsample(model.bbox_head.anchors.anchors[0])
+    fix["mean_std"] = subsample(model.bbox_head.anchors.anchor_mean_std)
+    cat = lambda name, i=None: torch.cat([(x if i is None else x[i]) for x in stages[name]], dim=0)
+    fix["vol4"] = subsample(cat("vol4"))
+    fix["vol8"] = subsample(cat("vol8"))
+    fix["vol16"] = subsample(cat("vol16"))
+    # backbone sees [left; right] per image: regroup to the batched order [L0, L1, R0, R1]
+    for j, nm in enumerate(["feat4", "feat8", "feat16"]):
+        per = [x[j] for x in stages["backbone"]]
+        fix[nm] = subsample(torch.cat([p[:1] for p in per] + [p[1:] for p in per], dim=0))
+    fix["features"] = subsample(torch.cat([x["features"] for x in stages["core"]], dim=0))
+    fix["cls_preds"] = subsample(cat("head", 0))
+    fix["reg_preds"] = subsample(cat("head", 1))
+    fix["meta"] = np.array([H, W, B, seed], dtype=np.int64)
+    np.savez_compressed(os.path.join(HERE, tag + ".npz"), **flatten_fixture(fix))
+    print("wrote", tag, {k: (v["shape"].tolist() if isinstance(v, dict) else np.asarray(v).shape) for k, v in fix.items()})
+
+    # immediate pin of the oracle port (also asserted by tests/test_oracle_golden.py)
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(HERE)), "oracle"))
+    import torch_port as tp
+    st = {}
+    o = tp.stereo3d_forward(sd, left, right, P2, cfg, pm, ps, st)
+    for b in range(B):
+        print("oracle vs ref image", b, "n", len(o[b][0]), len(outs[b][0]),
+              "max|dscore|", float((o[b][0] - outs[b][0]).abs().max()) if len(o[b][0]) == len(outs[b][0]) and len(o[b][0]) else None,
+              "max|dbox|", float((o[b][1] - outs[b][1]).abs().max()) if len(o[b][0]) == len(outs[b][0]) and len(o[b][0]) else None)
+    for nm in ["vol4", "vol8", "vol16", "features", "cls_preds", "reg_preds"]:
+        ref = fix[nm]
+        got = subsample(st[nm])
+        print(nm, "max abs diff", float(np.abs(ref["samples"] - got["samples"]).max()), "ref absmean", ref["abssum"] / np.prod(ref["shape"]))
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["stereo3d"]
+    torch.set_num_threads(os.cpu_count())
+    if "stereo3d" in which:
+        gen_stereo3d()
+        gen_stereo3d(H=192, W=640, B=1, tag="stereo3d_192x640")

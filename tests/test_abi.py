@@ -1,0 +1,87 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol the header declares,
+the registry mirrors the reference contract, and the detector's state_dict keys equal the reference's."""
+import json
+import os
+
+import pytest
+import torch
+
+from conftest import GOLDEN, ROOT
+
+
+def test_library_exports_every_declared_symbol():
+    from visualdet3d_b200 import _lib
+    lib = _lib.load()
+    syms = _lib.header_symbols()
+    assert len(syms) >= 15
+    for s in syms:
+        assert hasattr(lib, s), s
+    assert lib.vd3d_version() >= 100
+
+
+def test_registry_contract():
+    from visualdet3d_b200.plugin import Registry
+    r = Registry("detectors")
+
+    @r.register_module
+    class Foo:  # noqa
+        pass
+
+    assert r["Foo"] is Foo and r.get("Bar") is None
+    with pytest.raises(KeyError):
+        r["Bar"]
+    with pytest.raises(KeyError):
+        r._register_module(Foo)
+    r._register_module(Foo, force=True)
+    with pytest.raises(TypeError):
+        r._register_module(3)
+    assert "Foo" in repr(r)
+
+
+def test_stereo3d_registered_and_state_dict_keys_match_reference():
+    from visualdet3d_b200.plugin import DETECTOR_DICT
+    from visualdet3d_b200.detectors import build_synthetic_stereo3d
+    assert "Stereo3D" in DETECTOR_DICT
+    det, sd, cfg, _ = build_synthetic_stereo3d()
+    ref = json.load(open(os.path.join(GOLDEN, "stereo3d_keys.json")))
+    mine = {k: list(v.shape) for k, v in det.state_dict().items()}
+    assert list(mine.keys()) == list(ref.keys())        # same names, same order
+    assert mine == ref                                  # same shapes
+    assert sum(p.numel() for p in det.parameters()) == sum(
+        int(torch.tensor(v).prod()) for k, v in ref.items()
+        if not any(t in k for t in ("running_", "num_batches", "balance_weights", "regression_weight")))
+
+
+def test_product_path_has_no_cpu_fallback():
+    from visualdet3d_b200.detectors import build_synthetic_stereo3d
+    from visualdet3d_b200._lib import Vd3dError
+    from visualdet3d_b200 import synth
+    det, *_ = build_synthetic_stereo3d()
+    l, r, P2, P3 = synth.synth_stereo_inputs(1, 32, 64)
+    with pytest.raises(Vd3dError):
+        det([l, r, P2, P3])
+
+
+def test_product_does_not_import_oracle():
+    import re
+    bad = []
+    for dp, _, fs in os.walk(os.path.join(ROOT, "visualdet3d_b200")):
+        for f in fs:
+            if f.endswith(".py"):
+                txt = open(os.path.join(dp, f)).read()
+                if re.search(r"^\s*(from|import)\s+(oracle|torch_port)", txt, flags=re.M):
+                    bad.append(f)
+    assert not bad, bad
+
+
+def test_anchor_table_matches_oracle_bitwise():
+    import numpy as np
+    import torch_port as tp
+    from visualdet3d_b200 import synth
+    from visualdet3d_b200.anchors import AnchorTable
+    pm, ps = synth.synth_priors(16, 3, ["Car", "Pedestrian"])
+    cfg = synth.stereo3d_cfg("/x")
+    for hw in [(96, 320), (288, 1280), (100, 330)]:
+        a, ms, means = tp.build_anchors(hw, cfg["head"]["anchors_cfg"], pm, ps)
+        t = AnchorTable(hw, cfg["head"]["anchors_cfg"], pm, ps, "cpu")
+        assert torch.equal(t.anchors, a) and torch.equal(t.mean_std, ms) and torch.equal(t.means_z, means[:, :, 0])

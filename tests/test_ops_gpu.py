@@ -1,0 +1,152 @@
+"""Kernel-level parity (-m gpu): every CUDA op of libvd3d_b200 against the fp32 CPU oracle ops, through the C ABI."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import torch_port as tp
+
+pytestmark = pytest.mark.gpu
+
+
+def _E():
+    from visualdet3d_b200 import engine
+    return engine
+
+
+def nhwc(x_nchw):
+    return x_nchw.permute(0, 2, 3, 1).contiguous()
+
+
+CONV_CASES = [
+    # B, Cin, H, W, Cout, k, stride, pad, dil, bias, res, relu
+    (2, 3, 33, 47, 64, 7, 2, 3, 1, False, False, True),      # stem (scalar gather path)
+    (2, 4, 33, 47, 64, 7, 2, 3, 1, False, False, True),      # stem, padded to 4 channels
+    (1, 64, 24, 40, 64, 3, 1, 1, 1, False, True, True),
+    (2, 64, 24, 40, 128, 3, 2, 1, 1, False, False, True),
+    (2, 64, 24, 40, 128, 1, 2, 0, 1, False, False, False),   # downsample
+    (1, 24, 17, 23, 24, 3, 1, 1, 1, False, False, True),     # K tail (216 = 13.5 chunks)
+    (1, 72, 12, 20, 72, 3, 1, 1, 1, True, True, True),
+    (1, 256, 6, 20, 8, 1, 1, 0, 1, True, False, True),       # cost-volume down-sample (Cout = 8)
+    (1, 256, 6, 20, 144, 3, 1, 1, 1, True, False, False),
+    (1, 128, 9, 11, 256, 3, 1, 2, 2, True, False, True),     # dilation 2
+    (1, 1408, 6, 20, 256, 3, 1, 1, 1, True, False, True),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv2d_vs_torch(case):
+    E = _E()
+    B, Cin, H, W, Cout, k, s, p, d, has_b, has_r, relu = case
+    g = torch.Generator().manual_seed(sum(case[:6]))
+    x = torch.randn(B, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, k, k, generator=g) / np.sqrt(Cin * k * k)
+    b = torch.randn(Cout, generator=g) if has_b else None
+    ref = F.conv2d(x, w, b, stride=s, padding=p, dilation=d)
+    r = torch.randn(ref.shape, generator=g) if has_r else None
+    if r is not None:
+        ref = ref + r
+    if relu:
+        ref = F.relu(ref)
+    layer = E.ConvLayer(w, b, None, stride=s, pad=p, dil=d, relu=relu, device="cuda")
+    xa = E.Act(nhwc(x).cuda())
+    Ho, Wo = layer.out_hw(H, W)
+    # write into a channel slice of a wider buffer to exercise pitch / offset handling
+    out = E.Act(torch.full((B, Ho, Wo, Cout + 8), 7.0, device="cuda"), 4, Cout)
+    ra = E.Act(nhwc(r).cuda()) if r is not None else None
+    layer(xa, out, res=ra)
+    got = out.to_nchw().cpu()
+    assert float(out.t[..., :4].min()) == 7.0 and float(out.t[..., 4 + Cout:].min()) == 7.0   # neighbours untouched
+    np.testing.assert_allclose(got.numpy(), ref.numpy(), rtol=1e-4, atol=2e-5)
+
+
+def test_conv_bn_folding_matches_conv_then_bn():
+    E = _E()
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 32, 10, 12, generator=g)
+    w = torch.randn(48, 32, 3, 3, generator=g) * 0.1
+    bn = dict(weight=torch.rand(48, generator=g) + 0.5, bias=torch.randn(48, generator=g) * 0.1,
+              running_mean=torch.randn(48, generator=g) * 0.1, running_var=torch.rand(48, generator=g) + 0.5)
+    ref = F.relu(F.batch_norm(F.conv2d(x, w, None, padding=1), bn["running_mean"], bn["running_var"], bn["weight"], bn["bias"], False, 0.0, 1e-5))
+    layer = E.ConvLayer(w, None, bn, pad=1, relu=True, device="cuda")
+    out = layer(E.Act(nhwc(x).cuda()), E.Act(torch.empty(2, 10, 12, 48, device="cuda")))
+    np.testing.assert_allclose(out.to_nchw().cpu().numpy(), ref.numpy(), rtol=1e-4, atol=2e-5)
+
+
+def test_pools_dwconv_copy():
+    E = _E()
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(2, 24, 18, 26, generator=g)
+    xa = E.Act(nhwc(x).cuda())
+    mp = E.maxpool3x3s2(xa, E.Act(torch.empty(2, 9, 13, 24, device="cuda")))
+    assert torch.equal(mp.to_nchw().cpu(), F.max_pool2d(x, 3, 2, 1))
+    ap = E.avgpool2(xa, E.Act(torch.empty(2, 9, 13, 24, device="cuda")))
+    np.testing.assert_allclose(ap.to_nchw().cpu().numpy(), F.avg_pool2d(x, 2).numpy(), atol=1e-6)
+    w = torch.randn(24, 1, 3, 3, generator=g)
+    dw = E.DwConvLayer(w, None, relu=True, device="cuda")
+    o = dw(xa, E.Act(torch.empty(2, 18, 26, 24, device="cuda")))
+    np.testing.assert_allclose(o.to_nchw().cpu().numpy(), F.relu(F.conv2d(x, w, None, padding=1, groups=24)).numpy(), atol=1e-5)
+    big = E.Act(torch.zeros(2, 18, 26, 40, device="cuda"))
+    E.copy_channels(xa, big.slice(8, 24))
+    assert torch.equal(big.slice(8, 24).to_nchw().cpu(), x) and float(big.t[..., :8].abs().max()) == 0
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 5, 80), (1, 128, 3, 40), (1, 64, 4, 200), (2, 32, 3, 50), (1, 64, 2, 20), (1, 128, 2, 7)])
+def test_psm_cosine_vs_oracle(shape):
+    """PSMCosine (R/lib/PSM_cost_volume.py:76-91): tiled kernel (C = 64/128, D = 24), generic kernel, ragged widths,
+    W < D (planes beyond the width stay zero)."""
+    E = _E()
+    B, C, H, W = shape
+    g = torch.Generator().manual_seed(C + W)
+    L, R = torch.randn(B, C, H, W, generator=g), torch.randn(B, C, H, W, generator=g)
+    ref = tp.psm_cosine(L, R, 96, 4)
+    out = E.Act(torch.full((B, H, W, 32), 3.0, device="cuda"), 4, 24)
+    E.psm_cosine(E.Act(nhwc(L).cuda()), E.Act(nhwc(R).cuda()), 24, out)
+    np.testing.assert_allclose(out.to_nchw().cpu().numpy(), ref.numpy(), rtol=1e-5, atol=2e-6)
+    assert float(out.t[..., :4].min()) == 3.0 and float(out.t[..., 28:].min()) == 3.0
+    # exact zeros where w < i
+    got = out.to_nchw().cpu()
+    for i in range(1, min(24, W)):
+        assert float(got[:, i, :, :i].abs().max()) == 0.0
+    # NCHW op-level mirror
+    from visualdet3d_b200._lib import call
+    o2 = torch.empty(B, 24, H, W, device="cuda")
+    Lc, Rc = L.cuda(), R.cuda()
+    call("vd3d_psm_cosine_nchw", Lc.data_ptr(), Rc.data_ptr(), B, C, H, W, 24, o2.data_ptr(), None)
+    np.testing.assert_allclose(o2.cpu().numpy(), ref.numpy(), rtol=1e-5, atol=2e-6)
+
+
+def test_psm_cosine_linearity_full_size():
+    """Size-independent property at the BASELINE shape (B=8, 64ch, 96x320): cost(L, a*R1 + R2) = a*cost(L,R1) + cost(L,R2)."""
+    E = _E()
+    B, C, H, W = 8, 64, 96, 320
+    g = torch.Generator(device="cuda").manual_seed(0)
+    L = torch.randn(B, H, W, C, device="cuda", generator=g)
+    R1 = torch.randn(B, H, W, C, device="cuda", generator=g)
+    R2 = torch.randn(B, H, W, C, device="cuda", generator=g)
+    outs = []
+    for Rr in (R1, R2, 0.5 * R1 + R2):
+        o = E.Act(torch.empty(B, H, W, 24, device="cuda"))
+        E.psm_cosine(E.Act(L), E.Act(Rr.contiguous()), 24, o)
+        outs.append(o.t)
+    assert float((outs[2] - (0.5 * outs[0] + outs[1])).abs().max()) < 1e-5
+    assert float(outs[0][:, :, 0, 1:].abs().max()) == 0.0        # w = 0: only disparity 0 is defined
+
+
+def test_concat_volume_conv3d_vs_oracle():
+    E = _E()
+    from visualdet3d_b200._lib import call
+    g = torch.Generator().manual_seed(9)
+    B, Fc, H, W, D = 2, 8, 6, 20, 12
+    lf, rf = torch.rand(B, Fc, H, W, generator=g), torch.rand(B, Fc, H, W, generator=g)
+    w1, b1 = torch.randn(8, 16, 3, 3, 3, generator=g) * 0.1, torch.randn(8, generator=g) * 0.1
+    w2, b2 = torch.randn(8, 8, 3, 3, 3, generator=g) * 0.1, torch.randn(8, generator=g) * 0.1
+    vol = tp.concat_volume(lf, rf, D)
+    ref = F.relu(F.conv3d(F.relu(F.conv3d(vol, w1, b1, padding=1)), w2, b2, padding=1)).reshape(B, -1, H, W)
+    pk = lambda w: w.permute(2, 3, 4, 1, 0).reshape(27, w.shape[1], w.shape[0]).contiguous().cuda()
+    mid = torch.empty(B, D, H, W, Fc, device="cuda")
+    out = E.Act(torch.zeros(B, H, W, 100, device="cuda"), 4, 96)
+    call("vd3d_concat_volume_conv3d", nhwc(lf).cuda().data_ptr(), nhwc(rf).cuda().data_ptr(), B, H, W, Fc, D,
+         pk(w1).data_ptr(), b1.cuda().data_ptr(), pk(w2).data_ptr(), b2.cuda().data_ptr(), mid.data_ptr(),
+         out.ptr, out.cs, out.co, None)
+    np.testing.assert_allclose(out.to_nchw().cpu().numpy(), ref.numpy(), rtol=1e-4, atol=1e-5)

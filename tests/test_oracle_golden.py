@@ -1,0 +1,56 @@
+"""Pins oracle/torch_port.py to the reference: the fixtures under tests/golden were produced by running the
+UNMODIFIED reference (tests/golden/make_golden.py); here the port must reproduce them on CPU."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, load_fixture, subsample_like
+from visualdet3d_b200 import synth
+import torch_port as tp
+
+
+def _stereo_setup(H, W, B, seed):
+    shapes = json.load(open(os.path.join(GOLDEN, "stereo3d_keys.json")))
+    sd = synth.synth_state_dict(shapes, seed)
+    pm, ps = synth.synth_priors(16, 3, ["Car", "Pedestrian"])
+    cfg = synth.stereo3d_cfg("/nonexistent")
+    left, right, P2, P3 = synth.synth_stereo_inputs(B, H, W, seed=1)
+    return sd, pm, ps, cfg, left, right, P2
+
+
+@pytest.mark.parametrize("tag", ["stereo3d_96x320", "stereo3d_192x640"])
+def test_stereo3d_port_matches_reference(tag):
+    fx = load_fixture(tag)
+    H, W, B, seed = [int(v) for v in fx["meta"]]
+    sd, pm, ps, cfg, left, right, P2 = _stereo_setup(H, W, B, seed)
+    st = {}
+    outs = tp.stereo3d_forward(sd, left, right, P2, cfg, pm, ps, st)
+    # stage tensors: the reference ran batch 1 per image, the port runs batched -> oneDNN may pick other kernels: 2e-4
+    for nm in ["vol4", "vol8", "vol16", "features", "cls_preds", "reg_preds"]:
+        got = subsample_like(st[nm], fx[nm])
+        np.testing.assert_allclose(got, fx[nm]["samples"], rtol=0, atol=2e-4, err_msg=nm)
+    bb = torch.cat([st["feat4"][:B], st["feat4"][B:]], 0)
+    np.testing.assert_allclose(subsample_like(bb, fx["feat4"]), fx["feat4"]["samples"], atol=2e-4)
+    np.testing.assert_array_equal(subsample_like(st["anchors"], fx["anchors"]), fx["anchors"]["samples"])
+    np.testing.assert_array_equal(subsample_like(st["mean_std"], fx["mean_std"]), fx["mean_std"]["samples"])
+    for b in range(B):
+        np.testing.assert_array_equal(np.packbits(st["mask"][b].numpy()), fx[f"mask_{b}"])   # bit-exact useful mask
+        s, bx, ci, _ = outs[b]
+        assert len(s) == len(fx[f"scores_{b}"])
+        np.testing.assert_array_equal(ci.numpy(), fx[f"cls_{b}"])                              # bit-exact class / keep set
+        np.testing.assert_allclose(s.numpy(), fx[f"scores_{b}"], atol=1e-4)
+        np.testing.assert_allclose(bx.numpy(), fx[f"bboxes_{b}"], atol=1e-3)
+
+
+def test_psm_cosine_port_edge_cases():
+    # narrower than the disparity range, single channel, batch > 1
+    g = torch.Generator().manual_seed(0)
+    L, R = torch.randn(2, 4, 3, 10, generator=g), torch.randn(2, 4, 3, 10, generator=g)
+    c = tp.psm_cosine(L, R, 96, 4)
+    assert c.shape == (2, 24, 3, 10)
+    assert float(c[:, 10:].abs().max()) == 0.0           # planes i >= W stay zero
+    assert float(c[:, 5, :, :5].abs().max()) == 0.0       # columns w < i stay zero
+    np.testing.assert_allclose(c[:, 3, :, 3:], (L[..., 3:] * R[..., :-3]).mean(1))

@@ -1,0 +1,320 @@
+// Stereo cost volumes (R/lib/PSM_cost_volume.py): correlation volume (PSMCosineModule) and the scale-16
+// concat volume fused into its two Conv3d layers (CostVolume).  HBM-bound: every input element is read once
+// from HBM (re-reads are served from shared memory / L2), every output element written once.
+#include "common.cuh"
+
+namespace vd3d {
+
+// ---------------------------------------------------------------------------------------------------------
+// PSMCosine, NHWC.   out[b,h,w,i] = (1/C) sum_c L[b,h,w,c] * R[b,h,w-i,c]  (w >= i), 0 otherwise.
+//
+// v2 kernel: CTA = (b, h, 64-pixel tile); the L tile and the R window (64 + 24 pixels) are transposed on the
+// way into shared memory to [c][w] so that each thread register-tiles 4 pixels x 24 disparities and reuses every
+// shared-memory word 24x / 4x.  A warp = 4 pixel groups x 8 channel splits; the 8 partial sums are combined with a
+// transpose-reduce (84 shuffles for 96 accumulators).  See DESIGN.md "cost volume".
+// ---------------------------------------------------------------------------------------------------------
+constexpr int PSM_TW = 64;      // pixels per CTA
+constexpr int PSM_D = 24;       // disparities (both PSMCosine layers of the path have D = 24)
+constexpr int PSM_THREADS = 128;
+constexpr int PSM_RW = PSM_TW + PSM_D;             // R window incl. halo, 88 columns: cols [w0-24, w0+64)
+constexpr int PSM_LP = PSM_TW + 2;                 // row pitch of Ls, == 2 (mod 32) -> conflict-free transposed stores
+constexpr int PSM_RP = PSM_RW + 10;                // 98 == 2 (mod 32)
+
+template <int C>
+__global__ void __launch_bounds__(PSM_THREADS) psm_cosine_nhwc_kernel(
+    const float* __restrict__ L, const float* __restrict__ R, int H, int W, int lr_cs, int lr_co,
+    float* __restrict__ out, int out_cs, int out_co) {
+    extern __shared__ __align__(16) float smem[];
+    float* Ls = smem;                       // [C][PSM_LP]
+    float* Rs = smem + C * PSM_LP;          // [C][PSM_RP]
+    const int t = threadIdx.x;
+    const int w0 = blockIdx.x * PSM_TW;
+    const int h = blockIdx.y, b = blockIdx.z;
+    const long long rowbase = ((long long)b * H + h) * W;
+
+    // ---- load + transpose: lanes = (pixel p in 0..7) x (channel quad cq in 0..3) -> 8 x 64B segments / warp-load
+    {
+        const int p = t & 7, cq = (t >> 3) & 3, wrp = t >> 5;   // 4 warps
+        constexpr int CQ = C / 4;                                  // channel quads per pixel
+        // L tile: 64 pixels x CQ quads; per pass a warp covers 8 pixels x 4 quads
+        for (int it = wrp; it < (PSM_TW / 8) * (CQ / 4); it += PSM_THREADS / 32) {
+            int pg = it / (CQ / 4), qg = it - pg * (CQ / 4);
+            int px = pg * 8 + p, q = qg * 4 + cq;
+            int w = w0 + px;
+            float4 v = (w < W) ? ldg4(L + (rowbase + w) * lr_cs + lr_co + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float* d = Ls + (4 * q) * PSM_LP + px;
+            d[0] = v.x; d[PSM_LP] = v.y; d[2 * PSM_LP] = v.z; d[3 * PSM_LP] = v.w;
+        }
+        for (int it = wrp; it < (PSM_RW / 8) * (CQ / 4); it += PSM_THREADS / 32) {
+            int pg = it / (CQ / 4), qg = it - pg * (CQ / 4);
+            int px = pg * 8 + p, q = qg * 4 + cq;
+            int w = w0 - PSM_D + px;
+            float4 v = (w >= 0 && w < W) ? ldg4(R + (rowbase + w) * lr_cs + lr_co + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float* d = Rs + (4 * q) * PSM_RP + px;
+            d[0] = v.x; d[PSM_RP] = v.y; d[2 * PSM_RP] = v.z; d[3 * PSM_RP] = v.w;
+        }
+    }
+    __syncthreads();
+
+    // ---- compute: lane = pg*8 + s ; pixel group pg (4 pixels at 16*pg + 4*warp), channel split s (c = s + 8k)
+    const int lane = t & 31, wrp = t >> 5;
+    const int s = lane & 7, pg = lane >> 3;
+    const int px0 = 16 * pg + 4 * wrp;            // first of this thread's 4 pixels (tile-local)
+    float acc[4][PSM_D];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < PSM_D; ++j) acc[i][j] = 0.f;
+
+#pragma unroll 1
+    for (int c = s; c < C; c += 8) {
+        const float* lr = Ls + c * PSM_LP + px0;
+        const float* rr = Rs + c * PSM_RP + px0;   // Rs column j <-> pixel (w0 - 24 + j): pixel px0+i-d <-> column px0+i-d+24
+        float l[4], r[28];
+        {
+            float2 a = *reinterpret_cast<const float2*>(lr), bq = *reinterpret_cast<const float2*>(lr + 2);
+            l[0] = a.x; l[1] = a.y; l[2] = bq.x; l[3] = bq.y;
+        }
+#pragma unroll
+        for (int j = 0; j < 28; j += 2) {
+            float2 v = *reinterpret_cast<const float2*>(rr + j);
+            r[j] = v.x; r[j + 1] = v.y;
+        }
+        // r[j] holds pixel (px0 - 24 + j); disparity d for pixel i needs pixel px0+i-d -> r[24 + i - d]
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int d = 0; d < PSM_D; ++d) acc[i][d] = fmaf(l[i], r[24 + i - d], acc[i][d]);
+    }
+
+    // ---- transpose-reduce across the 8 channel splits (lanes differing in bits 0..2) -------------------------
+    // after step k each lane keeps half of its values; lane s ends with the 12 values v[12*... ] of its share.
+    float* a = &acc[0][0];   // 96 values, index = i*24 + d
+    // step 1: partner = lane ^ 4 ; lanes with (s&4)==0 keep [0,48), others keep [48,96)
+#pragma unroll
+    for (int j = 0; j < 48; ++j) {
+        bool hi = (s & 4) != 0;
+        float send = hi ? a[j] : a[j + 48];
+        float recv = __shfl_xor_sync(0xffffffffu, send, 4);
+        a[j] = (hi ? a[j + 48] : a[j]) + recv;
+    }
+#pragma unroll
+    for (int j = 0; j < 24; ++j) {
+        bool hi = (s & 2) != 0;
+        float send = hi ? a[j] : a[j + 24];
+        float recv = __shfl_xor_sync(0xffffffffu, send, 2);
+        a[j] = (hi ? a[j + 24] : a[j]) + recv;
+    }
+#pragma unroll
+    for (int j = 0; j < 12; ++j) {
+        bool hi = (s & 1) != 0;
+        float send = hi ? a[j] : a[j + 12];
+        float recv = __shfl_xor_sync(0xffffffffu, send, 1);
+        a[j] = (hi ? a[j + 12] : a[j]) + recv;
+    }
+    // lane s now owns flat indices [12*rank, 12*rank+12) with rank = (s&4 ? 4:0) + (s&2 ? 2:0) + (s&1) = s
+    // -> pixel i = s/2, disparities (s&1)*12 .. +12
+    {
+        const int i = s >> 1, d0 = (s & 1) * 12;
+        const int w = w0 + px0 + i;
+        if (w < W) {
+            float* op = out + (rowbase + w) * out_cs + out_co + d0;
+            const float inv = 1.0f / (float)C;
+            float o[12];
+#pragma unroll
+            for (int j = 0; j < 12; ++j) o[j] = (w >= d0 + j) ? a[j] * inv : 0.f;
+#pragma unroll
+            for (int j = 0; j < 12; j += 4) *reinterpret_cast<float4*>(op + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+        }
+    }
+}
+
+// Generic fallback (any C % 4 == 0, any D <= 64): thread = (pixel, disparity), reads through L1.
+__global__ void psm_cosine_nhwc_generic_kernel(const float* __restrict__ L, const float* __restrict__ R, long long npix, int W, int C,
+                                               int lr_cs, int lr_co, int D, float* __restrict__ out, int out_cs, int out_co) {
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= npix * D) return;
+    int i = (int)(idx % D); long long pix = idx / D;
+    int w = (int)(pix % W);
+    float s = 0.f;
+    if (w >= i) {
+        const float* lp = L + pix * lr_cs + lr_co;
+        const float* rp = R + (pix - i) * lr_cs + lr_co;
+        for (int c = 0; c < C; c += 4) {
+            float4 a = ldg4(lp + c), bq = ldg4(rp + c);
+            s = fmaf(a.x, bq.x, s); s = fmaf(a.y, bq.y, s); s = fmaf(a.z, bq.z, s); s = fmaf(a.w, bq.w, s);
+        }
+        s = s / (float)C;
+    }
+    out[pix * out_cs + out_co + i] = s;
+}
+
+// NCHW op-level mirror: thread = (b, h, w); loops c with coalesced reads along w.
+__global__ void psm_cosine_nchw_kernel(const float* __restrict__ L, const float* __restrict__ R, int B, int C, int H, int W, int D,
+                                       float* __restrict__ out) {
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long HW = (long long)H * W;
+    if (idx >= (long long)B * HW) return;
+    int w = (int)(idx % W); long long r = idx / W; int h = (int)(r % H); int b = (int)(r / H);
+    for (int d0 = 0; d0 < D; d0 += 8) {
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        for (int c = 0; c < C; ++c) {
+            const float* lp = L + ((long long)b * C + c) * HW + (long long)h * W;
+            const float* rp = R + ((long long)b * C + c) * HW + (long long)h * W;
+            float l = __ldg(lp + w);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                int i = d0 + j;
+                if (i < D && w >= i) acc[j] = fmaf(l, __ldg(rp + w - i), acc[j]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            int i = d0 + j;
+            if (i < D) out[((long long)b * D + i) * HW + (long long)h * W + w] = (w >= i) ? acc[j] / (float)C : 0.f;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// concat volume + Conv3d #1 (2F -> F) : thread = (b, d, h, w), F = 8 outputs.  The volume is gathered from lf / rf.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int CV_F = 8;
+
+__global__ void __launch_bounds__(128) concat_conv3d_1_kernel(const float* __restrict__ lf, const float* __restrict__ rf,
+                                                               const float* __restrict__ w1, const float* __restrict__ b1,
+                                                               float* __restrict__ mid, int B, int D, int H, int W) {
+    __shared__ __align__(16) float ws[27 * 2 * CV_F * CV_F];
+    for (int i = threadIdx.x; i < 27 * 2 * CV_F * CV_F; i += blockDim.x) ws[i] = w1[i];
+    __syncthreads();
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = (long long)B * D * H * W;
+    if (idx >= total) return;
+    int w = (int)(idx % W); long long r = idx / W; int h = (int)(r % H); r /= H; int d = (int)(r % D); int b = (int)(r / D);
+    float acc[CV_F];
+#pragma unroll
+    for (int f = 0; f < CV_F; ++f) acc[f] = 0.f;
+    for (int kd = 0; kd < 3; ++kd) {
+        int dd = d - 1 + kd;
+        if (dd < 0 || dd >= D) continue;
+        for (int kh = 0; kh < 3; ++kh) {
+            int hh = h - 1 + kh;
+            if (hh < 0 || hh >= H) continue;
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+                int ww = w - 1 + kw;
+                if (ww < 0 || ww >= W || ww < dd) continue;          // volume is zero where w < disparity
+                const float* lp = lf + (((long long)b * H + hh) * W + ww) * CV_F;
+                const float* rp = rf + (((long long)b * H + hh) * W + ww - dd) * CV_F;
+                float v[2 * CV_F];
+                float4 x0 = ldg4(lp), x1 = ldg4(lp + 4), y0 = ldg4(rp), y1 = ldg4(rp + 4);
+                v[0] = x0.x; v[1] = x0.y; v[2] = x0.z; v[3] = x0.w; v[4] = x1.x; v[5] = x1.y; v[6] = x1.z; v[7] = x1.w;
+                v[8] = y0.x; v[9] = y0.y; v[10] = y0.z; v[11] = y0.w; v[12] = y1.x; v[13] = y1.y; v[14] = y1.z; v[15] = y1.w;
+                const float* wt = ws + ((kd * 3 + kh) * 3 + kw) * (2 * CV_F * CV_F);
+#pragma unroll
+                for (int c = 0; c < 2 * CV_F; ++c)
+#pragma unroll
+                    for (int f = 0; f < CV_F; ++f) acc[f] = fmaf(v[c], wt[c * CV_F + f], acc[f]);
+            }
+        }
+    }
+    float* op = mid + idx * CV_F;
+#pragma unroll
+    for (int f = 0; f < CV_F; ++f) acc[f] = fmaxf(acc[f] + __ldg(b1 + f), 0.f);
+    *reinterpret_cast<float4*>(op) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    *reinterpret_cast<float4*>(op + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+}
+
+__global__ void __launch_bounds__(128) conv3d_2_kernel(const float* __restrict__ mid, const float* __restrict__ w2, const float* __restrict__ b2,
+                                                        float* __restrict__ out, int B, int D, int H, int W, int out_cs, int out_co) {
+    __shared__ __align__(16) float ws[27 * CV_F * CV_F];
+    for (int i = threadIdx.x; i < 27 * CV_F * CV_F; i += blockDim.x) ws[i] = w2[i];
+    __syncthreads();
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = (long long)B * D * H * W;
+    if (idx >= total) return;
+    // thread order here: d fastest so the D outputs of one (pixel, f) are written by neighbouring threads
+    int d = (int)(idx % D); long long r = idx / D; int w = (int)(r % W); r /= W; int h = (int)(r % H); int b = (int)(r / H);
+    float acc[CV_F];
+#pragma unroll
+    for (int f = 0; f < CV_F; ++f) acc[f] = 0.f;
+    for (int kd = 0; kd < 3; ++kd) {
+        int dd = d - 1 + kd;
+        if (dd < 0 || dd >= D) continue;
+        for (int kh = 0; kh < 3; ++kh) {
+            int hh = h - 1 + kh;
+            if (hh < 0 || hh >= H) continue;
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+                int ww = w - 1 + kw;
+                if (ww < 0 || ww >= W) continue;
+                const float* mp = mid + ((((long long)b * D + dd) * H + hh) * W + ww) * CV_F;
+                float4 x0 = ldg4(mp), x1 = ldg4(mp + 4);
+                float v[CV_F] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+                const float* wt = ws + ((kd * 3 + kh) * 3 + kw) * (CV_F * CV_F);
+#pragma unroll
+                for (int c = 0; c < CV_F; ++c)
+#pragma unroll
+                    for (int f = 0; f < CV_F; ++f) acc[f] = fmaf(v[c], wt[c * CV_F + f], acc[f]);
+            }
+        }
+    }
+    float* op = out + (((long long)b * H + h) * W + w) * out_cs + out_co + d;
+#pragma unroll
+    for (int f = 0; f < CV_F; ++f) op[f * D] = fmaxf(acc[f] + __ldg(b2 + f), 0.f);
+}
+
+}  // namespace vd3d
+
+using namespace vd3d;
+
+extern "C" int vd3d_psm_cosine_nhwc(const float* L, const float* R, int B, int H, int W, int C, int lr_cs, int lr_co,
+                                    int D, float* out, int out_cs, int out_co, void* stream) {
+    VD3D_REQUIRE(L && R && out, "psm_cosine: null pointer");
+    VD3D_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && D > 0 && D <= 64, "psm_cosine: bad shape");
+    VD3D_REQUIRE(C % 4 == 0 && lr_cs % 4 == 0 && lr_co % 4 == 0, "psm_cosine: C, pitch, offset must be multiples of 4");
+    cudaStream_t st = (cudaStream_t)stream;
+    bool fast = (D == PSM_D) && (C == 64 || C == 128) && out_cs % 4 == 0 && out_co % 4 == 0 && H < 65536 && B < 65536;
+    if (fast) {
+        dim3 grid(cdiv(W, PSM_TW), H, B);
+        size_t smem = (size_t)C * (PSM_LP + PSM_RP) * sizeof(float);
+        if (C == 64) {
+            VD3D_CUDA(cudaFuncSetAttribute(psm_cosine_nhwc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            psm_cosine_nhwc_kernel<64><<<grid, PSM_THREADS, smem, st>>>(L, R, H, W, lr_cs, lr_co, out, out_cs, out_co);
+        } else {
+            VD3D_CUDA(cudaFuncSetAttribute(psm_cosine_nhwc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            psm_cosine_nhwc_kernel<128><<<grid, PSM_THREADS, smem, st>>>(L, R, H, W, lr_cs, lr_co, out, out_cs, out_co);
+        }
+        VD3D_CHECK_LAUNCH("psm_cosine_nhwc");
+    } else {
+        long long npix = (long long)B * H * W;
+        psm_cosine_nhwc_generic_kernel<<<cdiv(npix * D, 256), 256, 0, st>>>(L, R, npix, W, C, lr_cs, lr_co, D, out, out_cs, out_co);
+        VD3D_CHECK_LAUNCH("psm_cosine_nhwc_generic");
+    }
+    return VD3D_OK;
+}
+
+extern "C" int vd3d_psm_cosine_nchw(const float* L, const float* R, int B, int C, int H, int W, int D, float* out, void* stream) {
+    VD3D_REQUIRE(L && R && out && B > 0 && C > 0 && H > 0 && W > 0 && D > 0, "psm_cosine_nchw: bad args");
+    long long n = (long long)B * H * W;
+    psm_cosine_nchw_kernel<<<cdiv(n, 128), 128, 0, (cudaStream_t)stream>>>(L, R, B, C, H, W, D, out);
+    VD3D_CHECK_LAUNCH("psm_cosine_nchw");
+    return VD3D_OK;
+}
+
+extern "C" int vd3d_concat_volume_conv3d(const float* lf, const float* rf, int B, int H, int W, int F, int D,
+                                         const float* w1, const float* b1, const float* w2, const float* b2,
+                                         float* mid, float* out, int out_cs, int out_co, void* stream) {
+    VD3D_REQUIRE(lf && rf && w1 && b1 && w2 && b2 && mid && out, "concat_volume_conv3d: null pointer");
+    VD3D_REQUIRE(F == CV_F, "concat_volume_conv3d: PSM_features must be 8 (got %d)", F);
+    VD3D_REQUIRE(B > 0 && H > 0 && W > 0 && D > 0, "concat_volume_conv3d: bad shape");
+    long long total = (long long)B * D * H * W;
+    cudaStream_t st = (cudaStream_t)stream;
+    concat_conv3d_1_kernel<<<cdiv(total, 128), 128, 0, st>>>(lf, rf, w1, b1, mid, B, D, H, W);
+    VD3D_CHECK_LAUNCH("concat_conv3d_1");
+    conv3d_2_kernel<<<cdiv(total, 128), 128, 0, st>>>(mid, w2, b2, out, B, D, H, W, out_cs, out_co);
+    VD3D_CHECK_LAUNCH("conv3d_2");
+    return VD3D_OK;
+}

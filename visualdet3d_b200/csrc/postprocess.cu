@@ -1,0 +1,244 @@
+// Anchor filtering, box decode, clipping and NMS for the anchor-based 3-D head, batched, fixed capacity, no host
+// round trips (the reference does ~30 tiny eager kernels and >= 6 D2H syncs per image,
+// R/heads/detection_3d_head.py:341-400).
+//
+// Bit-exactness: index sets (useful mask, score threshold, prior validity, NMS keep) are decided by fp32
+// comparisons whose operands are computed with the SAME operation order as the reference's eager ops and with
+// FMA contraction disabled (explicit __fmul_rn/__fadd_rn/__fdiv_rn), so they only differ where the CUDA libm
+// (expf/atan2f) differs from the host libm by an ulp on a knife edge.
+#include "common.cuh"
+
+namespace vd3d {
+
+__device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+
+// ---------------------------------------------------------------------------------------------------------
+// useful mask (R/heads/anchors.py:93-111)
+//   x3d = (xc*z - cx*z)/fy ; y3d = (yc*z - cy*z)/fy ; mask = any_t( y3d > ymin && y3d < ymax && |x3d| < xthr )
+//   xc = mean(x1, x2) computed by torch as (x1 + x2) / 2
+// ---------------------------------------------------------------------------------------------------------
+__global__ void anchor_mask_kernel(const float* __restrict__ anchors, const float* __restrict__ means_z, const float* __restrict__ P2,
+                                   int B, int N, int T, float y_min, float y_max, float x_thr, uint8_t* __restrict__ mask) {
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)B * N) return;
+    int n = (int)(idx % N), b = (int)(idx / N);
+    float4 a = ldg4(anchors + 4 * (long long)n);
+    float xc = __fdiv_rn(add(a.x, a.z), 2.0f);
+    float yc = __fdiv_rn(add(a.y, a.w), 2.0f);
+    const float* P = P2 + 12 * b;
+    float fy = P[5], cy = P[6], cx = P[2];
+    bool any = false;
+    for (int t = 0; t < T; ++t) {
+        float z = __ldg(means_z + (long long)t * N + n);
+        float x3 = __fdiv_rn(sub(mul(xc, z), mul(cx, z)), fy);
+        float y3 = __fdiv_rn(sub(mul(yc, z), mul(cy, z)), fy);
+        any = any || ((y3 > y_min) && (y3 < y_max) && (fabsf(x3) < x_thr));
+    }
+    mask[idx] = any ? 1 : 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// stage 1: score + threshold + validity -> unordered candidate list (atomic compaction).  The order is fixed
+// afterwards by the sort key (score desc, anchor index asc) == torchvision's stable descending sort of the
+// index-ordered candidate list.
+// workspace layout per image: keys u64[cap], boxes f32[cap][11], labels i32[cap]
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sigmoidf_ref(float x) {
+    // torch CPU sigmoid: 1 / (1 + exp(-x))
+    return __fdiv_rn(1.0f, add(1.0f, expf(-x)));
+}
+
+struct DecodeWs {
+    unsigned long long* keys;   // [B][cap]
+    float* boxes;               // [B][cap][11]
+    int* labels;                // [B][cap]
+    int* ncand;                 // [B]
+};
+
+__global__ void decode_candidates_kernel(const float* __restrict__ cls, const float* __restrict__ reg, const float* __restrict__ anchors,
+                                         const float* __restrict__ mean_std, const uint8_t* __restrict__ mask,
+                                         int B, int N, int ncls, int T, float score_thr, float img_w, float img_h, int cap, DecodeWs ws) {
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)B * N) return;
+    int n = (int)(idx % N), b = (int)(idx / N);
+    if (!mask[idx]) return;
+    const float* cp = cls + idx * (ncls + 1);
+    float best = -1.f; int label = 0;
+    for (int c = 0; c < ncls; ++c) {
+        float p = sigmoidf_ref(__ldg(cp + c));
+        if (p > best) { best = p; label = c; }     // first maximum wins (torch.max over dim)
+    }
+    if (!(best > score_thr)) return;
+    const float* ms = mean_std + ((long long)n * T + label) * 12;   // [6][2]
+    float z_mean = __ldg(ms + 0);
+    if (!(z_mean > 0.f)) return;                                    // `mask = selected_mean_std[:,0,0] > 0` (:242)
+    float alpha_score = sigmoidf_ref(__ldg(cp + ncls));
+
+    float4 a = ldg4(anchors + 4 * (long long)n);
+    const float* d = reg + idx * 12;
+    float widths = sub(a.z, a.x), heights = sub(a.w, a.y);
+    float ctr_x = add(a.x, mul(0.5f, widths)), ctr_y = add(a.y, mul(0.5f, heights));
+    float dx = mul(__ldg(d + 0), 0.1f), dy = mul(__ldg(d + 1), 0.1f);
+    float dw = mul(__ldg(d + 2), 0.2f), dh = mul(__ldg(d + 3), 0.2f);
+    float pcx = add(ctr_x, mul(dx, widths)), pcy = add(ctr_y, mul(dy, heights));
+    float pw = mul(expf(dw), widths), ph = mul(expf(dh), heights);
+    float x1 = sub(pcx, mul(0.5f, pw)), y1 = sub(pcy, mul(0.5f, ph));
+    float x2 = add(pcx, mul(0.5f, pw)), y2 = add(pcy, mul(0.5f, ph));
+    float cx1 = add(ctr_x, mul(mul(__ldg(d + 4), 0.1f), widths));
+    float cy1 = add(ctr_y, mul(mul(__ldg(d + 5), 0.1f), heights));
+    float z = add(mul(__ldg(d + 6), __ldg(ms + 1)), z_mean);
+    float sn = add(mul(__ldg(d + 7), __ldg(ms + 3)), __ldg(ms + 2));
+    float cs = add(mul(__ldg(d + 8), __ldg(ms + 5)), __ldg(ms + 4));
+    float alpha = __fdiv_rn(atan2f(sn, cs), 2.0f);
+    float w3 = add(mul(__ldg(d + 9), __ldg(ms + 7)), __ldg(ms + 6));
+    float h3 = add(mul(__ldg(d + 10), __ldg(ms + 9)), __ldg(ms + 8));
+    float l3 = add(mul(__ldg(d + 11), __ldg(ms + 11)), __ldg(ms + 10));
+    if (alpha_score < 0.5f) alpha = add(alpha, 3.14159265358979323846f);   // `+= np.pi` on an f32 tensor
+    // ClipBoxes (R/utils/utils.py:181-196)
+    x1 = fmaxf(x1, 0.f); y1 = fmaxf(y1, 0.f); x2 = fminf(x2, img_w); y2 = fminf(y2, img_h);
+
+    int slot = atomicAdd(ws.ncand + b, 1);
+    if (slot >= cap) return;                       // overflow: flagged through ncand > cap
+    unsigned int sb = __float_as_uint(best);       // best in (0.75, 1] -> positive float, bit pattern monotone
+    ws.keys[(long long)b * cap + slot] = ((unsigned long long)(~sb) << 32) | (unsigned int)n;   // ascending key = score desc, index asc
+    float* bp = ws.boxes + ((long long)b * cap + slot) * 11;
+    bp[0] = x1; bp[1] = y1; bp[2] = x2; bp[3] = y2; bp[4] = cx1; bp[5] = cy1; bp[6] = z; bp[7] = w3; bp[8] = h3; bp[9] = l3; bp[10] = alpha;
+    ws.labels[(long long)b * cap + slot] = label;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// stage 2 (one CTA per image): bitonic sort of (key, slot) in shared memory, greedy NMS, ordered write-out.
+// torchvision CPU nms: areas = (x2-x1)*(y2-y1); inter = max(0, xx2-xx1)*max(0, yy2-yy1);
+//                      ovr = inter / (area_i + area_j - inter); suppress j if ovr > thr.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int NMS_THREADS = 1024;
+
+__global__ void __launch_bounds__(NMS_THREADS) sort_nms_kernel(DecodeWs ws, int cap, int cap_pow2, double iou_thr,
+                                                                float* __restrict__ out_scores, float* __restrict__ out_boxes,
+                                                                int64_t* __restrict__ out_cls, int32_t* __restrict__ out_anchor,
+                                                                int32_t* __restrict__ out_count, int32_t* __restrict__ out_ncand) {
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    unsigned long long* skey = reinterpret_cast<unsigned long long*>(sm_raw);            // [cap_pow2]
+    int* sslot = reinterpret_cast<int*>(skey + cap_pow2);                                // [cap_pow2]
+    float4* sbox = reinterpret_cast<float4*>(sslot + cap_pow2);                          // [cap_pow2]
+    float* sarea = reinterpret_cast<float*>(sbox + cap_pow2);                            // [cap_pow2]
+    unsigned char* ssup = reinterpret_cast<unsigned char*>(sarea + cap_pow2);            // [cap_pow2]
+    __shared__ int s_nkeep;
+    const int b = blockIdx.x, t = threadIdx.x;
+    int n = ws.ncand[b];
+    if (t == 0) out_ncand[b] = n;
+    if (n > cap) { if (t == 0) out_count[b] = -1; return; }
+
+    for (int i = t; i < cap_pow2; i += NMS_THREADS) {
+        skey[i] = (i < n) ? ws.keys[(long long)b * cap + i] : ~0ull;
+        sslot[i] = i;
+    }
+    __syncthreads();
+    // bitonic sort ascending on key
+    for (int k = 2; k <= cap_pow2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = t; i < cap_pow2; i += NMS_THREADS) {
+                int ixj = i ^ j;
+                if (ixj > i) {
+                    bool up = ((i & k) == 0);
+                    unsigned long long a = skey[i], c = skey[ixj];
+                    if ((a > c) == up) {
+                        skey[i] = c; skey[ixj] = a;
+                        int s0 = sslot[i]; sslot[i] = sslot[ixj]; sslot[ixj] = s0;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = t; i < n; i += NMS_THREADS) {
+        const float* bp = ws.boxes + ((long long)b * cap + sslot[i]) * 11;
+        float4 bx = make_float4(bp[0], bp[1], bp[2], bp[3]);
+        sbox[i] = bx;
+        sarea[i] = mul(sub(bx.z, bx.x), sub(bx.w, bx.y));
+        ssup[i] = 0;
+    }
+    if (t == 0) s_nkeep = 0;
+    __syncthreads();
+    // greedy sweep: i is kept iff not suppressed by an earlier kept box
+    for (int i = 0; i < n; ++i) {
+        if (ssup[i]) continue;                       // uniform branch (shared value, synced below)
+        float4 bi = sbox[i];
+        float ai = sarea[i];
+        for (int j = i + 1 + t; j < n; j += NMS_THREADS) {
+            if (ssup[j]) continue;
+            float4 bj = sbox[j];
+            float xx1 = fmaxf(bi.x, bj.x), yy1 = fmaxf(bi.y, bj.y);
+            float xx2 = fminf(bi.z, bj.z), yy2 = fminf(bi.w, bj.w);
+            float w = fmaxf(0.f, sub(xx2, xx1)), h = fmaxf(0.f, sub(yy2, yy1));
+            float inter = mul(w, h);
+            float ovr = __fdiv_rn(inter, sub(add(ai, sarea[j]), inter));
+            if ((double)ovr > iou_thr) ssup[j] = 1;   // torchvision compares the f32 IoU with a double threshold
+        }
+        if (t == 0) {
+            int k = s_nkeep++;
+            int slot = sslot[i];
+            unsigned long long key = skey[i];
+            out_scores[(long long)b * cap + k] = __uint_as_float(~(unsigned int)(key >> 32));
+            out_anchor[(long long)b * cap + k] = (int)(unsigned int)(key & 0xffffffffu);
+            out_cls[(long long)b * cap + k] = (int64_t)ws.labels[(long long)b * cap + slot];
+            const float* bp = ws.boxes + ((long long)b * cap + slot) * 11;
+            float* op = out_boxes + ((long long)b * cap + k) * 11;
+#pragma unroll
+            for (int q = 0; q < 11; ++q) op[q] = bp[q];
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    if (t == 0) out_count[b] = s_nkeep;
+}
+
+}  // namespace vd3d
+
+using namespace vd3d;
+
+static int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+extern "C" int vd3d_anchor_mask(const float* anchors, const float* means_z, const float* P2, int B, int N, int T,
+                                float y_min, float y_max, float x_thr, uint8_t* mask, void* stream) {
+    VD3D_REQUIRE(anchors && means_z && P2 && mask && B > 0 && N > 0 && T > 0, "anchor_mask: bad args");
+    anchor_mask_kernel<<<cdiv((long long)B * N, 256), 256, 0, (cudaStream_t)stream>>>(anchors, means_z, P2, B, N, T, y_min, y_max, x_thr, mask);
+    VD3D_CHECK_LAUNCH("anchor_mask");
+    return VD3D_OK;
+}
+
+extern "C" long long vd3d_decode_nms_workspace(int B, int cap) {
+    // keys u64 + boxes 11 f32 + labels i32 per slot, + ncand i32 per image (16-byte aligned blocks)
+    long long per = (long long)cap * (8 + 44 + 4);
+    return (long long)B * per + 16 * ((B * 4 + 15) / 16) + 64;
+}
+
+extern "C" int vd3d_decode_nms(const float* cls, const float* reg, const float* anchors, const float* mean_std,
+                               const uint8_t* mask, int B, int N, int ncls, int T, float score_thr, double iou_thr,
+                               float img_w, float img_h, int cap, void* wsp,
+                               float* out_scores, float* out_boxes, int64_t* out_cls, int32_t* out_anchor,
+                               int32_t* out_count, int32_t* out_ncand, void* stream) {
+    VD3D_REQUIRE(cls && reg && anchors && mean_std && mask && wsp && out_scores && out_boxes && out_cls && out_anchor && out_count && out_ncand,
+                 "decode_nms: null pointer");
+    VD3D_REQUIRE(B > 0 && N > 0 && ncls > 0 && ncls <= T && cap > 0 && cap <= 4096, "decode_nms: bad shape (cap must be <= 4096)");
+    VD3D_REQUIRE(score_thr > 0.f, "decode_nms: score_thr must be positive (sort key relies on positive scores)");
+    cudaStream_t st = (cudaStream_t)stream;
+    DecodeWs ws;
+    unsigned char* p = (unsigned char*)wsp;
+    ws.keys = (unsigned long long*)p; p += (long long)B * cap * 8;
+    ws.boxes = (float*)p; p += (long long)B * cap * 44;
+    ws.labels = (int*)p; p += (long long)B * cap * 4;
+    ws.ncand = (int*)p;
+    VD3D_CUDA(cudaMemsetAsync(ws.ncand, 0, sizeof(int) * B, st));
+    decode_candidates_kernel<<<cdiv((long long)B * N, 256), 256, 0, st>>>(cls, reg, anchors, mean_std, mask, B, N, ncls, T,
+                                                                         score_thr, img_w, img_h, cap, ws);
+    VD3D_CHECK_LAUNCH("decode_candidates");
+    int cp2 = next_pow2(cap);
+    size_t smem = (size_t)cp2 * (8 + 4 + 16 + 4 + 1) + 16;
+    VD3D_CUDA(cudaFuncSetAttribute(sort_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    sort_nms_kernel<<<B, NMS_THREADS, smem, st>>>(ws, cap, cp2, iou_thr, out_scores, out_boxes, out_cls, out_anchor, out_count, out_ncand);
+    VD3D_CHECK_LAUNCH("sort_nms");
+    return VD3D_OK;
+}

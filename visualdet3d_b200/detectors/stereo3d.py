@@ -1,0 +1,329 @@
+"""`Stereo3D` — YOLOStereo3D inference forward on B200 (drop-in for R/detectors/yolostereo3d_detector.py:16-103).
+
+Same construction (`DETECTOR_DICT['Stereo3D'](cfg.detector)`), same checkpoint keys, same list protocol:
+``module([left[1,3,H,W], right, P2[1,3,4], P3])`` -> ``(scores[K], bboxes[K,11], cls_indexes[K] int64)``.
+New: ``forward_batch`` runs B pairs at once (the reference asserts B == 1, :78) and returns one triple per image.
+
+Execution plan per forward (all kernels from libvd3d_b200, NHWC fp32, every torch.cat fused into producers):
+  NCHW->NHWC(4ch) -> stem 7x7s2 -> maxpool -> ResNet stages (conv+BN+ReLU+residual fused)
+  -> PSMCosine x2 (written straight into the ghost-module concat buffers) + concat-volume/Conv3d x2
+  -> CostVolumePyramid -> features[1408] -> cls / reg towers -> anchors mask -> decode + NMS.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import engine as E
+from .._lib import Vd3dError, call
+from ..anchors import AnchorTable, load_priors
+from ..plugin import DETECTOR_DICT
+from . import modules as M
+
+
+class ResNetRunner:
+    """Folded ResNet stages (R/backbones/resnet.py:184-198) over the engine."""
+
+    def __init__(self, p: M.ResNetP, device):
+        self.p = p
+        self.stem = E.ConvLayer(p.conv1.weight, None, E.bn_dict(p.bn1), stride=2, pad=3, relu=True, device=device, cin_pad=4)
+        self.stages = []
+        for i in range(p.num_stages):
+            blocks = []
+            for blk in getattr(p, f"layer{i + 1}"):
+                d = {}
+                if isinstance(blk, M.BasicBlockP):
+                    d["kind"] = "basic"
+                    d["c1"] = E.ConvLayer(blk.conv1.weight, None, E.bn_dict(blk.bn1), stride=blk.stride, pad=1, relu=True, device=device)
+                    d["c2"] = E.ConvLayer(blk.conv2.weight, None, E.bn_dict(blk.bn2), stride=1, pad=blk.dilation, dil=blk.dilation, relu=True, device=device)
+                else:
+                    d["kind"] = "bottle"
+                    d["c1"] = E.ConvLayer(blk.conv1.weight, None, E.bn_dict(blk.bn1), relu=True, device=device)
+                    d["c2"] = E.ConvLayer(blk.conv2.weight, None, E.bn_dict(blk.bn2), stride=blk.stride, pad=blk.dilation, dil=blk.dilation, relu=True, device=device)
+                    d["c3"] = E.ConvLayer(blk.conv3.weight, None, E.bn_dict(blk.bn3), relu=True, device=device)
+                if blk.downsample is not None:
+                    d["ds"] = E.ConvLayer(blk.downsample[0].weight, None, E.bn_dict(blk.downsample[1]), stride=blk.stride, relu=False, device=device)
+                blocks.append(d)
+            self.stages.append(blocks)
+
+    def run(self, img_nchw: torch.Tensor, arena: E.Arena, tag: str = "bb") -> List[E.Act]:
+        dev = img_nchw.device
+        B, _, H, W = img_nchw.shape
+        x0 = E.Act(arena.get(tag + ".in4", (B, H, W, 4), dev, zero=True))
+        E.nchw_to_nhwc(img_nchw, x0)
+        Hs, Ws = self.stem.out_hw(H, W)
+        x = self.stem(x0, E.Act(arena.get(tag + ".stem", (B, Hs, Ws, 64), dev)))
+        Hp, Wp = (Hs + 2 - 3) // 2 + 1, (Ws + 2 - 3) // 2 + 1
+        outs = []
+        if -1 in self.p.out_indices:
+            outs.append(x)
+        x = E.maxpool3x3s2(x, E.Act(arena.get(tag + ".pool", (B, Hp, Wp, 64), dev)))
+        for i, blocks in enumerate(self.stages):
+            for j, d in enumerate(blocks):
+                name = f"{tag}.s{i}b{j}"
+                if d["kind"] == "basic":
+                    c1, c2 = d["c1"], d["c2"]
+                    Ho, Wo = c1.out_hw(x.H, x.W)
+                    t = c1(x, E.Act(arena.get(name + ".t", (B, Ho, Wo, c1.Cout), dev)))
+                    r = x if "ds" not in d else d["ds"](x, E.Act(arena.get(name + ".r", (B, Ho, Wo, c2.Cout), dev)))
+                    x = c2(t, E.Act(arena.get(name + ".o", (B, Ho, Wo, c2.Cout), dev)), res=r)
+                else:
+                    c1, c2, c3 = d["c1"], d["c2"], d["c3"]
+                    t1 = c1(x, E.Act(arena.get(name + ".t1", (B, x.H, x.W, c1.Cout), dev)))
+                    Ho, Wo = c2.out_hw(x.H, x.W)
+                    t2 = c2(t1, E.Act(arena.get(name + ".t2", (B, Ho, Wo, c2.Cout), dev)))
+                    r = x if "ds" not in d else d["ds"](x, E.Act(arena.get(name + ".r", (B, Ho, Wo, c3.Cout), dev)))
+                    x = c3(t2, E.Act(arena.get(name + ".o", (B, Ho, Wo, c3.Cout), dev)), res=r)
+            if i in self.p.out_indices:
+                outs.append(x)
+        return outs
+
+
+class GhostRunner:
+    """ResGhostModule (R/lib/ghost_module.py:46-64): out = cat[x, x1, x2][:, :oup], executed in place in the concat buffer:
+    x already sits in channels [0, inp) of `buf`; x1 -> [inp, inp+init), x2 -> [inp+init, ...)."""
+
+    def __init__(self, p: M.GhostP, device):
+        self.p = p
+        k = p.kernel_size
+        self.primary = E.ConvLayer(p.primary_conv[1].weight, None, E.bn_dict(p.primary_conv[2]), pad=k // 2, relu=True, device=device)
+        self.cheap = E.DwConvLayer(p.cheap_operation[0].weight, E.bn_dict(p.cheap_operation[1]), relu=True, device=device)
+        assert p.new_channels == p.init_channels, "depthwise multiplier != 1 is not on the path"
+        assert p.inp + p.init_channels + p.new_channels == p.oup, "channel truncation [:oup] is not on the path"
+
+    def run(self, buf: E.Act):
+        p = self.p
+        x = buf.slice(0, p.inp)
+        x1 = self.primary(x, buf.slice(p.inp, p.init_channels))
+        self.cheap(x1, buf.slice(p.inp + p.init_channels, p.new_channels))
+        return buf
+
+
+def basic_block_runner(blk: M.BasicBlockP, device):
+    c1 = E.ConvLayer(blk.conv1.weight, None, E.bn_dict(blk.bn1), stride=blk.stride, pad=1, relu=True, device=device)
+    c2 = E.ConvLayer(blk.conv2.weight, None, E.bn_dict(blk.bn2), pad=blk.dilation, dil=blk.dilation, relu=True, device=device)
+    return c1, c2
+
+
+@DETECTOR_DICT.register_module
+class Stereo3D(nn.Module):
+    """YOLOStereo3D detector (inference).  `network_cfg` is the reference's `cfg.detector` (R/config/Stereo3D_example:111-167)."""
+
+    def __init__(self, network_cfg):
+        super().__init__()
+        self.obj_types = network_cfg["obj_types"]
+        head = network_cfg["head"]
+        acfg = head["anchors_cfg"]
+        self.anchors_cfg = {k: acfg[k] for k in ("pyramid_levels", "strides", "sizes", "ratios", "scales")}
+        self.num_anchors = len(acfg["pyramid_levels"]) * len(acfg["ratios"]) * len(acfg["scales"])
+        self.num_classes = head["num_classes"]
+        self.test_cfg = dict(head.get("test_cfg", {}))
+        self.filter_anchor = bool(self.test_cfg.get("filter_anchor", head.get("loss_cfg", {}).get("filter_anchor", True)))
+        lc = dict(head["layer_cfg"])
+        lc.setdefault("num_anchors", self.num_anchors)
+        self.num_cls_output, self.num_reg_output = lc["num_cls_output"], lc["num_reg_output"]
+        if self.num_reg_output != 12:
+            raise ValueError("num_reg_output must be 12 (decode layout, detection_3d_head.py:218-263)")
+        self.bbox_head = M.StereoHeadP(loss_cfg=dict(head.get("loss_cfg", {})),
+                                       num_regression_loss_terms=head.get("num_regression_loss_terms", 12), **lc)
+        self.core = M.YoloStereo3DCoreP(dict(network_cfg["backbone"]))
+        self.network_cfg = network_cfg
+        n_rows = len(acfg["scales"]) * len(acfg["pyramid_levels"])
+        self.prior_mean, self.prior_std = load_priors(head["preprocessed_path"], acfg.get("obj_types", self.obj_types),
+                                                      n_rows, len(acfg["ratios"]))
+        self.max_detections = int(self.test_cfg.get("max_candidates", 2048))   # fixed capacity of the decode / NMS stage
+        self._plan = None
+        self._plan_version = None
+        self._arena = E.Arena()
+        self._anchor_tables = {}
+        self._decoders = {}
+        self.stage_hook = None            # tests: callable(name, Act-or-tensor)
+        self.profile_events = None        # bench: list collecting (start, end) CUDA events of the scale-4 PSMCosine launch
+
+    # ---- plan (folded / packed weights) -------------------------------------------------------------------
+    def _param_version(self):
+        return tuple(p._version for p in self.parameters()) + tuple(b._version for b in self.buffers())
+
+    def _device(self):
+        return next(self.parameters()).device
+
+    def prepare(self, force: bool = False):
+        """Fold BN into conv weights, pack for the kernels, upload.  Re-run automatically when parameters change."""
+        dev = self._device()
+        if dev.type != "cuda":
+            raise Vd3dError("Stereo3D (B200) has no CPU path: move the module to a CUDA device first")
+        ver = (self._param_version(), str(dev))
+        if self._plan is not None and not force and ver == self._plan_version:
+            return self._plan
+        pl = {}
+        pl["backbone"] = ResNetRunner(self.core.backbone, dev)
+        neck = self.core.neck
+        cv2 = neck.cost_volume_2
+        pl["cv2_down"] = E.ConvLayer(cv2.down_sample[0].weight, cv2.down_sample[0].bias, E.bn_dict(cv2.down_sample[1]), relu=True, device=dev)
+        w1, b1 = E.fold_bn(cv2.conv3d[0].weight, cv2.conv3d[0].bias, E.bn_dict(cv2.conv3d[1]))     # [F, 2F, 3,3,3]
+        w2, b2 = E.fold_bn(cv2.conv3d[3].weight, cv2.conv3d[3].bias, E.bn_dict(cv2.conv3d[4]))
+        pl["cv2_w1"] = w1.permute(2, 3, 4, 1, 0).reshape(27, w1.shape[1], w1.shape[0]).contiguous().float().to(dev)
+        pl["cv2_b1"] = b1.float().to(dev)
+        pl["cv2_w2"] = w2.permute(2, 3, 4, 1, 0).reshape(27, w2.shape[1], w2.shape[0]).contiguous().float().to(dev)
+        pl["cv2_b2"] = b2.float().to(dev)
+        dr = neck.depth_reasoning
+        pl["g4"], pl["bb4"] = GhostRunner(dr.four_to_eight[0], dev), basic_block_runner(dr.four_to_eight[2], dev)
+        pl["g8"], pl["bb8"] = GhostRunner(dr.eight_to_sixteen[0], dev), basic_block_runner(dr.eight_to_sixteen[2], dev)
+        pl["g16"], pl["bb16"] = GhostRunner(dr.depth_reason[0], dev), basic_block_runner(dr.depth_reason[1], dev)
+        ct, rt = self.bbox_head.cls_feature_extraction, self.bbox_head.reg_feature_extraction
+        pl["cls"] = [E.ConvLayer(ct[0].weight, ct[0].bias, None, pad=1, relu=True, device=dev),
+                     E.ConvLayer(ct[3].weight, ct[3].bias, None, pad=1, relu=True, device=dev),
+                     E.ConvLayer(ct[6].weight, ct[6].bias, None, pad=1, relu=False, device=dev)]
+        pl["reg0"] = E.ConvLayer(rt[0].sequence[0].weight, rt[0].sequence[0].bias, E.bn_dict(rt[0].sequence[1]), pad=1, relu=True, device=dev)
+        pl["reg_bb"] = basic_block_runner(rt[1], dev)
+        pl["reg_out"] = E.ConvLayer(rt[3].weight, rt[3].bias, None, pad=1, relu=False, device=dev)
+        self._plan, self._plan_version = pl, ver
+        return pl
+
+    def _hook(self, name, value):
+        if self.stage_hook is not None:
+            self.stage_hook(name, value)
+
+    # ---- forward ------------------------------------------------------------------------------------------
+    def core_forward(self, left: torch.Tensor, right: torch.Tensor) -> Tuple[E.Act, E.Act, E.Act]:
+        """R/detectors/yolostereo3d_core.py:110-126 + StereoMerging :88-94.  Returns (features, cls_preds, reg_preds) Acts."""
+        pl = self.prepare()
+        ar = self._arena
+        dev = left.device
+        B, _, H, W = left.shape
+        if H % 16 or W % 16:
+            raise Vd3dError(f"Stereo3D: image size {H}x{W} must be a multiple of 16")
+        imgs = ar.get("imgs", (2 * B, 3, H, W), dev)
+        imgs[:B].copy_(left)
+        imgs[B:].copy_(right)
+        f4, f8, f16 = pl["backbone"].run(imgs, ar)
+        self._hook("feat4", f4), self._hook("feat8", f8), self._hook("feat16", f16)
+        neck = self.core.neck
+        D4, D8, D16 = neck.cost_volume_0.depth_channel, neck.cost_volume_1.depth_channel, neck.cost_volume_2.depth_channel
+        h4, w4, h8, w8, h16, w16 = f4.H, f4.W, f8.H, f8.W, f16.H, f16.W
+        # scale 4: G4 = cat[vol4 | ghost x1 | ghost x2] (72)
+        G4 = E.Act(ar.get("G4", (B, h4, w4, 3 * D4), dev))
+        if self.profile_events is not None:          # bench.py: CUDA events around the dominant cost-volume kernel
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        E.psm_cosine(f4.batch(0, B), f4.batch(B, 2 * B), D4, G4.slice(0, D4))
+        if self.profile_events is not None:
+            e1.record()
+            self.profile_events.append((e0, e1))
+        self._hook("vol4", G4.slice(0, D4))
+        pl["g4"].run(G4)
+        P8 = E.avgpool2(G4, E.Act(ar.get("P8", (B, h8, w8, 3 * D4), dev)))
+        c8 = 3 * D4 + D8
+        G8 = E.Act(ar.get("G8", (B, h8, w8, 3 * c8), dev))
+        c1, c2 = pl["bb4"]
+        t = c1(P8, E.Act(ar.get("T8", (B, h8, w8, 3 * D4), dev)))
+        c2(t, G8.slice(0, 3 * D4), res=P8)
+        E.psm_cosine(f8.batch(0, B), f8.batch(B, 2 * B), D8, G8.slice(3 * D4, D8))
+        self._hook("vol8", G8.slice(3 * D4, D8))
+        pl["g8"].run(G8)
+        P16 = E.avgpool2(G8, E.Act(ar.get("P16", (B, h16, w16, 3 * c8), dev)))
+        Fv = neck.cost_volume_2.PSM_features
+        c16 = 3 * c8 + Fv * D16
+        G16 = E.Act(ar.get("G16", (B, h16, w16, 3 * c16), dev))
+        c1, c2 = pl["bb8"]
+        t = c1(P16, E.Act(ar.get("T16a", (B, h16, w16, 3 * c8), dev)))
+        c2(t, G16.slice(0, 3 * c8), res=P16)
+        # scale 16: 1x1 down-sample of left and right in one launch, concat volume fused into the Conv3d pair
+        lr = pl["cv2_down"](f16, E.Act(ar.get("cv2.lr", (2 * B, h16, w16, Fv), dev)))
+        mid = ar.get("cv2.mid", (B, D16, h16, w16, Fv), dev)
+        vol16 = G16.slice(3 * c8, Fv * D16)
+        call("vd3d_concat_volume_conv3d", lr.batch(0, B).ptr, lr.batch(B, 2 * B).ptr, B, h16, w16, Fv, D16,
+             pl["cv2_w1"].data_ptr(), pl["cv2_b1"].data_ptr(), pl["cv2_w2"].data_ptr(), pl["cv2_b2"].data_ptr(),
+             mid.data_ptr(), vol16.ptr, vol16.cs, vol16.co, E._stream())
+        self._hook("vol16", vol16)
+        pl["g16"].run(G16)
+        cf = f16.C
+        FEAT = E.Act(ar.get("FEAT", (B, h16, w16, cf + 3 * c16), dev))
+        E.copy_channels(f16.batch(0, B), FEAT.slice(0, cf))
+        c1, c2 = pl["bb16"]
+        t = c1(G16, E.Act(ar.get("T16b", (B, h16, w16, 3 * c16), dev)))
+        c2(t, FEAT.slice(cf, 3 * c16), res=G16)
+        self._hook("features", FEAT)
+        # head towers (R/heads/detection_3d_head.py:509-530); AnchorFlatten == the NHWC layout itself
+        k1, k2, k3 = pl["cls"]
+        a = k1(FEAT, E.Act(ar.get("C1", (B, h16, w16, k1.Cout), dev)))
+        a = k2(a, E.Act(ar.get("C2", (B, h16, w16, k2.Cout), dev)))
+        cls = k3(a, E.Act(ar.get("CLS", (B, h16, w16, k3.Cout), dev)))
+        r1 = pl["reg0"](FEAT, E.Act(ar.get("R1", (B, h16, w16, pl["reg0"].Cout), dev)))
+        c1, c2 = pl["reg_bb"]
+        t = c1(r1, E.Act(ar.get("R2", (B, h16, w16, c1.Cout), dev)))
+        r3 = c2(t, E.Act(ar.get("R3", (B, h16, w16, c2.Cout), dev)), res=r1)      # block ReLU; the extra nn.ReLU after it is idempotent
+        reg = pl["reg_out"](r3, E.Act(ar.get("REG", (B, h16, w16, pl["reg_out"].Cout), dev)))
+        self._hook("cls_preds", cls), self._hook("reg_preds", reg)
+        return FEAT, cls, reg
+
+    def _anchor_table(self, H, W, dev) -> AnchorTable:
+        key = (H, W, str(dev))
+        if key not in self._anchor_tables:
+            self._anchor_tables[key] = AnchorTable((H, W), self.anchors_cfg, self.prior_mean, self.prior_std, dev)
+        return self._anchor_tables[key]
+
+    def launch(self, left, right, P2, P3=None):
+        """Enqueue the whole forward (backbone .. NMS) on the current stream; no host synchronisation.
+        Returns the DecodeNms object holding the fixed-capacity device outputs."""
+        for t, nm in ((left, "left"), (right, "right"), (P2, "P2")):
+            E._require_cuda(t, nm)
+        left, right = left.float().contiguous(), right.float().contiguous()
+        P2 = P2.float().contiguous()
+        B, _, H, W = left.shape
+        _, cls, reg = self.core_forward(left, right)
+        tab = self._anchor_table(H, W, left.device)
+        N = tab.N
+        assert cls.H * cls.W * cls.C == N * self.num_cls_output and reg.C * reg.H * reg.W == N * 12
+        mask = self._arena.get("mask", (B, N), left.device, dtype=torch.uint8)
+        if self.filter_anchor:
+            E.anchor_mask(tab.anchors, tab.means_z, P2, mask)
+        else:
+            mask.fill_(1)
+        self._hook("mask", mask)
+        key = (B, str(left.device))
+        if key not in self._decoders:
+            self._decoders[key] = E.DecodeNms(B, self.max_detections, left.device)
+        dec = self._decoders[key]
+        dec.run(cls.t.view(B, N, self.num_cls_output), reg.t.view(B, N, 12), tab.anchors, tab.mean_std, mask,
+                self.num_classes, self.test_cfg.get("score_thr", 0.5), self.test_cfg.get("nms_iou_thr", 0.5), W, H)
+        self._last_decoder = dec
+        return dec
+
+    def forward_batch(self, left, right, P2, P3=None):
+        """B stereo pairs -> list of B (scores[K], bboxes[K,11], cls_indexes[K]) triples (new API; no reference counterpart).
+        One D2H read (the per-image counts) is the only host synchronisation."""
+        dec = self.launch(left, right, P2, P3)
+        return [(s.clone(), b.clone(), c.clone()) for (s, b, c) in dec.results()]
+
+    def test_forward(self, left_images, right_images, P2, P3=None):
+        assert left_images.shape[0] == 1   # reference contract (yolostereo3d_detector.py:78); use forward_batch for B > 1
+        return self.forward_batch(left_images, right_images, P2, P3)[0]
+
+    def train_forward(self, *a, **k):
+        raise NotImplementedError("training forward is out of scope of the B200 inference path (SURVEY.md section 2)")
+
+    def forward(self, inputs):
+        if isinstance(inputs, list) and len(inputs) >= 5:
+            return self.train_forward(*inputs)
+        return self.test_forward(*inputs)
+
+
+def build_synthetic_stereo3d(seed: int = 0, depth: int = 34, workdir: Optional[str] = None):
+    """Random-init (seeded, de-degenerated) Stereo3D + priors for the bench / smoke / tests: returns
+    (detector, state_dict, cfg, (prior_mean, prior_std))."""
+    import tempfile
+    from .. import synth
+    obj_types = ["Car", "Pedestrian"]
+    pm, ps = synth.synth_priors(16, 3, obj_types)
+    d = workdir or tempfile.mkdtemp(prefix="vd3d_priors_")
+    synth.write_priors(d, pm, ps, obj_types)
+    cfg = synth.stereo3d_cfg(d, obj_types, depth)
+    det = Stereo3D(cfg)
+    shapes = {k: tuple(v.shape) for k, v in det.state_dict().items()}
+    sd = synth.synth_state_dict(shapes, seed)
+    det.load_state_dict(sd, strict=False)
+    return det, sd, cfg, (pm, ps)

@@ -1,0 +1,223 @@
+"""Host-side execution engine: activation views, weight folding / packing and thin launchers over the C ABI.
+
+PyTorch is used for device memory and streams only; every arithmetic op on the path is a kernel of
+libvd3d_b200.so.  Activations are fp32 NHWC; an `Act` is a channel slice [co, co+C) of a [B,H,W,cs] tensor, which
+is how every torch.cat of the reference is fused away (producers write straight into their slice).
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import call
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _require_cuda(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise _lib.Vd3dError(f"{what}: tensor is on {t.device}; the B200 path has no CPU fallback")
+
+
+class Act:
+    """Channel slice [co, co+C) of an NHWC fp32 tensor `t` of shape [B, H, W, cs]."""
+    __slots__ = ("t", "co", "C")
+
+    def __init__(self, t: torch.Tensor, co: int = 0, C: Optional[int] = None):
+        assert t.dim() == 4 and t.dtype == torch.float32 and t.is_contiguous()
+        self.t, self.co = t, co
+        self.C = (t.shape[3] - co) if C is None else C
+        assert 0 <= co and co + self.C <= t.shape[3]
+
+    B = property(lambda s: s.t.shape[0])
+    H = property(lambda s: s.t.shape[1])
+    W = property(lambda s: s.t.shape[2])
+    cs = property(lambda s: s.t.shape[3])
+
+    def slice(self, co: int, C: int) -> "Act":
+        return Act(self.t, self.co + co, C)
+
+    def batch(self, b0: int, b1: int) -> "Act":
+        return Act(self.t[b0:b1], self.co, self.C)
+
+    @property
+    def ptr(self) -> int:
+        return self.t.data_ptr()
+
+    def to_nchw(self) -> torch.Tensor:
+        """Dense [B, C, H, W] copy (tests / NCHW-facing op mirrors)."""
+        out = torch.empty(self.B, self.C, self.H, self.W, device=self.t.device, dtype=torch.float32)
+        call("vd3d_nhwc_to_nchw", self.ptr, out.data_ptr(), self.B, self.C, self.H, self.W, self.cs, self.co, _stream())
+        return out
+
+
+class Arena:
+    """Named, shape-keyed device buffers: allocated once, pointer-stable across forwards (CUDA-graph friendly)."""
+
+    def __init__(self):
+        self._bufs: Dict[Tuple, torch.Tensor] = {}
+
+    def get(self, name: str, shape: Sequence[int], device, dtype=torch.float32, zero: bool = False) -> torch.Tensor:
+        key = (name, tuple(int(s) for s in shape), str(device), dtype)
+        t = self._bufs.get(key)
+        if t is None:
+            t = (torch.zeros if zero else torch.empty)(key[1], device=device, dtype=dtype)
+            self._bufs[key] = t
+        return t
+
+    def nbytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in self._bufs.values())
+
+
+# -------------------------------------------------------------------------------------------------------------
+# weight folding / packing (host, float64 -> float32)
+# -------------------------------------------------------------------------------------------------------------
+def fold_bn(weight: torch.Tensor, bias: Optional[torch.Tensor], bn: Optional[Dict[str, torch.Tensor]], eps: float = 1e-5):
+    """conv (+bias) followed by eval-mode BatchNorm -> (weight', bias') in float64.
+    y = (conv(x) + b - mean) * gamma / sqrt(var + eps) + beta."""
+    w = weight.detach().double().cpu()
+    b = bias.detach().double().cpu() if bias is not None else torch.zeros(w.shape[0], dtype=torch.float64)
+    if bn is not None:
+        scale = bn["weight"].detach().double().cpu() / torch.sqrt(bn["running_var"].detach().double().cpu() + eps)
+        w = w * scale.view(-1, *([1] * (w.dim() - 1)))
+        b = (b - bn["running_mean"].detach().double().cpu()) * scale + bn["bias"].detach().double().cpu()
+    return w, b
+
+
+def bn_dict(mod) -> Dict[str, torch.Tensor]:
+    return dict(weight=mod.weight, bias=mod.bias, running_mean=mod.running_mean, running_var=mod.running_var)
+
+
+class ConvLayer:
+    """A dense conv with everything after it fused: folded BN, bias, optional residual, optional ReLU.
+    Weights are packed [KH*KW*Cin_pad][Cout] (k = (kh*KW + kw)*Cin_pad + ci)."""
+
+    def __init__(self, weight, bias=None, bn=None, stride=1, pad=0, dil=1, relu=False, device="cuda", cin_pad: Optional[int] = None):
+        w, b = fold_bn(weight, bias, bn)
+        Cout, Cin, KH, KW = w.shape
+        cin_p = cin_pad or Cin
+        if cin_p != Cin:
+            wp = torch.zeros(Cout, cin_p, KH, KW, dtype=torch.float64)
+            wp[:, :Cin] = w
+            w = wp
+        self.Cin, self.Cout, self.KH, self.KW = cin_p, Cout, KH, KW
+        self.stride, self.pad, self.dil, self.relu = stride, pad, dil, relu
+        self.w = w.permute(2, 3, 1, 0).reshape(KH * KW * cin_p, Cout).contiguous().float().to(device)
+        self.b = b.float().to(device)
+        self.has_bias = True
+
+    def out_hw(self, H, W):
+        Ho = (H + 2 * self.pad - self.dil * (self.KH - 1) - 1) // self.stride + 1
+        Wo = (W + 2 * self.pad - self.dil * (self.KW - 1) - 1) // self.stride + 1
+        return Ho, Wo
+
+    def __call__(self, x: Act, out: Act, res: Optional[Act] = None, relu: Optional[bool] = None):
+        assert x.C == self.Cin, (x.C, self.Cin)
+        assert out.C == self.Cout and out.B == x.B
+        Ho, Wo = self.out_hw(x.H, x.W)
+        assert (out.H, out.W) == (Ho, Wo), ((out.H, out.W), (Ho, Wo))
+        r = self.relu if relu is None else relu
+        call("vd3d_conv2d_nhwc", x.ptr, x.B, x.H, x.W, x.C, x.cs, x.co, self.w.data_ptr(), self.b.data_ptr(),
+             self.KH, self.KW, self.stride, self.pad, self.dil,
+             res.ptr if res is not None else None, res.cs if res is not None else 0, res.co if res is not None else 0,
+             out.ptr, self.Cout, out.cs, out.co, 1 if r else 0, _stream())
+        return out
+
+
+class DwConvLayer:
+    """Depthwise 3x3 (stride 1, pad 1) + folded BN (+ReLU): weights [9][C]."""
+
+    def __init__(self, weight, bn=None, relu=True, device="cuda"):
+        w, b = fold_bn(weight, None, bn)          # [C,1,3,3]
+        C = w.shape[0]
+        assert w.shape[1] == 1 and w.shape[2] == 3 and w.shape[3] == 3
+        self.C, self.relu = C, relu
+        self.w = w.view(C, 9).t().contiguous().float().to(device)
+        self.b = b.float().to(device)
+
+    def __call__(self, x: Act, out: Act):
+        assert x.C == self.C and out.C == self.C
+        call("vd3d_dwconv3x3_nhwc", x.ptr, x.B, x.H, x.W, x.C, x.cs, x.co, self.w.data_ptr(), self.b.data_ptr(),
+             out.ptr, out.cs, out.co, 1 if self.relu else 0, _stream())
+        return out
+
+
+# -------------------------------------------------------------------------------------------------------------
+# functional launchers
+# -------------------------------------------------------------------------------------------------------------
+def nchw_to_nhwc(x: torch.Tensor, out: Act):
+    _require_cuda(x, "nchw_to_nhwc")
+    x = x.contiguous().float()
+    B, C, H, W = x.shape
+    assert out.C >= C and (out.B, out.H, out.W) == (B, H, W)
+    call("vd3d_nchw_to_nhwc", x.data_ptr(), out.ptr, B, C, H, W, out.cs, out.co, _stream())
+    return out
+
+
+def maxpool3x3s2(x: Act, out: Act):
+    call("vd3d_maxpool3x3s2_nhwc", x.ptr, x.B, x.H, x.W, x.C, x.cs, x.co, out.ptr, out.cs, out.co, _stream())
+    return out
+
+
+def avgpool2(x: Act, out: Act):
+    call("vd3d_avgpool2_nhwc", x.ptr, x.B, x.H, x.W, x.C, x.cs, x.co, out.ptr, out.cs, out.co, _stream())
+    return out
+
+
+def copy_channels(x: Act, out: Act):
+    assert x.C == out.C and x.B * x.H * x.W == out.B * out.H * out.W
+    call("vd3d_copy_channels_nhwc", x.ptr, x.B * x.H * x.W, x.C, x.cs, x.co, out.ptr, out.cs, out.co, _stream())
+    return out
+
+
+def psm_cosine(left: Act, right: Act, D: int, out: Act):
+    assert (left.cs, left.co, left.C) == (right.cs, right.co, right.C) and out.C == D
+    call("vd3d_psm_cosine_nhwc", left.ptr, right.ptr, left.B, left.H, left.W, left.C, left.cs, left.co, D,
+         out.ptr, out.cs, out.co, _stream())
+    return out
+
+
+def anchor_mask(anchors: torch.Tensor, means_z: torch.Tensor, P2: torch.Tensor, mask: torch.Tensor,
+                y_min=-0.5, y_max=1.8, x_thr=40.0):
+    B, N, T = P2.shape[0], anchors.shape[0], means_z.shape[0]
+    call("vd3d_anchor_mask", anchors.data_ptr(), means_z.data_ptr(), P2.data_ptr(), B, N, T,
+         float(np.float32(y_min)), float(np.float32(y_max)), float(np.float32(x_thr)), mask.data_ptr(), _stream())
+    return mask
+
+
+class DecodeNms:
+    """Fixed-capacity decode + NMS outputs for a batch (buffers are reused across calls)."""
+
+    def __init__(self, B: int, cap: int, device):
+        self.B, self.cap = B, cap
+        nbytes = int(_lib.load().vd3d_decode_nms_workspace(B, cap))
+        self.ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        self.scores = torch.empty(B, cap, dtype=torch.float32, device=device)
+        self.boxes = torch.empty(B, cap, 11, dtype=torch.float32, device=device)
+        self.cls = torch.empty(B, cap, dtype=torch.int64, device=device)
+        self.anchor = torch.empty(B, cap, dtype=torch.int32, device=device)
+        self.count = torch.empty(B, dtype=torch.int32, device=device)
+        self.ncand = torch.empty(B, dtype=torch.int32, device=device)
+
+    def run(self, cls_preds, reg_preds, anchors, mean_std, mask, ncls, score_thr, iou_thr, img_w, img_h):
+        B, N = cls_preds.shape[0], cls_preds.shape[1]
+        T = mean_std.shape[1]
+        call("vd3d_decode_nms", cls_preds.data_ptr(), reg_preds.data_ptr(), anchors.data_ptr(), mean_std.data_ptr(),
+             mask.data_ptr(), B, N, ncls, T, float(np.float32(score_thr)), float(iou_thr), float(img_w), float(img_h),
+             self.cap, self.ws.data_ptr(), self.scores.data_ptr(), self.boxes.data_ptr(), self.cls.data_ptr(),
+             self.anchor.data_ptr(), self.count.data_ptr(), self.ncand.data_ptr(), _stream())
+
+    def results(self):
+        """One D2H read of the counts (the only host sync of the forward), then per-image views."""
+        counts = self.count.tolist()
+        out = []
+        for b, k in enumerate(counts):
+            if k < 0:
+                raise _lib.Vd3dError(f"decode_nms: image {b} has {int(self.ncand[b])} candidates > capacity {self.cap}")
+            out.append((self.scores[b, :k], self.boxes[b, :k], self.cls[b, :k]))
+        return out

@@ -1,0 +1,62 @@
+"""Multi-GPU plumbing for the inference path: the per-image batch is sharded across ranks (one process per GPU,
+weights and anchor tables replicated) and the ONLY exchange is one NCCL all-gather of fixed-capacity detection
+records (the reference evaluates on a single GPU, R/docs/stereo3d.md:27, so parity target
+is "concatenation of the per-image single-GPU results in global batch order").
+
+Record block per rank: float32 [B_local, 1 + kmax*13]; slot 0 holds the detection count (as a float, exact below 2^24),
+then kmax rows of (11 box floats, score, class).  ~53 KB per rank at B_local = 8, kmax = 128: latency-bound, so it is
+a plain ncclAllGather on the compute stream right after NMS.
+"""
+from __future__ import annotations
+
+from typing import List, Tuple
+
+import torch
+import torch.distributed as dist
+
+REC = 13
+
+
+def pack_records(results, kmax: int, device) -> torch.Tensor:
+    """results: list of (scores[K], boxes[K,11], cls[K]) -> [B, 1 + kmax*13] float32 on `device`."""
+    B = len(results)
+    buf = torch.zeros(B, 1 + kmax * REC, dtype=torch.float32, device=device)
+    for b, (s, bx, c) in enumerate(results):
+        k = int(s.shape[0])
+        if k > kmax:
+            raise RuntimeError(f"image {b}: {k} detections exceed the all-gather record capacity {kmax}")
+        buf[b, 0] = float(k)
+        if k:
+            rows = buf[b, 1:1 + k * REC].view(k, REC)
+            rows[:, :11] = bx
+            rows[:, 11] = s
+            rows[:, 12] = c.to(torch.float32)
+    return buf
+
+
+def unpack_records(buf: torch.Tensor) -> List[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]]:
+    out = []
+    counts = buf[:, 0].round().to(torch.int64).tolist()
+    for b, k in enumerate(counts):
+        rows = buf[b, 1:1 + k * REC].view(k, REC)
+        out.append((rows[:, 11].clone(), rows[:, :11].clone(), rows[:, 12].round().to(torch.int64)))
+    return out
+
+
+def shard_range(n_items: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous shard of the global batch owned by `rank` (rank r gets pairs [r*n/world, (r+1)*n/world))."""
+    per = (n_items + world - 1) // world
+    lo = min(n_items, rank * per)
+    return lo, min(n_items, lo + per)
+
+
+def all_gather_detections(local_results, kmax: int, device, group=None):
+    """One all-gather of the padded record blocks; returns the per-image results of the GLOBAL batch on every rank.
+    All ranks must hold the same number of local images."""
+    buf = pack_records(local_results, kmax, device)
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return unpack_records(buf)
+    world = dist.get_world_size(group)
+    gathered = torch.empty(world * buf.shape[0], buf.shape[1], dtype=buf.dtype, device=device)
+    dist.all_gather_into_tensor(gathered, buf, group=group)
+    return unpack_records(gathered)
