@@ -149,6 +149,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=8, help="stereo pairs per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-mode", action="store_true", help="device-resident steps only (for ncu): no e2e leg, no CPU baseline")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -169,7 +170,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     args.warmup = max(args.warmup, 3)
     B = args.batch
-    kmax = 256
+    kmax = 512
 
     det, sd, cfg, _ = build_synthetic_stereo3d(seed=0)
     det = det.to(dev).eval()
@@ -199,7 +200,16 @@ def main():
     with torch.no_grad():
         for _ in range(args.warmup):
             step_device()
-            res, _h = step_e2e()
+            if not args.profile_mode:
+                res, _h = step_e2e()
+        if args.profile_mode:
+            torch.cuda.synchronize()
+            _lib.launch_count_reset()
+            for _ in range(args.steps):
+                step_device()
+            torch.cuda.synchronize()
+            print(json.dumps({"profile_mode": True, "launches_per_step": _lib.launch_count() / args.steps}))
+            return
         # ---------------- device-resident timing ----------------------------------------------------------------
         barrier()
         sampler = ClockSampler(local_rank)

@@ -53,6 +53,24 @@ int vd3d_conv2d_nhwc(const float* in, int B, int H, int W, int Cin, int in_cs, i
                      const float* res, int res_cs, int res_co,
                      float* out, int Cout, int out_cs, int out_co, int relu, void* stream);
 
+/* ---- dense convolution (tcgen05 tensor cores, "3xTF32" split accumulation) --------------------------------------
+ * Same op as vd3d_conv2d_nhwc for stride-1 convs with Cin % 32 == 0 and Cout % 16 == 0, on the 5th-gen tensor cores:
+ * operands staged by TMA (4-D box per filter tap, zero padding = TMA out-of-bounds fill), tcgen05.mma kind::tf32 with the
+ * fp32 accumulator in TMEM.  fp32-grade accuracy comes from splitting every operand v = hi + lo with
+ * hi = v & 0xFFFFE000 (what the MMA reads when handed v) and accumulating A*Whi + Alo*Whi + A*Wlo (passes = 3).
+ *   in / in_lo   : NHWC activation and its lo companion (in_lo may be NULL when passes == 1)
+ *   w_hi / w_lo  : [Cout][KH*KW*Cin] (k = (kh*KW + kw)*Cin + ci), BN folded, split on the host
+ *   out / out_lo : NHWC result and (optional) its lo companion, written by the epilogue
+ *   bn           : output-channel tile (multiple of 16, <= 256); 0 = vd3d_tc_pick_bn(Cout)
+ * passes == 1 is plain single-pass TF32 (diagnostics only: ~1e-3 relative error, not parity-grade). */
+int vd3d_tc_pick_bn(int Cout);
+int vd3d_conv2d_tc(const float* in, const float* in_lo, int B, int H, int W, int Cin, int in_cs, int in_co,
+                   const float* w_hi, const float* w_lo, const float* bias, int KH, int KW, int pad, int dil,
+                   const float* res, int res_cs, int res_co,
+                   float* out, float* out_lo, int Cout, int out_cs, int out_co, int relu, int passes, int bn, void* stream);
+/* lo[pix][c] = in[pix][c] - (in[pix][c] & 0xFFFFE000) on a channel slice (producers that are not tensor-core convs). */
+int vd3d_split_lo_nhwc(const float* in, float* lo, long long npix, int C, int cs, int co, void* stream);
+
 /* depthwise 3x3 (stride 1, pad 1) + folded BN + ReLU: GhostModule.cheap_operation (R/lib/ghost_module.py:33-38).
  * wgt [9][C] (tap-major), bias [C]. */
 int vd3d_dwconv3x3_nhwc(const float* in, int B, int H, int W, int C, int in_cs, int in_co,

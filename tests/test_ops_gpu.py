@@ -146,7 +146,86 @@ def test_concat_volume_conv3d_vs_oracle():
     pk = lambda w: w.permute(2, 3, 4, 1, 0).reshape(27, w.shape[1], w.shape[0]).contiguous().cuda()
     mid = torch.empty(B, D, H, W, Fc, device="cuda")
     out = E.Act(torch.zeros(B, H, W, 100, device="cuda"), 4, 96)
-    call("vd3d_concat_volume_conv3d", nhwc(lf).cuda().data_ptr(), nhwc(rf).cuda().data_ptr(), B, H, W, Fc, D,
-         pk(w1).data_ptr(), b1.cuda().data_ptr(), pk(w2).data_ptr(), b2.cuda().data_ptr(), mid.data_ptr(),
+    keep = [nhwc(lf).cuda(), nhwc(rf).cuda(), pk(w1), b1.cuda(), pk(w2), b2.cuda()]   # keep the device buffers alive
+    call("vd3d_concat_volume_conv3d", keep[0].data_ptr(), keep[1].data_ptr(), B, H, W, Fc, D,
+         keep[2].data_ptr(), keep[3].data_ptr(), keep[4].data_ptr(), keep[5].data_ptr(), mid.data_ptr(),
          out.ptr, out.cs, out.co, None)
     np.testing.assert_allclose(out.to_nchw().cpu().numpy(), ref.numpy(), rtol=1e-4, atol=1e-5)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# tcgen05 conv engine
+# ----------------------------------------------------------------------------------------------------------------
+def _trunc13(t):
+    return (t.contiguous().view(torch.int32) & -8192).view(torch.float32)
+
+
+def test_tc_mma_reads_top_19_bits_only():
+    """Hardware probe the 3xTF32 split relies on: kind::tf32 must use exactly x & 0xFFFFE000 of a 32-bit operand.
+    1x1 conv with power-of-two weights (products exact) in single-pass mode == conv(trunc13(x), w) bit for bit."""
+    E = _E()
+    g = torch.Generator().manual_seed(3)
+    B, C, H, W, Co = 1, 32, 8, 16, 16
+    x = torch.randn(B, C, H, W, generator=g)
+    w = torch.zeros(Co, C, 1, 1)
+    for o in range(Co):
+        w[o, (o * 5) % C, 0, 0] = 2.0 ** (o % 5 - 2)
+    layer = E.ConvLayer(w, None, None, relu=False, device="cuda", engine="tc1")
+    assert layer.engine == "tc1"
+    out = layer(E.Act(nhwc(x).cuda()), E.Act(torch.empty(B, H, W, Co, device="cuda")))
+    got = out.to_nchw().cpu()
+    exp_trunc = F.conv2d(_trunc13(x), w)
+    exp_plain = F.conv2d(x, w)
+    d_trunc = float((got - exp_trunc).abs().max())
+    d_plain = float((got - exp_plain).abs().max())
+    print("tf32 operand probe: |got - trunc| =", d_trunc, " |got - fp32| =", d_plain)
+    assert d_trunc == 0.0, "tensor core does not truncate fp32 operands to their top 19 bits"
+
+
+TC_CASES = [
+    # B, Cin, H, W, Cout, k, pad, dil, bias, res, relu
+    (1, 32, 8, 16, 16, 1, 0, 1, False, False, False),
+    (2, 64, 24, 40, 64, 3, 1, 1, False, True, True),
+    (1, 64, 18, 80, 64, 3, 1, 1, True, False, True),       # H not a multiple of the 8-row tile
+    (1, 96, 12, 20, 96, 3, 1, 1, False, False, True),      # BN = 96
+    (1, 256, 6, 20, 144, 3, 1, 1, True, False, False),     # BN = 144 (single N tile)
+    (1, 128, 9, 11, 256, 3, 2, 2, True, True, True),       # dilation 2, ragged tile
+    (1, 288, 6, 20, 288, 3, 1, 1, False, True, True),
+    (2, 1408, 6, 20, 256, 3, 1, 1, True, False, True),     # long K (396 k-blocks)
+    (1, 256, 6, 20, 576, 3, 1, 1, True, False, False),
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+def test_conv2d_tc_3xtf32_vs_fp32(case):
+    E = _E()
+    B, Cin, H, W, Cout, k, p, d, has_b, has_r, relu = case
+    g = torch.Generator().manual_seed(sum(case[:6]))
+    x = torch.randn(B, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, k, k, generator=g) / np.sqrt(Cin * k * k)
+    b = torch.randn(Cout, generator=g) if has_b else None
+    ref64 = F.conv2d(x.double(), w.double(), b.double() if b is not None else None, padding=p, dilation=d)
+    r = torch.randn(ref64.shape, generator=g) if has_r else None
+    if r is not None:
+        ref64 = ref64 + r.double()
+    if relu:
+        ref64 = F.relu(ref64)
+    layer = E.ConvLayer(w, b, None, pad=p, dil=d, relu=relu, device="cuda", engine="tc")
+    assert layer.engine == "tc"
+    xa = E.split_lo(E.Act(nhwc(x).cuda(), 0, None, torch.zeros(B, H, W, Cin, device="cuda")))
+    Ho, Wo = layer.out_hw(H, W)
+    out = E.Act(torch.full((B, Ho, Wo, Cout + 8), 7.0, device="cuda"), 4, Cout, torch.full((B, Ho, Wo, Cout + 8), 7.0, device="cuda"))
+    layer(xa, out, res=E.Act(nhwc(r).cuda()) if r is not None else None)
+    got = out.to_nchw().cpu()
+    err = float((got.double() - ref64).abs().max())
+    # same conv on the exact-fp32 SIMT engine, for scale
+    simt = E.ConvLayer(w, b, None, pad=p, dil=d, relu=relu, device="cuda", engine="simt")
+    o2 = simt(E.Act(nhwc(x).cuda()), E.Act(torch.empty(B, Ho, Wo, Cout, device="cuda")), res=E.Act(nhwc(r).cuda()) if r is not None else None)
+    err_simt = float((o2.to_nchw().cpu().double() - ref64).abs().max())
+    print(case, "max|err| vs fp64: 3xTF32", err, " fp32-SIMT", err_simt)
+    assert err < 2e-5, err
+    assert float(out.t[..., :4].min()) == 7.0 and float(out.t[..., 4 + Cout:].min()) == 7.0
+    # lo companion written by the epilogue
+    got_lo = out.lo[..., 4:4 + Cout].cpu()
+    val = out.t[..., 4:4 + Cout].cpu()
+    assert torch.equal(got_lo, val - _trunc13(val))

@@ -47,6 +47,9 @@ _SIGS = {
     "vd3d_psm_cosine_nhwc": (I, [P, P, I, I, I, I, I, I, I, P, I, I, P]),
     "vd3d_psm_cosine_nchw": (I, [P, P, I, I, I, I, I, P, P]),
     "vd3d_concat_volume_conv3d": (I, [P, P, I, I, I, I, I, P, P, P, P, P, P, I, I, P]),
+    "vd3d_tc_pick_bn": (I, [I]),
+    "vd3d_conv2d_tc": (I, [P, P, I, I, I, I, I, I, P, P, P, I, I, I, I, P, I, I, P, P, I, I, I, I, I, I, P]),
+    "vd3d_split_lo_nhwc": (I, [P, P, c_longlong, I, I, I, P]),
     "vd3d_anchor_mask": (I, [P, P, P, I, I, I, F, F, F, P, P]),
     "vd3d_decode_nms_workspace": (c_longlong, [I, I]),
     "vd3d_decode_nms": (I, [P, P, P, P, P, I, I, I, I, F, c_double, F, F, I, P, P, P, P, P, P, P, P]),

@@ -1,0 +1,371 @@
+// tcgen05 implicit-GEMM convolution (stride 1) on NHWC fp32 activations with fp32-grade accuracy ("3xTF32").
+//
+//   D[m, n] = sum_{tap, c} A[pixel(m) + tap, c] * W[n, tap, c]          M = B*Ho*Wo, N = Cout, K = KH*KW*Cin
+//
+// * The tensor core (kind::tf32) reads 32-bit operands from shared memory and uses their top 19 bits.  Every value v
+//   is therefore used as  v = hi + lo  with  hi = v & 0xFFFFE000 (what the MMA sees when handed v itself) and
+//   lo = v - hi (exact in fp32, kept in a second tensor by the producer).  Three MMAs per k-step accumulate
+//   A*Whi + Alo*Whi + A*Wlo in the fp32 TMEM accumulator; the dropped Alo*Wlo term is ~2^-22 relative.
+// * No im2col: for k-block (tap, 32-channel chunk) the A operand is ONE 4-D TMA box [32 c][16 w][8 h][1 b] of the
+//   input shifted by the tap offset; conv zero padding is TMA out-of-bounds fill.  128-byte swizzle on both operands.
+// * Warp roles: warp 0 = TMA producer (one lane), warp 1 = MMA issuer (one lane) + TMEM owner, warps 2..5 = epilogue
+//   (TMEM -> registers -> bias / residual / ReLU -> value and its `lo` part -> global, channel-slice aware).
+// * One 128-pixel x BN-channel output tile per CTA; multi-stage mbarrier ring between TMA and MMA.
+#include "common.cuh"
+#include <cuda.h>
+#include <mutex>
+#include <unordered_map>
+#include <string>
+#include <cstring>
+
+namespace vd3d {
+
+constexpr int TC_TW = 16, TC_TH = 8;          // output tile = 8 rows x 16 columns = 128 pixels (UMMA M = 128)
+constexpr int TC_BK = 32;                     // channels per k-block (32 floats = one 128-byte swizzle row)
+constexpr int TC_THREADS = 192;
+constexpr int TC_A_BYTES = 128 * 128;         // one A (or Alo) stage: 128 rows x 128 B
+
+struct TcParams {
+    int B, H, W, Cin, KH, KW, pad, dil;
+    int Ho, Wo, Cout, BN, stages, passes;
+    int tiles_w, tiles_h;
+    int out_cs, out_co, res_cs, res_co, relu;
+    const float* bias; const float* res; float* out; float* out_lo;
+    uint32_t idesc;
+    uint32_t tmem_cols;
+};
+
+// ----------------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ----------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t addr = smem_u32(bar);
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}\n" ::"r"(addr), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor layout)
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);        // start address
+    d |= (uint64_t)0 << 16;                          // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset: 8 rows * 128 B
+    d |= (uint64_t)1 << 46;                          // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
+    return d;
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// kernel
+// ----------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv2d_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapAlo,
+                 const __grid_constant__ CUtensorMap mapWhi, const __grid_constant__ CUtensorMap mapWlo, const TcParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // 1024-byte aligned operand ring: [stage][A | Alo | Whi | Wlo]
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t b_bytes = (uint32_t)p.BN * 128u;
+    const uint32_t stage_bytes = 2u * TC_A_BYTES + 2u * b_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+    uint64_t* full = bars;                       // [stages]
+    uint64_t* empty = bars + p.stages;           // [stages]
+    uint64_t* tmem_full = bars + 2 * p.stages;   // [1]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // tile coordinates
+    int tile = blockIdx.x;
+    const int tw = tile % p.tiles_w; tile /= p.tiles_w;
+    const int th = tile % p.tiles_h; const int b = tile / p.tiles_h;
+    const int w0 = tw * TC_TW, h0 = th * TC_TH;
+    const int n0 = blockIdx.y * p.BN;
+    const int cchunks = p.Cin / TC_BK;
+    const int KB = p.KH * p.KW * cchunks;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {   // TMEM allocation (whole warp, .sync.aligned)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ================= TMA producer =================
+            for (int kb = 0; kb < KB; ++kb) {
+                const int s = kb % p.stages, ph = (kb / p.stages) & 1;
+                mbar_wait(&empty[s], ph ^ 1);
+                const int tap = kb / cchunks, c0 = (kb - tap * cchunks) * TC_BK;
+                const int kh = tap / p.KW, kw = tap - kh * p.KW;
+                uint8_t* st = smem + (size_t)s * stage_bytes;
+                mbar_expect_tx(&full[s], p.passes == 3 ? stage_bytes : (TC_A_BYTES + b_bytes));
+                const int wi = w0 - p.pad + kw * p.dil, hi = h0 - p.pad + kh * p.dil;
+                tma_load_4d(st, &mapA, &full[s], c0, wi, hi, b);
+                tma_load_2d(st + 2 * TC_A_BYTES, &mapWhi, &full[s], tap * p.Cin + c0, n0);
+                if (p.passes == 3) {
+                    tma_load_4d(st + TC_A_BYTES, &mapAlo, &full[s], c0, wi, hi, b);
+                    tma_load_2d(st + 2 * TC_A_BYTES + b_bytes, &mapWlo, &full[s], tap * p.Cin + c0, n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ================= MMA issuer =================
+            for (int kb = 0; kb < KB; ++kb) {
+                const int s = kb % p.stages, ph = (kb / p.stages) & 1;
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+                const uint64_t dA = make_sdesc(sa), dAlo = make_sdesc(sa + TC_A_BYTES);
+                const uint64_t dB = make_sdesc(sa + 2 * TC_A_BYTES), dBlo = make_sdesc(sa + 2 * TC_A_BYTES + b_bytes);
+#pragma unroll
+                for (int k = 0; k < TC_BK / 8; ++k) {
+                    const uint64_t off = (uint64_t)((k * 32) >> 4);     // 8 tf32 = 32 bytes along K inside the swizzle row
+                    umma_tf32(tmem_base, dA + off, dB + off, p.idesc, (kb | k) != 0);
+                    if (p.passes == 3) {
+                        umma_tf32(tmem_base, dAlo + off, dB + off, p.idesc, 1);
+                        umma_tf32(tmem_base, dA + off, dBlo + off, p.idesc, 1);
+                    }
+                }
+                umma_commit(&empty[s]);          // frees the smem stage once the MMAs above have read it
+            }
+            umma_commit(tmem_full);              // accumulator complete
+        }
+    } else {
+        // ================= epilogue (warps 2..5 <-> TMEM lane quadrants (warp % 4)) =================
+        const int q = warp & 3;
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        const int r = q * 32 + lane;                   // accumulator row = tile pixel
+        const int ho = h0 + r / TC_TW, wo = w0 + r % TC_TW;
+        const bool ok = ho < p.Ho && wo < p.Wo;
+        const long long pix = ((long long)b * p.Ho + ho) * p.Wo + wo;
+        float* op = p.out + pix * p.out_cs + p.out_co;
+        float* olo = p.out_lo ? p.out_lo + pix * p.out_cs + p.out_co : nullptr;
+        const float* rp = p.res ? p.res + pix * p.res_cs + p.res_co : nullptr;
+        for (int j = 0; j < p.BN; j += 32) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)j, v);
+            const int nb = n0 + j;
+            if (ok) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    const int n = nb + i;
+                    if (n < p.Cout) {          // Cout % 4 == 0
+                        float4 a = make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+                        if (p.bias) { float4 bb = ldg4(p.bias + n); a.x += bb.x; a.y += bb.y; a.z += bb.z; a.w += bb.w; }
+                        if (rp) { float4 rr = ldg4(rp + n); a.x += rr.x; a.y += rr.y; a.z += rr.z; a.w += rr.w; }
+                        if (p.relu) { a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f); }
+                        *reinterpret_cast<float4*>(op + n) = a;
+                        if (olo) {
+                            float4 l;
+                            l.x = a.x - __uint_as_float(__float_as_uint(a.x) & 0xFFFFE000u);
+                            l.y = a.y - __uint_as_float(__float_as_uint(a.y) & 0xFFFFE000u);
+                            l.z = a.z - __uint_as_float(__float_as_uint(a.z) & 0xFFFFE000u);
+                            l.w = a.w - __uint_as_float(__float_as_uint(a.w) & 0xFFFFE000u);
+                            *reinterpret_cast<float4*>(olo + n) = l;
+                        }
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+    }
+}
+
+// lo = v - (v & 0xFFFFE000): the part of v the tf32 MMA does not see.  Elementwise, float4, channel-slice aware.
+__global__ void split_lo_kernel(const float* __restrict__ in, float* __restrict__ lo, long long npix, int C4, int cs, int co) {
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= npix * C4) return;
+    int c4 = (int)(idx % C4); long long pix = idx / C4;
+    float4 a = ldg4(in + pix * cs + co + 4 * c4);
+    float4 l;
+    l.x = a.x - __uint_as_float(__float_as_uint(a.x) & 0xFFFFE000u);
+    l.y = a.y - __uint_as_float(__float_as_uint(a.y) & 0xFFFFE000u);
+    l.z = a.z - __uint_as_float(__float_as_uint(a.z) & 0xFFFFE000u);
+    l.w = a.w - __uint_as_float(__float_as_uint(a.w) & 0xFFFFE000u);
+    *reinterpret_cast<float4*>(lo + pix * cs + co + 4 * c4) = l;
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// host: tensor maps (driver entry point fetched at run time: the library does not link libcuda)
+// ----------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+static int make_map_act(CUtensorMap* m, const float* base, int B, int H, int W, int C, int cs, int co) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { set_error("conv2d_tc: cuTensorMapEncodeTiled unavailable"); return VD3D_ECUDA; }
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)cs * 4, (cuuint64_t)W * cs * 4, (cuuint64_t)H * W * cs * 4};
+    cuuint32_t box[4] = {TC_BK, TC_TW, TC_TH, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)(base + co), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("conv2d_tc: cuTensorMapEncodeTiled(activation) failed: %d", (int)r); return VD3D_ECUDA; }
+    return VD3D_OK;
+}
+
+static int make_map_wgt(CUtensorMap* m, const float* base, int Cout, int K, int BN) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { set_error("conv2d_tc: cuTensorMapEncodeTiled unavailable"); return VD3D_ECUDA; }
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)Cout};
+    cuuint64_t strides[1] = {(cuuint64_t)K * 4};
+    cuuint32_t box[2] = {TC_BK, (cuuint32_t)BN};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("conv2d_tc: cuTensorMapEncodeTiled(weights) failed: %d", (int)r); return VD3D_ECUDA; }
+    return VD3D_OK;
+}
+
+}  // namespace vd3d
+
+using namespace vd3d;
+
+extern "C" int vd3d_tc_pick_bn(int Cout) {
+    // largest tile <= 128 that divides Cout evenly into 16-multiples; otherwise the single-tile / 64 fallbacks
+    if (Cout % 128 == 0) return 128;
+    if (Cout <= 256 && Cout % 16 == 0 && Cout > 128 && Cout % 96 != 0) return Cout <= 160 ? Cout : 128;
+    if (Cout % 96 == 0) return 96;
+    if (Cout % 64 == 0) return 64;
+    if (Cout % 48 == 0) return 48;
+    if (Cout % 32 == 0) return 32;
+    return 128;
+}
+
+extern "C" int vd3d_conv2d_tc(const float* in, const float* in_lo, int B, int H, int W, int Cin, int in_cs, int in_co,
+                              const float* w_hi, const float* w_lo, const float* bias, int KH, int KW, int pad, int dil,
+                              const float* res, int res_cs, int res_co,
+                              float* out, float* out_lo, int Cout, int out_cs, int out_co, int relu, int passes, int bn, void* stream) {
+    VD3D_REQUIRE(in && w_hi && out, "conv2d_tc: null pointer");
+    VD3D_REQUIRE(passes == 1 || passes == 3, "conv2d_tc: passes must be 1 or 3");
+    VD3D_REQUIRE(passes == 1 || (in_lo && w_lo), "conv2d_tc: 3-pass mode needs the lo tensors");
+    VD3D_REQUIRE(Cin % TC_BK == 0, "conv2d_tc: Cin must be a multiple of 32 (got %d)", Cin);
+    VD3D_REQUIRE(in_cs % 4 == 0 && in_co % 4 == 0 && out_cs % 4 == 0 && out_co % 4 == 0 && Cout % 4 == 0, "conv2d_tc: pitches/offsets must be multiples of 4");
+    VD3D_REQUIRE(!res || (res_cs % 4 == 0 && res_co % 4 == 0), "conv2d_tc: residual pitch/offset must be multiples of 4");
+    VD3D_REQUIRE(((uintptr_t)in & 15) == 0 && ((uintptr_t)w_hi & 15) == 0 && ((uintptr_t)out & 15) == 0, "conv2d_tc: pointers must be 16-byte aligned");
+    int BN = bn > 0 ? bn : vd3d_tc_pick_bn(Cout);
+    VD3D_REQUIRE(BN % 16 == 0 && BN >= 16 && BN <= 256, "conv2d_tc: BN must be a multiple of 16 in [16, 256]");
+    TcParams p;
+    memset(&p, 0, sizeof(p));
+    p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.KH = KH; p.KW = KW; p.pad = pad; p.dil = dil;
+    p.Ho = H + 2 * pad - dil * (KH - 1); p.Wo = W + 2 * pad - dil * (KW - 1);
+    VD3D_REQUIRE(p.Ho > 0 && p.Wo > 0, "conv2d_tc: empty output");
+    p.Cout = Cout; p.BN = BN; p.passes = passes;
+    p.tiles_w = cdiv(p.Wo, TC_TW); p.tiles_h = cdiv(p.Ho, TC_TH);
+    p.out_cs = out_cs; p.out_co = out_co; p.res_cs = res_cs; p.res_co = res_co; p.relu = relu;
+    p.bias = bias; p.res = res; p.out = out; p.out_lo = out_lo;
+    // instruction descriptor (cute::UMMA::InstrDescriptor): D = f32, A = B = tf32, both K-major, N>>3 @17, M>>4 @24
+    p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    uint32_t cols = 32; while (cols < (uint32_t)BN) cols <<= 1;
+    p.tmem_cols = cols;
+    const size_t stage_bytes = 2 * (size_t)TC_A_BYTES + 2 * (size_t)BN * 128;
+    int stages = (int)((200 * 1024) / stage_bytes);
+    if (stages > 6) stages = 6;
+    VD3D_REQUIRE(stages >= 2, "conv2d_tc: tile too large for shared memory");
+    p.stages = stages;
+    const size_t smem = stages * stage_bytes + (2 * stages + 2) * sizeof(uint64_t) + 1024;
+    const int K = KH * KW * Cin;
+    CUtensorMap mA, mAlo, mWhi, mWlo;
+    int rc;
+    if ((rc = make_map_act(&mA, in, B, H, W, Cin, in_cs, in_co))) return rc;
+    if ((rc = make_map_act(&mAlo, in_lo ? in_lo : in, B, H, W, Cin, in_cs, in_co))) return rc;
+    if ((rc = make_map_wgt(&mWhi, w_hi, Cout, K, BN))) return rc;
+    if ((rc = make_map_wgt(&mWlo, w_lo ? w_lo : w_hi, Cout, K, BN))) return rc;
+    static bool attr_set = false;
+    if (!attr_set) {
+        VD3D_CUDA(cudaFuncSetAttribute(conv2d_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    dim3 grid(p.tiles_w * p.tiles_h * B, cdiv(Cout, BN));
+    conv2d_tc_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(mA, mAlo, mWhi, mWlo, p);
+    VD3D_CHECK_LAUNCH("conv2d_tc");
+    return VD3D_OK;
+}
+
+extern "C" int vd3d_split_lo_nhwc(const float* in, float* lo, long long npix, int C, int cs, int co, void* stream) {
+    VD3D_REQUIRE(in && lo && C % 4 == 0 && cs % 4 == 0 && co % 4 == 0, "split_lo: bad args");
+    long long total = npix * (C / 4);
+    split_lo_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(in, lo, npix, C / 4, cs, co);
+    VD3D_CHECK_LAUNCH("split_lo");
+    return VD3D_OK;
+}

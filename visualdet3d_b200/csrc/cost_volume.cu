@@ -21,7 +21,7 @@ constexpr int PSM_LP = PSM_TW + 2;                 // row pitch of Ls, == 2 (mod
 constexpr int PSM_RP = PSM_RW + 10;                // 98 == 2 (mod 32)
 
 template <int C>
-__global__ void __launch_bounds__(PSM_THREADS) psm_cosine_nhwc_kernel(
+__global__ void __launch_bounds__(PSM_THREADS, 4) psm_cosine_nhwc_kernel(
     const float* __restrict__ L, const float* __restrict__ R, int H, int W, int lr_cs, int lr_co,
     float* __restrict__ out, int out_cs, int out_co) {
     extern __shared__ __align__(16) float smem[];
@@ -36,22 +36,56 @@ __global__ void __launch_bounds__(PSM_THREADS) psm_cosine_nhwc_kernel(
     {
         const int p = t & 7, cq = (t >> 3) & 3, wrp = t >> 5;   // 4 warps
         constexpr int CQ = C / 4;                                  // channel quads per pixel
-        // L tile: 64 pixels x CQ quads; per pass a warp covers 8 pixels x 4 quads
-        for (int it = wrp; it < (PSM_TW / 8) * (CQ / 4); it += PSM_THREADS / 32) {
-            int pg = it / (CQ / 4), qg = it - pg * (CQ / 4);
-            int px = pg * 8 + p, q = qg * 4 + cq;
-            int w = w0 + px;
-            float4 v = (w < W) ? ldg4(L + (rowbase + w) * lr_cs + lr_co + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
-            float* d = Ls + (4 * q) * PSM_LP + px;
-            d[0] = v.x; d[PSM_LP] = v.y; d[2 * PSM_LP] = v.z; d[3 * PSM_LP] = v.w;
+        // L tile: 64 pixels x CQ quads, R window: 88 pixels x CQ quads; per pass a warp covers 8 pixels x 4 quads.
+        // All global loads of a batch are issued before the first shared store so NB 16-byte requests are in
+        // flight per thread (the round-1 ncu capture showed 71% long-scoreboard stalls with one load in flight).
+        constexpr int NWARP = PSM_THREADS / 32;
+        constexpr int QG = CQ / 4;                                   // quad groups per pixel group
+        constexpr int NL = (PSM_TW / 8) * QG / NWARP;                // L iterations per warp  (8 for C=64)
+        constexpr int NR = ((PSM_RW / 8) * QG + NWARP - 1) / NWARP;  // R iterations per warp  (11 for C=64)
+        constexpr int NB = 8;                                        // loads in flight per batch
+        static_assert((PSM_TW / 8) * QG % NWARP == 0, "L tile must split evenly over the warps");
+#pragma unroll
+        for (int base = 0; base < NL; base += NB) {
+            float4 v[NB];
+#pragma unroll
+            for (int u = 0; u < NB; ++u) {
+                int it = wrp + (base + u) * NWARP;
+                int pg = it / QG, qg = it - pg * QG;
+                int w = w0 + pg * 8 + p;
+                v[u] = (base + u < NL && w < W) ? ldg4(L + (rowbase + w) * lr_cs + lr_co + 4 * (qg * 4 + cq))
+                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < NB; ++u) {
+                if (base + u < NL) {
+                    int it = wrp + (base + u) * NWARP;
+                    int pg = it / QG, qg = it - pg * QG;
+                    float* d = Ls + (4 * (qg * 4 + cq)) * PSM_LP + pg * 8 + p;
+                    d[0] = v[u].x; d[PSM_LP] = v[u].y; d[2 * PSM_LP] = v[u].z; d[3 * PSM_LP] = v[u].w;
+                }
+            }
         }
-        for (int it = wrp; it < (PSM_RW / 8) * (CQ / 4); it += PSM_THREADS / 32) {
-            int pg = it / (CQ / 4), qg = it - pg * (CQ / 4);
-            int px = pg * 8 + p, q = qg * 4 + cq;
-            int w = w0 - PSM_D + px;
-            float4 v = (w >= 0 && w < W) ? ldg4(R + (rowbase + w) * lr_cs + lr_co + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
-            float* d = Rs + (4 * q) * PSM_RP + px;
-            d[0] = v.x; d[PSM_RP] = v.y; d[2 * PSM_RP] = v.z; d[3 * PSM_RP] = v.w;
+#pragma unroll
+        for (int base = 0; base < NR; base += NB) {
+            float4 v[NB];
+#pragma unroll
+            for (int u = 0; u < NB; ++u) {
+                int it = wrp + (base + u) * NWARP;
+                int pg = it / QG, qg = it - pg * QG;
+                int w = w0 - PSM_D + pg * 8 + p;
+                bool ok = (base + u < NR) && it < (PSM_RW / 8) * QG && w >= 0 && w < W;
+                v[u] = ok ? ldg4(R + (rowbase + w) * lr_cs + lr_co + 4 * (qg * 4 + cq)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < NB; ++u) {
+                int it = wrp + (base + u) * NWARP;
+                if (base + u < NR && it < (PSM_RW / 8) * QG) {
+                    int pg = it / QG, qg = it - pg * QG;
+                    float* d = Rs + (4 * (qg * 4 + cq)) * PSM_RP + pg * 8 + p;
+                    d[0] = v[u].x; d[PSM_RP] = v[u].y; d[2 * PSM_RP] = v[u].z; d[3 * PSM_RP] = v[u].w;
+                }
+            }
         }
     }
     __syncthreads();
@@ -282,9 +316,11 @@ extern "C" int vd3d_psm_cosine_nhwc(const float* L, const float* R, int B, int H
         size_t smem = (size_t)C * (PSM_LP + PSM_RP) * sizeof(float);
         if (C == 64) {
             VD3D_CUDA(cudaFuncSetAttribute(psm_cosine_nhwc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            VD3D_CUDA(cudaFuncSetAttribute(psm_cosine_nhwc_kernel<64>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
             psm_cosine_nhwc_kernel<64><<<grid, PSM_THREADS, smem, st>>>(L, R, H, W, lr_cs, lr_co, out, out_cs, out_co);
         } else {
             VD3D_CUDA(cudaFuncSetAttribute(psm_cosine_nhwc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            VD3D_CUDA(cudaFuncSetAttribute(psm_cosine_nhwc_kernel<128>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
             psm_cosine_nhwc_kernel<128><<<grid, PSM_THREADS, smem, st>>>(L, R, H, W, lr_cs, lr_co, out, out_cs, out_co);
         }
         VD3D_CHECK_LAUNCH("psm_cosine_nhwc");

@@ -52,33 +52,54 @@ class ResNetRunner:
     def run(self, img_nchw: torch.Tensor, arena: E.Arena, tag: str = "bb") -> List[E.Act]:
         dev = img_nchw.device
         B, _, H, W = img_nchw.shape
-        x0 = E.Act(arena.get(tag + ".in4", (B, H, W, 4), dev, zero=True))
+        x0 = arena.act(tag + ".in4", (B, H, W, 4), dev, zero=True)
         E.nchw_to_nhwc(img_nchw, x0)
         Hs, Ws = self.stem.out_hw(H, W)
-        x = self.stem(x0, E.Act(arena.get(tag + ".stem", (B, Hs, Ws, 64), dev)))
+        x = self.stem(x0, arena.act(tag + ".stem", (B, Hs, Ws, 64), dev))
         Hp, Wp = (Hs + 2 - 3) // 2 + 1, (Ws + 2 - 3) // 2 + 1
         outs = []
         if -1 in self.p.out_indices:
             outs.append(x)
-        x = E.maxpool3x3s2(x, E.Act(arena.get(tag + ".pool", (B, Hp, Wp, 64), dev)))
+        x = E.maxpool3x3s2(x, arena.act(tag + ".pool", (B, Hp, Wp, 64), dev, lo=True))
+        fresh = True                       # x.lo is stale (x was written by a non-tensor-core kernel)
+
+        def feed(layer, a, stale):
+            """make sure `a` carries a valid lo companion if `layer` runs on the tensor cores"""
+            if layer.engine != "simt" and stale:
+                E.split_lo(a)
+                return False
+            return stale
+
         for i, blocks in enumerate(self.stages):
             for j, d in enumerate(blocks):
                 name = f"{tag}.s{i}b{j}"
                 if d["kind"] == "basic":
                     c1, c2 = d["c1"], d["c2"]
                     Ho, Wo = c1.out_hw(x.H, x.W)
-                    t = c1(x, E.Act(arena.get(name + ".t", (B, Ho, Wo, c1.Cout), dev)))
-                    r = x if "ds" not in d else d["ds"](x, E.Act(arena.get(name + ".r", (B, Ho, Wo, c2.Cout), dev)))
-                    x = c2(t, E.Act(arena.get(name + ".o", (B, Ho, Wo, c2.Cout), dev)), res=r)
+                    fresh = feed(c1, x, fresh)
+                    t = c1(x, arena.act(name + ".t", (B, Ho, Wo, c1.Cout), dev, lo=True))
+                    feed(c2, t, c1.engine == "simt")
+                    r = x if "ds" not in d else d["ds"](x, arena.act(name + ".r", (B, Ho, Wo, c2.Cout), dev))
+                    x = c2(t, arena.act(name + ".o", (B, Ho, Wo, c2.Cout), dev, lo=True), res=r)
+                    fresh = c2.engine == "simt"
                 else:
                     c1, c2, c3 = d["c1"], d["c2"], d["c3"]
-                    t1 = c1(x, E.Act(arena.get(name + ".t1", (B, x.H, x.W, c1.Cout), dev)))
+                    fresh = feed(c1, x, fresh)
+                    t1 = c1(x, arena.act(name + ".t1", (B, x.H, x.W, c1.Cout), dev, lo=True))
                     Ho, Wo = c2.out_hw(x.H, x.W)
-                    t2 = c2(t1, E.Act(arena.get(name + ".t2", (B, Ho, Wo, c2.Cout), dev)))
-                    r = x if "ds" not in d else d["ds"](x, E.Act(arena.get(name + ".r", (B, Ho, Wo, c3.Cout), dev)))
-                    x = c3(t2, E.Act(arena.get(name + ".o", (B, Ho, Wo, c3.Cout), dev)), res=r)
+                    feed(c2, t1, c1.engine == "simt")
+                    t2 = c2(t1, arena.act(name + ".t2", (B, Ho, Wo, c2.Cout), dev, lo=True))
+                    feed(c3, t2, c2.engine == "simt")
+                    if "ds" in d:
+                        fresh = feed(d["ds"], x, fresh)
+                        r = d["ds"](x, arena.act(name + ".r", (B, Ho, Wo, c3.Cout), dev))
+                    else:
+                        r = x
+                    x = c3(t2, arena.act(name + ".o", (B, Ho, Wo, c3.Cout), dev, lo=True), res=r)
+                    fresh = c3.engine == "simt"
             if i in self.p.out_indices:
                 outs.append(x)
+        self.last_lo_stale = fresh
         return outs
 
 
@@ -95,10 +116,18 @@ class GhostRunner:
         assert p.inp + p.init_channels + p.new_channels == p.oup, "channel truncation [:oup] is not on the path"
 
     def run(self, buf: E.Act):
+        """`buf` channels [0, inp) hold x.  On return every channel of `buf` carries a valid lo companion if it has one."""
         p = self.p
         x = buf.slice(0, p.inp)
+        if self.primary.engine != "simt":
+            E.split_lo(x)
         x1 = self.primary(x, buf.slice(p.inp, p.init_channels))
-        self.cheap(x1, buf.slice(p.inp + p.init_channels, p.new_channels))
+        x2 = self.cheap(x1, buf.slice(p.inp + p.init_channels, p.new_channels))
+        if buf.lo is not None:
+            if self.primary.engine == "simt":
+                E.split_lo(buf)
+            else:
+                E.split_lo(x2)
         return buf
 
 
@@ -204,8 +233,9 @@ class Stereo3D(nn.Module):
         neck = self.core.neck
         D4, D8, D16 = neck.cost_volume_0.depth_channel, neck.cost_volume_1.depth_channel, neck.cost_volume_2.depth_channel
         h4, w4, h8, w8, h16, w16 = f4.H, f4.W, f8.H, f8.W, f16.H, f16.W
+        tc = lambda layer: layer.engine != "simt"
         # scale 4: G4 = cat[vol4 | ghost x1 | ghost x2] (72)
-        G4 = E.Act(ar.get("G4", (B, h4, w4, 3 * D4), dev))
+        G4 = ar.act("G4", (B, h4, w4, 3 * D4), dev, lo=tc(pl["g4"].primary))
         if self.profile_events is not None:          # bench.py: CUDA events around the dominant cost-volume kernel
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -215,48 +245,75 @@ class Stereo3D(nn.Module):
             self.profile_events.append((e0, e1))
         self._hook("vol4", G4.slice(0, D4))
         pl["g4"].run(G4)
-        P8 = E.avgpool2(G4, E.Act(ar.get("P8", (B, h8, w8, 3 * D4), dev)))
-        c8 = 3 * D4 + D8
-        G8 = E.Act(ar.get("G8", (B, h8, w8, 3 * c8), dev))
         c1, c2 = pl["bb4"]
-        t = c1(P8, E.Act(ar.get("T8", (B, h8, w8, 3 * D4), dev)))
+        P8 = E.avgpool2(G4, ar.act("P8", (B, h8, w8, 3 * D4), dev, lo=tc(c1)))
+        if tc(c1):
+            E.split_lo(P8)
+        c8 = 3 * D4 + D8
+        G8 = ar.act("G8", (B, h8, w8, 3 * c8), dev, lo=tc(pl["g8"].primary))
+        t = c1(P8, ar.act("T8", (B, h8, w8, 3 * D4), dev, lo=tc(c2)))
+        if tc(c2) and not tc(c1):
+            E.split_lo(t)
         c2(t, G8.slice(0, 3 * D4), res=P8)
         E.psm_cosine(f8.batch(0, B), f8.batch(B, 2 * B), D8, G8.slice(3 * D4, D8))
         self._hook("vol8", G8.slice(3 * D4, D8))
-        pl["g8"].run(G8)
-        P16 = E.avgpool2(G8, E.Act(ar.get("P16", (B, h16, w16, 3 * c8), dev)))
+        pl["g8"].run(G8)                       # refreshes lo of x = G8[0:96] itself when its primary conv is tensor-core
+        c1, c2 = pl["bb8"]
+        P16 = E.avgpool2(G8, ar.act("P16", (B, h16, w16, 3 * c8), dev, lo=tc(c1)))
+        if tc(c1):
+            E.split_lo(P16)
         Fv = neck.cost_volume_2.PSM_features
         c16 = 3 * c8 + Fv * D16
-        G16 = E.Act(ar.get("G16", (B, h16, w16, 3 * c16), dev))
-        c1, c2 = pl["bb8"]
-        t = c1(P16, E.Act(ar.get("T16a", (B, h16, w16, 3 * c8), dev)))
+        G16 = ar.act("G16", (B, h16, w16, 3 * c16), dev, lo=True)
+        t = c1(P16, ar.act("T16a", (B, h16, w16, 3 * c8), dev, lo=tc(c2)))
+        if tc(c2) and not tc(c1):
+            E.split_lo(t)
         c2(t, G16.slice(0, 3 * c8), res=P16)
         # scale 16: 1x1 down-sample of left and right in one launch, concat volume fused into the Conv3d pair
-        lr = pl["cv2_down"](f16, E.Act(ar.get("cv2.lr", (2 * B, h16, w16, Fv), dev)))
+        if tc(pl["cv2_down"]) and pl["backbone"].last_lo_stale:
+            E.split_lo(f16)
+        lr = pl["cv2_down"](f16, ar.act("cv2.lr", (2 * B, h16, w16, Fv), dev))
         mid = ar.get("cv2.mid", (B, D16, h16, w16, Fv), dev)
         vol16 = G16.slice(3 * c8, Fv * D16)
         call("vd3d_concat_volume_conv3d", lr.batch(0, B).ptr, lr.batch(B, 2 * B).ptr, B, h16, w16, Fv, D16,
              pl["cv2_w1"].data_ptr(), pl["cv2_b1"].data_ptr(), pl["cv2_w2"].data_ptr(), pl["cv2_b2"].data_ptr(),
              mid.data_ptr(), vol16.ptr, vol16.cs, vol16.co, E._stream())
         self._hook("vol16", vol16)
-        pl["g16"].run(G16)
+        pl["g16"].run(G16)                     # x = G16[0:384]: split_lo covers the SIMT-written parts
         cf = f16.C
-        FEAT = E.Act(ar.get("FEAT", (B, h16, w16, cf + 3 * c16), dev))
+        FEAT = ar.act("FEAT", (B, h16, w16, cf + 3 * c16), dev, lo=True)
         E.copy_channels(f16.batch(0, B), FEAT.slice(0, cf))
+        E.split_lo(FEAT.slice(0, cf))
         c1, c2 = pl["bb16"]
-        t = c1(G16, E.Act(ar.get("T16b", (B, h16, w16, 3 * c16), dev)))
+        t = c1(G16, ar.act("T16b", (B, h16, w16, 3 * c16), dev, lo=True))
+        if tc(c2) and not tc(c1):
+            E.split_lo(t)
         c2(t, FEAT.slice(cf, 3 * c16), res=G16)
+        if not tc(c2):
+            E.split_lo(FEAT.slice(cf, 3 * c16))
         self._hook("features", FEAT)
         # head towers (R/heads/detection_3d_head.py:509-530); AnchorFlatten == the NHWC layout itself
         k1, k2, k3 = pl["cls"]
-        a = k1(FEAT, E.Act(ar.get("C1", (B, h16, w16, k1.Cout), dev)))
-        a = k2(a, E.Act(ar.get("C2", (B, h16, w16, k2.Cout), dev)))
-        cls = k3(a, E.Act(ar.get("CLS", (B, h16, w16, k3.Cout), dev)))
-        r1 = pl["reg0"](FEAT, E.Act(ar.get("R1", (B, h16, w16, pl["reg0"].Cout), dev)))
+        a = k1(FEAT, ar.act("C1", (B, h16, w16, k1.Cout), dev, lo=True))
+        if tc(k2) and not tc(k1):
+            E.split_lo(a)
+        a = k2(a, ar.act("C2", (B, h16, w16, k2.Cout), dev, lo=True))
+        if tc(k3) and not tc(k2):
+            E.split_lo(a)
+        cls = k3(a, ar.act("CLS", (B, h16, w16, k3.Cout), dev))
+        r0 = pl["reg0"]
+        r1 = r0(FEAT, ar.act("R1", (B, h16, w16, r0.Cout), dev, lo=True))
         c1, c2 = pl["reg_bb"]
-        t = c1(r1, E.Act(ar.get("R2", (B, h16, w16, c1.Cout), dev)))
-        r3 = c2(t, E.Act(ar.get("R3", (B, h16, w16, c2.Cout), dev)), res=r1)      # block ReLU; the extra nn.ReLU after it is idempotent
-        reg = pl["reg_out"](r3, E.Act(ar.get("REG", (B, h16, w16, pl["reg_out"].Cout), dev)))
+        if tc(c1) and not tc(r0):
+            E.split_lo(r1)
+        t = c1(r1, ar.act("R2", (B, h16, w16, c1.Cout), dev, lo=True))
+        if tc(c2) and not tc(c1):
+            E.split_lo(t)
+        r3 = c2(t, ar.act("R3", (B, h16, w16, c2.Cout), dev, lo=True), res=r1)   # block ReLU; the extra nn.ReLU after it is idempotent
+        ro = pl["reg_out"]
+        if tc(ro) and not tc(c2):
+            E.split_lo(r3)
+        reg = ro(r3, ar.act("REG", (B, h16, w16, ro.Cout), dev))
         self._hook("cls_preds", cls), self._hook("reg_preds", reg)
         return FEAT, cls, reg
 

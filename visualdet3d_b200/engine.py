@@ -25,14 +25,19 @@ def _require_cuda(t: torch.Tensor, what: str):
 
 
 class Act:
-    """Channel slice [co, co+C) of an NHWC fp32 tensor `t` of shape [B, H, W, cs]."""
-    __slots__ = ("t", "co", "C")
+    """Channel slice [co, co+C) of an NHWC fp32 tensor `t` of shape [B, H, W, cs].
 
-    def __init__(self, t: torch.Tensor, co: int = 0, C: Optional[int] = None):
+    `lo` (optional, same shape as `t`) holds  t - (t & 0xFFFFE000): the low part of every value that the tf32 tensor
+    core does not see.  The tcgen05 conv engine consumes (t, lo) pairs and produces them; other producers leave `lo`
+    stale and the plan calls `split_lo` before a tensor-core consumer."""
+    __slots__ = ("t", "co", "C", "lo")
+
+    def __init__(self, t: torch.Tensor, co: int = 0, C: Optional[int] = None, lo: Optional[torch.Tensor] = None):
         assert t.dim() == 4 and t.dtype == torch.float32 and t.is_contiguous()
-        self.t, self.co = t, co
+        self.t, self.co, self.lo = t, co, lo
         self.C = (t.shape[3] - co) if C is None else C
         assert 0 <= co and co + self.C <= t.shape[3]
+        assert lo is None or (lo.shape == t.shape and lo.is_contiguous())
 
     B = property(lambda s: s.t.shape[0])
     H = property(lambda s: s.t.shape[1])
@@ -40,10 +45,14 @@ class Act:
     cs = property(lambda s: s.t.shape[3])
 
     def slice(self, co: int, C: int) -> "Act":
-        return Act(self.t, self.co + co, C)
+        return Act(self.t, self.co + co, C, self.lo)
 
     def batch(self, b0: int, b1: int) -> "Act":
-        return Act(self.t[b0:b1], self.co, self.C)
+        return Act(self.t[b0:b1], self.co, self.C, None if self.lo is None else self.lo[b0:b1])
+
+    @property
+    def lo_ptr(self):
+        return None if self.lo is None else self.lo.data_ptr()
 
     @property
     def ptr(self) -> int:
@@ -70,6 +79,11 @@ class Arena:
             self._bufs[key] = t
         return t
 
+    def act(self, name: str, shape: Sequence[int], device, lo: bool = False, zero: bool = False) -> Act:
+        """NHWC activation buffer (optionally with its `lo` companion for the tensor-core engine)."""
+        t = self.get(name, shape, device, zero=zero)
+        return Act(t, 0, None, self.get(name + "#lo", shape, device, zero=True) if lo else None)
+
     def nbytes(self) -> int:
         return sum(t.numel() * t.element_size() for t in self._bufs.values())
 
@@ -93,11 +107,28 @@ def bn_dict(mod) -> Dict[str, torch.Tensor]:
     return dict(weight=mod.weight, bias=mod.bias, running_mean=mod.running_mean, running_var=mod.running_var)
 
 
+def conv_engine_default() -> str:
+    """'tc' = tcgen05 3xTF32 engine wherever a layer is eligible (default), 'simt' = exact-fp32 SIMT engine everywhere,
+    'tc1' = single-pass TF32 (NOT parity-grade; diagnostics only)."""
+    import os
+    return os.environ.get("VD3D_CONV_ENGINE", "tc")
+
+
+def tf32_split(w: torch.Tensor):
+    """w (float32) -> (hi, lo) with hi = w & 0xFFFFE000 (the bits the tf32 MMA reads) and lo = tf32-truncated (w - hi)."""
+    wi = w.contiguous().view(torch.int32)
+    hi = (wi & -8192).view(torch.float32)
+    lo = ((w - hi).contiguous().view(torch.int32) & -8192).view(torch.float32)
+    return hi.contiguous(), lo.contiguous()
+
+
 class ConvLayer:
     """A dense conv with everything after it fused: folded BN, bias, optional residual, optional ReLU.
-    Weights are packed [KH*KW*Cin_pad][Cout] (k = (kh*KW + kw)*Cin_pad + ci)."""
+    SIMT engine weights are packed [KH*KW*Cin_pad][Cout] (k = (kh*KW + kw)*Cin_pad + ci); tensor-core engine weights
+    [Cout][KH*KW*Cin] (K contiguous) as a (hi, lo) pair."""
 
-    def __init__(self, weight, bias=None, bn=None, stride=1, pad=0, dil=1, relu=False, device="cuda", cin_pad: Optional[int] = None):
+    def __init__(self, weight, bias=None, bn=None, stride=1, pad=0, dil=1, relu=False, device="cuda", cin_pad: Optional[int] = None,
+                 engine: Optional[str] = None):
         w, b = fold_bn(weight, bias, bn)
         Cout, Cin, KH, KW = w.shape
         cin_p = cin_pad or Cin
@@ -107,9 +138,18 @@ class ConvLayer:
             w = wp
         self.Cin, self.Cout, self.KH, self.KW = cin_p, Cout, KH, KW
         self.stride, self.pad, self.dil, self.relu = stride, pad, dil, relu
-        self.w = w.permute(2, 3, 1, 0).reshape(KH * KW * cin_p, Cout).contiguous().float().to(device)
+        eng = engine or conv_engine_default()
+        eligible = stride == 1 and cin_p % 32 == 0 and Cout % 16 == 0 and str(device).startswith("cuda")
+        self.engine = eng if (eng in ("tc", "tc1") and eligible) else "simt"
         self.b = b.float().to(device)
-        self.has_bias = True
+        self.w = self.w_hi = self.w_lo = None
+        if self.engine == "simt":
+            self.w = w.permute(2, 3, 1, 0).reshape(KH * KW * cin_p, Cout).contiguous().float().to(device)
+        else:
+            wk = w.permute(0, 2, 3, 1).reshape(Cout, KH * KW * cin_p).contiguous().float()
+            hi, lo = tf32_split(wk)
+            self.w_hi, self.w_lo = hi.to(device), lo.to(device)
+            self.bn_tile = int(_lib.load().vd3d_tc_pick_bn(Cout))
 
     def out_hw(self, H, W):
         Ho = (H + 2 * self.pad - self.dil * (self.KH - 1) - 1) // self.stride + 1
@@ -122,10 +162,21 @@ class ConvLayer:
         Ho, Wo = self.out_hw(x.H, x.W)
         assert (out.H, out.W) == (Ho, Wo), ((out.H, out.W), (Ho, Wo))
         r = self.relu if relu is None else relu
-        call("vd3d_conv2d_nhwc", x.ptr, x.B, x.H, x.W, x.C, x.cs, x.co, self.w.data_ptr(), self.b.data_ptr(),
-             self.KH, self.KW, self.stride, self.pad, self.dil,
+        if self.engine == "simt":
+            call("vd3d_conv2d_nhwc", x.ptr, x.B, x.H, x.W, x.C, x.cs, x.co, self.w.data_ptr(), self.b.data_ptr(),
+                 self.KH, self.KW, self.stride, self.pad, self.dil,
+                 res.ptr if res is not None else None, res.cs if res is not None else 0, res.co if res is not None else 0,
+                 out.ptr, self.Cout, out.cs, out.co, 1 if r else 0, _stream())
+            return out
+        passes = 3 if self.engine == "tc" else 1
+        if passes == 3 and x.lo is None:
+            raise _lib.Vd3dError("tensor-core conv: input activation has no `lo` companion (plan bug: missing split_lo)")
+        if CHECK_LO and passes == 3:
+            check_lo(x)
+        call("vd3d_conv2d_tc", x.ptr, x.lo_ptr, x.B, x.H, x.W, x.C, x.cs, x.co, self.w_hi.data_ptr(), self.w_lo.data_ptr(),
+             self.b.data_ptr(), self.KH, self.KW, self.pad, self.dil,
              res.ptr if res is not None else None, res.cs if res is not None else 0, res.co if res is not None else 0,
-             out.ptr, self.Cout, out.cs, out.co, 1 if r else 0, _stream())
+             out.ptr, out.lo_ptr, self.Cout, out.cs, out.co, 1 if r else 0, passes, self.bn_tile, _stream())
         return out
 
 
@@ -150,6 +201,26 @@ class DwConvLayer:
 # -------------------------------------------------------------------------------------------------------------
 # functional launchers
 # -------------------------------------------------------------------------------------------------------------
+import os as _os
+CHECK_LO = _os.environ.get("VD3D_CHECK_LO", "0") == "1"
+
+
+def split_lo(x: Act) -> Act:
+    """Refresh the `lo` companion of a channel slice written by a non-tensor-core producer."""
+    if x.lo is None:
+        return x
+    call("vd3d_split_lo_nhwc", x.ptr, x.lo_ptr, x.B * x.H * x.W, x.C, x.cs, x.co, _stream())
+    return x
+
+
+def check_lo(x: Act):
+    """Debug (VD3D_CHECK_LO=1): assert lo == t - (t & 0xFFFFE000) on the slice a tensor-core conv is about to read."""
+    t = x.t[..., x.co:x.co + x.C]
+    hi = (t.contiguous().view(torch.int32) & -8192).view(torch.float32)
+    if not torch.equal(x.lo[..., x.co:x.co + x.C], t - hi):
+        raise _lib.Vd3dError("stale `lo` companion in front of a tensor-core conv")
+
+
 def nchw_to_nhwc(x: torch.Tensor, out: Act):
     _require_cuda(x, "nchw_to_nhwc")
     x = x.contiguous().float()
