@@ -48,7 +48,7 @@ def test_conv2d_vs_torch(case):
         ref = ref + r
     if relu:
         ref = F.relu(ref)
-    layer = E.ConvLayer(w, b, None, stride=s, pad=p, dil=d, relu=relu, device="cuda")
+    layer = E.ConvLayer(w, b, None, stride=s, pad=p, dil=d, relu=relu, device="cuda", engine="simt")
     xa = E.Act(nhwc(x).cuda())
     Ho, Wo = layer.out_hw(H, W)
     # write into a channel slice of a wider buffer to exercise pitch / offset handling
@@ -68,7 +68,7 @@ def test_conv_bn_folding_matches_conv_then_bn():
     bn = dict(weight=torch.rand(48, generator=g) + 0.5, bias=torch.randn(48, generator=g) * 0.1,
               running_mean=torch.randn(48, generator=g) * 0.1, running_var=torch.rand(48, generator=g) + 0.5)
     ref = F.relu(F.batch_norm(F.conv2d(x, w, None, padding=1), bn["running_mean"], bn["running_var"], bn["weight"], bn["bias"], False, 0.0, 1e-5))
-    layer = E.ConvLayer(w, None, bn, pad=1, relu=True, device="cuda")
+    layer = E.ConvLayer(w, None, bn, pad=1, relu=True, device="cuda", engine="simt")
     out = layer(E.Act(nhwc(x).cuda()), E.Act(torch.empty(2, 10, 12, 48, device="cuda")))
     np.testing.assert_allclose(out.to_nchw().cpu().numpy(), ref.numpy(), rtol=1e-4, atol=2e-5)
 

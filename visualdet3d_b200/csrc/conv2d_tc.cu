@@ -17,6 +17,7 @@
 #include <unordered_map>
 #include <string>
 #include <cstring>
+#include <cstdlib>
 
 namespace vd3d {
 
@@ -27,7 +28,7 @@ constexpr int TC_A_BYTES = 128 * 128;         // one A (or Alo) stage: 128 rows 
 
 struct TcParams {
     int B, H, W, Cin, KH, KW, pad, dil;
-    int Ho, Wo, Cout, BN, stages, passes;
+    int Ho, Wo, Cout, BN, stages, passes, chunk;
     int tiles_w, tiles_h;
     int out_cs, out_co, res_cs, res_co, relu;
     const float* bias; const float* res; float* out; float* out_lo;
@@ -110,7 +111,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 
 // ----------------------------------------------------------------------------------------------------------------
 // kernel
+//
+// Accumulation precision: the tensor core adds every MMA result into the TMEM accumulator with truncation (measured on
+// B200: ~0.5 ulp(|acc|) of bias per accumulation, i.e. 4e-4 relative after the 4752 accumulations of a 1408-channel 3x3
+// conv).  The K loop is therefore cut into chunks of `chunk` k-blocks: each chunk is accumulated in one of TWO TMEM
+// buffers starting from zero, then "promoted": the epilogue warps read it (tcgen05.ld) and add it with round-to-nearest
+// into per-thread fp32 registers while the MMA warp is already filling the other buffer.
 // ----------------------------------------------------------------------------------------------------------------
+template <int NG>   // NG = number of 32-column groups of the accumulator held in registers (BN <= 32*NG)
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv2d_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapAlo,
                  const __grid_constant__ CUtensorMap mapWhi, const __grid_constant__ CUtensorMap mapWlo, const TcParams p) {
@@ -120,13 +128,13 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     const uint32_t b_bytes = (uint32_t)p.BN * 128u;
     const uint32_t stage_bytes = 2u * TC_A_BYTES + 2u * b_bytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
-    uint64_t* full = bars;                       // [stages]
-    uint64_t* empty = bars + p.stages;           // [stages]
-    uint64_t* tmem_full = bars + 2 * p.stages;   // [1]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 1);
+    uint64_t* full = bars;                        // [stages]  TMA -> MMA
+    uint64_t* empty = bars + p.stages;            // [stages]  MMA -> TMA
+    uint64_t* tmem_full = bars + 2 * p.stages;    // [2]       MMA -> epilogue (chunk accumulated)
+    uint64_t* tmem_empty = tmem_full + 2;         // [2]       epilogue -> MMA (chunk promoted)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // tile coordinates
     int tile = blockIdx.x;
     const int tw = tile % p.tiles_w; tile /= p.tiles_w;
     const int th = tile % p.tiles_h; const int b = tile / p.tiles_h;
@@ -134,10 +142,11 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     const int n0 = blockIdx.y * p.BN;
     const int cchunks = p.Cin / TC_BK;
     const int KB = p.KH * p.KW * cchunks;
+    const int NC = (KB + p.chunk - 1) / p.chunk;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        mbar_init(tmem_full, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {   // TMEM allocation (whole warp, .sync.aligned)
@@ -171,31 +180,62 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     } else if (warp == 1) {
         if (lane == 0) {
             // ================= MMA issuer =================
-            for (int kb = 0; kb < KB; ++kb) {
-                const int s = kb % p.stages, ph = (kb / p.stages) & 1;
-                mbar_wait(&full[s], ph);
+            int kb = 0;
+            for (int ci = 0; ci < NC; ++ci) {
+                const int buf = ci & 1, use = ci >> 1;
+                mbar_wait(&tmem_empty[buf], (use & 1) ^ 1);          // the epilogue has promoted this buffer's previous chunk
                 tc_fence_after();
-                const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
-                const uint64_t dA = make_sdesc(sa), dAlo = make_sdesc(sa + TC_A_BYTES);
-                const uint64_t dB = make_sdesc(sa + 2 * TC_A_BYTES), dBlo = make_sdesc(sa + 2 * TC_A_BYTES + b_bytes);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.BN);
+                const int kend = min(KB, kb + p.chunk);
+                for (bool first = true; kb < kend; ++kb) {
+                    const int s = kb % p.stages, ph = (kb / p.stages) & 1;
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+                    const uint64_t dA = make_sdesc(sa), dAlo = make_sdesc(sa + TC_A_BYTES);
+                    const uint64_t dB = make_sdesc(sa + 2 * TC_A_BYTES), dBlo = make_sdesc(sa + 2 * TC_A_BYTES + b_bytes);
 #pragma unroll
-                for (int k = 0; k < TC_BK / 8; ++k) {
-                    const uint64_t off = (uint64_t)((k * 32) >> 4);     // 8 tf32 = 32 bytes along K inside the swizzle row
-                    umma_tf32(tmem_base, dA + off, dB + off, p.idesc, (kb | k) != 0);
-                    if (p.passes == 3) {
-                        umma_tf32(tmem_base, dAlo + off, dB + off, p.idesc, 1);
-                        umma_tf32(tmem_base, dA + off, dBlo + off, p.idesc, 1);
+                    for (int k = 0; k < TC_BK / 8; ++k) {
+                        const uint64_t off = (uint64_t)((k * 32) >> 4);     // 8 tf32 = 32 bytes along K inside the swizzle row
+                        if (p.passes == 3) {   // small terms first, then the main product
+                            umma_tf32(d_tmem, dAlo + off, dB + off, p.idesc, first ? 0u : 1u);
+                            umma_tf32(d_tmem, dA + off, dBlo + off, p.idesc, 1);
+                            umma_tf32(d_tmem, dA + off, dB + off, p.idesc, 1);
+                        } else {
+                            umma_tf32(d_tmem, dA + off, dB + off, p.idesc, first ? 0u : 1u);
+                        }
+                        first = false;
                     }
+                    umma_commit(&empty[s]);          // frees the smem stage once the MMAs above have read it
                 }
-                umma_commit(&empty[s]);          // frees the smem stage once the MMAs above have read it
+                umma_commit(&tmem_full[buf]);        // chunk complete
             }
-            umma_commit(tmem_full);              // accumulator complete
         }
     } else {
         // ================= epilogue (warps 2..5 <-> TMEM lane quadrants (warp % 4)) =================
         const int q = warp & 3;
-        mbar_wait(tmem_full, 0);
-        tc_fence_after();
+        float acc[NG][32];
+#pragma unroll
+        for (int g = 0; g < NG; ++g)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc[g][i] = 0.f;
+        for (int ci = 0; ci < NC; ++ci) {
+            const int buf = ci & 1, use = ci >> 1;
+            mbar_wait(&tmem_full[buf], use & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int g = 0; g < NG; ++g) {
+                if (g * 32 < p.BN) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.BN + g * 32), v);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) acc[g][i] += __uint_as_float(v[i]);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty[buf])) : "memory");
+        }
         const int r = q * 32 + lane;                   // accumulator row = tile pixel
         const int ho = h0 + r / TC_TW, wo = w0 + r % TC_TW;
         const bool ok = ho < p.Ho && wo < p.Wo;
@@ -203,16 +243,14 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         float* op = p.out + pix * p.out_cs + p.out_co;
         float* olo = p.out_lo ? p.out_lo + pix * p.out_cs + p.out_co : nullptr;
         const float* rp = p.res ? p.res + pix * p.res_cs + p.res_co : nullptr;
-        for (int j = 0; j < p.BN; j += 32) {
-            uint32_t v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)j, v);
-            const int nb = n0 + j;
-            if (ok) {
+        if (ok) {
+#pragma unroll
+            for (int g = 0; g < NG; ++g) {
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) {
-                    const int n = nb + i;
-                    if (n < p.Cout) {          // Cout % 4 == 0
-                        float4 a = make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+                    const int n = n0 + g * 32 + i;
+                    if (g * 32 + i < p.BN && n < p.Cout) {          // Cout % 4 == 0
+                        float4 a = make_float4(acc[g][i], acc[g][i + 1], acc[g][i + 2], acc[g][i + 3]);
                         if (p.bias) { float4 bb = ldg4(p.bias + n); a.x += bb.x; a.y += bb.y; a.z += bb.z; a.w += bb.w; }
                         if (rp) { float4 rr = ldg4(rp + n); a.x += rr.x; a.y += rr.y; a.z += rr.z; a.w += rr.w; }
                         if (p.relu) { a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f); }
@@ -304,7 +342,7 @@ using namespace vd3d;
 extern "C" int vd3d_tc_pick_bn(int Cout) {
     // largest tile <= 128 that divides Cout evenly into 16-multiples; otherwise the single-tile / 64 fallbacks
     if (Cout % 128 == 0) return 128;
-    if (Cout <= 256 && Cout % 16 == 0 && Cout > 128 && Cout % 96 != 0) return Cout <= 160 ? Cout : 128;
+    if (Cout <= 160 && Cout % 16 == 0 && Cout > 128) return Cout;
     if (Cout % 96 == 0) return 96;
     if (Cout % 64 == 0) return 64;
     if (Cout % 48 == 0) return 48;
@@ -324,7 +362,7 @@ extern "C" int vd3d_conv2d_tc(const float* in, const float* in_lo, int B, int H,
     VD3D_REQUIRE(!res || (res_cs % 4 == 0 && res_co % 4 == 0), "conv2d_tc: residual pitch/offset must be multiples of 4");
     VD3D_REQUIRE(((uintptr_t)in & 15) == 0 && ((uintptr_t)w_hi & 15) == 0 && ((uintptr_t)out & 15) == 0, "conv2d_tc: pointers must be 16-byte aligned");
     int BN = bn > 0 ? bn : vd3d_tc_pick_bn(Cout);
-    VD3D_REQUIRE(BN % 16 == 0 && BN >= 16 && BN <= 256, "conv2d_tc: BN must be a multiple of 16 in [16, 256]");
+    VD3D_REQUIRE(BN % 16 == 0 && BN >= 16 && BN <= 160, "conv2d_tc: BN must be a multiple of 16 in [16, 160]");
     TcParams p;
     memset(&p, 0, sizeof(p));
     p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.KH = KH; p.KW = KW; p.pad = pad; p.dil = dil;
@@ -336,14 +374,19 @@ extern "C" int vd3d_conv2d_tc(const float* in, const float* in_lo, int B, int H,
     p.bias = bias; p.res = res; p.out = out; p.out_lo = out_lo;
     // instruction descriptor (cute::UMMA::InstrDescriptor): D = f32, A = B = tf32, both K-major, N>>3 @17, M>>4 @24
     p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    uint32_t cols = 32; while (cols < (uint32_t)BN) cols <<= 1;
+    uint32_t cols = 32; while (cols < (uint32_t)(2 * BN)) cols <<= 1;     // two accumulator buffers (chunked promotion)
     p.tmem_cols = cols;
+    {
+        const char* e = getenv("VD3D_TC_CHUNK");
+        p.chunk = e ? atoi(e) : 4;
+        if (p.chunk < 1) p.chunk = 1;
+    }
     const size_t stage_bytes = 2 * (size_t)TC_A_BYTES + 2 * (size_t)BN * 128;
     int stages = (int)((200 * 1024) / stage_bytes);
     if (stages > 6) stages = 6;
     VD3D_REQUIRE(stages >= 2, "conv2d_tc: tile too large for shared memory");
     p.stages = stages;
-    const size_t smem = stages * stage_bytes + (2 * stages + 2) * sizeof(uint64_t) + 1024;
+    const size_t smem = stages * stage_bytes + (2 * stages + 6) * sizeof(uint64_t) + 1024;
     const int K = KH * KW * Cin;
     CUtensorMap mA, mAlo, mWhi, mWlo;
     int rc;
@@ -353,11 +396,16 @@ extern "C" int vd3d_conv2d_tc(const float* in, const float* in_lo, int B, int H,
     if ((rc = make_map_wgt(&mWlo, w_lo ? w_lo : w_hi, Cout, K, BN))) return rc;
     static bool attr_set = false;
     if (!attr_set) {
-        VD3D_CUDA(cudaFuncSetAttribute(conv2d_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        VD3D_CUDA(cudaFuncSetAttribute(conv2d_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        VD3D_CUDA(cudaFuncSetAttribute(conv2d_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        VD3D_CUDA(cudaFuncSetAttribute(conv2d_tc_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
     dim3 grid(p.tiles_w * p.tiles_h * B, cdiv(Cout, BN));
-    conv2d_tc_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(mA, mAlo, mWhi, mWlo, p);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (BN <= 64) conv2d_tc_kernel<2><<<grid, TC_THREADS, smem, st>>>(mA, mAlo, mWhi, mWlo, p);
+    else if (BN <= 128) conv2d_tc_kernel<4><<<grid, TC_THREADS, smem, st>>>(mA, mAlo, mWhi, mWlo, p);
+    else conv2d_tc_kernel<5><<<grid, TC_THREADS, smem, st>>>(mA, mAlo, mWhi, mWlo, p);
     VD3D_CHECK_LAUNCH("conv2d_tc");
     return VD3D_OK;
 }
