@@ -43,47 +43,43 @@ __global__ void __launch_bounds__(PSM_THREADS, 4) psm_cosine_nhwc_kernel(
         constexpr int QG = CQ / 4;                                   // quad groups per pixel group
         constexpr int NL = (PSM_TW / 8) * QG / NWARP;                // L iterations per warp  (8 for C=64)
         constexpr int NR = ((PSM_RW / 8) * QG + NWARP - 1) / NWARP;  // R iterations per warp  (11 for C=64)
-        constexpr int NB = 8;                                        // loads in flight per batch
+        constexpr int NT = NL + NR;                                  // 19 for C = 64, 38 for C = 128
+        constexpr int NB = (NT <= 20) ? NT : (NT + 1) / 2;          // loads in flight per batch (one batch for C = 64)
         static_assert((PSM_TW / 8) * QG % NWARP == 0, "L tile must split evenly over the warps");
 #pragma unroll
-        for (int base = 0; base < NL; base += NB) {
+        for (int base = 0; base < NT; base += NB) {
             float4 v[NB];
 #pragma unroll
             for (int u = 0; u < NB; ++u) {
-                int it = wrp + (base + u) * NWARP;
-                int pg = it / QG, qg = it - pg * QG;
-                int w = w0 + pg * 8 + p;
-                v[u] = (base + u < NL && w < W) ? ldg4(L + (rowbase + w) * lr_cs + lr_co + 4 * (qg * 4 + cq))
-                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+                const int i = base + u;                               // compile-time after unrolling
+                if (i < NL) {
+                    int it = wrp + i * NWARP;
+                    int pg = it / QG, qg = it - pg * QG;
+                    int w = w0 + pg * 8 + p;
+                    v[u] = (w < W) ? ldg4(L + (rowbase + w) * lr_cs + lr_co + 4 * (qg * 4 + cq)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                } else if (i < NT) {
+                    int it = wrp + (i - NL) * NWARP;
+                    int pg = it / QG, qg = it - pg * QG;
+                    int w = w0 - PSM_D + pg * 8 + p;
+                    bool ok = it < (PSM_RW / 8) * QG && w >= 0 && w < W;
+                    v[u] = ok ? ldg4(R + (rowbase + w) * lr_cs + lr_co + 4 * (qg * 4 + cq)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
             }
 #pragma unroll
             for (int u = 0; u < NB; ++u) {
-                if (base + u < NL) {
-                    int it = wrp + (base + u) * NWARP;
+                const int i = base + u;
+                if (i < NL) {
+                    int it = wrp + i * NWARP;
                     int pg = it / QG, qg = it - pg * QG;
                     float* d = Ls + (4 * (qg * 4 + cq)) * PSM_LP + pg * 8 + p;
                     d[0] = v[u].x; d[PSM_LP] = v[u].y; d[2 * PSM_LP] = v[u].z; d[3 * PSM_LP] = v[u].w;
-                }
-            }
-        }
-#pragma unroll
-        for (int base = 0; base < NR; base += NB) {
-            float4 v[NB];
-#pragma unroll
-            for (int u = 0; u < NB; ++u) {
-                int it = wrp + (base + u) * NWARP;
-                int pg = it / QG, qg = it - pg * QG;
-                int w = w0 - PSM_D + pg * 8 + p;
-                bool ok = (base + u < NR) && it < (PSM_RW / 8) * QG && w >= 0 && w < W;
-                v[u] = ok ? ldg4(R + (rowbase + w) * lr_cs + lr_co + 4 * (qg * 4 + cq)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-#pragma unroll
-            for (int u = 0; u < NB; ++u) {
-                int it = wrp + (base + u) * NWARP;
-                if (base + u < NR && it < (PSM_RW / 8) * QG) {
-                    int pg = it / QG, qg = it - pg * QG;
-                    float* d = Rs + (4 * (qg * 4 + cq)) * PSM_RP + pg * 8 + p;
-                    d[0] = v[u].x; d[PSM_RP] = v[u].y; d[2 * PSM_RP] = v[u].z; d[3 * PSM_RP] = v[u].w;
+                } else if (i < NT) {
+                    int it = wrp + (i - NL) * NWARP;
+                    if (it < (PSM_RW / 8) * QG) {
+                        int pg = it / QG, qg = it - pg * QG;
+                        float* d = Rs + (4 * (qg * 4 + cq)) * PSM_RP + pg * 8 + p;
+                        d[0] = v[u].x; d[PSM_RP] = v[u].y; d[2 * PSM_RP] = v[u].z; d[3 * PSM_RP] = v[u].w;
+                    }
                 }
             }
         }
