@@ -34,7 +34,10 @@ __global__ void __launch_bounds__(PSM_THREADS, 4) psm_cosine_nhwc_kernel(
 
     // ---- load + transpose: lanes = (pixel p in 0..7) x (channel quad cq in 0..3) -> 8 x 64B segments / warp-load
     {
-        const int p = t & 7, cq = (t >> 3) & 3, wrp = t >> 5;   // 4 warps
+        // lane -> (pixel p, channel quad cq) with cq fastest: 4 adjacent lanes read 64 contiguous bytes, so a quarter-warp
+        // touches 2 lines instead of 8 (round-1 ncu: 32 L1 data-pipe wavefronts per LDG.128 with p fastest).  The transposed
+        // stores stay conflict-free: bank = 8*cq + p + 2*j is the same set for any lane order.
+        const int cq = t & 3, p = (t >> 2) & 7, wrp = t >> 5;   // 4 warps
         constexpr int CQ = C / 4;                                  // channel quads per pixel
         // L tile: 64 pixels x CQ quads, R window: 88 pixels x CQ quads; per pass a warp covers 8 pixels x 4 quads.
         // All global loads of a batch are issued before the first shared store so NB 16-byte requests are in
