@@ -127,6 +127,31 @@ int vd3d_decode_nms(const float* cls, const float* reg, const float* anchors, co
                     float* out_scores, float* out_boxes, int64_t* out_cls, int32_t* out_anchor,
                     int32_t* out_count, int32_t* out_ncand, void* stream);
 
+/* ---- deformable convolution (R/lib/ops/dcn, make.sh) ----------------------------------------------------------
+ * Deformable / modulated-deformable im2col on NHWC activations; the GEMM that the reference runs per image with cuBLAS
+ * (deform_conv_cuda.cpp:540-556) is then ONE batched 1x1 convolution on vd3d_conv2d_tc over K = KH*KW*C.
+ *   col[pix][k*C + c] = mask[pix][k] * bilinear(x[b,:,:,c], ho*s - pad + kh*dil + dh_k, wo*s - pad + kw*dil + dw_k)
+ * sampling rule of modulated_deformable_im2col_gpu_kernel / dmcn_im2col_bilinear (deform_conv_cuda_kernel.cu:467-497,570-633;
+ * DCNv1 :190-243 is the same with mask == 1, msk = NULL).
+ *   off : NHWC, channel off_co + g*2*K + 2*k = dh, +1 = dw of tap k of deformable group g   (the (dh,dw)-interleaved layout)
+ *   msk : NHWC, channel msk_co + g*K + k; mask_sigmoid != 0 applies the sigmoid of ModulatedDeformConvPack.forward (deform_conv.py:463)
+ *   col / col_lo : [B*Ho*Wo][col_cs] columns and their lo companion (col_lo may be NULL)                                      */
+int vd3d_deform_im2col_nhwc(const float* x, int B, int H, int W, int C, int x_cs, int x_co,
+                            const float* off, int off_cs, int off_co,
+                            const float* msk, int msk_cs, int msk_co, int mask_sigmoid,
+                            int KH, int KW, int stride, int pad, int dil, int deform_groups,
+                            float* col, float* col_lo, int col_cs, void* stream);
+
+/* ---- iou3d (R/lib/ops/iou3d, make.sh) ---------------------------------------------------------------------------
+ * boxes [n][5] = (x1, y1, x2, y2, ry) f32.  Replace iou3d_cuda.boxes_overlap_bev_gpu / boxes_iou_bev_gpu (iou3d.cpp:31-71,
+ * kernels iou3d_kernel.cu:223-248) and nms_gpu / nms_normal_gpu (iou3d.cpp:73-170, kernels :250-348).  NMS runs entirely on
+ * the device: keep [N] i64 and count [1] i32 are DEVICE buffers; boxes must be sorted by descending score by the caller
+ * (as in the reference); rotated != 0 -> rotated IoU (nms_gpu), 0 -> axis-aligned IoU (nms_normal_gpu). */
+int vd3d_boxes_overlap_bev(const float* a, int M, const float* b, int N, float* out, void* stream);
+int vd3d_boxes_iou_bev(const float* a, int M, const float* b, int N, float* out, void* stream);
+long long vd3d_nms_bev_workspace(int N);
+int vd3d_nms_bev(const float* boxes, int N, float thresh, int rotated, void* ws, long long* keep, int* count, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

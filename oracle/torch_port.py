@@ -335,3 +335,59 @@ def stereo3d_forward(sd: SD, left, right, P2, cfg: dict, prior_mean, prior_std, 
             if stages is not None:
                 stages.setdefault("per_image", []).append(st)
         return outs
+
+
+# --------------------------------------------------------------------------------------------------------
+# deformable conv / iou3d restatements (CPU).  The GPU oracle for these two ops is the reference's own compiled
+# extension (oracle/build_ref.py -> oracle/_ref); these CPU versions are the independent second opinion.
+# --------------------------------------------------------------------------------------------------------
+def modulated_deform_conv(x, offset, mask, weight, bias=None, stride=1, padding=0, dilation=1):
+    """R/lib/ops/dcn/src/cuda/deform_conv_cuda_kernel.cu:467-497,570-633 == torchvision.ops.deform_conv2d (same mmcv
+    lineage: (dh, dw)-interleaved offsets, `> -1 / < H` validity, zero outside) — SURVEY.md section 8(c).6."""
+    import torchvision
+    return torchvision.ops.deform_conv2d(x, offset, weight, bias, stride=stride, padding=padding, dilation=dilation, mask=mask)
+
+
+def modulated_deform_conv_pack(sd: SD, p: str, x, stride=1, padding=1, dilation=1):
+    """ModulatedDeformConvPack.forward (R/lib/ops/dcn/deform_conv.py:459-466)."""
+    out = conv(sd, p + ".conv_offset", x, stride=stride, padding=padding)
+    o1, o2, m = torch.chunk(out, 3, dim=1)
+    return modulated_deform_conv(x, torch.cat((o1, o2), dim=1), torch.sigmoid(m), sd[p + ".weight"], sd.get(p + ".bias"),
+                                 stride, padding, dilation)
+
+
+def rotated_overlap_bev(box_a: np.ndarray, box_b: np.ndarray) -> float:
+    """Area of intersection of two rotated rectangles [x1,y1,x2,y2,ry] by Sutherland-Hodgman clipping in float64 — an
+    independent algorithm from R/lib/ops/iou3d/src/iou3d_kernel.cu:108-212 (edge intersections + contained corners +
+    angular sort); corner convention (rotation about the centre with (cos, sin; -sin, cos)) from :99-103,124-146."""
+    def corners(b):
+        x1, y1, x2, y2, a = [float(v) for v in b]
+        cx, cy = (x1 + x2) / 2, (y1 + y2) / 2
+        c, s = math.cos(a), math.sin(a)
+        pts = []
+        for (px, py) in ((x1, y1), (x2, y1), (x2, y2), (x1, y2)):
+            pts.append(((px - cx) * c + (py - cy) * s + cx, -(px - cx) * s + (py - cy) * c + cy))
+        return pts
+
+    def area(poly):
+        return 0.5 * sum(poly[i][0] * poly[(i + 1) % len(poly)][1] - poly[(i + 1) % len(poly)][0] * poly[i][1] for i in range(len(poly)))
+
+    subj, clip = corners(box_a), corners(box_b)
+    if area(clip) < 0:
+        clip = clip[::-1]
+    out = subj
+    for i in range(4):
+        a, b = clip[i], clip[(i + 1) % 4]
+        inp, out = out, []
+        if not inp:
+            break
+        side = lambda p: (b[0] - a[0]) * (p[1] - a[1]) - (b[1] - a[1]) * (p[0] - a[0])
+        for j in range(len(inp)):
+            p, q = inp[j], inp[(j + 1) % len(inp)]
+            sp, sq = side(p), side(q)
+            if sp >= 0:
+                out.append(p)
+            if (sp >= 0) != (sq >= 0):
+                t = sp / (sp - sq)
+                out.append((p[0] + t * (q[0] - p[0]), p[1] + t * (q[1] - p[1])))
+    return abs(area(out)) if len(out) >= 3 else 0.0

@@ -1,0 +1,137 @@
+"""-m gpu: the two op families the reference builds under make.sh (DCN v1/v2, iou3d) against (a) the reference's OWN
+compiled extensions (oracle/_ref, built by oracle/build_ref.py from the reference sources) and (b) CPU restatements."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import torch_port as tp
+
+pytestmark = pytest.mark.gpu
+
+
+def ref_ext(name):
+    import build_ref
+    try:
+        return build_ref.load(name)
+    except FileNotFoundError as e:
+        pytest.skip(str(e))
+
+
+def rand_boxes(n, g, spread=10.0):
+    c = torch.rand(n, 2, generator=g) * spread
+    wh = torch.rand(n, 2, generator=g) * 4 + 0.5
+    ry = (torch.rand(n, generator=g) - 0.5) * 2 * np.pi
+    return torch.cat([c - wh / 2, c + wh / 2, ry[:, None]], dim=1).contiguous()
+
+
+def test_iou3d_pairwise_vs_reference_extension_and_clipping():
+    from visualdet3d_b200.ops import iou3d
+    ref = ref_ext("ref_iou3d_cuda")
+    g = torch.Generator().manual_seed(0)
+    a, b = rand_boxes(70, g).cuda(), rand_boxes(45, g).cuda()
+    for mine, theirs in ((iou3d.boxes_overlap_bev_gpu, ref.boxes_overlap_bev_gpu), (iou3d.boxes_iou_bev_gpu, ref.boxes_iou_bev_gpu)):
+        o1 = torch.zeros(70, 45, device="cuda"); o2 = torch.zeros(70, 45, device="cuda")
+        assert mine(a, b, o1) == 1 and theirs(a, b, o2) == 1
+        torch.cuda.synchronize()
+        np.testing.assert_allclose(o1.cpu().numpy(), o2.cpu().numpy(), rtol=1e-4, atol=1e-5)
+    ov = torch.zeros(70, 45, device="cuda")
+    iou3d.boxes_overlap_bev_gpu(a, b, ov)
+    ac, bc, ovc = a.cpu().numpy(), b.cpu().numpy(), ov.cpu().numpy()
+    for i in range(0, 70, 7):
+        for j in range(0, 45, 5):
+            assert abs(ovc[i, j] - tp.rotated_overlap_bev(ac[i], bc[j])) < 2e-3, (i, j)
+    # identical boxes: overlap == area, IoU == 1
+    io = torch.zeros(70, 70, device="cuda")
+    iou3d.boxes_iou_bev_gpu(a, a, io)
+    np.testing.assert_allclose(torch.diagonal(io).cpu().numpy(), 1.0, atol=1e-3)
+
+
+@pytest.mark.parametrize("n", [1, 63, 64, 65, 300])
+def test_iou3d_nms_vs_reference_extension(n):
+    from visualdet3d_b200.ops import iou3d
+    ref = ref_ext("ref_iou3d_cuda")
+    g = torch.Generator().manual_seed(n)
+    boxes = rand_boxes(n, g, spread=8.0).cuda()
+    for mine, theirs in ((iou3d.nms_gpu, ref.nms_gpu), (iou3d.nms_normal_gpu, ref.nms_normal_gpu)):
+        k1, k2 = torch.zeros(n, dtype=torch.int64), torch.zeros(n, dtype=torch.int64)
+        n1, n2 = mine(boxes, k1, 0.3), theirs(boxes, k2, 0.3)
+        assert n1 == n2 and torch.equal(k1[:n1], k2[:n2])            # bit-exact keep indices
+    assert iou3d.nms_gpu(boxes[:0], torch.zeros(0, dtype=torch.int64), 0.3) == 0
+    with pytest.raises(RuntimeError):
+        iou3d.nms_gpu(boxes.cpu(), torch.zeros(n, dtype=torch.int64), 0.3)
+
+
+def test_boxes_iou3d_wrapper():
+    from visualdet3d_b200.ops import iou3d
+    g = torch.Generator().manual_seed(2)
+    b = torch.rand(9, 7, generator=g) * 3 + 1
+    b[:, 6] = (torch.rand(9, generator=g) - 0.5) * 3
+    b = b.cuda()
+    iou = iou3d.boxes_iou3d_gpu(b, b)
+    np.testing.assert_allclose(torch.diagonal(iou).cpu().numpy(), 1.0, atol=1e-3)
+    assert float(iou.max()) <= 1.0 + 1e-3 and float(iou.min()) >= 0.0
+
+
+DCN_CASES = [  # B, C, H, W, Cout, k, stride, pad, dil, dg
+    (2, 64, 20, 30, 64, 3, 1, 1, 1, 1),
+    (1, 32, 17, 23, 48, 3, 1, 1, 1, 1),
+    (2, 64, 12, 16, 32, 3, 2, 1, 1, 1),
+    (1, 64, 10, 14, 64, 3, 1, 2, 2, 2),
+    (1, 16, 9, 11, 24, 1, 1, 0, 1, 1),
+]
+
+
+@pytest.mark.parametrize("case", DCN_CASES)
+def test_modulated_deform_conv_vs_reference_extension(case):
+    from visualdet3d_b200.ops import dcn
+    B, C, H, W, Co, k, s, p, d, dg = case
+    g = torch.Generator().manual_seed(sum(case))
+    x = torch.randn(B, C, H, W, generator=g)
+    w = torch.randn(Co, C, k, k, generator=g) / np.sqrt(C * k * k)
+    bias = torch.randn(Co, generator=g)
+    Ho, Wo = (H + 2 * p - (d * (k - 1) + 1)) // s + 1, (W + 2 * p - (d * (k - 1) + 1)) // s + 1
+    off = torch.randn(B, 2 * k * k * dg, Ho, Wo, generator=g) * 2.0
+    off[0, :, 0, 0] = 50.0                 # far outside -> contributes zero
+    off[0, :, 1, 1] = -0.999               # the `> -1` knife edge
+    mask = torch.sigmoid(torch.randn(B, k * k * dg, Ho, Wo, generator=g))
+    xc, wc, bc, oc, mc = x.cuda(), w.cuda(), bias.cuda(), off.cuda(), mask.cuda()
+    out = torch.empty(B, Co, Ho, Wo, device="cuda")
+    dcn.modulated_deform_conv_forward(xc, wc, bc, xc.new_empty(0), oc, mc, out, xc.new_empty(0), k, k, s, s, p, p, d, d, 1, dg, True)
+    ref = ref_ext("ref_deform_conv_ext")
+    out_ref = torch.empty(B, Co, Ho, Wo, device="cuda")
+    ref.modulated_deform_conv_forward(xc, wc, bc, xc.new_empty(0), oc, mc, out_ref, xc.new_empty(0), k, k, s, s, p, p, d, d, 1, dg, True)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(out.cpu().numpy(), out_ref.cpu().numpy(), rtol=1e-4, atol=2e-5)
+    if dg == 1:
+        cpu = tp.modulated_deform_conv(x, off, mask, w, bias, s, p, d)
+        np.testing.assert_allclose(out.cpu().numpy(), cpu.numpy(), rtol=1e-4, atol=2e-5)
+    # DCN v1 (no mask, no bias)
+    o1 = torch.empty(B, Co, Ho, Wo, device="cuda"); o2 = torch.empty(B, Co, Ho, Wo, device="cuda")
+    assert dcn.deform_conv_forward(xc, wc, oc, o1, xc.new_empty(0), xc.new_empty(0), k, k, s, s, p, p, d, d, 1, dg, B) == 1
+    ref.deform_conv_forward(xc, wc, oc, o2, xc.new_empty(0), xc.new_empty(0), k, k, s, s, p, p, d, d, 1, dg, B)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(o1.cpu().numpy(), o2.cpu().numpy(), rtol=1e-4, atol=2e-5)
+
+
+def test_dcn_error_behaviour_and_pack_module():
+    from visualdet3d_b200.ops import dcn
+    x = torch.randn(1, 32, 8, 8)
+    w = torch.randn(16, 32, 3, 3)
+    with pytest.raises(RuntimeError):
+        dcn.modulated_deform_conv_forward(x, w, None, x, torch.zeros(1, 18, 8, 8), torch.ones(1, 9, 8, 8), torch.empty(1, 16, 8, 8), x,
+                                          3, 3, 1, 1, 1, 1, 1, 1, 1, 1, False)
+    with pytest.raises(NotImplementedError):
+        dcn.modulated_deform_conv_backward()
+    # module mirror vs the CPU restatement, conv_offset re-randomised (the reference zero-fills it)
+    m = dcn.ModulatedDeformConvPack(64, 64, 3, padding=1)
+    g = torch.Generator().manual_seed(0)
+    m.conv_offset.weight.data = torch.randn(m.conv_offset.weight.shape, generator=g) * 0.05
+    m.conv_offset.bias.data = torch.randn(27, generator=g) * 0.1
+    sd = {"d." + k: v.detach().clone() for k, v in m.state_dict().items()}
+    assert sorted(sd) == ["d.bias", "d.conv_offset.bias", "d.conv_offset.weight", "d.weight"]
+    xin = torch.randn(2, 64, 14, 18, generator=g)
+    ref = tp.modulated_deform_conv_pack(sd, "d", xin, 1, 1, 1)
+    got = m.cuda()(xin.cuda()).cpu()
+    np.testing.assert_allclose(got.numpy(), ref.numpy(), rtol=1e-4, atol=5e-5)

@@ -180,6 +180,46 @@ class ConvLayer:
         return out
 
 
+class DeformConvLayer:
+    """ModulatedDeformConvPack (R/lib/ops/dcn/deform_conv.py:408-466) [+ folded BN] [+ ReLU] on NHWC activations:
+    3x3 offset/mask conv (conv engine) -> deformable im2col with the mask sigmoid fused -> ONE tcgen05 1x1 GEMM over
+    K = KH*KW*C for the whole batch (the reference loops over images and calls cuBLAS per image)."""
+
+    def __init__(self, weight, bias, off_weight, off_bias, bn=None, stride=1, pad=1, dil=1, deform_groups=1, relu=False, device="cuda"):
+        Cout, C, KH, KW = weight.shape
+        self.C, self.Cout, self.KH, self.KW = C, Cout, KH, KW
+        self.stride, self.pad, self.dil, self.dg = stride, pad, dil, deform_groups
+        K = KH * KW
+        n_off = 3 * K * deform_groups
+        assert off_weight.shape[0] == n_off
+        n_pad = (n_off + 15) // 16 * 16                      # tensor-core eligible width (zero filters)
+        ow = torch.zeros(n_pad, C, KH, KW, dtype=off_weight.dtype)
+        ow[:n_off] = off_weight.detach().cpu()
+        ob = torch.zeros(n_pad, dtype=off_weight.dtype)
+        ob[:n_off] = off_bias.detach().cpu()
+        self.n_off_pad = n_pad
+        self.off_conv = ConvLayer(ow, ob, None, stride=stride, pad=pad, dil=1, relu=False, device=device)   # conv_offset has dilation 1
+        w1 = weight.detach().cpu().permute(0, 2, 3, 1).reshape(Cout, K * C, 1, 1)
+        self.main = ConvLayer(w1, bias, bn, relu=relu, device=device)
+
+    def out_hw(self, H, W):
+        Ho = (H + 2 * self.pad - (self.dil * (self.KH - 1) + 1)) // self.stride + 1
+        Wo = (W + 2 * self.pad - (self.dil * (self.KW - 1) + 1)) // self.stride + 1
+        return Ho, Wo
+
+    def __call__(self, x: Act, out: Act, arena: "Arena", name: str, res: Optional[Act] = None):
+        """x must carry a fresh lo companion when the offset conv runs on the tensor cores."""
+        B, dev = x.B, x.t.device
+        Ho, Wo = self.out_hw(x.H, x.W)
+        K = self.KH * self.KW
+        om = self.off_conv(x, arena.act(name + ".om", (B, Ho, Wo, self.n_off_pad), dev))
+        cols = arena.act(name + ".cols", (B, Ho, Wo, K * self.C), dev, lo=self.main.engine != "simt")
+        call("vd3d_deform_im2col_nhwc", x.ptr, B, x.H, x.W, x.C, x.cs, x.co, om.ptr, om.cs, 0,
+             om.ptr, om.cs, 2 * K * self.dg, 1, self.KH, self.KW, self.stride, self.pad, self.dil, self.dg,
+             cols.ptr, cols.lo_ptr, cols.cs, _stream())
+        return self.main(cols, out, res=res)
+
+
 class DwConvLayer:
     """Depthwise 3x3 (stride 1, pad 1) + folded BN (+ReLU): weights [9][C]."""
 

@@ -1,0 +1,194 @@
+"""`deform_conv_ext`-compatible forward entry points over libvd3d_b200 (R/lib/ops/dcn) + module mirrors.
+
+pybind signatures mirrored (deform_conv_ext.cpp:51-56,106-112), same in-place contract: the caller allocates `output`
+(`new_empty`, deform_conv.py:78-80,179-180) and passes scratch `columns` / `ones` tensors, which — like in the reference,
+where they are re-bound locally (deform_conv_cuda.cpp:198-205,524-535) — are ignored; `output` is written in place.
+
+  deform_conv_forward(input, weight, offset, output, columns, ones, kW, kH, dW, dH, padW, padH, dilationW, dilationH,
+                      group, deformable_group, im2col_step) -> int
+  modulated_deform_conv_forward(input, weight, bias, ones, offset, mask, output, columns, kernel_h, kernel_w, stride_h,
+                      stride_w, pad_h, pad_w, dilation_h, dilation_w, group, deformable_group, with_bias) -> None
+
+Tensors are the reference's NCHW fp32 CUDA tensors.  Internally: NCHW -> NHWC, deformable im2col (one launch for the whole
+batch, not one per image), ONE tcgen05 1x1 GEMM over K = KH*KW*C with 3xTF32 accuracy, NHWC -> NCHW.
+Errors mirror the reference: CPU tensors -> RuntimeError("... not implemented on CPU"), non-contiguous input/weight and
+shape mismatches -> RuntimeError.  `group > 1` is not supported (no in-scope caller uses it); backward entries raise
+NotImplementedError (training is out of scope).
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from .. import engine as E
+from .._lib import call
+
+
+class _WeightCache:
+    """packed (hi, lo) tensor-core weights per weight tensor, re-packed when the tensor changes in place"""
+
+    def __init__(self):
+        self._d = {}
+
+    def get(self, weight: torch.Tensor):
+        key = (weight.data_ptr(), tuple(weight.shape))
+        ent = self._d.get(key)
+        if ent is None or ent[0] != weight._version:
+            Cout, C, KH, KW = weight.shape
+            wk = weight.detach().permute(0, 2, 3, 1).reshape(Cout, KH * KW * C).contiguous().float()
+            hi, lo = E.tf32_split(wk)
+            ent = (weight._version, hi, lo)
+            if len(self._d) > 256:
+                self._d.clear()
+            self._d[key] = ent
+        return ent[1], ent[2]
+
+
+_wcache = _WeightCache()
+
+
+def _check_inputs(input, weight, offset, kh, kw, group, deformable_group):
+    if not input.is_cuda:
+        raise RuntimeError("deform conv is not implemented on CPU")
+    if not input.is_contiguous() or not weight.is_contiguous():
+        raise RuntimeError("input and weight tensors have to be contiguous")
+    if weight.shape[2] != kh or weight.shape[3] != kw:
+        raise RuntimeError(f"Input shape and kernel shape wont match: ({kh} x {kw} vs {weight.shape[2]} x {weight.shape[3]}).")
+    if group != 1:
+        raise RuntimeError("visualdet3d_b200 deform conv: group > 1 is not supported")
+    if input.shape[1] != weight.shape[1] * group:
+        raise RuntimeError(f"Input shape and kernel channels wont match: ({input.shape[1]} vs {weight.shape[1] * group}).")
+    if input.shape[1] % deformable_group or (input.shape[1] // deformable_group) % 4:
+        raise RuntimeError("channels per deformable group must be a multiple of 4")
+
+
+def _forward(input, weight, bias, offset, mask, output, kh, kw, sh, sw, ph, pw, dh, dw, deformable_group):
+    if sh != sw or ph != pw or dh != dw:
+        raise RuntimeError("visualdet3d_b200 deform conv: only square stride / padding / dilation are supported")
+    B, C, H, W = input.shape
+    Cout = weight.shape[0]
+    Ho = (H + 2 * ph - (dh * (kh - 1) + 1)) // sh + 1
+    Wo = (W + 2 * pw - (dw * (kw - 1) + 1)) // sw + 1
+    K = kh * kw
+    if tuple(output.shape) != (B, Cout, Ho, Wo):
+        raise RuntimeError(f"output tensor has shape {tuple(output.shape)}, expected {(B, Cout, Ho, Wo)}")
+    if tuple(offset.shape) != (B, 2 * K * deformable_group, Ho, Wo):
+        raise RuntimeError(f"invalid spatial size / channels of offset: {tuple(offset.shape)}")
+    dev = input.device
+    st = E._stream()
+    x = E.Act(torch.empty(B, H, W, C, device=dev))
+    E.nchw_to_nhwc(input, x)
+    nom = 2 * K * deformable_group + (K * deformable_group if mask is not None else 0)
+    om = E.Act(torch.zeros(B, Ho, Wo, (nom + 3) // 4 * 4, device=dev))
+    call("vd3d_nchw_to_nhwc", offset.contiguous().data_ptr(), om.ptr, B, 2 * K * deformable_group, Ho, Wo, om.cs, 0, st)
+    if mask is not None:
+        call("vd3d_nchw_to_nhwc", mask.contiguous().data_ptr(), om.ptr, B, K * deformable_group, Ho, Wo, om.cs, 2 * K * deformable_group, st)
+    KC = K * C
+    kc_pad = (KC + 31) // 32 * 32
+    cols = E.Act(torch.zeros(B, Ho, Wo, kc_pad, device=dev), 0, None, torch.zeros(B, Ho, Wo, kc_pad, device=dev))
+    call("vd3d_deform_im2col_nhwc", x.ptr, B, H, W, C, x.cs, 0, om.ptr, om.cs, 0,
+         om.ptr if mask is not None else None, om.cs, 2 * K * deformable_group, 0,
+         kh, kw, sh, ph, dh, deformable_group, cols.ptr, cols.lo_ptr, cols.cs, st)
+    w_hi, w_lo = _wcache.get(weight)
+    if kc_pad != KC:
+        pad = torch.zeros(Cout, kc_pad - KC, device=w_hi.device)
+        w_hi, w_lo = torch.cat([w_hi, pad], 1).contiguous(), torch.cat([w_lo, pad], 1).contiguous()
+    w_hi, w_lo = w_hi.to(dev), w_lo.to(dev)
+    cout_pad = (Cout + 15) // 16 * 16
+    if cout_pad != Cout:
+        z = torch.zeros(cout_pad - Cout, w_hi.shape[1], device=dev)
+        w_hi, w_lo = torch.cat([w_hi, z], 0).contiguous(), torch.cat([w_lo, z], 0).contiguous()
+    b = None
+    if bias is not None:
+        b = torch.zeros(cout_pad, device=dev)
+        b[:Cout] = bias.detach().float()
+    out = E.Act(torch.empty(B, Ho, Wo, cout_pad, device=dev))
+    call("vd3d_conv2d_tc", cols.ptr, cols.lo_ptr, B, Ho, Wo, kc_pad, cols.cs, 0, w_hi.data_ptr(), w_lo.data_ptr(),
+         b.data_ptr() if b is not None else None, 1, 1, 0, 1, None, 0, 0, out.ptr, None, cout_pad, out.cs, 0, 0, 3, 0, st)
+    call("vd3d_nhwc_to_nchw", out.ptr, output.data_ptr(), B, Cout, Ho, Wo, out.cs, 0, st)
+    return output
+
+
+def modulated_deform_conv_forward(input, weight, bias, ones, offset, mask, output, columns, kernel_h, kernel_w, stride_h, stride_w,
+                                  pad_h, pad_w, dilation_h, dilation_w, group, deformable_group, with_bias) -> None:
+    _check_inputs(input, weight, offset, kernel_h, kernel_w, group, deformable_group)
+    _forward(input, weight, bias if with_bias else None, offset, mask, output, kernel_h, kernel_w, stride_h, stride_w, pad_h, pad_w,
+             dilation_h, dilation_w, deformable_group)
+
+
+def deform_conv_forward(input, weight, offset, output, columns, ones, kW, kH, dW, dH, padW, padH, dilationW, dilationH, group,
+                        deformable_group, im2col_step) -> int:
+    _check_inputs(input, weight, offset, kH, kW, group, deformable_group)
+    _forward(input, weight, None, offset, None, output, kH, kW, dH, dW, padH, padW, dilationH, dilationW, deformable_group)
+    return 1
+
+
+def deform_conv_backward_input(*a, **k):
+    raise NotImplementedError("deform conv backward is out of scope of the B200 inference path")
+
+
+deform_conv_backward_parameters = modulated_deform_conv_backward = deform_conv_backward_input
+
+
+# ---- functional + module mirrors (deform_conv.py:55-96,154-187,408-466) ------------------------------------------------
+def modulated_deform_conv(input, offset, mask, weight, bias=None, stride=1, padding=0, dilation=1, groups=1, deformable_groups=1):
+    B, C, H, W = input.shape
+    kh, kw = weight.shape[2], weight.shape[3]
+    Ho = (H + 2 * padding - (dilation * (kh - 1) + 1)) // stride + 1
+    Wo = (W + 2 * padding - (dilation * (kw - 1) + 1)) // stride + 1
+    if not input.is_cuda:
+        raise NotImplementedError
+    out = input.new_empty((B, weight.shape[0], Ho, Wo))
+    modulated_deform_conv_forward(input.contiguous(), weight.contiguous(), bias, input.new_empty(0), offset, mask, out, input.new_empty(0),
+                                  kh, kw, stride, stride, padding, padding, dilation, dilation, groups, deformable_groups, bias is not None)
+    return out
+
+
+def deform_conv(input, offset, weight, stride=1, padding=0, dilation=1, groups=1, deformable_groups=1, im2col_step=64):
+    B, C, H, W = input.shape
+    kh, kw = weight.shape[2], weight.shape[3]
+    Ho = (H + 2 * padding - (dilation * (kh - 1) + 1)) // stride + 1
+    Wo = (W + 2 * padding - (dilation * (kw - 1) + 1)) // stride + 1
+    if not input.is_cuda:
+        raise NotImplementedError
+    out = input.new_empty((B, weight.shape[0], Ho, Wo))
+    deform_conv_forward(input.contiguous(), weight.contiguous(), offset, out, input.new_empty(0), input.new_empty(0), kw, kh, stride, stride,
+                        padding, padding, dilation, dilation, groups, deformable_groups, min(im2col_step, B))
+    return out
+
+
+class ModulatedDeformConvPack(nn.Module):
+    """ModulatedDeformConvPack (deform_conv.py:408-466): `weight`, `bias`, `conv_offset.{weight,bias}`; forward runs the 3x3 offset conv on
+    the conv engine (NCHW in / out) then the modulated deformable conv."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1, deformable_groups=1, bias=True):
+        super().__init__()
+        k = kernel_size if isinstance(kernel_size, int) else kernel_size[0]
+        self.in_channels, self.out_channels, self.kernel_size = in_channels, out_channels, (k, k)
+        self.stride, self.padding, self.dilation, self.groups, self.deformable_groups = stride, padding, dilation, groups, deformable_groups
+        self.with_bias = bias
+        self.weight = nn.Parameter(torch.empty(out_channels, in_channels // groups, k, k))
+        self.bias = nn.Parameter(torch.zeros(out_channels)) if bias else None
+        self.conv_offset = nn.Conv2d(in_channels, deformable_groups * 3 * k * k, kernel_size=k, stride=stride, padding=padding, bias=True)
+        stdv = 1.0 / math.sqrt(in_channels * k * k)
+        self.weight.data.uniform_(-stdv, stdv)
+        self.conv_offset.weight.data.zero_()
+        self.conv_offset.bias.data.zero_()
+
+    def forward(self, x):
+        if not x.is_cuda:
+            raise NotImplementedError
+        ver = tuple(p._version for p in self.parameters()) + (str(x.device),)
+        if getattr(self, "_layer_ver", None) != ver:
+            self._layer = E.DeformConvLayer(self.weight, self.bias, self.conv_offset.weight, self.conv_offset.bias, None, self.stride,
+                                            self.padding, self.dilation, self.deformable_groups, relu=False, device=x.device)
+            self._layer_ver, self._arena = ver, E.Arena()
+        B, C, H, W = x.shape
+        xa = E.nchw_to_nhwc(x, self._arena.act("x", (B, H, W, C), x.device, lo=True))
+        E.split_lo(xa)
+        Ho, Wo = self._layer.out_hw(H, W)
+        out = self._layer(xa, self._arena.act("out", (B, Ho, Wo, self.out_channels), x.device), self._arena, "dcn")
+        return out.to_nchw()
