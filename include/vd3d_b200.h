@@ -142,6 +142,16 @@ int vd3d_deform_im2col_nhwc(const float* x, int B, int H, int W, int C, int x_cs
                             int KH, int KW, int stride, int pad, int dil, int deform_groups,
                             float* col, float* col_lo, int col_cs, void* stream);
 
+/* ---- Ground-Aware Convolution sampling (LookGround.forward, R/lib/look_ground.py:24-71) ---------------------------
+ * x NHWC [B][H][W] (stride-16 features), dconv = output of disp_create's 3x3 conv (channel d_co; tanh applied here),
+ * P2 [B][3][4] (full-resolution calibration; rows 0..1 are divided by 16 here like :29-30).
+ * out[pix] = [grid_sample(x) (C) | grid_sample(disparity plane) (1) | untouched padding], out_lo its lo companion (or NULL);
+ * the 1x1 `extract` conv + alpha + residual + ReLU (:71) is a vd3d_conv2d_tc call on `out`. */
+int vd3d_look_ground_sample(const float* x, int B, int H, int W, int C, int x_cs, int x_co,
+                            const float* dconv, int d_cs, int d_co, const float* P2,
+                            float baseline, float relative_elevation,
+                            float* out, float* out_lo, int out_cs, void* stream);
+
 /* ---- iou3d (R/lib/ops/iou3d, make.sh) ---------------------------------------------------------------------------
  * boxes [n][5] = (x1, y1, x2, y2, ry) f32.  Replace iou3d_cuda.boxes_overlap_bev_gpu / boxes_iou_bev_gpu (iou3d.cpp:31-71,
  * kernels iou3d_kernel.cu:223-248) and nms_gpu / nms_normal_gpu (iou3d.cpp:73-170, kernels :250-348).  NMS runs entirely on

@@ -391,3 +391,79 @@ def rotated_overlap_bev(box_a: np.ndarray, box_b: np.ndarray) -> float:
                 t = sp / (sp - sq)
                 out.append((p[0] + t * (q[0] - p[0]), p[1] + t * (q[1] - p[1])))
     return abs(area(out)) if len(out) >= 3 else 0.0
+
+
+# --------------------------------------------------------------------------------------------------------
+# monocular detectors (R/detectors/yolomono3d_detector.py, R/lib/look_ground.py)
+# --------------------------------------------------------------------------------------------------------
+def look_ground(sd: SD, p: str, x: torch.Tensor, P2: torch.Tensor, baseline=0.54, relative_elevation=1.65) -> torch.Tensor:
+    """LookGround.forward (R/lib/look_ground.py:24-71), same op order."""
+    P2 = P2.clone()
+    P2[:, 0:2] /= 16.0
+    disp = torch.tanh(conv(sd, p + ".disp_create.0", x, padding=1))
+    disp = 0.1 * (0.05 * disp + 0.95 * disp)
+    B, _, H, W = x.shape
+    yy = torch.arange(H, dtype=torch.float32).view(1, H, 1).expand(1, H, W)
+    fy, cy, Ty = P2[:, 1:2, 1:2], P2[:, 1:2, 2:3], P2[:, 1:2, 3:4]
+    disparity = F.relu(fy * baseline * (yy - cy) / (torch.abs(fy * relative_elevation + Ty) + 1e-10))
+    x_base = torch.linspace(-1, 1, W).repeat(B, H, 1).type_as(x)
+    y_base = torch.linspace(-1, 1, H).repeat(B, W, 1).transpose(1, 2).type_as(x)
+    h_mean = 1.535
+    y_shifts_base = F.relu(h_mean * (yy - cy) / (2 * (relative_elevation - 0.5 * h_mean))) / (yy.shape[1] * 0.5)
+    y_shifts = y_shifts_base + disp[:, 0, :, :]
+    flow = torch.stack((x_base, y_base + y_shifts), dim=3)
+    feats = torch.cat([disparity.unsqueeze(1), x], dim=1)
+    out = F.grid_sample(feats, flow, mode="bilinear", padding_mode="border", align_corners=True)
+    return F.relu(x + conv(sd, p + ".extract", out) * sd[p + ".alpha"])
+
+
+def mono_cls_tower(sd: SD, feats: torch.Tensor, ncls_out: int) -> torch.Tensor:
+    p = "bbox_head.cls_feature_extraction"
+    x = F.relu(conv(sd, p + ".0", feats, padding=1))
+    x = F.relu(conv(sd, p + ".3", x, padding=1))
+    return anchor_flatten(conv(sd, p + ".6", x, padding=1), ncls_out)
+
+
+def yolo3d_head(sd: SD, feats: torch.Tensor, ncls_out: int):
+    """AnchorBasedDetection3DHead (R/heads/detection_3d_head.py:47-88): DCNv2+BN+ReLU, conv+BN+ReLU, conv."""
+    cls = mono_cls_tower(sd, feats, ncls_out)
+    p = "bbox_head.reg_feature_extraction"
+    x = F.relu(bn(sd, p + ".1", modulated_deform_conv_pack(sd, p + ".0", feats, 1, 1, 1)))
+    x = F.relu(bn(sd, p + ".4", conv(sd, p + ".3", x, padding=1)))
+    return cls, anchor_flatten(conv(sd, p + ".6", x, padding=1), 12)
+
+
+def gac_head(sd: SD, feats: torch.Tensor, P2: torch.Tensor, ncls_out: int, stages: dict | None = None):
+    """GroundAwareHead (R/detectors/yolomono3d_detector.py:12-53)."""
+    cls = mono_cls_tower(sd, feats, ncls_out)
+    p = "bbox_head.reg_feature_extraction"
+    x = look_ground(sd, p + ".0", feats, P2)
+    if stages is not None:
+        stages["gac"] = x
+    x = F.relu(bn(sd, p + ".2", conv(sd, p + ".1", x, padding=1)))
+    x = F.relu(bn(sd, p + ".5", conv(sd, p + ".4", x, padding=1)))
+    return cls, anchor_flatten(conv(sd, p + ".7", x, padding=1), 12)
+
+
+def mono3d_forward(sd: SD, images, P2, cfg: dict, prior_mean, prior_std, stages: dict | None = None):
+    """Yolo3D / GroundAwareYolo3D test_forward (R/detectors/yolomono3d_detector.py:100-120), looped per image for B > 1."""
+    with torch.no_grad():
+        bb = cfg["backbone"]
+        feats = resnet(sd, "core.backbone", images, bb["depth"], num_stages=bb["num_stages"], out_indices=tuple(bb["out_indices"]))[0]
+        ncls = cfg["head"]["num_classes"]
+        if cfg["name"] == "GroundAwareYolo3D":
+            cls_preds, reg_preds = gac_head(sd, feats, P2, ncls + 1, stages)
+        else:
+            cls_preds, reg_preds = yolo3d_head(sd, feats, ncls + 1)
+        anchors, mean_std, means = build_anchors(images.shape[2:], cfg["head"]["anchors_cfg"], prior_mean, prior_std)
+        mask = useful_mask(anchors, means, P2)
+        if stages is not None:
+            stages.update(features=feats, cls_preds=cls_preds, reg_preds=reg_preds, anchors=anchors, mean_std=mean_std, mask=mask)
+        outs = []
+        for b in range(images.shape[0]):
+            st = {} if stages is not None else None
+            outs.append(get_bboxes(cls_preds[b], reg_preds[b], anchors, mean_std, mask[b], images.shape[2:], ncls,
+                                   cfg["head"]["test_cfg"]["score_thr"], cfg["head"]["test_cfg"]["nms_iou_thr"], st))
+            if stages is not None:
+                stages.setdefault("per_image", []).append(st)
+        return outs

@@ -136,9 +136,72 @@ def gen_stereo3d(H=96, W=320, B=2, seed=0, tag="stereo3d_96x320"):
         print(nm, "max abs diff", float(np.abs(ref["samples"] - got["samples"]).max()), "ref absmean", ref["abssum"] / np.prod(ref["shape"]))
 
 
+def gen_mono3d(kind, H=96, W=320, B=2, seed=0, depth=None):
+    """Yolo3D (ResNet-18 + DCNv2 head; BASELINE configs[0]) / GroundAwareYolo3D (ResNet-101 + LookGround head; configs[2])."""
+    refload.load_reference()
+    from visualDet3D.networks.utils.registry import DETECTOR_DICT
+    obj_types = ["Car"]
+    pm, ps = synth.synth_priors(16, 2, obj_types)
+    tmp = tempfile.mkdtemp()
+    synth.write_priors(tmp, pm, ps, obj_types)
+    cfg = synth.mono3d_cfg(tmp, kind, obj_types, depth)
+    model = DETECTOR_DICT[kind](to_edict(cfg))
+    shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    tag = f"{kind.lower()}_{H}x{W}"
+    with open(os.path.join(HERE, f"{kind.lower()}_keys.json"), "w") as f:
+        json.dump({k: list(v) for k, v in shapes.items()}, f, indent=0)
+    sd = synth.synth_state_dict(shapes, seed, cls_gain=synth.CLS_GAIN.get(kind, 1.6))
+    missing = model.load_state_dict(sd, strict=False)
+    print("missing:", missing.missing_keys, "unexpected:", missing.unexpected_keys)
+    model.eval()
+    img, P2 = synth.synth_mono_inputs(B, H, W, seed=1)
+    stages = {}
+    hooks = [model.core.register_forward_hook(lambda m, i, o: stages.setdefault("features", []).append(o.detach().clone())),
+             model.bbox_head.register_forward_hook(lambda m, i, o: stages.setdefault("head", []).append(o))]
+    if kind == "GroundAwareYolo3D":
+        hooks.append(model.bbox_head.reg_feature_extraction[0].register_forward_hook(
+            lambda m, i, o: stages.setdefault("gac", []).append(o.detach().clone())))
+    fix, outs = {}, []
+    with torch.no_grad():
+        for b in range(B):
+            s, bb, ci = model([img[b:b + 1], P2[b:b + 1]])
+            outs.append((s, bb, ci))
+            fix[f"mask_{b}"] = np.packbits(model.bbox_head.anchors.useful_mask[0].numpy())
+    for h in hooks:
+        h.remove()
+    for b in range(B):
+        s, bb, ci = outs[b]
+        fix[f"scores_{b}"], fix[f"bboxes_{b}"], fix[f"cls_{b}"] = s.numpy(), bb.numpy(), ci.numpy()
+        print(f"{kind} image {b}: {len(s)} detections")
+    fix["features"] = subsample(torch.cat(stages["features"], 0))
+    fix["cls_preds"] = subsample(torch.cat([x[0] for x in stages["head"]], 0))
+    fix["reg_preds"] = subsample(torch.cat([x[1] for x in stages["head"]], 0))
+    if "gac" in stages:
+        fix["gac"] = subsample(torch.cat(stages["gac"], 0))
+    fix["meta"] = np.array([H, W, B, seed], dtype=np.int64)
+    np.savez_compressed(os.path.join(HERE, tag + ".npz"), **flatten_fixture(fix))
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(HERE)), "oracle"))
+    import torch_port as tp
+    st = {}
+    o = tp.mono3d_forward(sd, img, P2, cfg, pm, ps, st)
+    for b in range(B):
+        same = len(o[b][0]) == len(outs[b][0])
+        print("oracle vs ref image", b, "n", len(o[b][0]), len(outs[b][0]),
+              "max|dbox|", float((o[b][1] - outs[b][1]).abs().max()) if same and len(o[b][0]) else None)
+    for nm in ["features", "cls_preds", "reg_preds"] + (["gac"] if "gac" in fix else []):
+        print(nm, "max abs diff", float(np.abs(fix[nm]["samples"] - subsample(st[nm])["samples"]).max()),
+              "ref absmean", fix[nm]["abssum"] / np.prod(fix[nm]["shape"]))
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["stereo3d"]
     torch.set_num_threads(os.cpu_count())
     if "stereo3d" in which:
         gen_stereo3d()
         gen_stereo3d(H=192, W=640, B=1, tag="stereo3d_192x640")
+    if "yolo3d" in which:
+        gen_mono3d("Yolo3D", 96, 320, 2)
+        gen_mono3d("Yolo3D", 288, 1280, 1)       # BASELINE.json configs[0]
+    if "gac" in which:
+        gen_mono3d("GroundAwareYolo3D", 96, 320, 2)
+        gen_mono3d("GroundAwareYolo3D", 288, 640, 1)

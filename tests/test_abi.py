@@ -85,3 +85,16 @@ def test_anchor_table_matches_oracle_bitwise():
         a, ms, means = tp.build_anchors(hw, cfg["head"]["anchors_cfg"], pm, ps)
         t = AnchorTable(hw, cfg["head"]["anchors_cfg"], pm, ps, "cpu")
         assert torch.equal(t.anchors, a) and torch.equal(t.mean_std, ms) and torch.equal(t.means_z, means[:, :, 0])
+
+
+@pytest.mark.parametrize("kind", ["Yolo3D", "GroundAwareYolo3D"])
+def test_mono3d_registered_and_state_dict_keys_match_reference(kind):
+    from visualdet3d_b200.plugin import DETECTOR_DICT
+    from visualdet3d_b200.detectors import build_synthetic_mono3d
+    assert kind in DETECTOR_DICT
+    det, sd, cfg, _ = build_synthetic_mono3d(kind)
+    ref = json.load(open(os.path.join(GOLDEN, f"{kind.lower()}_keys.json")))
+    mine = {k: list(v.shape) for k, v in det.state_dict().items()}
+    assert list(mine.keys()) == list(ref.keys()) and mine == ref
+    with pytest.raises(NotImplementedError):
+        det([torch.zeros(1, 3, 32, 32), None, torch.zeros(1, 3, 4)])          # 3-element list = training protocol

@@ -54,3 +54,27 @@ def test_psm_cosine_port_edge_cases():
     assert float(c[:, 10:].abs().max()) == 0.0           # planes i >= W stay zero
     assert float(c[:, 5, :, :5].abs().max()) == 0.0       # columns w < i stay zero
     np.testing.assert_allclose(c[:, 3, :, 3:], (L[..., 3:] * R[..., :-3]).mean(1))
+
+
+@pytest.mark.parametrize("kind,tag", [("Yolo3D", "yolo3d_96x320"), ("Yolo3D", "yolo3d_288x1280"),
+                                      ("GroundAwareYolo3D", "groundawareyolo3d_96x320"), ("GroundAwareYolo3D", "groundawareyolo3d_288x640")])
+def test_mono3d_port_matches_reference(kind, tag):
+    """Yolo3D (ResNet-18 + DCNv2 head, BASELINE configs[0] shape 1x3x288x1280) and GroundAwareYolo3D (ResNet-101 + LookGround)."""
+    fx = load_fixture(tag)
+    H, W, B, seed = [int(v) for v in fx["meta"]]
+    shapes = json.load(open(os.path.join(GOLDEN, f"{kind.lower()}_keys.json")))
+    sd = synth.synth_state_dict(shapes, seed, cls_gain=synth.CLS_GAIN.get(kind, 1.6))
+    pm, ps = synth.synth_priors(16, 2, ["Car"])
+    cfg = synth.mono3d_cfg("/nonexistent", kind)
+    img, P2 = synth.synth_mono_inputs(B, H, W, seed=1)
+    st = {}
+    outs = tp.mono3d_forward(sd, img, P2, cfg, pm, ps, st)
+    for nm in ["features", "cls_preds", "reg_preds"] + (["gac"] if "gac" in fx else []):
+        np.testing.assert_allclose(subsample_like(st[nm], fx[nm]), fx[nm]["samples"], rtol=0, atol=2e-4, err_msg=nm)
+    for b in range(B):
+        np.testing.assert_array_equal(np.packbits(st["mask"][b].numpy()), fx[f"mask_{b}"])
+        s, bx, ci, _ = outs[b]
+        assert len(s) == len(fx[f"scores_{b}"])
+        np.testing.assert_array_equal(ci.numpy(), fx[f"cls_{b}"])
+        np.testing.assert_allclose(s.numpy(), fx[f"scores_{b}"], atol=1e-4)
+        np.testing.assert_allclose(bx.numpy(), fx[f"bboxes_{b}"], atol=1e-3)

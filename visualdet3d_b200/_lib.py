@@ -55,6 +55,7 @@ _SIGS = {
     "vd3d_boxes_iou_bev": (I, [P, I, P, I, P, P]),
     "vd3d_nms_bev_workspace": (c_longlong, [I]),
     "vd3d_nms_bev": (I, [P, I, F, I, P, P, P, P]),
+    "vd3d_look_ground_sample": (I, [P, I, I, I, I, I, I, P, I, I, P, F, F, P, P, I, P]),
     "vd3d_anchor_mask": (I, [P, P, P, I, I, I, F, F, F, P, P]),
     "vd3d_decode_nms_workspace": (c_longlong, [I, I]),
     "vd3d_decode_nms": (I, [P, P, P, P, P, I, I, I, I, F, c_double, F, F, I, P, P, P, P, P, P, P, P]),

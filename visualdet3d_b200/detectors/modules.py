@@ -215,3 +215,63 @@ class StereoHeadP(HeadBaseP):
         self.reg_feature_extraction = seq(ConvBnReLUP(num_features_in, reg_feature_size, 3),
                                           BasicBlockP(reg_feature_size, reg_feature_size), nn.ReLU(),
                                           nn.Conv2d(reg_feature_size, num_anchors * num_reg_output, 3, padding=1), nn.Identity())
+
+
+class DCNPackP(Holder):
+    """keys of ModulatedDeformConvPack (R/lib/ops/dcn/deform_conv.py:408-457): weight, bias, conv_offset.{weight,bias}."""
+
+    def __init__(self, cin, cout, k=3, stride=1, padding=1, dilation=1, deformable_groups=1, bias=True):
+        super().__init__()
+        self.cin, self.cout, self.k = cin, cout, k
+        self.stride, self.padding, self.dilation, self.deformable_groups = stride, padding, dilation, deformable_groups
+        self.weight = nn.Parameter(torch.empty(cout, cin, k, k).uniform_(-1, 1) / math.sqrt(cin * k * k))
+        self.bias = nn.Parameter(torch.zeros(cout)) if bias else None
+        self.conv_offset = nn.Conv2d(cin, deformable_groups * 3 * k * k, k, stride, padding, bias=True)
+        nn.init.zeros_(self.conv_offset.weight)
+        nn.init.zeros_(self.conv_offset.bias)
+
+
+class MonoHeadP(HeadBaseP):
+    """keys of AnchorBasedDetection3DHead.init_layers (R/heads/detection_3d_head.py:47-82): DCNv2 reg tower."""
+
+    def __init__(self, num_features_in, num_anchors, num_cls_output, num_reg_output, cls_feature_size=1024,
+                 reg_feature_size=1024, loss_cfg=None, num_regression_loss_terms=12, **_):
+        super().__init__(loss_cfg or {}, num_regression_loss_terms)
+        self.cls_feature_extraction = cls_tower(num_features_in, cls_feature_size, num_anchors * num_cls_output)
+        self.reg_feature_extraction = seq(DCNPackP(num_features_in, reg_feature_size, 3, padding=1), nn.BatchNorm2d(reg_feature_size),
+                                          nn.ReLU(inplace=True), nn.Conv2d(reg_feature_size, reg_feature_size, 3, padding=1),
+                                          nn.BatchNorm2d(reg_feature_size), nn.ReLU(inplace=True),
+                                          nn.Conv2d(reg_feature_size, num_anchors * num_reg_output, 3, padding=1), nn.Identity())
+
+
+class LookGroundP(Holder):
+    """keys of LookGround (R/lib/look_ground.py:13-22): disp_create.0.{weight,bias}, extract.{weight,bias}, alpha."""
+
+    def __init__(self, input_features, baseline=0.54, relative_elevation=1.65):
+        super().__init__()
+        self.disp_create = seq(nn.Conv2d(input_features, 1, 3, padding=1), nn.Tanh())
+        self.extract = nn.Conv2d(1 + input_features, input_features, 1)
+        self.baseline, self.relative_elevation = baseline, relative_elevation
+        self.alpha = nn.Parameter(torch.tensor([0.0], dtype=torch.float32))
+
+
+class GroundAwareHeadP(HeadBaseP):
+    """keys of GroundAwareHead.init_layers (R/detectors/yolomono3d_detector.py:12-47)."""
+
+    def __init__(self, num_features_in, num_anchors, num_cls_output, num_reg_output, cls_feature_size=1024,
+                 reg_feature_size=1024, loss_cfg=None, num_regression_loss_terms=12, **_):
+        super().__init__(loss_cfg or {}, num_regression_loss_terms)
+        self.cls_feature_extraction = cls_tower(num_features_in, cls_feature_size, num_anchors * num_cls_output)
+        self.reg_feature_extraction = seq(LookGroundP(reg_feature_size), nn.Conv2d(num_features_in, reg_feature_size, 3, padding=1),
+                                          nn.BatchNorm2d(reg_feature_size), nn.ReLU(),
+                                          nn.Conv2d(reg_feature_size, reg_feature_size, 3, padding=1), nn.BatchNorm2d(reg_feature_size),
+                                          nn.ReLU(inplace=True), nn.Conv2d(reg_feature_size, num_anchors * num_reg_output, 3, padding=1),
+                                          nn.Identity())
+
+
+class YoloMono3DCoreP(Holder):
+    """keys of YoloMono3DCore (R/detectors/yolomono3d_core.py:9-18)."""
+
+    def __init__(self, backbone_arguments):
+        super().__init__()
+        self.backbone = ResNetP(**backbone_arguments)

@@ -19,9 +19,9 @@ import torch.nn as nn
 
 from .. import engine as E
 from .._lib import Vd3dError, call
-from ..anchors import AnchorTable, load_priors
 from ..plugin import DETECTOR_DICT
 from . import modules as M
+from .base import Anchor3DDetector, synth_load
 
 
 class ResNetRunner:
@@ -131,6 +131,27 @@ class GhostRunner:
         return buf
 
 
+def cls_tower_runner(ct, device):
+    """conv3x3+ReLU, conv3x3+ReLU, conv3x3 (R/heads/detection_3d_head.py:55-65); Dropout2d is identity in eval."""
+    return [E.ConvLayer(ct[0].weight, ct[0].bias, None, pad=1, relu=True, device=device),
+            E.ConvLayer(ct[3].weight, ct[3].bias, None, pad=1, relu=True, device=device),
+            E.ConvLayer(ct[6].weight, ct[6].bias, None, pad=1, relu=False, device=device)]
+
+
+def run_cls_tower(layers, feat: E.Act, arena: E.Arena, tag: str = "") -> E.Act:
+    """`feat` must carry a fresh lo companion if the first conv runs on the tensor cores."""
+    tc = lambda l: l.engine != "simt"
+    k1, k2, k3 = layers
+    B, h, w, dev = feat.B, feat.H, feat.W, feat.t.device
+    a = k1(feat, arena.act(tag + "C1", (B, h, w, k1.Cout), dev, lo=True))
+    if tc(k2) and not tc(k1):
+        E.split_lo(a)
+    a = k2(a, arena.act(tag + "C2", (B, h, w, k2.Cout), dev, lo=True))
+    if tc(k3) and not tc(k2):
+        E.split_lo(a)
+    return k3(a, arena.act(tag + "CLS", (B, h, w, k3.Cout), dev))
+
+
 def basic_block_runner(blk: M.BasicBlockP, device):
     c1 = E.ConvLayer(blk.conv1.weight, None, E.bn_dict(blk.bn1), stride=blk.stride, pad=1, relu=True, device=device)
     c2 = E.ConvLayer(blk.conv2.weight, None, E.bn_dict(blk.bn2), pad=blk.dilation, dil=blk.dilation, relu=True, device=device)
@@ -138,55 +159,15 @@ def basic_block_runner(blk: M.BasicBlockP, device):
 
 
 @DETECTOR_DICT.register_module
-class Stereo3D(nn.Module):
+class Stereo3D(Anchor3DDetector):
     """YOLOStereo3D detector (inference).  `network_cfg` is the reference's `cfg.detector` (R/config/Stereo3D_example:111-167)."""
 
     def __init__(self, network_cfg):
-        super().__init__()
-        self.obj_types = network_cfg["obj_types"]
-        head = network_cfg["head"]
-        acfg = head["anchors_cfg"]
-        self.anchors_cfg = {k: acfg[k] for k in ("pyramid_levels", "strides", "sizes", "ratios", "scales")}
-        self.num_anchors = len(acfg["pyramid_levels"]) * len(acfg["ratios"]) * len(acfg["scales"])
-        self.num_classes = head["num_classes"]
-        self.test_cfg = dict(head.get("test_cfg", {}))
-        self.filter_anchor = bool(self.test_cfg.get("filter_anchor", head.get("loss_cfg", {}).get("filter_anchor", True)))
-        lc = dict(head["layer_cfg"])
-        lc.setdefault("num_anchors", self.num_anchors)
-        self.num_cls_output, self.num_reg_output = lc["num_cls_output"], lc["num_reg_output"]
-        if self.num_reg_output != 12:
-            raise ValueError("num_reg_output must be 12 (decode layout, detection_3d_head.py:218-263)")
-        self.bbox_head = M.StereoHeadP(loss_cfg=dict(head.get("loss_cfg", {})),
-                                       num_regression_loss_terms=head.get("num_regression_loss_terms", 12), **lc)
+        super().__init__(network_cfg)
+        self.bbox_head = M.StereoHeadP(**self.head_kwargs)
         self.core = M.YoloStereo3DCoreP(dict(network_cfg["backbone"]))
-        self.network_cfg = network_cfg
-        n_rows = len(acfg["scales"]) * len(acfg["pyramid_levels"])
-        self.prior_mean, self.prior_std = load_priors(head["preprocessed_path"], acfg.get("obj_types", self.obj_types),
-                                                      n_rows, len(acfg["ratios"]))
-        self.max_detections = int(self.test_cfg.get("max_candidates", 2048))   # fixed capacity of the decode / NMS stage
-        self._plan = None
-        self._plan_version = None
-        self._arena = E.Arena()
-        self._anchor_tables = {}
-        self._decoders = {}
-        self.stage_hook = None            # tests: callable(name, Act-or-tensor)
-        self.profile_events = None        # bench: list collecting (start, end) CUDA events of the scale-4 PSMCosine launch
 
-    # ---- plan (folded / packed weights) -------------------------------------------------------------------
-    def _param_version(self):
-        return tuple(p._version for p in self.parameters()) + tuple(b._version for b in self.buffers())
-
-    def _device(self):
-        return next(self.parameters()).device
-
-    def prepare(self, force: bool = False):
-        """Fold BN into conv weights, pack for the kernels, upload.  Re-run automatically when parameters change."""
-        dev = self._device()
-        if dev.type != "cuda":
-            raise Vd3dError("Stereo3D (B200) has no CPU path: move the module to a CUDA device first")
-        ver = (self._param_version(), str(dev))
-        if self._plan is not None and not force and ver == self._plan_version:
-            return self._plan
+    def build_plan(self, dev) -> dict:
         pl = {}
         pl["backbone"] = ResNetRunner(self.core.backbone, dev)
         neck = self.core.neck
@@ -203,18 +184,11 @@ class Stereo3D(nn.Module):
         pl["g8"], pl["bb8"] = GhostRunner(dr.eight_to_sixteen[0], dev), basic_block_runner(dr.eight_to_sixteen[2], dev)
         pl["g16"], pl["bb16"] = GhostRunner(dr.depth_reason[0], dev), basic_block_runner(dr.depth_reason[1], dev)
         ct, rt = self.bbox_head.cls_feature_extraction, self.bbox_head.reg_feature_extraction
-        pl["cls"] = [E.ConvLayer(ct[0].weight, ct[0].bias, None, pad=1, relu=True, device=dev),
-                     E.ConvLayer(ct[3].weight, ct[3].bias, None, pad=1, relu=True, device=dev),
-                     E.ConvLayer(ct[6].weight, ct[6].bias, None, pad=1, relu=False, device=dev)]
+        pl["cls"] = cls_tower_runner(ct, dev)
         pl["reg0"] = E.ConvLayer(rt[0].sequence[0].weight, rt[0].sequence[0].bias, E.bn_dict(rt[0].sequence[1]), pad=1, relu=True, device=dev)
         pl["reg_bb"] = basic_block_runner(rt[1], dev)
         pl["reg_out"] = E.ConvLayer(rt[3].weight, rt[3].bias, None, pad=1, relu=False, device=dev)
-        self._plan, self._plan_version = pl, ver
         return pl
-
-    def _hook(self, name, value):
-        if self.stage_hook is not None:
-            self.stage_hook(name, value)
 
     # ---- forward ------------------------------------------------------------------------------------------
     def core_forward(self, left: torch.Tensor, right: torch.Tensor) -> Tuple[E.Act, E.Act, E.Act]:
@@ -293,14 +267,7 @@ class Stereo3D(nn.Module):
             E.split_lo(FEAT.slice(cf, 3 * c16))
         self._hook("features", FEAT)
         # head towers (R/heads/detection_3d_head.py:509-530); AnchorFlatten == the NHWC layout itself
-        k1, k2, k3 = pl["cls"]
-        a = k1(FEAT, ar.act("C1", (B, h16, w16, k1.Cout), dev, lo=True))
-        if tc(k2) and not tc(k1):
-            E.split_lo(a)
-        a = k2(a, ar.act("C2", (B, h16, w16, k2.Cout), dev, lo=True))
-        if tc(k3) and not tc(k2):
-            E.split_lo(a)
-        cls = k3(a, ar.act("CLS", (B, h16, w16, k3.Cout), dev))
+        cls = run_cls_tower(pl["cls"], FEAT, ar)
         r0 = pl["reg0"]
         r1 = r0(FEAT, ar.act("R1", (B, h16, w16, r0.Cout), dev, lo=True))
         c1, c2 = pl["reg_bb"]
@@ -317,12 +284,6 @@ class Stereo3D(nn.Module):
         self._hook("cls_preds", cls), self._hook("reg_preds", reg)
         return FEAT, cls, reg
 
-    def _anchor_table(self, H, W, dev) -> AnchorTable:
-        key = (H, W, str(dev))
-        if key not in self._anchor_tables:
-            self._anchor_tables[key] = AnchorTable((H, W), self.anchors_cfg, self.prior_mean, self.prior_std, dev)
-        return self._anchor_tables[key]
-
     def launch(self, left, right, P2, P3=None):
         """Enqueue the whole forward (backbone .. NMS) on the current stream; no host synchronisation.
         Returns the DecodeNms object holding the fixed-capacity device outputs."""
@@ -330,38 +291,18 @@ class Stereo3D(nn.Module):
             E._require_cuda(t, nm)
         left, right = left.float().contiguous(), right.float().contiguous()
         P2 = P2.float().contiguous()
-        B, _, H, W = left.shape
+        _, _, H, W = left.shape
         _, cls, reg = self.core_forward(left, right)
-        tab = self._anchor_table(H, W, left.device)
-        N = tab.N
-        assert cls.H * cls.W * cls.C == N * self.num_cls_output and reg.C * reg.H * reg.W == N * 12
-        mask = self._arena.get("mask", (B, N), left.device, dtype=torch.uint8)
-        if self.filter_anchor:
-            E.anchor_mask(tab.anchors, tab.means_z, P2, mask)
-        else:
-            mask.fill_(1)
-        self._hook("mask", mask)
-        key = (B, str(left.device))
-        if key not in self._decoders:
-            self._decoders[key] = E.DecodeNms(B, self.max_detections, left.device)
-        dec = self._decoders[key]
-        dec.run(cls.t.view(B, N, self.num_cls_output), reg.t.view(B, N, 12), tab.anchors, tab.mean_std, mask,
-                self.num_classes, self.test_cfg.get("score_thr", 0.5), self.test_cfg.get("nms_iou_thr", 0.5), W, H)
-        self._last_decoder = dec
-        return dec
+        return self.decode(cls, reg, P2, H, W)
 
     def forward_batch(self, left, right, P2, P3=None):
         """B stereo pairs -> list of B (scores[K], bboxes[K,11], cls_indexes[K]) triples (new API; no reference counterpart).
         One D2H read (the per-image counts) is the only host synchronisation."""
-        dec = self.launch(left, right, P2, P3)
-        return [(s.clone(), b.clone(), c.clone()) for (s, b, c) in dec.results()]
+        return self.results(self.launch(left, right, P2, P3))
 
     def test_forward(self, left_images, right_images, P2, P3=None):
         assert left_images.shape[0] == 1   # reference contract (yolostereo3d_detector.py:78); use forward_batch for B > 1
         return self.forward_batch(left_images, right_images, P2, P3)[0]
-
-    def train_forward(self, *a, **k):
-        raise NotImplementedError("training forward is out of scope of the B200 inference path (SURVEY.md section 2)")
 
     def forward(self, inputs):
         if isinstance(inputs, list) and len(inputs) >= 5:
@@ -380,7 +321,5 @@ def build_synthetic_stereo3d(seed: int = 0, depth: int = 34, workdir: Optional[s
     synth.write_priors(d, pm, ps, obj_types)
     cfg = synth.stereo3d_cfg(d, obj_types, depth)
     det = Stereo3D(cfg)
-    shapes = {k: tuple(v.shape) for k, v in det.state_dict().items()}
-    sd = synth.synth_state_dict(shapes, seed)
-    det.load_state_dict(sd, strict=False)
+    sd = synth_load(det, seed)
     return det, sd, cfg, (pm, ps)

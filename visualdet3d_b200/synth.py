@@ -33,7 +33,10 @@ def _gen(key: str, seed: int) -> torch.Generator:
     return g
 
 
-def synth_state_dict(shapes: Mapping[str, Sequence[int]], seed: int = 0, gain: float = 0.8) -> "OrderedDict[str, torch.Tensor]":
+CLS_GAIN = {"GroundAwareYolo3D": 3.2}     # final cls conv gain per detector kind (default 1.6): keeps ~1 % of anchors above score_thr
+
+
+def synth_state_dict(shapes: Mapping[str, Sequence[int]], seed: int = 0, gain: float = 0.8, cls_gain: float = 1.6) -> "OrderedDict[str, torch.Tensor]":
     """shapes: name -> shape for every entry of a reference-format state_dict.  Returns fp32 CPU tensors for all
     parameters and BN buffers (training-only buffers such as balance_weights are left out -> load with strict=False)."""
     names = set(shapes.keys())
@@ -62,7 +65,7 @@ def synth_state_dict(shapes: Mapping[str, Sequence[int]], seed: int = 0, gain: f
             fan_in = int(np.prod(shp[1:]))
             std = gain * math.sqrt(2.0 / fan_in)
             if k.endswith("cls_feature_extraction.6.weight"):
-                std = 1.6 / math.sqrt(fan_in)
+                std = cls_gain / math.sqrt(fan_in)
             elif "reg_feature_extraction" in k and len(shp) == 4 and stem.rsplit(".", 1)[-1].isdigit() \
                     and _is_last_reg(k, names):
                 std = 0.5 / math.sqrt(fan_in)
@@ -222,5 +225,28 @@ def stereo3d_cfg(preprocessed_path: str, obj_types=("Car", "Pedestrian"), depth:
         loss_cfg=AttrDict(fg_iou_threshold=0.5, bg_iou_threshold=0.4, L1_regression_alpha=5 ** 2, focal_loss_gamma=2.0,
                           balance_weight=[20.0, 40], regression_weight=[1, 1, 1, 1, 1, 1, 12, 1, 1, 0.5, 0.5, 0.5, 1]),
         test_cfg=AttrDict(score_thr=0.75, cls_agnostic=False, nms_iou_thr=0.4, post_optimization=False))
+    det.anchors = anchors
+    return det
+
+
+def mono3d_cfg(preprocessed_path: str, kind: str = "Yolo3D", obj_types=("Car",), depth=None) -> AttrDict:
+    """cfg.detector of R/config/Yolo3D_example:110-167.  kind 'GroundAwareYolo3D' = the shipped config (ResNet-101,
+    1024-channel head); kind 'Yolo3D' = BASELINE.json configs[0] (ResNet-18 plumbing case: 256-channel features, DCNv2 head)."""
+    obj_types = list(obj_types)
+    depth = depth or (101 if kind == "GroundAwareYolo3D" else 18)
+    feat = 1024 if depth > 34 else 256
+    anchors = AttrDict(obj_types=obj_types, pyramid_levels=[4], strides=[2 ** 4], sizes=[24],
+                       ratios=np.array([0.5, 1]), scales=np.array([2 ** (i / 4.0) for i in range(16)]))
+    det = AttrDict(obj_types=obj_types, name=kind)
+    det.backbone = AttrDict(depth=depth, pretrained=False, frozen_stages=-1, num_stages=3, out_indices=(2,), norm_eval=False,
+                            dilations=(1, 1, 1))
+    det.head = AttrDict(
+        num_regression_loss_terms=13, preprocessed_path=preprocessed_path, num_classes=len(obj_types), anchors_cfg=anchors,
+        layer_cfg=AttrDict(num_features_in=feat, num_cls_output=len(obj_types) + 1, num_reg_output=12,
+                           cls_feature_size=feat // 2, reg_feature_size=feat),
+        loss_cfg=AttrDict(fg_iou_threshold=0.5, bg_iou_threshold=0.4, L1_regression_alpha=5 ** 2, focal_loss_gamma=2.0,
+                          match_low_quality=False, balance_weight=[20.0],
+                          regression_weight=[1, 1, 1, 1, 1, 1, 3, 1, 1, 0.5, 0.5, 0.5, 1]),
+        test_cfg=AttrDict(score_thr=0.75, cls_agnostic=False, nms_iou_thr=0.5, post_optimization=False))
     det.anchors = anchors
     return det
