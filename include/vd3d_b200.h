@@ -82,6 +82,14 @@ int vd3d_maxpool3x3s2_nhwc(const float* in, int B, int H, int W, int C, int in_c
 /* nn.AvgPool2d(2) (R/detectors/yolostereo3d_core.py:25,34). H, W even. */
 int vd3d_avgpool2_nhwc(const float* in, int B, int H, int W, int C, int in_cs, int in_co,
                        float* out, int out_cs, int out_co, void* stream);
+/* nn.MaxPool2d(2, stride=2) (DLA Tree.downsample, R/backbones/dla.py:203-204). */
+int vd3d_maxpool2x2s2_nhwc(const float* in, int B, int H, int W, int C, int in_cs, int in_co,
+                           float* out, int out_cs, int out_co, void* stream);
+/* depthwise nn.ConvTranspose2d(C, C, 2f, stride=f, padding=f//2, groups=C, bias=False) (IDAUp.up_i, R/backbones/dla_utils.py:69-72)
+ * with the `layers[i] + layers[i-1]` add of IDAUp.forward (:84) fused: out = up(in) + addend (addend may be NULL).
+ * wgt [2f*2f][C] (tap-major); out is [B][H*f][W*f]. */
+int vd3d_dw_convtranspose_nhwc(const float* in, int B, int H, int W, int C, int in_cs, int in_co, const float* wgt, int f,
+                               const float* addend, int add_cs, int add_co, float* out, int out_cs, int out_co, void* stream);
 /* channel-slice copy (the torch.cat legs that cannot be fused into a producer). */
 int vd3d_copy_channels_nhwc(const float* in, int npix, int C, int in_cs, int in_co, float* out, int out_cs, int out_co, void* stream);
 
@@ -126,6 +134,18 @@ int vd3d_decode_nms(const float* cls, const float* reg, const float* anchors, co
                     float img_w, float img_h, int cap, void* ws,
                     float* out_scores, float* out_boxes, int64_t* out_cls, int32_t* out_anchor,
                     int32_t* out_count, int32_t* out_ncand, void* stream);
+
+/* ---- CenterNet-style decode of the MonoFlex head (MonoFlexHead.get_bboxes, R/heads/monoflex_head.py:114-179) ----------
+ * heads: NHWC [B][H][W][cs] holding all head outputs at the given channel offsets (hm: ncls, bbox2d 4, hps 20, rot 8, dim 3,
+ * reg 2, depth 1, depth_uncertainty 1, corner_uncertainty 3); P2 [B][3][4].  sigmoid + 3x3 peak test + top-K + gather +
+ * depth merge + alpha + x4 + clip + class-agnostic NMS, all on the device.  Outputs like vd3d_decode_nms
+ * (out_index = flat (c*H + y)*W + x of every kept peak). */
+long long vd3d_monoflex_decode_workspace(int B, int cap);
+int vd3d_monoflex_decode(const float* heads, int B, int H, int W, int ncls, int cs, int hm_co, int bbox2d_co, int hps_co, int rot_co,
+                         int dim_co, int reg_co, int depth_co, int dunc_co, int cunc_co, const float* P2,
+                         float score_thr, double iou_thr, int K, float unc_lo, float unc_hi, float img_w, float img_h,
+                         int cap, void* ws, int out_cap, float* out_scores, float* out_boxes, long long* out_cls,
+                         int* out_index, int* out_count, int* out_ncand, void* stream);
 
 /* ---- deformable convolution (R/lib/ops/dcn, make.sh) ----------------------------------------------------------
  * Deformable / modulated-deformable im2col on NHWC activations; the GEMM that the reference runs per image with cuBLAS

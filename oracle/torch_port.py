@@ -467,3 +467,150 @@ def mono3d_forward(sd: SD, images, P2, cfg: dict, prior_mean, prior_std, stages:
             if stages is not None:
                 stages.setdefault("per_image", []).append(st)
         return outs
+
+
+# --------------------------------------------------------------------------------------------------------
+# DLA-34 + DLA up-sampling + MonoFlex head  (R/backbones/dla.py, dla_utils.py, R/heads/monoflex_head.py)
+# --------------------------------------------------------------------------------------------------------
+def dla_block(sd: SD, p: str, x, residual=None, stride=1):
+    """BasicBlock.forward (R/backbones/dla.py:56-70)."""
+    if residual is None:
+        residual = x
+    out = F.relu(bn(sd, p + ".bn1", conv(sd, p + ".conv1", x, stride=stride, padding=1)))
+    out = bn(sd, p + ".bn2", conv(sd, p + ".conv2", out, padding=1))
+    return F.relu(out + residual)
+
+
+def dla_tree(sd: SD, p: str, x, levels: int, stride: int, level_root: bool, children=None):
+    """Tree.forward (R/backbones/dla.py:216-230); root_residual is False for DLA-34."""
+    children = [] if children is None else children
+    bottom = F.max_pool2d(x, stride, stride=stride) if stride > 1 else x
+    residual = bn(sd, p + ".project.1", conv(sd, p + ".project.0", bottom)) if (p + ".project.0.weight") in sd else bottom
+    if level_root:
+        children.append(bottom)
+    if levels == 1:
+        x1 = dla_block(sd, p + ".tree1", x, residual, stride)
+        x2 = dla_block(sd, p + ".tree2", x1)
+        k = sd[p + ".root.conv.weight"].shape[-1]
+        return F.relu(bn(sd, p + ".root.bn", conv(sd, p + ".root.conv", torch.cat([x2, x1] + children, 1), padding=(k - 1) // 2)))
+    x1 = dla_tree(sd, p + ".tree1", x, levels - 1, stride, False)          # (the `residual` argument is overwritten inside, :219)
+    children.append(x1)
+    return dla_tree(sd, p + ".tree2", x1, levels - 1, 1, False, children)
+
+
+def dla34(sd: SD, p: str, img):
+    """DLA.forward (R/backbones/dla.py:317-326) for dla34, out_indices (0..5)."""
+    x = F.relu(bn(sd, p + ".base_layer.1", conv(sd, p + ".base_layer.0", img, padding=3)))
+    ys = []
+    x = F.relu(bn(sd, p + ".level0.1", conv(sd, p + ".level0.0", x, padding=1))); ys.append(x)
+    x = F.relu(bn(sd, p + ".level1.1", conv(sd, p + ".level1.0", x, stride=2, padding=1))); ys.append(x)
+    for i, (lv, root) in enumerate([(1, False), (2, True), (2, True), (1, True)]):
+        x = dla_tree(sd, f"{p}.level{i + 2}", x, lv, 2, root)
+        ys.append(x)
+    return ys
+
+
+def dla_deform(sd: SD, p: str, x):
+    """DeformConv.forward (R/backbones/dla_utils.py:52-56)."""
+    return F.relu(bn(sd, p + ".actf.0", modulated_deform_conv_pack(sd, p + ".conv", x, 1, 1, 1)))
+
+
+def ida_up(sd: SD, p: str, layers, startp, endp):
+    """IDAUp.forward (R/backbones/dla_utils.py:79-85)."""
+    for i in range(startp + 1, endp):
+        k = i - startp
+        w = sd[f"{p}.up_{k}.weight"]
+        f = w.shape[-1] // 2
+        up = F.conv_transpose2d(dla_deform(sd, f"{p}.proj_{k}", layers[i]), w, None, stride=f, padding=f // 2, groups=w.shape[0])
+        layers[i] = dla_deform(sd, f"{p}.node_{k}", up + layers[i - 1])
+
+
+def dla_seg_upsample(sd: SD, p: str, tensors, first_level=2, last_level=5):
+    """DLASegUpsample.forward (R/backbones/dla_utils.py:147-155) incl. DLAUp.forward (:106-112)."""
+    layers = list(tensors)
+    out = [layers[-1]]
+    for i in range(len(layers) - first_level - 1):
+        ida_up(sd, f"{p}.dla_up.ida_{i}", layers, len(layers) - i - 2, len(layers))
+        out.insert(0, layers[-1])
+    y = [out[i].clone() for i in range(last_level - first_level)]
+    ida_up(sd, p + ".ida_up", y, 0, len(y))
+    return y[-1]
+
+
+def km3d_heads(sd: SD, feat, names):
+    """KM3DHead.forward (R/heads/km3d_head.py:353-357)."""
+    return {n: conv(sd, f"bbox_head.head_layers.{n}.2", F.relu(conv(sd, f"bbox_head.head_layers.{n}.0", feat, padding=1))) for n in names}
+
+
+def monoflex_get_bboxes(output, P2, image_hw, score_thr=0.1, nms_iou_thr=0.5, unc_range=(-10, 10), K=100):
+    """MonoFlexHead.get_bboxes (R/heads/monoflex_head.py:114-179) for ONE image (output maps [1, n, H, W])."""
+    from torchvision.ops import nms
+    hm = torch.sigmoid(output["hm"])
+    hmax = F.max_pool2d(hm, (3, 3), stride=1, padding=1)
+    heat = hm * (hmax == hm).float()
+    batch, cat, height, width = heat.shape
+    topk_scores, topk_inds = torch.topk(heat.view(batch, cat, -1), K)
+    topk_inds = topk_inds % (height * width)
+    topk_ys = (topk_inds / width).int().float()
+    topk_xs = (topk_inds % width).int().float()
+    scores, topk_ind = torch.topk(topk_scores.view(batch, -1), K)
+    clses = (topk_ind / K).int()
+    g = lambda t: t.view(batch, -1, 1).gather(1, topk_ind.unsqueeze(2)).view(batch, K)
+    inds, ys, xs = g(topk_inds), g(topk_ys), g(topk_xs)
+    gather = lambda name: output[name].permute(0, 2, 3, 1).reshape(batch, height * width, -1).gather(
+        1, inds.long().unsqueeze(2).expand(batch, K, output[name].shape[1]))[0]
+    scores, clses, ys, xs = scores[0], clses[0], ys[0], xs[0]
+    reg2d = gather("bbox2d")
+    bbox2d = torch.stack([xs - reg2d[:, 0], ys - reg2d[:, 1], xs + reg2d[:, 2], ys + reg2d[:, 3]], dim=-1)
+    depth_decoded = torch.exp(-gather("depth"))
+    hps = gather("hps").reshape(K, -1, 2)
+    dim = gather("dim")
+    ph = dim[..., 1]
+    f = P2[0, 0, 0]
+    center_h = hps[..., -2, 1] - hps[:, -1, 1]
+    h02 = hps[..., (7, 3), 1] - hps[..., (0, 4), 1]
+    h13 = hps[..., (2, 6), 1] - hps[..., (1, 5), 1]
+    cd = f * ph / (F.relu(center_h) * 4 + 1e-8)
+    d02 = ((f * ph).unsqueeze(-1) / (F.relu(h02) * 4 + 1e-8)).mean(dim=1)
+    d13 = ((f * ph).unsqueeze(-1) / (F.relu(h13) * 4 + 1e-8)).mean(dim=1)
+    kpd = torch.clamp(torch.stack([cd, d02, d13], dim=-1), 0.1, 100)
+    du = torch.clamp(gather("depth_uncertainty"), unc_range[0], unc_range[1])
+    cu = torch.clamp(gather("corner_uncertainty"), unc_range[0], unc_range[1])
+    unc = torch.cat((du, cu), dim=1).exp()
+    depths = torch.cat((depth_decoded, kpd), dim=1)
+    wts = 1 / unc
+    wts = wts / wts.sum(dim=1, keepdim=True)
+    merged = torch.sum(depths * wts, dim=1)
+    mask = scores > score_thr
+    rot = gather("rot")[mask]
+    aidx = (rot[..., 1] > rot[..., 5]).float()
+    alpha = (torch.atan(rot[..., 2] / rot[..., 3]) + (-0.5 * np.pi)) * aidx + (torch.atan(rot[..., 6] / rot[..., 7]) + (0.5 * np.pi)) * (1 - aidx)
+    off = gather("reg")[mask]
+    cx = (xs[mask] + off[..., 0]).unsqueeze(-1) * 4
+    cy = (ys[mask] + off[..., 1]).unsqueeze(-1) * 4
+    b2 = bbox2d[mask] * 4
+    Hh, Ww = image_hw
+    b2[:, 0] = torch.clamp(b2[:, 0], min=0); b2[:, 1] = torch.clamp(b2[:, 1], min=0)
+    b2[:, 2] = torch.clamp(b2[:, 2], max=Ww); b2[:, 3] = torch.clamp(b2[:, 3], max=Hh)
+    box = torch.cat([b2, cx, cy, merged[mask].unsqueeze(-1), dim[mask], alpha.unsqueeze(-1)], dim=1)
+    sc = scores[mask]
+    flat = (clses[mask].long() * height + ys[mask].long()) * width + xs[mask].long()
+    keep = nms(box[:, :4], sc, nms_iou_thr)
+    return sc[keep], box[keep], clses[mask].long()[keep], flat[keep]
+
+
+def monoflex_forward(sd: SD, images, P2, cfg: dict, stages: dict | None = None):
+    """MonoFlex.test_forward (R/detectors/KM3D.py:61-79), looped per image for the decode."""
+    with torch.no_grad():
+        ys = dla34(sd, "core.backbone", images)
+        feat = dla_seg_upsample(sd, "core.deconv_layers", ys)
+        names = list(cfg["head"]["layer_cfg"]["head_dict"].keys())
+        outs = km3d_heads(sd, feat, names)
+        if stages is not None:
+            stages.update(features=feat, heads=outs, levels=ys)
+        res = []
+        for b in range(images.shape[0]):
+            ob = {k: v[b:b + 1] for k, v in outs.items()}
+            res.append(monoflex_get_bboxes(ob, P2[b:b + 1], images.shape[2:], cfg["head"]["test_cfg"].get("score_thr", 0.1),
+                                           cfg["head"]["test_cfg"].get("nms_iou_thr", 0.5)))
+        return res

@@ -193,6 +193,55 @@ def gen_mono3d(kind, H=96, W=320, B=2, seed=0, depth=None):
               "ref absmean", fix[nm]["abssum"] / np.prod(fix[nm]["shape"]))
 
 
+def gen_monoflex(H=96, W=320, B=2, seed=0):
+    """MonoFlex: DLA-34 + DCNv2 up-sampling + 9 heads + CenterNet decode (BASELINE configs[3] family)."""
+    refload.load_reference()
+    from visualDet3D.networks.utils.registry import DETECTOR_DICT
+    from visualdet3d_b200.detectors.centernet import monoflex_cfg
+    cfg = monoflex_cfg()
+    model = DETECTOR_DICT["MonoFlex"](to_edict(cfg))
+    shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    with open(os.path.join(HERE, "monoflex_keys.json"), "w") as f:
+        json.dump({k: list(v) for k, v in shapes.items()}, f, indent=0)
+    sd = synth.synth_state_dict(shapes, seed)
+    missing = model.load_state_dict(sd, strict=False)
+    print("missing:", missing.missing_keys, "unexpected:", missing.unexpected_keys)
+    model.eval()
+    img, P2 = synth.synth_mono_inputs(B, H, W, seed=1)
+    stages = {}
+    hooks = [model.core.register_forward_hook(lambda m, i, o: stages.setdefault("features", []).append(o.detach().clone())),
+             model.bbox_head.register_forward_hook(lambda m, i, o: stages.setdefault("heads", []).append({k: v.detach().clone() for k, v in o.items()}))]
+    fix, outs = {}, []
+    with torch.no_grad():
+        for b in range(B):
+            outs.append(model([img[b:b + 1], P2[b:b + 1]]))
+    for h in hooks:
+        h.remove()
+    for b in range(B):
+        s, bb, ci = outs[b]
+        fix[f"scores_{b}"], fix[f"bboxes_{b}"], fix[f"cls_{b}"] = s.numpy(), bb.numpy(), ci.numpy()
+        print(f"MonoFlex image {b}: {len(s)} detections")
+    fix["features"] = subsample(torch.cat(stages["features"], 0))
+    for n in cfg["head"]["layer_cfg"]["head_dict"]:
+        fix["head_" + n] = subsample(torch.cat([x[n] for x in stages["heads"]], 0))
+    fix["meta"] = np.array([H, W, B, seed], dtype=np.int64)
+    np.savez_compressed(os.path.join(HERE, f"monoflex_{H}x{W}.npz"), **flatten_fixture(fix))
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(HERE)), "oracle"))
+    import torch_port as tp
+    st = {}
+    o = tp.monoflex_forward(sd, img, P2, cfg, st)
+    for b in range(B):
+        same = len(o[b][0]) == len(outs[b][0])
+        print("oracle vs ref image", b, "n", len(o[b][0]), len(outs[b][0]),
+              "max|dscore|", float((o[b][0] - outs[b][0]).abs().max()) if same and len(o[b][0]) else None,
+              "max|dbox|", float((o[b][1] - outs[b][1]).abs().max()) if same and len(o[b][0]) else None)
+    print("features max abs diff", float(np.abs(fix["features"]["samples"] - subsample(st["features"])["samples"]).max()),
+          "absmean", fix["features"]["abssum"] / np.prod(fix["features"]["shape"]))
+    for n in cfg["head"]["layer_cfg"]["head_dict"]:
+        print(n, "max abs diff", float(np.abs(fix["head_" + n]["samples"] - subsample(st["heads"][n])["samples"]).max()),
+              "absmean", fix["head_" + n]["abssum"] / np.prod(fix["head_" + n]["shape"]))
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["stereo3d"]
     torch.set_num_threads(os.cpu_count())
@@ -202,6 +251,9 @@ if __name__ == "__main__":
     if "yolo3d" in which:
         gen_mono3d("Yolo3D", 96, 320, 2)
         gen_mono3d("Yolo3D", 288, 1280, 1)       # BASELINE.json configs[0]
+    if "monoflex" in which:
+        gen_monoflex(96, 320, 2)
+        gen_monoflex(192, 640, 1)
     if "gac" in which:
         gen_mono3d("GroundAwareYolo3D", 96, 320, 2)
         gen_mono3d("GroundAwareYolo3D", 288, 640, 1)

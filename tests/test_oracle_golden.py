@@ -78,3 +78,26 @@ def test_mono3d_port_matches_reference(kind, tag):
         np.testing.assert_array_equal(ci.numpy(), fx[f"cls_{b}"])
         np.testing.assert_allclose(s.numpy(), fx[f"scores_{b}"], atol=1e-4)
         np.testing.assert_allclose(bx.numpy(), fx[f"bboxes_{b}"], atol=1e-3)
+
+
+@pytest.mark.parametrize("tag", ["monoflex_96x320", "monoflex_192x640"])
+def test_monoflex_port_matches_reference(tag):
+    """MonoFlex (DLA-34 + 16 DCNv2 layers + 9 heads + CenterNet decode) vs the reference fixtures."""
+    from visualdet3d_b200.detectors.centernet import monoflex_cfg
+    fx = load_fixture(tag)
+    H, W, B, seed = [int(v) for v in fx["meta"]]
+    shapes = json.load(open(os.path.join(GOLDEN, "monoflex_keys.json")))
+    sd = synth.synth_state_dict(shapes, seed)
+    cfg = monoflex_cfg()
+    img, P2 = synth.synth_mono_inputs(B, H, W, seed=1)
+    st = {}
+    outs = tp.monoflex_forward(sd, img, P2, cfg, st)
+    np.testing.assert_allclose(subsample_like(st["features"], fx["features"]), fx["features"]["samples"], atol=2e-4)
+    for n in cfg["head"]["layer_cfg"]["head_dict"]:
+        np.testing.assert_allclose(subsample_like(st["heads"][n], fx["head_" + n]), fx["head_" + n]["samples"], atol=5e-4, err_msg=n)
+    for b in range(B):
+        s, bx, ci, _ = outs[b]
+        assert len(s) == len(fx[f"scores_{b}"])
+        np.testing.assert_array_equal(ci.numpy(), fx[f"cls_{b}"])
+        np.testing.assert_allclose(s.numpy(), fx[f"scores_{b}"], atol=1e-4)
+        np.testing.assert_allclose(bx.numpy(), fx[f"bboxes_{b}"], atol=1e-3, rtol=1e-5)

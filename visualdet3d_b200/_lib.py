@@ -42,6 +42,8 @@ _SIGS = {
     "vd3d_conv2d_nhwc": (I, [P, I, I, I, I, I, I, P, P, I, I, I, I, I, P, I, I, P, I, I, I, I, P]),
     "vd3d_dwconv3x3_nhwc": (I, [P, I, I, I, I, I, I, P, P, P, I, I, I, P]),
     "vd3d_maxpool3x3s2_nhwc": (I, [P, I, I, I, I, I, I, P, I, I, P]),
+    "vd3d_maxpool2x2s2_nhwc": (I, [P, I, I, I, I, I, I, P, I, I, P]),
+    "vd3d_dw_convtranspose_nhwc": (I, [P, I, I, I, I, I, I, P, I, P, I, I, P, I, I, P]),
     "vd3d_avgpool2_nhwc": (I, [P, I, I, I, I, I, I, P, I, I, P]),
     "vd3d_copy_channels_nhwc": (I, [P, I, I, I, I, P, I, I, P]),
     "vd3d_psm_cosine_nhwc": (I, [P, P, I, I, I, I, I, I, I, P, I, I, P]),
@@ -55,6 +57,8 @@ _SIGS = {
     "vd3d_boxes_iou_bev": (I, [P, I, P, I, P, P]),
     "vd3d_nms_bev_workspace": (c_longlong, [I]),
     "vd3d_nms_bev": (I, [P, I, F, I, P, P, P, P]),
+    "vd3d_monoflex_decode_workspace": (c_longlong, [I, I]),
+    "vd3d_monoflex_decode": (I, [P, I, I, I, I, I, I, I, I, I, I, I, I, I, I, P, F, c_double, I, F, F, F, F, I, P, I, P, P, P, P, P, P, P]),
     "vd3d_look_ground_sample": (I, [P, I, I, I, I, I, I, P, I, I, P, F, F, P, P, I, P]),
     "vd3d_anchor_mask": (I, [P, P, P, I, I, I, F, F, F, P, P]),
     "vd3d_decode_nms_workspace": (c_longlong, [I, I]),

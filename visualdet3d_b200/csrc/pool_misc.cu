@@ -123,6 +123,55 @@ __global__ void dwconv3x3_kernel(const float* __restrict__ in, const float* __re
     *reinterpret_cast<float4*>(out + (((long long)b * H + h) * W + w) * out_cs + out_co + 4 * c4) = acc;
 }
 
+__global__ void maxpool2x2s2_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int H, int W, int C4,
+                                    int in_cs, int in_co, int out_cs, int out_co) {
+    int Ho = H / 2, Wo = W / 2;
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = (long long)B * Ho * Wo * C4;
+    if (idx >= total) return;
+    int c4 = (int)(idx % C4); long long r = idx / C4;
+    int wo = (int)(r % Wo); r /= Wo; int ho = (int)(r % Ho); int b = (int)(r / Ho);
+    const float* p = in + (((long long)b * H + 2 * ho) * W + 2 * wo) * in_cs + in_co + 4 * c4;
+    float4 a = ldg4(p), b4 = ldg4(p + in_cs), c = ldg4(p + (long long)W * in_cs), d = ldg4(p + (long long)(W + 1) * in_cs);
+    float4 o;
+    o.x = fmaxf(fmaxf(a.x, b4.x), fmaxf(c.x, d.x)); o.y = fmaxf(fmaxf(a.y, b4.y), fmaxf(c.y, d.y));
+    o.z = fmaxf(fmaxf(a.z, b4.z), fmaxf(c.z, d.z)); o.w = fmaxf(fmaxf(a.w, b4.w), fmaxf(c.w, d.w));
+    *reinterpret_cast<float4*>(out + (((long long)b * Ho + ho) * Wo + wo) * out_cs + out_co + 4 * c4) = o;
+}
+
+// depthwise ConvTranspose2d(C, C, 2f, stride f, padding f/2, groups C, bias False) [+ addend]: the DLA up-sampling node
+// (R/backbones/dla_utils.py:62-85).  out[y][x] = sum over the (at most) 2x2 input pixels whose kernel footprint covers (y, x).
+__global__ void dw_convtranspose_kernel(const float* __restrict__ in, const float* __restrict__ wgt, const float* __restrict__ addend,
+                                        float* __restrict__ out, int B, int H, int W, int C4, int f, int in_cs, int in_co,
+                                        int add_cs, int add_co, int out_cs, int out_co) {
+    const int Ho = H * f, Wo = W * f, K = 2 * f, pad = f / 2, C = C4 * 4;
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = (long long)B * Ho * Wo * C4;
+    if (idx >= total) return;
+    int c4 = (int)(idx % C4); long long r = idx / C4;
+    int x = (int)(r % Wo); r /= Wo; int y = (int)(r % Ho); int b = (int)(r / Ho);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    // torch's transposed conv accumulates input pixels in increasing (iy, ix) order for a given output pixel
+    int iy_hi = (y + pad) / f, ix_hi = (x + pad) / f;
+    for (int iy = iy_hi - 1; iy <= iy_hi; ++iy) {
+        int ky = y + pad - iy * f;
+        if (iy < 0 || iy >= H || ky < 0 || ky >= K) continue;
+        for (int ix = ix_hi - 1; ix <= ix_hi; ++ix) {
+            int kx = x + pad - ix * f;
+            if (ix < 0 || ix >= W || kx < 0 || kx >= K) continue;
+            float4 v = ldg4(in + (((long long)b * H + iy) * W + ix) * in_cs + in_co + 4 * c4);
+            float4 k = ldg4(wgt + (ky * K + kx) * C + 4 * c4);
+            acc.x = fmaf(v.x, k.x, acc.x); acc.y = fmaf(v.y, k.y, acc.y); acc.z = fmaf(v.z, k.z, acc.z); acc.w = fmaf(v.w, k.w, acc.w);
+        }
+    }
+    long long opix = ((long long)b * Ho + y) * Wo + x;
+    if (addend) {
+        float4 a = ldg4(addend + opix * add_cs + add_co + 4 * c4);
+        acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+    }
+    *reinterpret_cast<float4*>(out + opix * out_cs + out_co + 4 * c4) = acc;
+}
+
 __global__ void copy_channels_kernel(const float* __restrict__ in, float* __restrict__ out, long long npix, int C4,
                                      int in_cs, int in_co, int out_cs, int out_co) {
     long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -177,6 +226,28 @@ extern "C" int vd3d_avgpool2_nhwc(const float* in, int B, int H, int W, int C, i
     long long total = (long long)B * (H / 2) * (W / 2) * (C / 4);
     avgpool2_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(in, out, B, H, W, C / 4, in_cs, in_co, out_cs, out_co);
     VD3D_CHECK_LAUNCH("avgpool2");
+    return VD3D_OK;
+}
+
+extern "C" int vd3d_maxpool2x2s2_nhwc(const float* in, int B, int H, int W, int C, int in_cs, int in_co,
+                                      float* out, int out_cs, int out_co, void* stream) {
+    VD3D_REQ_VEC4("maxpool2x2s2");
+    VD3D_REQUIRE(H >= 2 && W >= 2, "maxpool2x2s2: input too small");
+    long long total = (long long)B * (H / 2) * (W / 2) * (C / 4);
+    maxpool2x2s2_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(in, out, B, H, W, C / 4, in_cs, in_co, out_cs, out_co);
+    VD3D_CHECK_LAUNCH("maxpool2x2s2");
+    return VD3D_OK;
+}
+
+extern "C" int vd3d_dw_convtranspose_nhwc(const float* in, int B, int H, int W, int C, int in_cs, int in_co, const float* wgt, int f,
+                                          const float* addend, int add_cs, int add_co, float* out, int out_cs, int out_co, void* stream) {
+    VD3D_REQ_VEC4("dw_convtranspose");
+    VD3D_REQUIRE(wgt && f >= 2 && f % 2 == 0, "dw_convtranspose: up-sampling factor must be even (kernel 2f, stride f, padding f/2)");
+    VD3D_REQUIRE(!addend || (add_cs % 4 == 0 && add_co % 4 == 0), "dw_convtranspose: addend pitch/offset must be multiples of 4");
+    long long total = (long long)B * H * f * W * f * (C / 4);
+    dw_convtranspose_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(in, wgt, addend, out, B, H, W, C / 4, f, in_cs, in_co,
+                                                                             add_cs, add_co, out_cs, out_co);
+    VD3D_CHECK_LAUNCH("dw_convtranspose");
     return VD3D_OK;
 }
 

@@ -71,11 +71,20 @@ def synth_state_dict(shapes: Mapping[str, Sequence[int]], seed: int = 0, gain: f
                 std = 0.5 / math.sqrt(fan_in)
             elif "conv_offset" in k:
                 std = 0.6 / math.sqrt(fan_in)
+            elif "head_layers." in k and k.endswith(".2.weight"):      # CenterNet head outputs (zero-ish in the reference init)
+                std = 1.2 / math.sqrt(fan_in)
+            if (stem + ".conv_offset.weight") in names:              # DCNv2 main weights: the sigmoid mask (~0.5) halves the response
+                std = std * 2.0
+            if ".up_" in k and len(shp) == 4 and shp[1] == 1:          # depthwise ConvTranspose2d of IDAUp: bilinear-like, positive
+                out[k] = torch.rand(shp, generator=g) * 0.2 + 0.15
+                continue
             out[k] = torch.randn(shp, generator=g) * std
         elif leaf == "bias":
             b = torch.randn(shp, generator=g) * 0.05
             if k.endswith("cls_feature_extraction.6.bias"):
                 b = b - 3.3
+            elif k.endswith("head_layers.hm.2.bias"):         # CenterNet heat-map prior (km3d_head.py:146-148 uses -2.19)
+                b = b - 3.5
             out[k] = b
         elif leaf == "alpha" and shp == (1,):            # LookGround.alpha
             out[k] = torch.full(shp, 0.5)
