@@ -147,6 +147,17 @@ int vd3d_monoflex_decode(const float* heads, int B, int H, int W, int ncls, int 
                          int cap, void* ws, int out_cap, float* out_scores, float* out_boxes, long long* out_cls,
                          int* out_index, int* out_count, int* out_ncand, void* stream);
 
+/* KM3DHead.get_bboxes / _decode (R/heads/km3d_head.py:155-314) + gen_position (R/utils/rtm3d_utils.py:314-455): peaks + top-K,
+ * keypoint refinement against the per-joint heat-map peaks, float64 3x3 least-squares position solve (the reference's 1e-8
+ * random jitter of A^T A is omitted), projection, ClipBoxes, class-agnostic NMS.  heads channels: hm ncls, wh 2, hps 18, rot 8,
+ * dim 3, prob 1, reg 2, hm_hp 9, hp_offset 2. */
+long long vd3d_km3d_decode_workspace(int B, int cap, int hp_cap);
+int vd3d_km3d_decode(const float* heads, int B, int H, int W, int ncls, int cs, int hm_co, int wh_co, int hps_co, int rot_co,
+                     int dim_co, int prob_co, int reg_co, int hm_hp_co, int hp_offset_co, const float* P2,
+                     float score_thr, double iou_thr, int K, float img_w, float img_h, int cap, int hp_cap, void* ws,
+                     int out_cap, float* out_scores, float* out_boxes, long long* out_cls, int* out_index, int* out_count,
+                     int* out_ncand, void* stream);
+
 /* ---- deformable convolution (R/lib/ops/dcn, make.sh) ----------------------------------------------------------
  * Deformable / modulated-deformable im2col on NHWC activations; the GEMM that the reference runs per image with cuBLAS
  * (deform_conv_cuda.cpp:540-556) is then ONE batched 1x1 convolution on vd3d_conv2d_tc over K = KH*KW*C.

@@ -614,3 +614,111 @@ def monoflex_forward(sd: SD, images, P2, cfg: dict, stages: dict | None = None):
             res.append(monoflex_get_bboxes(ob, P2[b:b + 1], images.shape[2:], cfg["head"]["test_cfg"].get("score_thr", 0.1),
                                            cfg["head"]["test_cfg"].get("nms_iou_thr", 0.5)))
         return res
+
+
+def km3d_get_bboxes(output, P2, image_hw, score_thr=0.3, nms_iou_thr=0.5, K=100):
+    """KM3DHead.get_bboxes + _decode (R/heads/km3d_head.py:155-314) + gen_position (R/utils/rtm3d_utils.py:314-455) for ONE
+    image (maps [1, n, H, W]); the 1e-8 random jitter of A^T A (:447) is omitted."""
+    from torchvision.ops import nms
+    nmsf = lambda h: h * (F.max_pool2d(h, 3, stride=1, padding=1) == h).float()
+    heat, hm_hp = nmsf(torch.sigmoid(output["hm"])), nmsf(torch.sigmoid(output["hm_hp"]))
+    batch, cat, height, width = heat.shape
+    HW = height * width
+    ts, ti = torch.topk(heat.view(batch, cat, -1), K)
+    ti = ti % HW
+    scores, tind = torch.topk(ts.view(batch, -1), K)
+    clses = (tind / K).int()
+    inds = ti.view(batch, -1).gather(1, tind)
+    ys, xs = (inds / width).int().float(), (inds % width).int().float()
+    gat = lambda name, idx: output[name].permute(0, 2, 3, 1).reshape(batch, HW, -1).gather(
+        1, idx.long().unsqueeze(2).expand(batch, idx.shape[1], output[name].shape[1]))
+    J = 9
+    kps = gat("hps", inds).view(batch, K, J * 2).clone()
+    kps[..., ::2] += xs.view(batch, K, 1)
+    kps[..., 1::2] += ys.view(batch, K, 1)
+    reg = gat("reg", inds)
+    xs2, ys2 = xs.view(batch, K, 1) + reg[:, :, 0:1], ys.view(batch, K, 1) + reg[:, :, 1:2]
+    wh = gat("wh", inds)
+    bboxes = torch.cat([xs2 - wh[..., 0:1] / 2, ys2 - wh[..., 1:2] / 2, xs2 + wh[..., 0:1] / 2, ys2 + wh[..., 1:2] / 2], dim=2)
+    dim, rot = gat("dim", inds), gat("rot", inds)
+    # keypoint refinement
+    kpsj = kps.view(batch, K, J, 2).permute(0, 2, 1, 3).contiguous()
+    reg_kps = kpsj.unsqueeze(3).expand(batch, J, K, K, 2)
+    hs, hi = torch.topk(hm_hp.view(batch, J, -1), K)
+    hi = hi % HW
+    hys, hxs = (hi / width).int().float(), (hi % width).int().float()
+    hpo = gat("hp_offset", hi.view(batch, -1)).view(batch, J, K, 2)
+    hxs, hys = hxs + hpo[..., 0], hys + hpo[..., 1]
+    m = (hs > 0.1).float()
+    hs = (1 - m) * -1 + m * hs
+    hys = (1 - m) * (-10000) + m * hys
+    hxs = (1 - m) * (-10000) + m * hxs
+    hm_kps = torch.stack([hxs, hys], dim=-1).unsqueeze(2).expand(batch, J, K, K, 2)
+    dist = (((reg_kps - hm_kps) ** 2).sum(dim=4) ** 0.5)
+    min_dist, min_ind = dist.min(dim=3)
+    hsel = hs.gather(2, min_ind).unsqueeze(-1)
+    min_dist = min_dist.unsqueeze(-1)
+    hm_sel = hm_kps.gather(3, min_ind.view(batch, J, K, 1, 1).expand(batch, J, K, 1, 2)).view(batch, J, K, 2)
+    ex = lambda t: t.view(batch, 1, K, 1).expand(batch, J, K, 1)
+    l, t, r, b = ex(bboxes[:, :, 0]), ex(bboxes[:, :, 1]), ex(bboxes[:, :, 2]), ex(bboxes[:, :, 3])
+    bad = (hm_sel[..., 0:1] < l) + (hm_sel[..., 0:1] > r) + (hm_sel[..., 1:2] < t) + (hm_sel[..., 1:2] > b) + \
+          (hsel < 0.1) + (min_dist > (torch.max(b - t, r - l) * 0.3))
+    bad = (bad > 0).float().expand(batch, J, K, 2)
+    kps = ((1 - bad) * hm_sel + bad * kpsj).permute(0, 2, 1, 3).contiguous().view(batch, K, J * 2) * 4
+    bboxes = bboxes * 4
+    # gen_position
+    calib = P2
+    off_set = calib[:, 0, 3] / calib[:, 0, 0]
+    si = torch.zeros_like(kps[:, :, 0:1]) + calib[:, 0:1, 0:1]
+    aidx = (rot[:, :, 1] > rot[:, :, 5]).float()
+    alpha = ((torch.atan(rot[:, :, 2] / rot[:, :, 3]) + (-0.5 * np.pi)) * aidx + (torch.atan(rot[:, :, 6] / rot[:, :, 7]) + (0.5 * np.pi)) * (1 - aidx)).unsqueeze(2)
+    rot_y = alpha + torch.atan2(kps[:, :, 16:17] - calib[:, 0:1, 2:3], si)
+    rot_y[rot_y > np.pi] -= 2 * np.pi
+    rot_y[rot_y < -np.pi] += 2 * np.pi
+    kpoint = kps[:, :, :16]
+    f = calib[:, 0, 0].view(batch, 1, 1)
+    cxy = torch.stack([calib[:, 0, 2], calib[:, 1, 2]], dim=-1).view(batch, 1, 2).repeat(1, 1, 8)
+    kp_norm = (kpoint - cxy) / f
+    ll, hh, ww = dim[:, :, 2:3], dim[:, :, 1:2], dim[:, :, 0:1]
+    co, sn = torch.cos(rot_y), torch.sin(rot_y)
+    lc, ls, wc, wsn, h2 = ll * 0.5 * co, ll * 0.5 * sn, ww * 0.5 * co, ww * 0.5 * sn, hh * 0.5
+    Bx = [-lc - wsn, -lc + wsn, -lc + wsn, lc + wsn, lc + wsn, lc - wsn, lc - wsn, -lc - wsn]
+    By = [-h2, -h2, h2, h2, -h2, -h2, h2, h2]
+    Cc = [ls - wc, ls + wc, ls + wc, -ls + wc, -ls + wc, -ls - wc, -ls - wc, ls - wc]
+    Bm = torch.cat([t for j in range(8) for t in (Bx[j], By[j])], dim=2)
+    Cm = torch.cat([t for j in range(8) for t in (Cc[j], Cc[j])], dim=2)
+    Bm = Bm - kp_norm * Cm
+    const = torch.tensor([[-1.0, 0.0], [0.0, -1.0]] * 8).view(1, 1, 16, 2).expand(batch, K, -1, -1)
+    A = torch.cat([const, kp_norm.unsqueeze(3)], dim=3).double().view(batch * K, 16, 3)
+    AT = A.permute(0, 2, 1)
+    pinv = torch.inverse(torch.bmm(AT, A))
+    pos = torch.bmm(torch.bmm(pinv, AT).float(), Bm.view(batch * K, 16, 1).float()).view(batch, K, 3)
+    pos[:, :, 0] -= off_set.unsqueeze(1)
+    # get_bboxes
+    sc, pos, bx, dm, al, cl = scores[0], pos[0], bboxes[0], dim[0], alpha[0], clses[0]
+    mask = sc > score_thr
+    p2 = P2[0]
+    z3 = pos[mask][:, 2:3]
+    cx3 = (pos[mask][:, 0:1] * p2[0, 0] + p2[0, 3] + p2[0, 2] * z3) / z3
+    cy3 = (pos[mask][:, 1:2] * p2[1, 1] + p2[1, 3] + p2[1, 2] * z3) / z3
+    b2 = bx[mask].clone()
+    Hh, Ww = image_hw
+    b2[:, 0] = torch.clamp(b2[:, 0], min=0); b2[:, 1] = torch.clamp(b2[:, 1], min=0)
+    b2[:, 2] = torch.clamp(b2[:, 2], max=Ww); b2[:, 3] = torch.clamp(b2[:, 3], max=Hh)
+    box = torch.cat([b2, cx3, cy3, z3, dm[mask], al[mask]], dim=1)
+    flat = (cl[mask].long() * height + ys[0][mask].long()) * width + xs[0][mask].long()
+    keep = nms(box[:, :4], sc[mask], nms_iou_thr)
+    return sc[mask][keep], box[keep], cl[mask].long()[keep], flat[keep]
+
+
+def km3d_forward(sd: SD, images, P2, cfg: dict, stages: dict | None = None):
+    """KM3D.test_forward (R/detectors/KM3D.py:61-79), decode looped per image."""
+    with torch.no_grad():
+        ys = dla34(sd, "core.backbone", images)
+        feat = dla_seg_upsample(sd, "core.deconv_layers", ys)
+        outs = km3d_heads(sd, feat, list(cfg["head"]["layer_cfg"]["head_dict"].keys()))
+        if stages is not None:
+            stages.update(features=feat, heads=outs)
+        return [km3d_get_bboxes({k: v[b:b + 1] for k, v in outs.items()}, P2[b:b + 1], images.shape[2:],
+                                cfg["head"]["test_cfg"].get("score_thr", 0.1), cfg["head"]["test_cfg"].get("nms_iou_thr", 0.5))
+                for b in range(images.shape[0])]

@@ -193,15 +193,16 @@ def gen_mono3d(kind, H=96, W=320, B=2, seed=0, depth=None):
               "ref absmean", fix[nm]["abssum"] / np.prod(fix[nm]["shape"]))
 
 
-def gen_monoflex(H=96, W=320, B=2, seed=0):
-    """MonoFlex: DLA-34 + DCNv2 up-sampling + 9 heads + CenterNet decode (BASELINE configs[3] family)."""
+def gen_monoflex(H=96, W=320, B=2, seed=0, kind="MonoFlex"):
+    """MonoFlex / KM3D: DLA-34 + DCNv2 up-sampling + 9 heads + CenterNet-style decode (BASELINE configs[3] family)."""
     refload.load_reference()
     from visualDet3D.networks.utils.registry import DETECTOR_DICT
-    from visualdet3d_b200.detectors.centernet import monoflex_cfg
-    cfg = monoflex_cfg()
-    model = DETECTOR_DICT["MonoFlex"](to_edict(cfg))
+    from visualdet3d_b200.detectors.centernet import monoflex_cfg, km3d_cfg
+    cfg = monoflex_cfg() if kind == "MonoFlex" else km3d_cfg()
+    torch.manual_seed(0)
+    model = DETECTOR_DICT[kind](to_edict(cfg))
     shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
-    with open(os.path.join(HERE, "monoflex_keys.json"), "w") as f:
+    with open(os.path.join(HERE, f"{kind.lower()}_keys.json"), "w") as f:
         json.dump({k: list(v) for k, v in shapes.items()}, f, indent=0)
     sd = synth.synth_state_dict(shapes, seed)
     missing = model.load_state_dict(sd, strict=False)
@@ -220,16 +221,16 @@ def gen_monoflex(H=96, W=320, B=2, seed=0):
     for b in range(B):
         s, bb, ci = outs[b]
         fix[f"scores_{b}"], fix[f"bboxes_{b}"], fix[f"cls_{b}"] = s.numpy(), bb.numpy(), ci.numpy()
-        print(f"MonoFlex image {b}: {len(s)} detections")
+        print(f"{kind} image {b}: {len(s)} detections")
     fix["features"] = subsample(torch.cat(stages["features"], 0))
     for n in cfg["head"]["layer_cfg"]["head_dict"]:
         fix["head_" + n] = subsample(torch.cat([x[n] for x in stages["heads"]], 0))
     fix["meta"] = np.array([H, W, B, seed], dtype=np.int64)
-    np.savez_compressed(os.path.join(HERE, f"monoflex_{H}x{W}.npz"), **flatten_fixture(fix))
+    np.savez_compressed(os.path.join(HERE, f"{kind.lower()}_{H}x{W}.npz"), **flatten_fixture(fix))
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(HERE)), "oracle"))
     import torch_port as tp
     st = {}
-    o = tp.monoflex_forward(sd, img, P2, cfg, st)
+    o = (tp.monoflex_forward if kind == "MonoFlex" else tp.km3d_forward)(sd, img, P2, cfg, st)
     for b in range(B):
         same = len(o[b][0]) == len(outs[b][0])
         print("oracle vs ref image", b, "n", len(o[b][0]), len(outs[b][0]),
@@ -251,6 +252,9 @@ if __name__ == "__main__":
     if "yolo3d" in which:
         gen_mono3d("Yolo3D", 96, 320, 2)
         gen_mono3d("Yolo3D", 288, 1280, 1)       # BASELINE.json configs[0]
+    if "km3d" in which:
+        gen_monoflex(96, 320, 2, kind="KM3D")
+        gen_monoflex(192, 640, 1, kind="KM3D")
     if "monoflex" in which:
         gen_monoflex(96, 320, 2)
         gen_monoflex(192, 640, 1)

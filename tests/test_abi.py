@@ -100,11 +100,12 @@ def test_mono3d_registered_and_state_dict_keys_match_reference(kind):
         det([torch.zeros(1, 3, 32, 32), None, torch.zeros(1, 3, 4)])          # 3-element list = training protocol
 
 
-def test_monoflex_registered_and_state_dict_keys_match_reference():
+@pytest.mark.parametrize("kind", ["MonoFlex", "KM3D"])
+def test_monoflex_registered_and_state_dict_keys_match_reference(kind):
     from visualdet3d_b200.plugin import DETECTOR_DICT
     from visualdet3d_b200.detectors import build_synthetic_monoflex
     assert "MonoFlex" in DETECTOR_DICT and "KM3D" in DETECTOR_DICT
-    det, sd, cfg = build_synthetic_monoflex()
-    ref = json.load(open(os.path.join(GOLDEN, "monoflex_keys.json")))
+    det, sd, cfg = build_synthetic_monoflex(name=kind)
+    ref = json.load(open(os.path.join(GOLDEN, f"{kind.lower()}_keys.json")))
     mine = {k: list(v.shape) for k, v in det.state_dict().items()}
     assert list(mine.keys()) == list(ref.keys()) and mine == ref

@@ -111,3 +111,28 @@ def test_batch8_384x1280_properties(mf):
     k = len(single[0])
     match_dets(single, ref, det._last_decoder.anchor[0, :k])
     print("MonoFlex 384x1280 image: detections", k)
+
+
+@pytest.mark.parametrize("tag", ["km3d_96x320", "km3d_192x640"])
+def test_km3d_against_reference_fixture_and_oracle(tag):
+    """KM3D: same network family, keypoint-refined least-squares decode (km3d_head.py:155-314, rtm3d_utils.py:314-455)."""
+    from visualdet3d_b200 import synth
+    from visualdet3d_b200.detectors import build_synthetic_monoflex
+    det, sd, cfg = build_synthetic_monoflex(seed=0, name="KM3D")
+    det = det.cuda().eval()
+    fx = load_fixture(tag)
+    H, W, B, seed = [int(v) for v in fx["meta"]]
+    img, P2 = synth.synth_mono_inputs(B, H, W, seed=1)
+    res, st = run_with_stages(det, img, P2)
+    off = det._plan["offsets"]
+    rep = {}
+    for n, k in cfg["head"]["layer_cfg"]["head_dict"].items():
+        got = st["heads"][:, off[n]:off[n] + k]
+        rep[n] = float(np.abs(subsample_like(got, fx["head_" + n]) - fx["head_" + n]["samples"]).max())
+    print(tag, "head max|diff| vs reference:", rep)
+    assert all(v < 1e-3 for v in rep.values()), rep
+    ref = tp.km3d_forward(sd, img, P2, cfg)
+    for b in range(B):
+        k = len(res[b][0])
+        assert k == len(fx[f"scores_{b}"])
+        match_dets(res[b], ref[b], det._last_decoder.anchor[b, :k], atol=5e-3)     # position = float64 3x3 solve of float32 keypoints

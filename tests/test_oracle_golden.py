@@ -101,3 +101,25 @@ def test_monoflex_port_matches_reference(tag):
         np.testing.assert_array_equal(ci.numpy(), fx[f"cls_{b}"])
         np.testing.assert_allclose(s.numpy(), fx[f"scores_{b}"], atol=1e-4)
         np.testing.assert_allclose(bx.numpy(), fx[f"bboxes_{b}"], atol=1e-3, rtol=1e-5)
+
+
+@pytest.mark.parametrize("tag", ["km3d_96x320", "km3d_192x640"])
+def test_km3d_port_matches_reference(tag):
+    """KM3D (DLA-34 + DCNv2 up-sampling + keypoint heads + least-squares position decode) vs the reference fixtures."""
+    from visualdet3d_b200.detectors.centernet import km3d_cfg
+    fx = load_fixture(tag)
+    H, W, B, seed = [int(v) for v in fx["meta"]]
+    shapes = json.load(open(os.path.join(GOLDEN, "km3d_keys.json")))
+    sd = synth.synth_state_dict(shapes, seed)
+    cfg = km3d_cfg()
+    img, P2 = synth.synth_mono_inputs(B, H, W, seed=1)
+    st = {}
+    outs = tp.km3d_forward(sd, img, P2, cfg, st)
+    for n in cfg["head"]["layer_cfg"]["head_dict"]:
+        np.testing.assert_allclose(subsample_like(st["heads"][n], fx["head_" + n]), fx["head_" + n]["samples"], atol=5e-4, err_msg=n)
+    for b in range(B):
+        s, bx, ci, _ = outs[b]
+        assert len(s) == len(fx[f"scores_{b}"])
+        np.testing.assert_array_equal(ci.numpy(), fx[f"cls_{b}"])
+        np.testing.assert_allclose(s.numpy(), fx[f"scores_{b}"], atol=1e-4)
+        np.testing.assert_allclose(bx.numpy(), fx[f"bboxes_{b}"], atol=2e-3, rtol=1e-4)   # the reference jitters A^T A by 1e-8 randn

@@ -42,7 +42,7 @@ class KM3DCoreP(M.Holder):
 class KM3DHeadP(M.Holder):
     """keys of KM3DHead (R/heads/km3d_head.py:23-41,132-153): buffer `const`, head_layers.<name>.{0,2}.{weight,bias}."""
 
-    def __init__(self, num_classes=3, num_joints=9, max_objects=32, layer_cfg=None, loss_cfg=None, test_cfg=None):
+    def __init__(self, num_classes=3, num_joints=9, max_objects=32, layer_cfg=None, loss_cfg=None, test_cfg=None, with_position_loss=False):
         super().__init__()
         lc = dict(layer_cfg or {})
         cin, feat = lc.get("input_features", 256), lc.get("head_features", 64)
@@ -58,18 +58,23 @@ class KM3DHeadP(M.Holder):
                 nn.init.constant_(last.bias, 0)
         const = torch.tensor([[-1, 0], [0, -1]] * 8, dtype=torch.float32).unsqueeze(0).unsqueeze(0)
         self.register_buffer("const", const)
+        if with_position_loss:        # KM3DHead.build_loss registers Position_loss (buffer `const`, rtm3d_utils.py:230-240); MonoFlexHead does not
+            self.position_loss = M.Holder()
+            self.position_loss.register_buffer("const", const.clone())
         self.num_classes, self.num_joints, self.max_objects = num_classes, num_joints, max_objects
         self.input_features, self.head_features = cin, feat
 
 
 class _CenterNetBase(nn.Module):
+    WITH_POSITION_LOSS = False
+
     def __init__(self, network_cfg):
         super().__init__()
         self.obj_types = network_cfg["obj_types"]
         head = network_cfg["head"]
         self.test_cfg = dict(head.get("test_cfg", {}))
         self.bbox_head = KM3DHeadP(head.get("num_classes", 3), head.get("num_joints", 9), head.get("max_objects", 32),
-                                   head.get("layer_cfg", {}), head.get("loss_cfg", {}), self.test_cfg)
+                                   head.get("layer_cfg", {}), head.get("loss_cfg", {}), self.test_cfg, self.WITH_POSITION_LOSS)
         self.core = KM3DCoreP(dict(network_cfg["backbone"]))
         self.network_cfg = network_cfg
         lc = dict(head.get("loss_cfg", {}))
@@ -192,12 +197,56 @@ class MonoFlex(_CenterNetBase):
 
 @DETECTOR_DICT.register_module
 class KM3D(_CenterNetBase):
-    """R/detectors/KM3D.py:16-88.  Network (DLA-34 + DCN up-sampling + heads) runs on the B200 engine; the keypoint
-    least-squares position decode of KM3DHead.get_bboxes (km3d_head.py:155-314, rtm3d_utils.py:314-455) is not ported yet."""
+    """R/detectors/KM3D.py:16-88 + KM3DHead.get_bboxes/_decode (R/heads/km3d_head.py:155-314) + gen_position
+    (R/utils/rtm3d_utils.py:314-455)."""
+    REQUIRED = ("hm", "wh", "hps", "rot", "dim", "prob", "reg", "hm_hp", "hp_offset")
+    WITH_POSITION_LOSS = True
+
+    def launch(self, images, P2):
+        for t, nm in ((images, "image"), (P2, "P2")):
+            E._require_cuda(t, nm)
+        images, P2 = images.float().contiguous(), P2.float().contiguous()
+        B, _, H, W = images.shape
+        out = self.network(images)
+        off = self._plan["offsets"]
+        missing = [k for k in self.REQUIRED if k not in off]
+        if missing:
+            raise Vd3dError(f"KM3D head_dict lacks {missing}")
+        if self.bbox_head.head_dict["hps"] != 18 or self.bbox_head.head_dict["hm_hp"] != 9:
+            raise Vd3dError("KM3D decode expects 9 keypoints (hps = 18, hm_hp = 9)")
+        dev = images.device
+        key = (B, str(dev))
+        if key not in self._decoders:
+            d = E.DecodeNms(B, 128, dev)
+            d.ws = torch.empty(int(_lib.load().vd3d_km3d_decode_workspace(B, 4096, 1024)), dtype=torch.uint8, device=dev)
+            self._decoders[key] = d
+        dec = self._decoders[key]
+        call("vd3d_km3d_decode", out.ptr, B, out.H, out.W, self.num_classes, out.cs, off["hm"], off["wh"], off["hps"], off["rot"], off["dim"],
+             off["prob"], off["reg"], off["hm_hp"], off["hp_offset"], P2.data_ptr(), float(self.test_cfg.get("score_thr", 0.1)),
+             float(self.test_cfg.get("nms_iou_thr", 0.5)), self.topk, float(W), float(H), 4096, 1024, dec.ws.data_ptr(), dec.cap,
+             dec.scores.data_ptr(), dec.boxes.data_ptr(), dec.cls.data_ptr(), dec.anchor.data_ptr(), dec.count.data_ptr(),
+             dec.ncand.data_ptr(), E._stream())
+        self._last_decoder = dec
+        return dec
 
     def forward_batch(self, images, P2):
-        raise NotImplementedError("KM3D decode (gen_position least squares) is not implemented on the B200 path yet; "
-                                  "`KM3D.network(images)` returns the head outputs")
+        return [(s.clone(), b.clone(), c.clone()) for (s, b, c) in self.launch(images, P2).results()]
+
+
+def km3d_cfg(obj_types=("Car", "Pedestrian", "Cyclist")):
+    """cfg.detector of R/config/KM3D_example:127-165 with the DLA-34 backbone of BASELINE.json configs[3]."""
+    from ..synth import AttrDict
+    obj_types = list(obj_types)
+    det = AttrDict(obj_types=obj_types, name="KM3D")
+    det.backbone = AttrDict(name="dlanet", depth=34, out_indices=(0, 1, 2, 3, 4, 5), pretrained=None)
+    det.head = AttrDict(num_classes=len(obj_types), num_joints=9, max_objects=32,
+                        layer_cfg=AttrDict(input_features=64, head_features=256,
+                                           head_dict={"hm": len(obj_types), "wh": 2, "hps": 18, "rot": 8, "dim": 3, "prob": 1, "reg": 2,
+                                                      "hm_hp": 9, "hp_offset": 2}),
+                        loss_cfg=AttrDict(gamma=2.0, rampup_length=100, output_w=320),
+                        test_cfg=AttrDict(score_thr=0.1))     # the shipped config uses 0.3; 0.1 keeps detections with the synthetic weights
+    det.loss = det.head.loss_cfg
+    return det
 
 
 def monoflex_cfg(obj_types=("Car", "Pedestrian", "Cyclist"), name: str = "MonoFlex"):
@@ -216,8 +265,8 @@ def monoflex_cfg(obj_types=("Car", "Pedestrian", "Cyclist"), name: str = "MonoFl
 
 
 def build_synthetic_monoflex(seed: int = 0, name: str = "MonoFlex"):
-    """Random-init (seeded, de-degenerated) MonoFlex: returns (detector, state_dict, cfg)."""
-    cfg = monoflex_cfg(name=name)
+    """Random-init (seeded, de-degenerated) MonoFlex / KM3D: returns (detector, state_dict, cfg)."""
+    cfg = km3d_cfg() if name == "KM3D" else monoflex_cfg(name=name)
     det = DETECTOR_DICT[name](cfg)
     sd = synth_load(det, seed)
     return det, sd, cfg

@@ -83,7 +83,7 @@ def synth_state_dict(shapes: Mapping[str, Sequence[int]], seed: int = 0, gain: f
             b = torch.randn(shp, generator=g) * 0.05
             if k.endswith("cls_feature_extraction.6.bias"):
                 b = b - 3.3
-            elif k.endswith("head_layers.hm.2.bias"):         # CenterNet heat-map prior (km3d_head.py:146-148 uses -2.19)
+            elif k.endswith("head_layers.hm.2.bias") or k.endswith("head_layers.hm_hp.2.bias"):   # heat-map prior (km3d_head.py:146-148: -2.19)
                 b = b - 3.5
             out[k] = b
         elif leaf == "alpha" and shp == (1,):            # LookGround.alpha
