@@ -708,7 +708,7 @@ def km3d_get_bboxes(output, P2, image_hw, score_thr=0.3, nms_iou_thr=0.5, K=100)
     box = torch.cat([b2, cx3, cy3, z3, dm[mask], al[mask]], dim=1)
     flat = (cl[mask].long() * height + ys[0][mask].long()) * width + xs[0][mask].long()
     keep = nms(box[:, :4], sc[mask], nms_iou_thr)
-    return sc[mask][keep], box[keep], cl[mask].long()[keep], flat[keep]
+    return sc[mask][keep], box[keep], cl[mask].long()[keep].unsqueeze(1), flat[keep]     # cls_indexes is [K, 1] in the reference (:276)
 
 
 def km3d_forward(sd: SD, images, P2, cfg: dict, stages: dict | None = None):

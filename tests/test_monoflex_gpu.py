@@ -68,7 +68,7 @@ def match_dets(got, ref, got_index, atol=1e-3):
         for i in (perm != torch.arange(len(perm))).nonzero()[:, 0].tolist():
             assert abs(float(rs[perm[i]]) - float(rs[i])) < 1e-5
         rs, rb, rc = rs[perm], rb[perm], rc[perm]
-    assert torch.equal(ci, rc)
+    assert ci.shape == rc.shape and torch.equal(ci, rc)
     assert float((s - rs).abs().max()) < atol
     np.testing.assert_allclose(bx.numpy(), rb.numpy(), atol=atol, rtol=1e-5)
 

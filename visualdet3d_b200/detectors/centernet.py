@@ -230,7 +230,8 @@ class KM3D(_CenterNetBase):
         return dec
 
     def forward_batch(self, images, P2):
-        return [(s.clone(), b.clone(), c.clone()) for (s, b, c) in self.launch(images, P2).results()]
+        # the reference's KM3D returns cls_indexes with shape [K, 1] (km3d_head.py:276 slices dets[mask, 40:41])
+        return [(s.clone(), b.clone(), c.clone().view(-1, 1)) for (s, b, c) in self.launch(images, P2).results()]
 
 
 def km3d_cfg(obj_types=("Car", "Pedestrian", "Cyclist")):
