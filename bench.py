@@ -220,10 +220,10 @@ def main():
         l = hl.to(dev, non_blocking=True)
         r = hr.to(dev, non_blocking=True)
         p = hp.to(dev, non_blocking=True)
-        res = det.forward_batch(l, r, p)
-        allres = parallel.all_gather_detections(res, kmax, dev)
-        host = [(s.cpu(), b.cpu(), c.cpu()) for (s, b, c) in allres] if rank == 0 else None
-        return res, host
+        dec = det.launch(l, r, p)
+        rec = parallel.all_gather_records(parallel.pack_records_device(dec, kmax))     # the single collective of the path
+        allres = parallel.unpack_records(rec.cpu())                                      # D2H of the global result (every rank)
+        return allres[rank * B:(rank + 1) * B], allres
 
     with torch.no_grad():
         for _ in range(args.warmup):
@@ -250,8 +250,8 @@ def main():
         e0.record()
         for _ in range(args.steps):
             dec = step_device()
-            # the all-gather belongs to the step: results -> record block -> NCCL
-            parallel.all_gather_detections(dec.results(), kmax, dev) if world > 1 else None
+            # the all-gather belongs to the step: device-built record block -> NCCL, no host synchronisation
+            parallel.all_gather_records(parallel.pack_records_device(dec, kmax))
         e1.record()
         barrier()
         launches = _lib.launch_count()
@@ -285,7 +285,7 @@ def main():
     achieved = (PSM4_BYTES_PER_PAIR * B / 1e9) / (psm_avg_ms / 1e3) if psm_avg_ms else None
     ndet = sum(len(r[0]) for r in res)
     h2d = int(hl.numel() * 4 + hr.numel() * 4 + hp.numel() * 4)
-    d2h = int(B * 4 + sum(len(s) * (4 + 44 + 8) for (s, _, _) in (host or [])))
+    d2h = int(world * B * (1 + kmax * 13) * 4)
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

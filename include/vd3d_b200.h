@@ -135,6 +135,11 @@ int vd3d_decode_nms(const float* cls, const float* reg, const float* anchors, co
                     float* out_scores, float* out_boxes, int64_t* out_cls, int32_t* out_anchor,
                     int32_t* out_count, int32_t* out_ncand, void* stream);
 
+/* Record block for the multi-GPU all-gather: rec [B][1 + kmax*13] f32 = count, then kmax rows of
+ * (11 box floats, score, class); count = -1 flags an overflow.  Built on the device from the vd3d_decode_nms outputs. */
+int vd3d_pack_records(const float* scores, const float* boxes, const int64_t* cls, const int32_t* count, int B, int cap, int kmax,
+                      float* rec, void* stream);
+
 /* ---- CenterNet-style decode of the MonoFlex head (MonoFlexHead.get_bboxes, R/heads/monoflex_head.py:114-179) ----------
  * heads: NHWC [B][H][W][cs] holding all head outputs at the given channel offsets (hm: ncls, bbox2d 4, hps 20, rot 8, dim 3,
  * reg 2, depth 1, depth_uncertainty 1, corner_uncertainty 3); P2 [B][3][4].  sigmoid + 3x3 peak test + top-K + gather +

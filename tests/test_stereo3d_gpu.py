@@ -213,3 +213,23 @@ def test_engines_agree(det_bundle):
         assert torch.equal(torch.sort(anchors_a[b])[0], torch.sort(anchors_b[b])[0])
         if torch.equal(anchors_a[b], anchors_b[b]) and len(a[b][0]):
             assert float((a[b][1] - bres[b][1]).abs().max()) < 1e-3
+
+
+def test_device_record_block_matches_results(det_bundle):
+    """parallel.pack_records_device (one kernel, no host sync) == the per-image results, through unpack_records."""
+    from visualdet3d_b200 import synth, parallel
+    det, *_ = det_bundle
+    left, right, P2, P3 = synth.synth_stereo_inputs(3, 128, 384, seed=2)
+    with torch.no_grad():
+        dec = det.launch(left.cuda(), right.cuda(), P2.cuda())
+        rec = parallel.all_gather_records(parallel.pack_records_device(dec, 64))
+    ref = dec.results()
+    got = parallel.unpack_records(rec.cpu())
+    assert len(got) == 3
+    for (s, b, c), (rs, rb, rc) in zip(got, ref):
+        assert torch.equal(s, rs.cpu()) and torch.equal(b, rb.cpu()) and torch.equal(c, rc.cpu())
+    # overflow is flagged, not truncated
+    small = parallel.pack_records_device(dec, 1)
+    if max(len(r[0]) for r in ref) > 1:
+        with pytest.raises(RuntimeError):
+            parallel.unpack_records(small.cpu())

@@ -195,9 +195,33 @@ __global__ void __launch_bounds__(NMS_THREADS) sort_nms_kernel(DecodeWs ws, int 
     if (t == 0) out_count[b] = s_nkeep;
 }
 
+// fixed-capacity detection record block for the multi-GPU all-gather: rec[b] = [count | kmax x (11 box floats, score, class)]
+__global__ void pack_records_kernel(const float* __restrict__ scores, const float* __restrict__ boxes, const int64_t* __restrict__ cls,
+                                    const int32_t* __restrict__ count, int cap, int kmax, float* __restrict__ rec) {
+    const int b = blockIdx.x;
+    const int n = count[b];
+    float* r = rec + (long long)b * (1 + kmax * 13);
+    if (threadIdx.x == 0) r[0] = (n > kmax) ? -1.0f : (float)n;       // -1: capacity overflow (also n == -1 from the decode stage)
+    const int m = n < 0 ? 0 : (n > kmax ? 0 : n);
+    for (int i = threadIdx.x; i < kmax * 13; i += blockDim.x) {
+        int k = i / 13, q = i - k * 13;
+        float v = 0.f;
+        if (k < m) v = (q < 11) ? boxes[((long long)b * cap + k) * 11 + q] : (q == 11 ? scores[(long long)b * cap + k] : (float)cls[(long long)b * cap + k]);
+        r[1 + i] = v;
+    }
+}
+
 }  // namespace vd3d
 
 using namespace vd3d;
+
+extern "C" int vd3d_pack_records(const float* scores, const float* boxes, const int64_t* cls, const int32_t* count, int B, int cap, int kmax,
+                                 float* rec, void* stream) {
+    VD3D_REQUIRE(scores && boxes && cls && count && rec && B > 0 && cap > 0 && kmax > 0, "pack_records: bad args");
+    pack_records_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(scores, boxes, cls, count, cap, kmax, rec);
+    VD3D_CHECK_LAUNCH("pack_records");
+    return VD3D_OK;
+}
 
 static int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 

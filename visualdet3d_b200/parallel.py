@@ -37,9 +37,31 @@ def pack_records(results, kmax: int, device) -> torch.Tensor:
 def unpack_records(buf: torch.Tensor) -> List[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]]:
     out = []
     counts = buf[:, 0].round().to(torch.int64).tolist()
+    if any(k < 0 for k in counts):
+        raise RuntimeError("detection record block overflowed its capacity on some rank")
     for b, k in enumerate(counts):
         rows = buf[b, 1:1 + k * REC].view(k, REC)
         out.append((rows[:, 11].clone(), rows[:, :11].clone(), rows[:, 12].round().to(torch.int64)))
+    return out
+
+
+def pack_records_device(dec, kmax: int) -> torch.Tensor:
+    """Record block built by a kernel from the fixed-capacity decode outputs (`engine.DecodeNms`): no host synchronisation."""
+    from ._lib import call
+    B = dec.B
+    rec = torch.empty(B, 1 + kmax * REC, dtype=torch.float32, device=dec.scores.device)
+    call("vd3d_pack_records", dec.scores.data_ptr(), dec.boxes.data_ptr(), dec.cls.data_ptr(), dec.count.data_ptr(), B, dec.cap, kmax,
+         rec.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    return rec
+
+
+def all_gather_records(rec: torch.Tensor, group=None) -> torch.Tensor:
+    """ONE collective: every rank's [B_local, 1 + kmax*13] block -> [world * B_local, ...] in rank order (stream-ordered NCCL)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return rec
+    world = dist.get_world_size(group)
+    out = torch.empty(world * rec.shape[0], rec.shape[1], dtype=rec.dtype, device=rec.device)
+    dist.all_gather_into_tensor(out, rec, group=group)
     return out
 
 
