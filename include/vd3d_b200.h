@@ -68,6 +68,20 @@ int vd3d_conv2d_tc(const float* in, const float* in_lo, int B, int H, int W, int
                    const float* w_hi, const float* w_lo, const float* bias, int KH, int KW, int pad, int dil,
                    const float* res, int res_cs, int res_co,
                    float* out, float* out_lo, int Cout, int out_cs, int out_co, int relu, int passes, int bn, void* stream);
+/* Same convolution with fp16-split operands ("3xFP16"): every operand v is kept as two fp16 planes hi = rn16(v), lo = rn16(v - hi)
+ * (22 significant bits); three kind::f16 MMAs per k-step (Alo*Whi + Ahi*Wlo + Ahi*Whi), 64 channels per k-block: half the
+ * shared-memory / L2 operand bytes and twice the MMA rate of the tf32 form at the same accuracy.  Weights are pre-scaled by a
+ * power of two S on the host (so that their lo parts stay normal fp16 numbers); out_scale = 1/S is applied to the accumulator.
+ *   in_hi / in_lo   : fp16 NHWC planes with the same pitch / offset convention as the fp32 tensors
+ *   w_hi / w_lo     : fp16 [Cout][KH*KW*cin_pad], cin_pad = Cin rounded up to 64 (zero filled)
+ *   out             : fp32 NHWC result; out_hi16 / out_lo16 (optional pair): its fp16 planes for the next conv            */
+int vd3d_conv2d_tc16(const void* in_hi, const void* in_lo, int B, int H, int W, int Cin, int in_cs, int in_co,
+                     const void* w_hi, const void* w_lo, float out_scale, const float* bias, int KH, int KW, int pad, int dil,
+                     const float* res, int res_cs, int res_co,
+                     float* out, void* out_hi16, void* out_lo16, int Cout, int out_cs, int out_co, int relu, int passes, int bn,
+                     void* stream);
+/* fp32 channel slice -> fp16 (hi, lo) planes (producers that are not tensor-core convs). */
+int vd3d_split_h16_nhwc(const float* in, void* hi16, void* lo16, long long npix, int C, int cs, int co, void* stream);
 /* lo[pix][c] = in[pix][c] - (in[pix][c] & 0xFFFFE000) on a channel slice (producers that are not tensor-core convs). */
 int vd3d_split_lo_nhwc(const float* in, float* lo, long long npix, int C, int cs, int co, void* stream);
 

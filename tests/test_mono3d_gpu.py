@@ -78,7 +78,8 @@ def test_look_ground_op_vs_oracle():
     ref = tp.look_ground(sd, "g", x, P2)
     run = LookGroundRunner(m, "cuda")
     ar = E.Arena()
-    xa = E.split_lo(E.Act(x.permute(0, 2, 3, 1).contiguous().cuda(), 0, None, torch.zeros(B, H, W, C, device="cuda")))
+    comp = torch.zeros(2, B, H, W, C, device="cuda", dtype=torch.float16) if ar.lo_form == "h16" else torch.zeros(B, H, W, C, device="cuda")
+    xa = E.split_lo(E.Act(x.permute(0, 2, 3, 1).contiguous().cuda(), 0, None, comp))
     out = run.run(xa, P2.cuda(), ar)
     np.testing.assert_allclose(out.to_nchw().cpu().numpy(), ref.numpy(), rtol=1e-4, atol=2e-5)
 

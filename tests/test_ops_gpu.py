@@ -229,3 +229,55 @@ def test_conv2d_tc_3xtf32_vs_fp32(case):
     got_lo = out.lo[..., 4:4 + Cout].cpu()
     val = out.t[..., 4:4 + Cout].cpu()
     assert torch.equal(got_lo, val - _trunc13(val))
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+def test_conv2d_tc16_fp16split_vs_fp64(case):
+    """fp16-split tensor-core conv (3 kind::f16 MMAs on (hi, lo) fp16 planes, 22 significant bits): same accuracy bar as the
+    3xTF32 form, checked against an fp64 convolution; also checks the fp16 planes the epilogue writes for the next layer."""
+    E = _E()
+    B, Cin, H, W, Cout, k, p, d, has_b, has_r, relu = case
+    g = torch.Generator().manual_seed(sum(case[:6]) + 1)
+    x = torch.randn(B, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, k, k, generator=g) / np.sqrt(Cin * k * k)
+    b = torch.randn(Cout, generator=g) if has_b else None
+    ref64 = F.conv2d(x.double(), w.double(), b.double() if b is not None else None, padding=p, dilation=d)
+    r = torch.randn(ref64.shape, generator=g) if has_r else None
+    if r is not None:
+        ref64 = ref64 + r.double()
+    if relu:
+        ref64 = F.relu(ref64)
+    layer = E.ConvLayer(w, b, None, pad=p, dil=d, relu=relu, device="cuda", engine="tc16")
+    assert layer.engine == "tc16"
+    xa = E.split_lo(E.Act(nhwc(x).cuda(), 0, None, torch.zeros(2, B, H, W, Cin, device="cuda", dtype=torch.float16)))
+    Ho, Wo = layer.out_hw(H, W)
+    out = E.Act(torch.full((B, Ho, Wo, Cout + 16), 7.0, device="cuda"), 8, Cout,
+                torch.full((2, B, Ho, Wo, Cout + 16), 7.0, device="cuda", dtype=torch.float16))
+    layer(xa, out, res=E.Act(nhwc(r).cuda()) if r is not None else None)
+    got = out.to_nchw().cpu()
+    err = float((got.double() - ref64).abs().max())
+    print(case, "max|err| vs fp64: fp16-split", err)
+    assert err < 2e-5, err
+    assert float(out.t[..., :8].min()) == 7.0 and float(out.t[..., 8 + Cout:].min()) == 7.0
+    val = out.t[..., 8:8 + Cout]
+    hi = val.half()
+    assert torch.equal(out.lo[0][..., 8:8 + Cout], hi)
+    assert torch.equal(out.lo[1][..., 8:8 + Cout], (val - hi.float()).half())
+    assert float(out.lo[..., :8].float().min()) == 7.0 and float(out.lo[..., 8 + Cout:].float().min()) == 7.0
+
+
+def test_tc16_large_and_tiny_magnitudes():
+    """weights are pre-scaled by a power of two so their fp16 lo parts stay normal; activations spanning 1e-3..1e3 keep
+    a relative error of ~2^-21 against fp64."""
+    E = _E()
+    g = torch.Generator().manual_seed(5)
+    for wscale, xscale in ((1e-3, 1.0), (30.0, 1.0), (1.0, 300.0), (1.0, 1e-2)):
+        x = torch.randn(1, 64, 16, 24, generator=g) * xscale
+        w = torch.randn(32, 64, 3, 3, generator=g) * wscale / 24.0
+        ref64 = F.conv2d(x.double(), w.double(), padding=1)
+        layer = E.ConvLayer(w, None, None, pad=1, relu=False, device="cuda", engine="tc16")
+        xa = E.split_lo(E.Act(nhwc(x).cuda(), 0, None, torch.zeros(2, 1, 16, 24, 64, device="cuda", dtype=torch.float16)))
+        out = layer(xa, E.Act(torch.empty(1, 16, 24, 32, device="cuda")))
+        rel = float((out.to_nchw().cpu().double() - ref64).abs().max() / ref64.abs().max())
+        print("wscale", wscale, "xscale", xscale, "rel err", rel)
+        assert rel < 4e-6, (wscale, xscale, rel)

@@ -191,28 +191,31 @@ def test_lo_companions_are_fresh_everywhere(det_bundle, monkeypatch):
 
 
 def test_engines_agree(det_bundle):
-    """The tcgen05 3xTF32 engine and the exact-fp32 SIMT engine give the same detections (sets) and values within 1e-3."""
+    """The tcgen05 engines (fp16-split default, 3xTF32) and the exact-fp32 SIMT engine give the same detections (sets) and
+    values within 1e-3."""
     import os
     from visualdet3d_b200 import synth
     from visualdet3d_b200.detectors import build_synthetic_stereo3d
     det, sd, cfg, _ = det_bundle
-    os.environ["VD3D_CONV_ENGINE"] = "simt"
-    try:
-        det2, *_ = build_synthetic_stereo3d(seed=0)
-        det2 = det2.cuda().eval()
-        det2.prepare()
-    finally:
-        os.environ.pop("VD3D_CONV_ENGINE", None)
     left, right, P2, P3 = synth.synth_stereo_inputs(2, 192, 640, seed=5)
     with torch.no_grad():
         a = det.forward_batch(left.cuda(), right.cuda(), P2.cuda())
         anchors_a = [det._last_decoder.anchor[b, :len(a[b][0])].cpu() for b in range(2)]
-        bres = det2.forward_batch(left.cuda(), right.cuda(), P2.cuda())
-        anchors_b = [det2._last_decoder.anchor[b, :len(bres[b][0])].cpu() for b in range(2)]
-    for b in range(2):
-        assert torch.equal(torch.sort(anchors_a[b])[0], torch.sort(anchors_b[b])[0])
-        if torch.equal(anchors_a[b], anchors_b[b]) and len(a[b][0]):
-            assert float((a[b][1] - bres[b][1]).abs().max()) < 1e-3
+    for eng in ("simt", "tc"):
+        os.environ["VD3D_CONV_ENGINE"] = eng
+        try:
+            det2, *_ = build_synthetic_stereo3d(seed=0)
+            det2 = det2.cuda().eval()
+            det2.prepare()
+        finally:
+            os.environ.pop("VD3D_CONV_ENGINE", None)
+        with torch.no_grad():
+            bres = det2.forward_batch(left.cuda(), right.cuda(), P2.cuda())
+            anchors_b = [det2._last_decoder.anchor[b, :len(bres[b][0])].cpu() for b in range(2)]
+        for b in range(2):
+            assert torch.equal(torch.sort(anchors_a[b])[0], torch.sort(anchors_b[b])[0]), eng
+            if torch.equal(anchors_a[b], anchors_b[b]) and len(a[b][0]):
+                assert float((a[b][1] - bres[b][1]).abs().max()) < 1e-3, eng
 
 
 def test_device_record_block_matches_results(det_bundle):

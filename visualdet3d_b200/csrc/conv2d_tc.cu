@@ -13,6 +13,7 @@
 // * One 128-pixel x BN-channel output tile per CTA; multi-stage mbarrier ring between TMA and MMA.
 #include "common.cuh"
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <mutex>
 #include <unordered_map>
 #include <string>
@@ -29,6 +30,11 @@ constexpr int TC_A_BYTES = 128 * 128;         // one A (or Alo) stage: 128 rows 
 struct TcParams {
     int B, H, W, Cin, KH, KW, pad, dil;
     int Ho, Wo, Cout, BN, stages, passes, chunk;
+    int f16;                 // 0: tf32 operands (32 channels / k-block), 1: fp16 hi/lo operands (64 channels / k-block)
+    int bk;                  // channels per k-block
+    int cin_pad;             // weight K layout: per-tap channel count rounded up to bk
+    float out_scale;         // multiplies the accumulator (undoes the power-of-two weight scaling of the fp16 path)
+    void* out_h16_hi; void* out_h16_lo;
     int tiles_w, tiles_h;
     int out_cs, out_co, res_cs, res_co, relu;
     const float* bias; const float* res; float* out; float* out_lo;
@@ -93,6 +99,15 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
         "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -140,7 +155,7 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     const int th = tile % p.tiles_h; const int b = tile / p.tiles_h;
     const int w0 = tw * TC_TW, h0 = th * TC_TH;
     const int n0 = blockIdx.y * p.BN;
-    const int cchunks = p.Cin / TC_BK;
+    const int cchunks = p.cin_pad / p.bk;
     const int KB = p.KH * p.KW * cchunks;
     const int NC = (KB + p.chunk - 1) / p.chunk;
 
@@ -164,16 +179,16 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             for (int kb = 0; kb < KB; ++kb) {
                 const int s = kb % p.stages, ph = (kb / p.stages) & 1;
                 mbar_wait(&empty[s], ph ^ 1);
-                const int tap = kb / cchunks, c0 = (kb - tap * cchunks) * TC_BK;
+                const int tap = kb / cchunks, c0 = (kb - tap * cchunks) * p.bk;
                 const int kh = tap / p.KW, kw = tap - kh * p.KW;
                 uint8_t* st = smem + (size_t)s * stage_bytes;
                 mbar_expect_tx(&full[s], p.passes == 3 ? stage_bytes : (TC_A_BYTES + b_bytes));
                 const int wi = w0 - p.pad + kw * p.dil, hi = h0 - p.pad + kh * p.dil;
                 tma_load_4d(st, &mapA, &full[s], c0, wi, hi, b);
-                tma_load_2d(st + 2 * TC_A_BYTES, &mapWhi, &full[s], tap * p.Cin + c0, n0);
+                tma_load_2d(st + 2 * TC_A_BYTES, &mapWhi, &full[s], tap * p.cin_pad + c0, n0);
                 if (p.passes == 3) {
                     tma_load_4d(st + TC_A_BYTES, &mapAlo, &full[s], c0, wi, hi, b);
-                    tma_load_2d(st + 2 * TC_A_BYTES + b_bytes, &mapWlo, &full[s], tap * p.Cin + c0, n0);
+                    tma_load_2d(st + 2 * TC_A_BYTES + b_bytes, &mapWlo, &full[s], tap * p.cin_pad + c0, n0);
                 }
             }
         }
@@ -195,9 +210,17 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                     const uint64_t dA = make_sdesc(sa), dAlo = make_sdesc(sa + TC_A_BYTES);
                     const uint64_t dB = make_sdesc(sa + 2 * TC_A_BYTES), dBlo = make_sdesc(sa + 2 * TC_A_BYTES + b_bytes);
 #pragma unroll
-                    for (int k = 0; k < TC_BK / 8; ++k) {
-                        const uint64_t off = (uint64_t)((k * 32) >> 4);     // 8 tf32 = 32 bytes along K inside the swizzle row
-                        if (p.passes == 3) {   // small terms first, then the main product
+                    for (int k = 0; k < 4; ++k) {
+                        const uint64_t off = (uint64_t)((k * 32) >> 4);     // one MMA K-step = 32 bytes (8 tf32 / 16 fp16) inside the swizzle row
+                        if (p.f16) {
+                            if (p.passes == 3) {   // small terms first, then the main product
+                                umma_f16(d_tmem, dAlo + off, dB + off, p.idesc, first ? 0u : 1u);
+                                umma_f16(d_tmem, dA + off, dBlo + off, p.idesc, 1);
+                                umma_f16(d_tmem, dA + off, dB + off, p.idesc, 1);
+                            } else {
+                                umma_f16(d_tmem, dA + off, dB + off, p.idesc, first ? 0u : 1u);
+                            }
+                        } else if (p.passes == 3) {
                             umma_tf32(d_tmem, dAlo + off, dB + off, p.idesc, first ? 0u : 1u);
                             umma_tf32(d_tmem, dA + off, dBlo + off, p.idesc, 1);
                             umma_tf32(d_tmem, dA + off, dB + off, p.idesc, 1);
@@ -242,6 +265,9 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         const long long pix = ((long long)b * p.Ho + ho) * p.Wo + wo;
         float* op = p.out + pix * p.out_cs + p.out_co;
         float* olo = p.out_lo ? p.out_lo + pix * p.out_cs + p.out_co : nullptr;
+        __half* oh = p.out_h16_hi ? reinterpret_cast<__half*>(p.out_h16_hi) + pix * p.out_cs + p.out_co : nullptr;
+        __half* ol16 = p.out_h16_lo ? reinterpret_cast<__half*>(p.out_h16_lo) + pix * p.out_cs + p.out_co : nullptr;
+        const float osc = p.out_scale;
         const float* rp = p.res ? p.res + pix * p.res_cs + p.res_co : nullptr;
         if (ok) {
 #pragma unroll
@@ -250,7 +276,7 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 for (int i = 0; i < 32; i += 4) {
                     const int n = n0 + g * 32 + i;
                     if (g * 32 + i < p.BN && n < p.Cout) {          // Cout % 4 == 0
-                        float4 a = make_float4(acc[g][i], acc[g][i + 1], acc[g][i + 2], acc[g][i + 3]);
+                        float4 a = make_float4(acc[g][i] * osc, acc[g][i + 1] * osc, acc[g][i + 2] * osc, acc[g][i + 3] * osc);
                         if (p.bias) { float4 bb = ldg4(p.bias + n); a.x += bb.x; a.y += bb.y; a.z += bb.z; a.w += bb.w; }
                         if (rp) { float4 rr = ldg4(rp + n); a.x += rr.x; a.y += rr.y; a.z += rr.z; a.w += rr.w; }
                         if (p.relu) { a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f); }
@@ -262,6 +288,17 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                             l.z = a.z - __uint_as_float(__float_as_uint(a.z) & 0xFFFFE000u);
                             l.w = a.w - __uint_as_float(__float_as_uint(a.w) & 0xFFFFE000u);
                             *reinterpret_cast<float4*>(olo + n) = l;
+                        }
+                        if (oh) {      // fp16 hi/lo planes for the next fp16-split conv: hi = rn16(v), lo = rn16(v - hi)
+                            __half hx = __float2half_rn(a.x), hy = __float2half_rn(a.y), hz = __float2half_rn(a.z), hw = __float2half_rn(a.w);
+                            __half lx = __float2half_rn(a.x - __half2float(hx)), ly = __float2half_rn(a.y - __half2float(hy));
+                            __half lz = __float2half_rn(a.z - __half2float(hz)), lw = __float2half_rn(a.w - __half2float(hw));
+                            __half2 h01 = __halves2half2(hx, hy), h23 = __halves2half2(hz, hw), l01 = __halves2half2(lx, ly), l23 = __halves2half2(lz, lw);
+                            uint2 hv, lv;
+                            hv.x = *reinterpret_cast<uint32_t*>(&h01); hv.y = *reinterpret_cast<uint32_t*>(&h23);
+                            lv.x = *reinterpret_cast<uint32_t*>(&l01); lv.y = *reinterpret_cast<uint32_t*>(&l23);
+                            *reinterpret_cast<uint2*>(oh + n) = hv;
+                            *reinterpret_cast<uint2*>(ol16 + n) = lv;
                         }
                     }
                 }
@@ -290,6 +327,23 @@ __global__ void split_lo_kernel(const float* __restrict__ in, float* __restrict_
     *reinterpret_cast<float4*>(lo + pix * cs + co + 4 * c4) = l;
 }
 
+// fp32 -> fp16 (hi, lo) planes: hi = rn16(v), lo = rn16(v - hi).  Elementwise, channel-slice aware (planes share the fp32 pitch).
+__global__ void split_h16_kernel(const float* __restrict__ in, __half* __restrict__ hi, __half* __restrict__ lo, long long npix, int C4, int cs, int co) {
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= npix * C4) return;
+    int c4 = (int)(idx % C4); long long pix = idx / C4;
+    float4 a = ldg4(in + pix * cs + co + 4 * c4);
+    __half hx = __float2half_rn(a.x), hy = __float2half_rn(a.y), hz = __float2half_rn(a.z), hw = __float2half_rn(a.w);
+    __half2 h01 = __halves2half2(hx, hy), h23 = __halves2half2(hz, hw);
+    __half2 l01 = __halves2half2(__float2half_rn(a.x - __half2float(hx)), __float2half_rn(a.y - __half2float(hy)));
+    __half2 l23 = __halves2half2(__float2half_rn(a.z - __half2float(hz)), __float2half_rn(a.w - __half2float(hw)));
+    uint2 hv, lv;
+    hv.x = *reinterpret_cast<uint32_t*>(&h01); hv.y = *reinterpret_cast<uint32_t*>(&h23);
+    lv.x = *reinterpret_cast<uint32_t*>(&l01); lv.y = *reinterpret_cast<uint32_t*>(&l23);
+    *reinterpret_cast<uint2*>(hi + pix * cs + co + 4 * c4) = hv;
+    *reinterpret_cast<uint2*>(lo + pix * cs + co + 4 * c4) = lv;
+}
+
 // ----------------------------------------------------------------------------------------------------------------
 // host: tensor maps (driver entry point fetched at run time: the library does not link libcuda)
 // ----------------------------------------------------------------------------------------------------------------
@@ -309,27 +363,28 @@ static EncodeTiledFn get_encode() {
     return fn;
 }
 
-static int make_map_act(CUtensorMap* m, const float* base, int B, int H, int W, int C, int cs, int co) {
+static int make_map_act(CUtensorMap* m, const void* base_v, int B, int H, int W, int C, int cs, int co, int esize = 4) {
     EncodeTiledFn enc = get_encode();
     if (!enc) { set_error("conv2d_tc: cuTensorMapEncodeTiled unavailable"); return VD3D_ECUDA; }
+    const char* base = (const char*)base_v + (size_t)co * esize;
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-    cuuint64_t strides[3] = {(cuuint64_t)cs * 4, (cuuint64_t)W * cs * 4, (cuuint64_t)H * W * cs * 4};
-    cuuint32_t box[4] = {TC_BK, TC_TW, TC_TH, 1};
+    cuuint64_t strides[3] = {(cuuint64_t)cs * esize, (cuuint64_t)W * cs * esize, (cuuint64_t)H * W * cs * esize};
+    cuuint32_t box[4] = {(cuuint32_t)(128 / esize), TC_TW, TC_TH, 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)(base + co), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    CUresult r = enc(m, esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("conv2d_tc: cuTensorMapEncodeTiled(activation) failed: %d", (int)r); return VD3D_ECUDA; }
     return VD3D_OK;
 }
 
-static int make_map_wgt(CUtensorMap* m, const float* base, int Cout, int K, int BN) {
+static int make_map_wgt(CUtensorMap* m, const void* base, int Cout, int K, int BN, int esize = 4) {
     EncodeTiledFn enc = get_encode();
     if (!enc) { set_error("conv2d_tc: cuTensorMapEncodeTiled unavailable"); return VD3D_ECUDA; }
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)Cout};
-    cuuint64_t strides[1] = {(cuuint64_t)K * 4};
-    cuuint32_t box[2] = {TC_BK, (cuuint32_t)BN};
+    cuuint64_t strides[1] = {(cuuint64_t)K * esize};
+    cuuint32_t box[2] = {(cuuint32_t)(128 / esize), (cuuint32_t)BN};
     cuuint32_t es[2] = {1, 1};
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    CUresult r = enc(m, esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("conv2d_tc: cuTensorMapEncodeTiled(weights) failed: %d", (int)r); return VD3D_ECUDA; }
     return VD3D_OK;
@@ -350,17 +405,19 @@ extern "C" int vd3d_tc_pick_bn(int Cout) {
     return 128;
 }
 
-extern "C" int vd3d_conv2d_tc(const float* in, const float* in_lo, int B, int H, int W, int Cin, int in_cs, int in_co,
-                              const float* w_hi, const float* w_lo, const float* bias, int KH, int KW, int pad, int dil,
-                              const float* res, int res_cs, int res_co,
-                              float* out, float* out_lo, int Cout, int out_cs, int out_co, int relu, int passes, int bn, void* stream) {
+static int conv2d_tc_launch(int f16, const void* in, const void* in_lo, int B, int H, int W, int Cin, int in_cs, int in_co,
+                            const void* w_hi, const void* w_lo, float out_scale, const float* bias, int KH, int KW, int pad, int dil,
+                            const float* res, int res_cs, int res_co, float* out, float* out_lo, void* out_h16_hi, void* out_h16_lo,
+                            int Cout, int out_cs, int out_co, int relu, int passes, int bn, void* stream) {
     VD3D_REQUIRE(in && w_hi && out, "conv2d_tc: null pointer");
     VD3D_REQUIRE(passes == 1 || passes == 3, "conv2d_tc: passes must be 1 or 3");
     VD3D_REQUIRE(passes == 1 || (in_lo && w_lo), "conv2d_tc: 3-pass mode needs the lo tensors");
-    VD3D_REQUIRE(Cin % TC_BK == 0, "conv2d_tc: Cin must be a multiple of 32 (got %d)", Cin);
-    VD3D_REQUIRE(in_cs % 4 == 0 && in_co % 4 == 0 && out_cs % 4 == 0 && out_co % 4 == 0 && Cout % 4 == 0, "conv2d_tc: pitches/offsets must be multiples of 4");
+    const int esize = f16 ? 2 : 4, bk = 128 / esize;
+    VD3D_REQUIRE(f16 ? (Cin % 8 == 0) : (Cin % bk == 0), "conv2d_tc: Cin must be a multiple of %d (got %d)", f16 ? 8 : bk, Cin);
+    VD3D_REQUIRE(in_cs % 8 == 0 && in_co % 8 == 0 && out_cs % 4 == 0 && out_co % 4 == 0 && Cout % 4 == 0, "conv2d_tc: pitches/offsets alignment");
     VD3D_REQUIRE(!res || (res_cs % 4 == 0 && res_co % 4 == 0), "conv2d_tc: residual pitch/offset must be multiples of 4");
     VD3D_REQUIRE(((uintptr_t)in & 15) == 0 && ((uintptr_t)w_hi & 15) == 0 && ((uintptr_t)out & 15) == 0, "conv2d_tc: pointers must be 16-byte aligned");
+    VD3D_REQUIRE(!out_h16_hi || (out_h16_lo && out_cs % 4 == 0), "conv2d_tc: fp16 output planes come in (hi, lo) pairs");
     int BN = bn > 0 ? bn : vd3d_tc_pick_bn(Cout);
     VD3D_REQUIRE(BN % 16 == 0 && BN >= 16 && BN <= 160, "conv2d_tc: BN must be a multiple of 16 in [16, 160]");
     TcParams p;
@@ -368,12 +425,13 @@ extern "C" int vd3d_conv2d_tc(const float* in, const float* in_lo, int B, int H,
     p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.KH = KH; p.KW = KW; p.pad = pad; p.dil = dil;
     p.Ho = H + 2 * pad - dil * (KH - 1); p.Wo = W + 2 * pad - dil * (KW - 1);
     VD3D_REQUIRE(p.Ho > 0 && p.Wo > 0, "conv2d_tc: empty output");
-    p.Cout = Cout; p.BN = BN; p.passes = passes;
+    p.Cout = Cout; p.BN = BN; p.passes = passes; p.f16 = f16; p.bk = bk; p.cin_pad = (Cin + bk - 1) / bk * bk; p.out_scale = out_scale;
     p.tiles_w = cdiv(p.Wo, TC_TW); p.tiles_h = cdiv(p.Ho, TC_TH);
     p.out_cs = out_cs; p.out_co = out_co; p.res_cs = res_cs; p.res_co = res_co; p.relu = relu;
-    p.bias = bias; p.res = res; p.out = out; p.out_lo = out_lo;
-    // instruction descriptor (cute::UMMA::InstrDescriptor): D = f32, A = B = tf32, both K-major, N>>3 @17, M>>4 @24
-    p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    p.bias = bias; p.res = res; p.out = out; p.out_lo = out_lo; p.out_h16_hi = out_h16_hi; p.out_h16_lo = out_h16_lo;
+    // instruction descriptor (cute::UMMA::InstrDescriptor): D = f32 (1 @4), A/B format @7/@10 (tf32 = 2, f16 = 0), K-major, N>>3 @17, M>>4 @24
+    const uint32_t fmt = f16 ? 0u : 2u;
+    p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     uint32_t cols = 32; while (cols < (uint32_t)(2 * BN)) cols <<= 1;     // two accumulator buffers (chunked promotion)
     p.tmem_cols = cols;
     {
@@ -387,13 +445,13 @@ extern "C" int vd3d_conv2d_tc(const float* in, const float* in_lo, int B, int H,
     VD3D_REQUIRE(stages >= 2, "conv2d_tc: tile too large for shared memory");
     p.stages = stages;
     const size_t smem = stages * stage_bytes + (2 * stages + 6) * sizeof(uint64_t) + 1024;
-    const int K = KH * KW * Cin;
+    const int K = KH * KW * p.cin_pad;
     CUtensorMap mA, mAlo, mWhi, mWlo;
     int rc;
-    if ((rc = make_map_act(&mA, in, B, H, W, Cin, in_cs, in_co))) return rc;
-    if ((rc = make_map_act(&mAlo, in_lo ? in_lo : in, B, H, W, Cin, in_cs, in_co))) return rc;
-    if ((rc = make_map_wgt(&mWhi, w_hi, Cout, K, BN))) return rc;
-    if ((rc = make_map_wgt(&mWlo, w_lo ? w_lo : w_hi, Cout, K, BN))) return rc;
+    if ((rc = make_map_act(&mA, in, B, H, W, Cin, in_cs, in_co, esize))) return rc;
+    if ((rc = make_map_act(&mAlo, in_lo ? in_lo : in, B, H, W, Cin, in_cs, in_co, esize))) return rc;
+    if ((rc = make_map_wgt(&mWhi, w_hi, Cout, K, BN, esize))) return rc;
+    if ((rc = make_map_wgt(&mWlo, w_lo ? w_lo : w_hi, Cout, K, BN, esize))) return rc;
     static bool attr_set = false;
     if (!attr_set) {
         VD3D_CUDA(cudaFuncSetAttribute(conv2d_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -410,10 +468,35 @@ extern "C" int vd3d_conv2d_tc(const float* in, const float* in_lo, int B, int H,
     return VD3D_OK;
 }
 
+extern "C" int vd3d_conv2d_tc(const float* in, const float* in_lo, int B, int H, int W, int Cin, int in_cs, int in_co,
+                              const float* w_hi, const float* w_lo, const float* bias, int KH, int KW, int pad, int dil,
+                              const float* res, int res_cs, int res_co,
+                              float* out, float* out_lo, int Cout, int out_cs, int out_co, int relu, int passes, int bn, void* stream) {
+    return conv2d_tc_launch(0, in, in_lo, B, H, W, Cin, in_cs, in_co, w_hi, w_lo, 1.0f, bias, KH, KW, pad, dil, res, res_cs, res_co,
+                            out, out_lo, nullptr, nullptr, Cout, out_cs, out_co, relu, passes, bn, stream);
+}
+
+extern "C" int vd3d_conv2d_tc16(const void* in_hi, const void* in_lo, int B, int H, int W, int Cin, int in_cs, int in_co,
+                                const void* w_hi, const void* w_lo, float out_scale, const float* bias, int KH, int KW, int pad, int dil,
+                                const float* res, int res_cs, int res_co,
+                                float* out, void* out_hi16, void* out_lo16, int Cout, int out_cs, int out_co, int relu, int passes, int bn,
+                                void* stream) {
+    return conv2d_tc_launch(1, in_hi, in_lo, B, H, W, Cin, in_cs, in_co, w_hi, w_lo, out_scale, bias, KH, KW, pad, dil, res, res_cs, res_co,
+                            out, nullptr, out_hi16, out_lo16, Cout, out_cs, out_co, relu, passes, bn, stream);
+}
+
 extern "C" int vd3d_split_lo_nhwc(const float* in, float* lo, long long npix, int C, int cs, int co, void* stream) {
     VD3D_REQUIRE(in && lo && C % 4 == 0 && cs % 4 == 0 && co % 4 == 0, "split_lo: bad args");
     long long total = npix * (C / 4);
     split_lo_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(in, lo, npix, C / 4, cs, co);
     VD3D_CHECK_LAUNCH("split_lo");
+    return VD3D_OK;
+}
+
+extern "C" int vd3d_split_h16_nhwc(const float* in, void* hi16, void* lo16, long long npix, int C, int cs, int co, void* stream) {
+    VD3D_REQUIRE(in && hi16 && lo16 && C % 4 == 0 && cs % 4 == 0 && co % 4 == 0, "split_h16: bad args");
+    long long total = npix * (C / 4);
+    split_h16_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(in, (__half*)hi16, (__half*)lo16, npix, C / 4, cs, co);
+    VD3D_CHECK_LAUNCH("split_h16");
     return VD3D_OK;
 }

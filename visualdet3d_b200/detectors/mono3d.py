@@ -50,6 +50,8 @@ class LookGroundRunner:
         S = arena.act(tag + ".S", (B, H, W, self.cin_pad), dev, lo=self.extract.engine != "simt", zero=True)
         call("vd3d_look_ground_sample", x.ptr, B, H, W, x.C, x.cs, x.co, d.ptr, d.cs, 0, P2.data_ptr(), self.baseline, self.elev,
              S.ptr, S.lo_ptr, S.cs, E._stream())
+        if S.h16:
+            E.split_lo(S)
         return self.extract(S, arena.act(tag + ".out", (B, H, W, self.C), dev, lo=True), res=x)
 
 

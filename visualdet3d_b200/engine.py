@@ -27,9 +27,11 @@ def _require_cuda(t: torch.Tensor, what: str):
 class Act:
     """Channel slice [co, co+C) of an NHWC fp32 tensor `t` of shape [B, H, W, cs].
 
-    `lo` (optional, same shape as `t`) holds  t - (t & 0xFFFFE000): the low part of every value that the tf32 tensor
-    core does not see.  The tcgen05 conv engine consumes (t, lo) pairs and produces them; other producers leave `lo`
-    stale and the plan calls `split_lo` before a tensor-core consumer."""
+    `lo` (optional) is the tensor-core companion of `t`, in one of two forms:
+      * float32, same shape as `t`:  t - (t & 0xFFFFE000), the part of every value the tf32 MMA does not see ("tc" engine);
+      * float16, shape [2, B, H, W, cs]: planes hi = rn16(t) and lo = rn16(t - hi) ("tc16" engine, the default).
+    The tcgen05 conv engine consumes and produces these; other producers leave them stale and the plan calls `split_lo`
+    before a tensor-core consumer."""
     __slots__ = ("t", "co", "C", "lo")
 
     def __init__(self, t: torch.Tensor, co: int = 0, C: Optional[int] = None, lo: Optional[torch.Tensor] = None):
@@ -37,7 +39,8 @@ class Act:
         self.t, self.co, self.lo = t, co, lo
         self.C = (t.shape[3] - co) if C is None else C
         assert 0 <= co and co + self.C <= t.shape[3]
-        assert lo is None or (lo.shape == t.shape and lo.is_contiguous())
+        assert lo is None or (lo.dtype == torch.float32 and lo.shape == t.shape) or \
+            (lo.dtype == torch.float16 and tuple(lo.shape) == (2,) + tuple(t.shape))
 
     B = property(lambda s: s.t.shape[0])
     H = property(lambda s: s.t.shape[1])
@@ -48,11 +51,22 @@ class Act:
         return Act(self.t, self.co + co, C, self.lo)
 
     def batch(self, b0: int, b1: int) -> "Act":
-        return Act(self.t[b0:b1], self.co, self.C, None if self.lo is None else self.lo[b0:b1])
+        # (a batch sub-range of the fp16 planes is not contiguous: such views drop the companion; they only feed non-TC kernels)
+        lo = self.lo[b0:b1] if (self.lo is not None and self.lo.dtype == torch.float32) else None
+        return Act(self.t[b0:b1], self.co, self.C, lo)
 
     @property
     def lo_ptr(self):
-        return None if self.lo is None else self.lo.data_ptr()
+        """fp32 lo companion pointer (None when absent or in fp16-plane form)."""
+        return self.lo.data_ptr() if (self.lo is not None and self.lo.dtype == torch.float32) else None
+
+    @property
+    def h16(self) -> bool:
+        return self.lo is not None and self.lo.dtype == torch.float16
+
+    @property
+    def h16_ptrs(self):
+        return (self.lo[0].data_ptr(), self.lo[1].data_ptr()) if self.h16 else (None, None)
 
     @property
     def ptr(self) -> int:
@@ -68,8 +82,9 @@ class Act:
 class Arena:
     """Named, shape-keyed device buffers: allocated once, pointer-stable across forwards (CUDA-graph friendly)."""
 
-    def __init__(self):
+    def __init__(self, lo_form: Optional[str] = None):
         self._bufs: Dict[Tuple, torch.Tensor] = {}
+        self.lo_form = lo_form or lo_mode()      # companion form is fixed when the owning detector is built
 
     def get(self, name: str, shape: Sequence[int], device, dtype=torch.float32, zero: bool = False) -> torch.Tensor:
         key = (name, tuple(int(s) for s in shape), str(device), dtype)
@@ -82,7 +97,11 @@ class Arena:
     def act(self, name: str, shape: Sequence[int], device, lo: bool = False, zero: bool = False) -> Act:
         """NHWC activation buffer (optionally with its `lo` companion for the tensor-core engine)."""
         t = self.get(name, shape, device, zero=zero)
-        return Act(t, 0, None, self.get(name + "#lo", shape, device, zero=True) if lo else None)
+        if not lo:
+            return Act(t)
+        if self.lo_form == "h16":
+            return Act(t, 0, None, self.get(name + "#h16", (2,) + tuple(shape), device, dtype=torch.float16, zero=True))
+        return Act(t, 0, None, self.get(name + "#lo", shape, device, zero=True))
 
     def nbytes(self) -> int:
         return sum(t.numel() * t.element_size() for t in self._bufs.values())
@@ -108,10 +127,23 @@ def bn_dict(mod) -> Dict[str, torch.Tensor]:
 
 
 def conv_engine_default() -> str:
-    """'tc' = tcgen05 3xTF32 engine wherever a layer is eligible (default), 'simt' = exact-fp32 SIMT engine everywhere,
-    'tc1' = single-pass TF32 (NOT parity-grade; diagnostics only)."""
+    """'tc16' = tcgen05 fp16-split engine (3 kind::f16 MMAs, default), 'tc' = tcgen05 3xTF32 engine, 'simt' = exact-fp32 SIMT
+    engine everywhere, 'tc1' = single-pass TF32 (NOT parity-grade; diagnostics only)."""
     import os
-    return os.environ.get("VD3D_CONV_ENGINE", "tc")
+    return os.environ.get("VD3D_CONV_ENGINE", "tc16")
+
+
+def lo_mode() -> str:
+    """form of the tensor-core companions allocated by Arena.act: 'h16' (fp16 hi/lo planes) or 'f32' (tf32 lo tensor)"""
+    return "h16" if conv_engine_default() == "tc16" else "f32"
+
+
+def fp16_split(w: torch.Tensor):
+    """w (float32/64, already scaled into fp16 range) -> (hi, lo) fp16 with hi = rn16(w), lo = rn16(w - hi)."""
+    w = w.float()
+    hi = w.half()
+    lo = (w - hi.float()).half()
+    return hi.contiguous(), lo.contiguous()
 
 
 def tf32_split(w: torch.Tensor):
@@ -140,11 +172,23 @@ class ConvLayer:
         self.stride, self.pad, self.dil, self.relu = stride, pad, dil, relu
         eng = engine or conv_engine_default()
         eligible = stride == 1 and cin_p % 32 == 0 and Cout % 16 == 0 and str(device).startswith("cuda")
-        self.engine = eng if (eng in ("tc", "tc1") and eligible) else "simt"
+        self.engine = eng if (eng in ("tc", "tc1", "tc16") and eligible) else "simt"
         self.b = b.float().to(device)
         self.w = self.w_hi = self.w_lo = None
+        self.out_scale = 1.0
         if self.engine == "simt":
             self.w = w.permute(2, 3, 1, 0).reshape(KH * KW * cin_p, Cout).contiguous().float().to(device)
+        elif self.engine == "tc16":
+            cin64 = (cin_p + 63) // 64 * 64
+            wk = torch.zeros(Cout, KH * KW, cin64, dtype=torch.float64)
+            wk[:, :, :cin_p] = w.permute(0, 2, 3, 1).reshape(Cout, KH * KW, cin_p)
+            wmax = float(wk.abs().max())
+            k = int(np.floor(np.log2(16384.0 / wmax))) if wmax > 0 else 0      # power-of-two scale: max |w| * S in [8192, 16384)
+            k = max(-24, min(24, k))
+            self.out_scale = float(2.0 ** (-k))
+            hi, lo = fp16_split(wk.reshape(Cout, KH * KW * cin64) * (2.0 ** k))
+            self.w_hi, self.w_lo = hi.to(device), lo.to(device)
+            self.bn_tile = int(_lib.load().vd3d_tc_pick_bn(Cout))
         else:
             wk = w.permute(0, 2, 3, 1).reshape(Cout, KH * KW * cin_p).contiguous().float()
             hi, lo = tf32_split(wk)
@@ -168,8 +212,20 @@ class ConvLayer:
                  res.ptr if res is not None else None, res.cs if res is not None else 0, res.co if res is not None else 0,
                  out.ptr, self.Cout, out.cs, out.co, 1 if r else 0, _stream())
             return out
+        if self.engine == "tc16":
+            if not x.h16:
+                raise _lib.Vd3dError("fp16-split tensor-core conv: input activation has no fp16 (hi, lo) planes (plan bug: missing split_lo)")
+            if CHECK_LO:
+                check_lo(x)
+            xh, xl = x.h16_ptrs
+            oh, ol = out.h16_ptrs
+            call("vd3d_conv2d_tc16", xh, xl, x.B, x.H, x.W, x.C, x.cs, x.co, self.w_hi.data_ptr(), self.w_lo.data_ptr(), self.out_scale,
+                 self.b.data_ptr(), self.KH, self.KW, self.pad, self.dil,
+                 res.ptr if res is not None else None, res.cs if res is not None else 0, res.co if res is not None else 0,
+                 out.ptr, oh, ol, self.Cout, out.cs, out.co, 1 if r else 0, 3, self.bn_tile, _stream())
+            return out
         passes = 3 if self.engine == "tc" else 1
-        if passes == 3 and x.lo is None:
+        if passes == 3 and x.lo_ptr is None:
             raise _lib.Vd3dError("tensor-core conv: input activation has no `lo` companion (plan bug: missing split_lo)")
         if CHECK_LO and passes == 3:
             check_lo(x)
@@ -217,6 +273,8 @@ class DeformConvLayer:
         call("vd3d_deform_im2col_nhwc", x.ptr, B, x.H, x.W, x.C, x.cs, x.co, om.ptr, om.cs, 0,
              om.ptr, om.cs, 2 * K * self.dg, 1, self.KH, self.KW, self.stride, self.pad, self.dil, self.dg,
              cols.ptr, cols.lo_ptr, cols.cs, _stream())
+        if cols.h16:
+            split_lo(cols)
         return self.main(cols, out, res=res)
 
 
@@ -249,13 +307,23 @@ def split_lo(x: Act) -> Act:
     """Refresh the `lo` companion of a channel slice written by a non-tensor-core producer."""
     if x.lo is None:
         return x
-    call("vd3d_split_lo_nhwc", x.ptr, x.lo_ptr, x.B * x.H * x.W, x.C, x.cs, x.co, _stream())
+    if x.h16:
+        h, l = x.h16_ptrs
+        call("vd3d_split_h16_nhwc", x.ptr, h, l, x.B * x.H * x.W, x.C, x.cs, x.co, _stream())
+    else:
+        call("vd3d_split_lo_nhwc", x.ptr, x.lo_ptr, x.B * x.H * x.W, x.C, x.cs, x.co, _stream())
     return x
 
 
 def check_lo(x: Act):
-    """Debug (VD3D_CHECK_LO=1): assert lo == t - (t & 0xFFFFE000) on the slice a tensor-core conv is about to read."""
+    """Debug (VD3D_CHECK_LO=1): assert the companion of the slice a tensor-core conv is about to read is fresh."""
     t = x.t[..., x.co:x.co + x.C]
+    if x.h16:
+        hi = t.half()
+        lo = (t - hi.float()).half()
+        if not (torch.equal(x.lo[0][..., x.co:x.co + x.C], hi) and torch.equal(x.lo[1][..., x.co:x.co + x.C], lo)):
+            raise _lib.Vd3dError("stale fp16 (hi, lo) planes in front of a tensor-core conv")
+        return
     hi = (t.contiguous().view(torch.int32) & -8192).view(torch.float32)
     if not torch.equal(x.lo[..., x.co:x.co + x.C], t - hi):
         raise _lib.Vd3dError("stale `lo` companion in front of a tensor-core conv")
