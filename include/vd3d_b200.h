@@ -74,10 +74,11 @@ int vd3d_conv2d_tc(const float* in, const float* in_lo, int B, int H, int W, int
  * power of two S on the host (so that their lo parts stay normal fp16 numbers); out_scale = 1/S is applied to the accumulator.
  *   in_hi / in_lo   : fp16 NHWC planes with the same pitch / offset convention as the fp32 tensors
  *   w_hi / w_lo     : fp16 [Cout][KH*KW*cin_pad], cin_pad = Cin rounded up to 64 (zero filled)
- *   out             : fp32 NHWC result; out_hi16 / out_lo16 (optional pair): its fp16 planes for the next conv            */
+ *   out             : fp32 NHWC result; out_hi16 / out_lo16 (optional pair): its fp16 planes for the next conv
+ *   stride          : 1..4 (strided convs load every stride-th pixel through the TMA traversal stride); Cin % 8 == 0, Cout % 4 == 0 */
 int vd3d_conv2d_tc16(const void* in_hi, const void* in_lo, int B, int H, int W, int Cin, int in_cs, int in_co,
                      const void* w_hi, const void* w_lo, float out_scale, const float* bias, int KH, int KW, int pad, int dil,
-                     const float* res, int res_cs, int res_co,
+                     int stride, const float* res, int res_cs, int res_co,
                      float* out, void* out_hi16, void* out_lo16, int Cout, int out_cs, int out_co, int relu, int passes, int bn,
                      void* stream);
 /* fp32 channel slice -> fp16 (hi, lo) planes (producers that are not tensor-core convs). */

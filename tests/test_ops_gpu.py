@@ -231,11 +231,14 @@ def test_conv2d_tc_3xtf32_vs_fp32(case):
     assert torch.equal(got_lo, val - _trunc13(val))
 
 
+@pytest.mark.parametrize("halo", [2, 1, 0])
 @pytest.mark.parametrize("case", TC_CASES)
-def test_conv2d_tc16_fp16split_vs_fp64(case):
+def test_conv2d_tc16_fp16split_vs_fp64(case, halo, monkeypatch):
     """fp16-split tensor-core conv (3 kind::f16 MMAs on (hi, lo) fp16 planes, 22 significant bits): same accuracy bar as the
-    3xTF32 form, checked against an fp64 convolution; also checks the fp16 planes the epilogue writes for the next layer."""
+    3xTF32 form, checked against an fp64 convolution; also checks the fp16 planes the epilogue writes for the next layer.
+    halo = 2 / 1: 3x3 convs stage the input halo once per channel chunk (full / vertical reuse); 0: generic per-tap boxes."""
     E = _E()
+    monkeypatch.setenv("VD3D_TC_HALO", str(halo))
     B, Cin, H, W, Cout, k, p, d, has_b, has_r, relu = case
     g = torch.Generator().manual_seed(sum(case[:6]) + 1)
     x = torch.randn(B, Cin, H, W, generator=g)
@@ -281,3 +284,40 @@ def test_tc16_large_and_tiny_magnitudes():
         rel = float((out.to_nchw().cpu().double() - ref64).abs().max() / ref64.abs().max())
         print("wscale", wscale, "xscale", xscale, "rel err", rel)
         assert rel < 4e-6, (wscale, xscale, rel)
+
+
+TC16_EXTRA = [
+    # B, Cin, H, W, Cout, k, pad, stride
+    (2, 64, 24, 40, 128, 3, 1, 2),       # ResNet stage entry: 3x3 stride 2
+    (1, 64, 17, 33, 128, 1, 0, 2),       # 1x1 stride-2 down-sample, odd sizes
+    (1, 128, 20, 36, 256, 3, 1, 2),
+    (1, 72, 12, 20, 72, 3, 1, 1),        # 72 channels: zero-filled up to the 64-channel k-block, Cout masked inside an 80-wide tile
+    (1, 24, 16, 32, 24, 1, 0, 1),
+    (1, 32, 15, 21, 64, 3, 1, 2),
+]
+
+
+@pytest.mark.parametrize("case", TC16_EXTRA)
+def test_conv2d_tc16_strided_and_ragged_channels(case):
+    """stride > 1 goes through the TMA traversal stride (every stride-th pixel lands densely in shared memory);
+    channel counts that are not multiples of the 64-channel k-block / 16-column MMA granule are zero-filled / masked."""
+    E = _E()
+    B, Cin, H, W, Cout, k, p, s_ = case
+    g = torch.Generator().manual_seed(sum(case))
+    x = torch.randn(B, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, k, k, generator=g) / np.sqrt(Cin * k * k)
+    b = torch.randn(Cout, generator=g)
+    ref64 = F.relu(F.conv2d(x.double(), w.double(), b.double(), padding=p, stride=s_))
+    layer = E.ConvLayer(w, b, None, stride=s_, pad=p, relu=True, device="cuda", engine="tc16")
+    assert layer.engine == "tc16"
+    xa = E.split_lo(E.Act(nhwc(x).cuda(), 0, None, torch.zeros(2, B, H, W, Cin, device="cuda", dtype=torch.float16)))
+    Ho, Wo = layer.out_hw(H, W)
+    assert (Ho, Wo) == tuple(ref64.shape[2:])
+    out = E.Act(torch.full((B, Ho, Wo, Cout + 8), 7.0, device="cuda"), 4, Cout,
+                torch.full((2, B, Ho, Wo, Cout + 8), 7.0, device="cuda", dtype=torch.float16))
+    layer(xa, out)
+    err = float((out.to_nchw().cpu().double() - ref64).abs().max())
+    print(case, "max|err| vs fp64", err)
+    assert err < 2e-5, err
+    assert float(out.t[..., :4].min()) == 7.0 and float(out.t[..., 4 + Cout:].min()) == 7.0
+    assert float(out.lo[..., :4].float().min()) == 7.0 and float(out.lo[..., 4 + Cout:].float().min()) == 7.0

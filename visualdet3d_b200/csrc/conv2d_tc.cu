@@ -28,7 +28,7 @@ constexpr int TC_THREADS = 192;
 constexpr int TC_A_BYTES = 128 * 128;         // one A (or Alo) stage: 128 rows x 128 B
 
 struct TcParams {
-    int B, H, W, Cin, KH, KW, pad, dil;
+    int B, H, W, Cin, KH, KW, pad, dil, stride;
     int Ho, Wo, Cout, BN, stages, passes, chunk;
     int f16;                 // 0: tf32 operands (32 channels / k-block), 1: fp16 hi/lo operands (64 channels / k-block)
     int bk;                  // channels per k-block
@@ -40,6 +40,10 @@ struct TcParams {
     const float* bias; const float* res; float* out; float* out_lo;
     uint32_t idesc;
     uint32_t tmem_cols;
+    // halo kernel (3x3, pad 1, dil 1, fp16 operands): one A item in shared memory serves `h_taps` taps
+    int h_mode;              // 2: full halo (10 rows x 2 half-rows of 10 px, 9 taps / item), 1: vertical halo (16 px x 10 rows per kx, 3 taps / item)
+    int h_taps, h_sa, h_sb;  // taps per A item, A stages, B stages
+    uint32_t h_rp, h_sbo;    // bytes per halo row, bytes between 8-pixel groups (UMMA stride byte offset)
 };
 
 // ----------------------------------------------------------------------------------------------------------------
@@ -81,11 +85,11 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
 // shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor layout)
-__device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr) {
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr, uint32_t sbo = 1024) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr >> 4) & 0x3FFF);        // start address
     d |= (uint64_t)0 << 16;                          // leading byte offset (unused for swizzled K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset: 8 rows * 128 B
+    d |= (uint64_t)(sbo >> 4) << 32;                 // stride byte offset between 8-row groups (1024 = dense 8 rows * 128 B)
     d |= (uint64_t)1 << 46;                          // descriptor version (Blackwell)
     d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
     return d;
@@ -122,6 +126,83 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
           "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// epilogue warps (4 warps <-> TMEM lane quadrants (warp % 4)): promote every accumulated chunk into registers, then
+// scale / bias / residual / ReLU and write the value plus the companions the next tensor-core conv reads.
+// ----------------------------------------------------------------------------------------------------------------
+template <int NG>
+__device__ __forceinline__ void tc_epilogue(const TcParams& p, uint32_t tmem_base, uint64_t* tmem_full, uint64_t* tmem_empty, int NC,
+                                            int warp, int lane, int b, int h0, int w0, int n0) {
+    const int q = warp & 3;
+    float acc[NG][32];
+#pragma unroll
+    for (int g = 0; g < NG; ++g)
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[g][i] = 0.f;
+    for (int ci = 0; ci < NC; ++ci) {
+        const int buf = ci & 1, use = ci >> 1;
+        mbar_wait(&tmem_full[buf], use & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+            if (g * 32 < p.BN) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.BN + g * 32), v);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) acc[g][i] += __uint_as_float(v[i]);
+            }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty[buf])) : "memory");
+    }
+    const int r = q * 32 + lane;                   // accumulator row = tile pixel
+    const int ho = h0 + r / TC_TW, wo = w0 + r % TC_TW;
+    const bool ok = ho < p.Ho && wo < p.Wo;
+    const long long pix = ((long long)b * p.Ho + ho) * p.Wo + wo;
+    float* op = p.out + pix * p.out_cs + p.out_co;
+    float* olo = p.out_lo ? p.out_lo + pix * p.out_cs + p.out_co : nullptr;
+    __half* oh = p.out_h16_hi ? reinterpret_cast<__half*>(p.out_h16_hi) + pix * p.out_cs + p.out_co : nullptr;
+    __half* ol16 = p.out_h16_lo ? reinterpret_cast<__half*>(p.out_h16_lo) + pix * p.out_cs + p.out_co : nullptr;
+    const float osc = p.out_scale;
+    const float* rp = p.res ? p.res + pix * p.res_cs + p.res_co : nullptr;
+    if (ok) {
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+                const int n = n0 + g * 32 + i;
+                if (g * 32 + i < p.BN && n < p.Cout) {          // Cout % 4 == 0
+                    float4 a = make_float4(acc[g][i] * osc, acc[g][i + 1] * osc, acc[g][i + 2] * osc, acc[g][i + 3] * osc);
+                    if (p.bias) { float4 bb = ldg4(p.bias + n); a.x += bb.x; a.y += bb.y; a.z += bb.z; a.w += bb.w; }
+                    if (rp) { float4 rr = ldg4(rp + n); a.x += rr.x; a.y += rr.y; a.z += rr.z; a.w += rr.w; }
+                    if (p.relu) { a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f); }
+                    *reinterpret_cast<float4*>(op + n) = a;
+                    if (olo) {
+                        float4 l;
+                        l.x = a.x - __uint_as_float(__float_as_uint(a.x) & 0xFFFFE000u);
+                        l.y = a.y - __uint_as_float(__float_as_uint(a.y) & 0xFFFFE000u);
+                        l.z = a.z - __uint_as_float(__float_as_uint(a.z) & 0xFFFFE000u);
+                        l.w = a.w - __uint_as_float(__float_as_uint(a.w) & 0xFFFFE000u);
+                        *reinterpret_cast<float4*>(olo + n) = l;
+                    }
+                    if (oh) {      // fp16 hi/lo planes for the next fp16-split conv: hi = rn16(v), lo = rn16(v - hi)
+                        __half hx = __float2half_rn(a.x), hy = __float2half_rn(a.y), hz = __float2half_rn(a.z), hw = __float2half_rn(a.w);
+                        __half lx = __float2half_rn(a.x - __half2float(hx)), ly = __float2half_rn(a.y - __half2float(hy));
+                        __half lz = __float2half_rn(a.z - __half2float(hz)), lw = __float2half_rn(a.w - __half2float(hw));
+                        __half2 h01 = __halves2half2(hx, hy), h23 = __halves2half2(hz, hw), l01 = __halves2half2(lx, ly), l23 = __halves2half2(lz, lw);
+                        uint2 hv, lv;
+                        hv.x = *reinterpret_cast<uint32_t*>(&h01); hv.y = *reinterpret_cast<uint32_t*>(&h23);
+                        lv.x = *reinterpret_cast<uint32_t*>(&l01); lv.y = *reinterpret_cast<uint32_t*>(&l23);
+                        *reinterpret_cast<uint2*>(oh + n) = hv;
+                        *reinterpret_cast<uint2*>(ol16 + n) = lv;
+                    }
+                }
+            }
+        }
+    }
 }
 
 // ----------------------------------------------------------------------------------------------------------------
@@ -183,7 +264,7 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 const int kh = tap / p.KW, kw = tap - kh * p.KW;
                 uint8_t* st = smem + (size_t)s * stage_bytes;
                 mbar_expect_tx(&full[s], p.passes == 3 ? stage_bytes : (TC_A_BYTES + b_bytes));
-                const int wi = w0 - p.pad + kw * p.dil, hi = h0 - p.pad + kh * p.dil;
+                const int wi = w0 * p.stride - p.pad + kw * p.dil, hi = h0 * p.stride - p.pad + kh * p.dil;
                 tma_load_4d(st, &mapA, &full[s], c0, wi, hi, b);
                 tma_load_2d(st + 2 * TC_A_BYTES, &mapWhi, &full[s], tap * p.cin_pad + c0, n0);
                 if (p.passes == 3) {
@@ -235,75 +316,160 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             }
         }
     } else {
-        // ================= epilogue (warps 2..5 <-> TMEM lane quadrants (warp % 4)) =================
-        const int q = warp & 3;
-        float acc[NG][32];
-#pragma unroll
-        for (int g = 0; g < NG; ++g)
-#pragma unroll
-            for (int i = 0; i < 32; ++i) acc[g][i] = 0.f;
-        for (int ci = 0; ci < NC; ++ci) {
-            const int buf = ci & 1, use = ci >> 1;
-            mbar_wait(&tmem_full[buf], use & 1);
-            tc_fence_after();
-#pragma unroll
-            for (int g = 0; g < NG; ++g) {
-                if (g * 32 < p.BN) {
-                    uint32_t v[32];
-                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.BN + g * 32), v);
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) acc[g][i] += __uint_as_float(v[i]);
+        tc_epilogue<NG>(p, tmem_base, tmem_full, tmem_empty, NC, warp, lane, b, h0, w0, n0);
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// Halo kernel: 3x3 / pad 1 / dilation 1 convolution on fp16 (hi, lo) operands with the A operand REUSED across taps.
+//
+// The generic kernel re-fetches the (shifted) 128-pixel A box for every tap, which makes the conv L2->shared-memory
+// bound (64 KB per k-block per CTA against ~42 B/clk/SM of L2 bandwidth).  Here the input halo of the tile is staged
+// ONCE per 64-channel chunk and the nine taps address it through shifted UMMA descriptors:
+//   h_mode 2 (full halo)   smem item = [10 halo rows][2 half rows][10 px][128 B]; (row r, half g) is one TMA box
+//                          {64 c, 10 w, 1 h}.  Tap (ky, kx) starts at ky*2560 + kx*128 and steps 1280 B per 8-pixel
+//                          group (m = r*16 + g*8 + i, as in the generic kernel).  A bytes per chunk: 200 px instead of 1152.
+//   h_mode 1 (vertical)    one item per (chunk, kx) = box {64 c, 16 w, 10 h} shifted by kx-1; tap ky starts at ky*2048,
+//                          groups 1024 B apart (every descriptor 1024-byte aligned).  480 px per chunk.
+// Swizzling is a function of the absolute shared-memory address bits for both TMA and the MMA, so 128-byte shifts of the
+// start address keep the two consistent.
+// Warp roles: 0 = A producer, 1 = MMA issuer + TMEM owner, 2..5 = epilogue, 6 = B (weights) producer; the A ring (h_sa
+// items) and the B ring (h_sb taps) are independent.
+// ----------------------------------------------------------------------------------------------------------------
+constexpr int TCH_THREADS = 224;
+constexpr int TCH_PLANE = 25600;             // bytes of one A plane item (full halo: 10 rows x 2560 B; vertical halo uses 20480 of it)
+
+template <int NG>
+__global__ void __launch_bounds__(TCH_THREADS, 1)
+conv2d_tc_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapAlo,
+                      const __grid_constant__ CUtensorMap mapWhi, const __grid_constant__ CUtensorMap mapWlo, const TcParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t b_bytes = (uint32_t)p.BN * 128u;
+    const uint32_t a_item = 2u * TCH_PLANE;              // hi plane, lo plane
+    const uint32_t b_stage = 2u * b_bytes;               // Whi, Wlo
+    uint8_t* smemA = smem;
+    uint8_t* smemB = smem + (size_t)p.h_sa * a_item;     // 51200 * h_sa is a multiple of 1024
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smemB + (size_t)p.h_sb * b_stage);
+    uint64_t* fullA = bars;
+    uint64_t* emptyA = fullA + p.h_sa;
+    uint64_t* fullB = emptyA + p.h_sa;
+    uint64_t* emptyB = fullB + p.h_sb;
+    uint64_t* tmem_full = emptyB + p.h_sb;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int tile = blockIdx.x;
+    const int tw = tile % p.tiles_w; tile /= p.tiles_w;
+    const int th = tile % p.tiles_h; const int b = tile / p.tiles_h;
+    const int w0 = tw * TC_TW, h0 = th * TC_TH;
+    const int n0 = blockIdx.y * p.BN;
+    const int cchunks = p.cin_pad / 64;
+    const int items = p.h_mode == 2 ? cchunks : cchunks * 3;
+    const int KB = items * p.h_taps;                      // = 9 * cchunks
+    const int NC = (KB + p.chunk - 1) / p.chunk;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.h_sa; ++s) { mbar_init(&fullA[s], 1); mbar_init(&emptyA[s], 1); }
+        for (int s = 0; s < p.h_sb; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ================= A producer: one halo item per 64-channel chunk (mode 2) or per (chunk, kx) (mode 1) =================
+            for (int it = 0; it < items; ++it) {
+                const int s = it % p.h_sa, ph = (it / p.h_sa) & 1;
+                mbar_wait(&emptyA[s], ph ^ 1);
+                uint8_t* st = smemA + (size_t)s * a_item;
+                if (p.h_mode == 2) {
+                    const int c0 = it * 64;
+                    mbar_expect_tx(&fullA[s], 2u * 20u * 1280u);
+                    for (int r = 0; r < 10; ++r)
+                        for (int g = 0; g < 2; ++g) {
+                            const uint32_t off = (uint32_t)r * 2560u + (uint32_t)g * 1280u;
+                            tma_load_4d(st + off, &mapA, &fullA[s], c0, w0 - 1 + 8 * g, h0 - 1 + r, b);
+                            tma_load_4d(st + TCH_PLANE + off, &mapAlo, &fullA[s], c0, w0 - 1 + 8 * g, h0 - 1 + r, b);
+                        }
+                } else {
+                    const int ch = it / 3, kx = it - ch * 3;
+                    mbar_expect_tx(&fullA[s], 2u * 20480u);
+                    tma_load_4d(st, &mapA, &fullA[s], ch * 64, w0 - 1 + kx, h0 - 1, b);
+                    tma_load_4d(st + TCH_PLANE, &mapAlo, &fullA[s], ch * 64, w0 - 1 + kx, h0 - 1, b);
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty[buf])) : "memory");
         }
-        const int r = q * 32 + lane;                   // accumulator row = tile pixel
-        const int ho = h0 + r / TC_TW, wo = w0 + r % TC_TW;
-        const bool ok = ho < p.Ho && wo < p.Wo;
-        const long long pix = ((long long)b * p.Ho + ho) * p.Wo + wo;
-        float* op = p.out + pix * p.out_cs + p.out_co;
-        float* olo = p.out_lo ? p.out_lo + pix * p.out_cs + p.out_co : nullptr;
-        __half* oh = p.out_h16_hi ? reinterpret_cast<__half*>(p.out_h16_hi) + pix * p.out_cs + p.out_co : nullptr;
-        __half* ol16 = p.out_h16_lo ? reinterpret_cast<__half*>(p.out_h16_lo) + pix * p.out_cs + p.out_co : nullptr;
-        const float osc = p.out_scale;
-        const float* rp = p.res ? p.res + pix * p.res_cs + p.res_co : nullptr;
-        if (ok) {
-#pragma unroll
-            for (int g = 0; g < NG; ++g) {
-#pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    const int n = n0 + g * 32 + i;
-                    if (g * 32 + i < p.BN && n < p.Cout) {          // Cout % 4 == 0
-                        float4 a = make_float4(acc[g][i] * osc, acc[g][i + 1] * osc, acc[g][i + 2] * osc, acc[g][i + 3] * osc);
-                        if (p.bias) { float4 bb = ldg4(p.bias + n); a.x += bb.x; a.y += bb.y; a.z += bb.z; a.w += bb.w; }
-                        if (rp) { float4 rr = ldg4(rp + n); a.x += rr.x; a.y += rr.y; a.z += rr.z; a.w += rr.w; }
-                        if (p.relu) { a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f); }
-                        *reinterpret_cast<float4*>(op + n) = a;
-                        if (olo) {
-                            float4 l;
-                            l.x = a.x - __uint_as_float(__float_as_uint(a.x) & 0xFFFFE000u);
-                            l.y = a.y - __uint_as_float(__float_as_uint(a.y) & 0xFFFFE000u);
-                            l.z = a.z - __uint_as_float(__float_as_uint(a.z) & 0xFFFFE000u);
-                            l.w = a.w - __uint_as_float(__float_as_uint(a.w) & 0xFFFFE000u);
-                            *reinterpret_cast<float4*>(olo + n) = l;
-                        }
-                        if (oh) {      // fp16 hi/lo planes for the next fp16-split conv: hi = rn16(v), lo = rn16(v - hi)
-                            __half hx = __float2half_rn(a.x), hy = __float2half_rn(a.y), hz = __float2half_rn(a.z), hw = __float2half_rn(a.w);
-                            __half lx = __float2half_rn(a.x - __half2float(hx)), ly = __float2half_rn(a.y - __half2float(hy));
-                            __half lz = __float2half_rn(a.z - __half2float(hz)), lw = __float2half_rn(a.w - __half2float(hw));
-                            __half2 h01 = __halves2half2(hx, hy), h23 = __halves2half2(hz, hw), l01 = __halves2half2(lx, ly), l23 = __halves2half2(lz, lw);
-                            uint2 hv, lv;
-                            hv.x = *reinterpret_cast<uint32_t*>(&h01); hv.y = *reinterpret_cast<uint32_t*>(&h23);
-                            lv.x = *reinterpret_cast<uint32_t*>(&l01); lv.y = *reinterpret_cast<uint32_t*>(&l23);
-                            *reinterpret_cast<uint2*>(oh + n) = hv;
-                            *reinterpret_cast<uint2*>(ol16 + n) = lv;
-                        }
-                    }
-                }
+    } else if (warp == 6) {
+        if (lane == 0) {
+            // ================= B producer: one (tap, chunk) weight block per k-block =================
+            for (int kb = 0; kb < KB; ++kb) {
+                const int s = kb % p.h_sb, ph = (kb / p.h_sb) & 1;
+                mbar_wait(&emptyB[s], ph ^ 1);
+                const int it = kb / p.h_taps, t = kb - it * p.h_taps;
+                int tap, c0;
+                if (p.h_mode == 2) { tap = t; c0 = it * 64; }
+                else { const int ch = it / 3, kx = it - ch * 3; tap = t * 3 + kx; c0 = ch * 64; }
+                uint8_t* st = smemB + (size_t)s * b_stage;
+                mbar_expect_tx(&fullB[s], b_stage);
+                tma_load_2d(st, &mapWhi, &fullB[s], tap * p.cin_pad + c0, n0);
+                tma_load_2d(st + b_bytes, &mapWlo, &fullB[s], tap * p.cin_pad + c0, n0);
             }
         }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ================= MMA issuer =================
+            bool first = true;
+            for (int kb = 0; kb < KB; ++kb) {
+                const int ci = kb / p.chunk, buf = ci & 1;
+                if (kb - ci * p.chunk == 0) {
+                    mbar_wait(&tmem_empty[buf], ((ci >> 1) & 1) ^ 1);
+                    tc_fence_after();
+                    first = true;
+                }
+                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.BN);
+                const int it = kb / p.h_taps, t = kb - it * p.h_taps;
+                const int sa = it % p.h_sa, sb = kb % p.h_sb;
+                if (t == 0) mbar_wait(&fullA[sa], (it / p.h_sa) & 1);
+                mbar_wait(&fullB[sb], (kb / p.h_sb) & 1);
+                tc_fence_after();
+                uint32_t aoff;
+                if (p.h_mode == 2) { const int ky = t / 3, kx = t - ky * 3; aoff = (uint32_t)ky * p.h_rp + (uint32_t)kx * 128u; }
+                else aoff = (uint32_t)t * p.h_rp;
+                const uint32_t a0 = smem_u32(smemA + (size_t)sa * a_item) + aoff;
+                const uint32_t b0 = smem_u32(smemB + (size_t)sb * b_stage);
+                const uint64_t dA = make_sdesc(a0, p.h_sbo), dAlo = make_sdesc(a0 + TCH_PLANE, p.h_sbo);
+                const uint64_t dB = make_sdesc(b0), dBlo = make_sdesc(b0 + b_bytes);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint64_t off = (uint64_t)((k * 32) >> 4);
+                    umma_f16(d_tmem, dAlo + off, dB + off, p.idesc, first ? 0u : 1u);      // small terms first, then the main product
+                    umma_f16(d_tmem, dA + off, dBlo + off, p.idesc, 1);
+                    umma_f16(d_tmem, dA + off, dB + off, p.idesc, 1);
+                    first = false;
+                }
+                umma_commit(&emptyB[sb]);
+                if (t == p.h_taps - 1) umma_commit(&emptyA[sa]);
+                if (kb - ci * p.chunk == p.chunk - 1 || kb == KB - 1) umma_commit(&tmem_full[buf]);
+            }
+        }
+    } else {
+        tc_epilogue<NG>(p, tmem_base, tmem_full, tmem_empty, NC, warp, lane, b, h0, w0, n0);
         tc_fence_before();
     }
     __syncthreads();
@@ -363,14 +529,17 @@ static EncodeTiledFn get_encode() {
     return fn;
 }
 
-static int make_map_act(CUtensorMap* m, const void* base_v, int B, int H, int W, int C, int cs, int co, int esize = 4) {
+// `stride` > 1: TMA traversal stride (elementStrides) on W and H, so the box holds every stride-th pixel: a strided conv
+// reads exactly the 16 x 8 input pixels its 128 outputs need for one tap, densely packed in shared memory.
+static int make_map_act(CUtensorMap* m, const void* base_v, int B, int H, int W, int C, int cs, int co, int esize = 4,
+                        int box_w = TC_TW, int box_h = TC_TH, int stride = 1) {
     EncodeTiledFn enc = get_encode();
     if (!enc) { set_error("conv2d_tc: cuTensorMapEncodeTiled unavailable"); return VD3D_ECUDA; }
     const char* base = (const char*)base_v + (size_t)co * esize;
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     cuuint64_t strides[3] = {(cuuint64_t)cs * esize, (cuuint64_t)W * cs * esize, (cuuint64_t)H * W * cs * esize};
-    cuuint32_t box[4] = {(cuuint32_t)(128 / esize), TC_TW, TC_TH, 1};
-    cuuint32_t es[4] = {1, 1, 1, 1};
+    cuuint32_t box[4] = {(cuuint32_t)(128 / esize), (cuuint32_t)(box_w * stride), (cuuint32_t)(box_h * stride), 1};
+    cuuint32_t es[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
     CUresult r = enc(m, esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("conv2d_tc: cuTensorMapEncodeTiled(activation) failed: %d", (int)r); return VD3D_ECUDA; }
@@ -397,7 +566,8 @@ using namespace vd3d;
 extern "C" int vd3d_tc_pick_bn(int Cout) {
     // largest tile <= 128 that divides Cout evenly into 16-multiples; otherwise the single-tile / 64 fallbacks
     if (Cout % 128 == 0) return 128;
-    if (Cout <= 160 && Cout % 16 == 0 && Cout > 128) return Cout;
+    if (Cout <= 160 && Cout > 128) return (Cout + 15) / 16 * 16;
+    if (Cout < 128 && Cout % 16) return (Cout + 15) / 16 * 16;        // single N tile, columns >= Cout masked (weight rows beyond Cout are TMA zero fill)
     if (Cout % 96 == 0) return 96;
     if (Cout % 64 == 0) return 64;
     if (Cout % 48 == 0) return 48;
@@ -406,7 +576,7 @@ extern "C" int vd3d_tc_pick_bn(int Cout) {
 }
 
 static int conv2d_tc_launch(int f16, const void* in, const void* in_lo, int B, int H, int W, int Cin, int in_cs, int in_co,
-                            const void* w_hi, const void* w_lo, float out_scale, const float* bias, int KH, int KW, int pad, int dil,
+                            const void* w_hi, const void* w_lo, float out_scale, const float* bias, int KH, int KW, int pad, int dil, int stride,
                             const float* res, int res_cs, int res_co, float* out, float* out_lo, void* out_h16_hi, void* out_h16_lo,
                             int Cout, int out_cs, int out_co, int relu, int passes, int bn, void* stream) {
     VD3D_REQUIRE(in && w_hi && out, "conv2d_tc: null pointer");
@@ -422,8 +592,9 @@ static int conv2d_tc_launch(int f16, const void* in, const void* in_lo, int B, i
     VD3D_REQUIRE(BN % 16 == 0 && BN >= 16 && BN <= 160, "conv2d_tc: BN must be a multiple of 16 in [16, 160]");
     TcParams p;
     memset(&p, 0, sizeof(p));
-    p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.KH = KH; p.KW = KW; p.pad = pad; p.dil = dil;
-    p.Ho = H + 2 * pad - dil * (KH - 1); p.Wo = W + 2 * pad - dil * (KW - 1);
+    VD3D_REQUIRE(stride >= 1 && stride <= 4, "conv2d_tc: stride must be in [1, 4]");
+    p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.KH = KH; p.KW = KW; p.pad = pad; p.dil = dil; p.stride = stride;
+    p.Ho = (H + 2 * pad - dil * (KH - 1) - 1) / stride + 1; p.Wo = (W + 2 * pad - dil * (KW - 1) - 1) / stride + 1;
     VD3D_REQUIRE(p.Ho > 0 && p.Wo > 0, "conv2d_tc: empty output");
     p.Cout = Cout; p.BN = BN; p.passes = passes; p.f16 = f16; p.bk = bk; p.cin_pad = (Cin + bk - 1) / bk * bk; p.out_scale = out_scale;
     p.tiles_w = cdiv(p.Wo, TC_TW); p.tiles_h = cdiv(p.Ho, TC_TH);
@@ -439,6 +610,44 @@ static int conv2d_tc_launch(int f16, const void* in, const void* in_lo, int B, i
         p.chunk = e ? atoi(e) : 4;
         if (p.chunk < 1) p.chunk = 1;
     }
+    {
+        const char* e = getenv("VD3D_TC_HALO");
+        p.h_mode = e ? atoi(e) : 0;     // opt-in: measured no faster than the generic kernel (the bound is UMMA operand reads, not L2)
+        if (!(f16 && passes == 3 && KH == 3 && KW == 3 && pad == 1 && dil == 1 && stride == 1 && BN <= 128) || p.h_mode < 0 || p.h_mode > 2) p.h_mode = 0;
+    }
+    if (p.h_mode) {
+        // ---- halo kernel: A staged once per 64-channel chunk and reused by the taps ----
+        p.h_taps = p.h_mode == 2 ? 9 : 3;
+        p.h_rp = p.h_mode == 2 ? 2560u : 2048u;
+        p.h_sbo = p.h_mode == 2 ? 1280u : 1024u;
+        p.h_sa = 2;
+        const size_t a_item = 2 * (size_t)TCH_PLANE, b_stage = 2 * (size_t)BN * 128;
+        const size_t budget = 227 * 1024 - 1024 - 512 - p.h_sa * a_item;
+        p.h_sb = (int)(budget / b_stage);
+        if (p.h_sb > 8) p.h_sb = 8;
+        VD3D_REQUIRE(p.h_sb >= 2, "conv2d_tc: halo tile too large for shared memory");
+        const size_t smem = p.h_sa * a_item + p.h_sb * b_stage + (2 * p.h_sa + 2 * p.h_sb + 6) * sizeof(uint64_t) + 1024;
+        const int K = 9 * p.cin_pad;
+        CUtensorMap mA, mAlo, mWhi, mWlo;
+        int rc;
+        const int bw = p.h_mode == 2 ? 10 : 16, bh = p.h_mode == 2 ? 1 : 10;
+        if ((rc = make_map_act(&mA, in, B, H, W, Cin, in_cs, in_co, 2, bw, bh))) return rc;
+        if ((rc = make_map_act(&mAlo, in_lo, B, H, W, Cin, in_cs, in_co, 2, bw, bh))) return rc;
+        if ((rc = make_map_wgt(&mWhi, w_hi, Cout, K, BN, 2))) return rc;
+        if ((rc = make_map_wgt(&mWlo, w_lo, Cout, K, BN, 2))) return rc;
+        static bool hattr_set = false;
+        if (!hattr_set) {
+            VD3D_CUDA(cudaFuncSetAttribute(conv2d_tc_halo_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            VD3D_CUDA(cudaFuncSetAttribute(conv2d_tc_halo_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            hattr_set = true;
+        }
+        dim3 grid(p.tiles_w * p.tiles_h * B, cdiv(Cout, BN));
+        cudaStream_t st = (cudaStream_t)stream;
+        if (BN <= 64) conv2d_tc_halo_kernel<2><<<grid, TCH_THREADS, smem, st>>>(mA, mAlo, mWhi, mWlo, p);
+        else conv2d_tc_halo_kernel<4><<<grid, TCH_THREADS, smem, st>>>(mA, mAlo, mWhi, mWlo, p);
+        VD3D_CHECK_LAUNCH("conv2d_tc_halo");
+        return VD3D_OK;
+    }
     const size_t stage_bytes = 2 * (size_t)TC_A_BYTES + 2 * (size_t)BN * 128;
     int stages = (int)((200 * 1024) / stage_bytes);
     if (stages > 6) stages = 6;
@@ -448,8 +657,8 @@ static int conv2d_tc_launch(int f16, const void* in, const void* in_lo, int B, i
     const int K = KH * KW * p.cin_pad;
     CUtensorMap mA, mAlo, mWhi, mWlo;
     int rc;
-    if ((rc = make_map_act(&mA, in, B, H, W, Cin, in_cs, in_co, esize))) return rc;
-    if ((rc = make_map_act(&mAlo, in_lo ? in_lo : in, B, H, W, Cin, in_cs, in_co, esize))) return rc;
+    if ((rc = make_map_act(&mA, in, B, H, W, Cin, in_cs, in_co, esize, TC_TW, TC_TH, stride))) return rc;
+    if ((rc = make_map_act(&mAlo, in_lo ? in_lo : in, B, H, W, Cin, in_cs, in_co, esize, TC_TW, TC_TH, stride))) return rc;
     if ((rc = make_map_wgt(&mWhi, w_hi, Cout, K, BN, esize))) return rc;
     if ((rc = make_map_wgt(&mWlo, w_lo ? w_lo : w_hi, Cout, K, BN, esize))) return rc;
     static bool attr_set = false;
@@ -472,16 +681,16 @@ extern "C" int vd3d_conv2d_tc(const float* in, const float* in_lo, int B, int H,
                               const float* w_hi, const float* w_lo, const float* bias, int KH, int KW, int pad, int dil,
                               const float* res, int res_cs, int res_co,
                               float* out, float* out_lo, int Cout, int out_cs, int out_co, int relu, int passes, int bn, void* stream) {
-    return conv2d_tc_launch(0, in, in_lo, B, H, W, Cin, in_cs, in_co, w_hi, w_lo, 1.0f, bias, KH, KW, pad, dil, res, res_cs, res_co,
+    return conv2d_tc_launch(0, in, in_lo, B, H, W, Cin, in_cs, in_co, w_hi, w_lo, 1.0f, bias, KH, KW, pad, dil, 1, res, res_cs, res_co,
                             out, out_lo, nullptr, nullptr, Cout, out_cs, out_co, relu, passes, bn, stream);
 }
 
 extern "C" int vd3d_conv2d_tc16(const void* in_hi, const void* in_lo, int B, int H, int W, int Cin, int in_cs, int in_co,
                                 const void* w_hi, const void* w_lo, float out_scale, const float* bias, int KH, int KW, int pad, int dil,
-                                const float* res, int res_cs, int res_co,
+                                int stride, const float* res, int res_cs, int res_co,
                                 float* out, void* out_hi16, void* out_lo16, int Cout, int out_cs, int out_co, int relu, int passes, int bn,
                                 void* stream) {
-    return conv2d_tc_launch(1, in_hi, in_lo, B, H, W, Cin, in_cs, in_co, w_hi, w_lo, out_scale, bias, KH, KW, pad, dil, res, res_cs, res_co,
+    return conv2d_tc_launch(1, in_hi, in_lo, B, H, W, Cin, in_cs, in_co, w_hi, w_lo, out_scale, bias, KH, KW, pad, dil, stride, res, res_cs, res_co,
                             out, nullptr, out_hi16, out_lo16, Cout, out_cs, out_co, relu, passes, bn, stream);
 }
 

@@ -36,6 +36,17 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, float* __restr
     }
 }
 
+// few-channel form (images, C <= 4): one thread per pixel, plane reads and pixel writes both coalesced, no smem transpose
+__global__ void nchw_to_nhwc_small_kernel(const float* __restrict__ in, float* __restrict__ out, int C, long long HW, long long total,
+                                          int out_cs, int out_co) {
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const long long b = idx / HW, p = idx - b * HW;
+    const float* ip = in + b * C * HW + p;
+    float* op = out + idx * out_cs + out_co;
+    for (int c = 0; c < C; ++c) op[c] = __ldg(ip + (long long)c * HW);
+}
+
 __global__ void nhwc_to_nchw_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int HW, int in_cs, int in_co) {
     __shared__ float tile[32][33];
     int b = blockIdx.z;
@@ -191,6 +202,12 @@ extern "C" void vd3d_launch_count_reset(void) { g_launches = 0; }
 
 extern "C" int vd3d_nchw_to_nhwc(const float* in, float* out, int B, int C, int H, int W, int out_cs, int out_co, void* stream) {
     VD3D_REQUIRE(in && out && B > 0 && C > 0 && H > 0 && W > 0 && out_cs >= out_co + C, "nchw_to_nhwc: bad args");
+    if (C <= 4) {
+        const long long total = (long long)B * H * W;
+        nchw_to_nhwc_small_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(in, out, C, (long long)H * W, total, out_cs, out_co);
+        VD3D_CHECK_LAUNCH("nchw_to_nhwc");
+        return VD3D_OK;
+    }
     dim3 grid(cdiv((long long)H * W, 32), cdiv(C, 32), B), block(32, 8);
     nchw_to_nhwc_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(in, out, C, H * W, out_cs, out_co);
     VD3D_CHECK_LAUNCH("nchw_to_nhwc");

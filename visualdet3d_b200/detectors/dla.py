@@ -246,12 +246,16 @@ class DLARunner:
         x0 = ar.act(tag + ".in4", (B, H, W, 4), dev, zero=True)
         E.nchw_to_nhwc(img, x0)
         ys = []
-        x = self.base(x0, ar.act(tag + ".base", (B, H, W, 16), dev))
+        x = self.base(x0, ar.act(tag + ".base", (B, H, W, 16), dev, lo=_tc(self.l0)))
         if -1 in self.p.out_indices:
             ys.append(x)
-        x = self.l0(x, ar.act(tag + ".l0", (B, H, W, 16), dev))
+        if _tc(self.l0) and not _tc(self.base):
+            E.split_lo(x)
+        x = self.l0(x, ar.act(tag + ".l0", (B, H, W, 16), dev, lo=_tc(self.l1)))
         if 0 in self.p.out_indices:
             ys.append(x)
+        if _tc(self.l1) and not _tc(self.l0):
+            E.split_lo(x)
         x = self.l1(x, ar.act(tag + ".l1", (B, H // 2, W // 2, 32), dev, lo=True))
         if 1 in self.p.out_indices:
             ys.append(x)

@@ -171,7 +171,12 @@ class ConvLayer:
         self.Cin, self.Cout, self.KH, self.KW = cin_p, Cout, KH, KW
         self.stride, self.pad, self.dil, self.relu = stride, pad, dil, relu
         eng = engine or conv_engine_default()
-        eligible = stride == 1 and cin_p % 32 == 0 and Cout % 16 == 0 and str(device).startswith("cuda")
+        on_gpu = str(device).startswith("cuda")
+        if eng == "tc16":      # fp16-split engine: any stride <= 4, Cin % 8 (zero-filled up to the 64-channel k-block), Cout % 4;
+            # below 32 input channels the 64-channel k-block is mostly padding and the SIMT engine is faster
+            eligible = on_gpu and stride <= 4 and cin_p % 8 == 0 and cin_p >= 32 and Cout % 4 == 0 and Cout >= 24
+        else:
+            eligible = on_gpu and stride == 1 and cin_p % 32 == 0 and Cout % 16 == 0
         self.engine = eng if (eng in ("tc", "tc1", "tc16") and eligible) else "simt"
         self.b = b.float().to(device)
         self.w = self.w_hi = self.w_lo = None
@@ -220,7 +225,7 @@ class ConvLayer:
             xh, xl = x.h16_ptrs
             oh, ol = out.h16_ptrs
             call("vd3d_conv2d_tc16", xh, xl, x.B, x.H, x.W, x.C, x.cs, x.co, self.w_hi.data_ptr(), self.w_lo.data_ptr(), self.out_scale,
-                 self.b.data_ptr(), self.KH, self.KW, self.pad, self.dil,
+                 self.b.data_ptr(), self.KH, self.KW, self.pad, self.dil, self.stride,
                  res.ptr if res is not None else None, res.cs if res is not None else 0, res.co if res is not None else 0,
                  out.ptr, oh, ol, self.Cout, out.cs, out.co, 1 if r else 0, 3, self.bn_tile, _stream())
             return out
