@@ -296,7 +296,9 @@ def main():
         "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"kernel": "psm_cosine_nhwc_kernel<64> (scale-4 PSMCosine)", "bound": "hbm", "achieved": achieved, "peak": peak,
+        "roofline": {"kernel": ("psm_cosine_tc_kernel (scale-4 PSMCosine, tcgen05 on fp16 hi/lo planes)"
+                                if (os.environ.get("VD3D_PSM_ENGINE", "tc") == "tc" and os.environ.get("VD3D_CONV_ENGINE", "tc16") == "tc16")
+                                else "psm_cosine_nhwc_v4_kernel<64> (scale-4 PSMCosine, SIMT)"), "bound": "hbm", "achieved": achieved, "peak": peak,
                      "peak_kind": peak_kind, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                      "avg_launch_ms": psm_avg_ms, "algorithmic_bytes_per_launch": PSM4_BYTES_PER_PAIR * B, "traffic": None},
     }

@@ -117,6 +117,11 @@ int vd3d_psm_cosine_nhwc(const float* L, const float* R, int B, int H, int W, in
 /* Same op on the reference's own layout: left/right [B][C][H][W] -> cost [B][D][H][W] (op-level mirror). */
 int vd3d_psm_cosine_nchw(const float* L, const float* R, int B, int C, int H, int W, int D, float* out, void* stream);
 
+/* PSMCosine on the tensor cores (R/lib/PSM_cost_volume.py:76-91), features given as the fp16 (hi, lo) planes the tensor-core
+ * convs write (hi = rn16(v), lo = rn16(v - hi)); pixels are addressed flat (npix = B*H*W of ONE side), out[q][d] =
+ * (q mod W >= d) ? mean_c L[q][c] * R[q-d][c] : 0.   C % 64 == 0, D % 4 == 0, D <= 32; cs / co: fp16 plane pitch / offset.    */
+int vd3d_psm_cosine_h16(const void* l_hi, const void* l_lo, const void* r_hi, const void* r_lo, long long npix, int W, int C,
+                        int cs, int co, int D, float* out, int out_cs, int out_co, void* stream);
 /* CostVolume.forward after the 1x1 down_sample (R/lib/PSM_cost_volume.py:44-63): concat volume
  *   vol[b, c, i, h, w] = lf[b,h,w,c] (c < F) | rf[b,h,w-i,c-F] (c >= F)  if w >= i else 0
  * gathered on the fly (never materialised) into Conv3d(2F->F,3,pad 1)+BN3d+ReLU; then Conv3d(F->F)+BN3d+ReLU.

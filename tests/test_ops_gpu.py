@@ -292,7 +292,7 @@ TC16_EXTRA = [
     (1, 64, 17, 33, 128, 1, 0, 2),       # 1x1 stride-2 down-sample, odd sizes
     (1, 128, 20, 36, 256, 3, 1, 2),
     (1, 72, 12, 20, 72, 3, 1, 1),        # 72 channels: zero-filled up to the 64-channel k-block, Cout masked inside an 80-wide tile
-    (1, 24, 16, 32, 24, 1, 0, 1),
+    (1, 40, 16, 32, 40, 1, 0, 1),
     (1, 32, 15, 21, 64, 3, 1, 2),
 ]
 
@@ -321,3 +321,26 @@ def test_conv2d_tc16_strided_and_ragged_channels(case):
     assert err < 2e-5, err
     assert float(out.t[..., :4].min()) == 7.0 and float(out.t[..., 4 + Cout:].min()) == 7.0
     assert float(out.lo[..., :4].float().min()) == 7.0 and float(out.lo[..., 4 + Cout:].float().min()) == 7.0
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 6, 80, 24), (1, 128, 5, 37, 12), (3, 64, 3, 50, 32), (1, 64, 2, 20, 4), (2, 192, 4, 64, 8)])
+def test_psm_cosine_tensor_core_vs_oracle(shape):
+    """tensor-core PSMCosine (flat 128-pixel tiles x 160-pixel window, band extracted in the epilogue) against the oracle;
+    shapes with npix not a multiple of 128, W < D + 32, two and three 64-channel k-blocks."""
+    E = _E()
+    B, C, H, W, D = shape
+    g = torch.Generator().manual_seed(sum(shape))
+    left, right = torch.randn(B, C, H, W, generator=g), torch.randn(B, C, H, W, generator=g)
+    ref = tp.psm_cosine(left, right, D * 4, 4)
+    f = E.Act(nhwc(torch.cat([left, right])).cuda(), 0, None, torch.zeros(2, 2 * B, H, W, C, device="cuda", dtype=torch.float16))
+    out = E.Act(torch.full((B, H, W, D + 8), 7.0, device="cuda"), 4, D)
+    E.psm_cosine_stereo(f, B, D, out, planes_fresh=False)
+    got = out.to_nchw().cpu()
+    err = float((got - ref).abs().max())
+    print(shape, "max|err|", err)
+    assert err < 5e-6, err
+    assert torch.equal(got == 0, ref == 0) or float((got - ref).abs().max()) < 5e-6
+    assert float(out.t[..., :4].min()) == 7.0 and float(out.t[..., 4 + D:].min()) == 7.0
+    # the masked triangle (w < d) is exactly zero
+    for d in range(1, D):
+        assert float(got[:, d, :, :min(d, W)].abs().max()) == 0.0

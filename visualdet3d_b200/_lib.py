@@ -53,6 +53,7 @@ _SIGS = {
     "vd3d_conv2d_tc": (I, [P, P, I, I, I, I, I, I, P, P, P, I, I, I, I, P, I, I, P, P, I, I, I, I, I, I, P]),
     "vd3d_conv2d_tc16": (I, [P, P, I, I, I, I, I, I, P, P, F, P, I, I, I, I, I, P, I, I, P, P, P, I, I, I, I, I, I, P]),
     "vd3d_split_h16_nhwc": (I, [P, P, P, c_longlong, I, I, I, P]),
+    "vd3d_psm_cosine_h16": (I, [P, P, P, P, c_longlong, I, I, I, I, I, P, I, I, P]),
     "vd3d_split_lo_nhwc": (I, [P, P, c_longlong, I, I, I, P]),
     "vd3d_deform_im2col_nhwc": (I, [P, I, I, I, I, I, I, P, I, I, P, I, I, I, I, I, I, I, I, I, P, P, I, P]),
     "vd3d_boxes_overlap_bev": (I, [P, I, P, I, P, P]),

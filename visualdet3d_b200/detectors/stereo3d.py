@@ -49,7 +49,9 @@ class ResNetRunner:
                 blocks.append(d)
             self.stages.append(blocks)
 
-    def run(self, img_nchw: torch.Tensor, arena: E.Arena, tag: str = "bb") -> List[E.Act]:
+    def run(self, img_nchw: torch.Tensor, arena: E.Arena, tag: str = "bb", on_output=None) -> List[E.Act]:
+        """on_output(act, lo_stale) -> lo_stale: called as soon as a returned feature map exists, i.e. while it is still
+        L2-resident (the stereo plan launches the cost-volume kernel of that scale from it)."""
         dev = img_nchw.device
         B, _, H, W = img_nchw.shape
         x0 = arena.act(tag + ".in4", (B, H, W, 4), dev, zero=True)
@@ -58,8 +60,10 @@ class ResNetRunner:
         x = self.stem(x0, arena.act(tag + ".stem", (B, Hs, Ws, 64), dev))
         Hp, Wp = (Hs + 2 - 3) // 2 + 1, (Ws + 2 - 3) // 2 + 1
         outs = []
+        self.out_lo_stale = []             # per returned feature map: True if its tensor-core companion is not up to date
         if -1 in self.p.out_indices:
             outs.append(x)
+            self.out_lo_stale.append(True)
         x = E.maxpool3x3s2(x, arena.act(tag + ".pool", (B, Hp, Wp, 64), dev, lo=True))
         fresh = True                       # x.lo is stale (x was written by a non-tensor-core kernel)
 
@@ -99,6 +103,9 @@ class ResNetRunner:
                     fresh = c3.engine == "simt"
             if i in self.p.out_indices:
                 outs.append(x)
+                if on_output is not None:
+                    fresh = on_output(x, fresh)
+                self.out_lo_stale.append(fresh)
         self.last_lo_stale = fresh
         return outs
 
@@ -202,34 +209,43 @@ class Stereo3D(Anchor3DDetector):
         imgs = ar.get("imgs", (2 * B, 3, H, W), dev)
         imgs[:B].copy_(left)
         imgs[B:].copy_(right)
-        f4, f8, f16 = pl["backbone"].run(imgs, ar)
-        self._hook("feat4", f4), self._hook("feat8", f8), self._hook("feat16", f16)
         neck = self.core.neck
         D4, D8, D16 = neck.cost_volume_0.depth_channel, neck.cost_volume_1.depth_channel, neck.cost_volume_2.depth_channel
-        h4, w4, h8, w8, h16, w16 = f4.H, f4.W, f8.H, f8.W, f16.H, f16.W
+        h4, w4, h8, w8, h16, w16 = H // 4, W // 4, H // 8, W // 8, H // 16, W // 16
         tc = lambda layer: layer.engine != "simt"
-        # scale 4: G4 = cat[vol4 | ghost x1 | ghost x2] (72)
+        # scale 4: G4 = cat[vol4 | ghost x1 | ghost x2] (72); scale 8: G8 = cat[bb4(pool G4) | vol8 | ghost x1 | ghost x2]
         G4 = ar.act("G4", (B, h4, w4, 3 * D4), dev, lo=tc(pl["g4"].primary))
-        if self.profile_events is not None:          # bench.py: CUDA events around the dominant cost-volume kernel
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-        E.psm_cosine(f4.batch(0, B), f4.batch(B, 2 * B), D4, G4.slice(0, D4))
-        if self.profile_events is not None:
-            e1.record()
-            self.profile_events.append((e0, e1))
+        c8 = 3 * D4 + D8
+        G8 = ar.act("G8", (B, h8, w8, 3 * c8), dev, lo=tc(pl["g8"].primary))
+
+        def cost_volume_early(f: E.Act, lo_stale: bool) -> bool:
+            """PSMCosine of a scale, launched the moment the backbone has produced its features (they are still in L2)."""
+            if f.H == h4:
+                if self.profile_events is not None:          # bench.py: CUDA events around the dominant cost-volume kernel
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                refreshed = E.psm_cosine_stereo(f, B, D4, G4.slice(0, D4), planes_fresh=not lo_stale)
+                if self.profile_events is not None:
+                    e1.record()
+                    self.profile_events.append((e0, e1))
+                return lo_stale and not refreshed
+            if f.H == h8:
+                refreshed = E.psm_cosine_stereo(f, B, D8, G8.slice(3 * D4, D8), planes_fresh=not lo_stale)
+                return lo_stale and not refreshed
+            return lo_stale
+
+        f4, f8, f16 = pl["backbone"].run(imgs, ar, on_output=cost_volume_early)
+        self._hook("feat4", f4), self._hook("feat8", f8), self._hook("feat16", f16)
         self._hook("vol4", G4.slice(0, D4))
         pl["g4"].run(G4)
         c1, c2 = pl["bb4"]
         P8 = E.avgpool2(G4, ar.act("P8", (B, h8, w8, 3 * D4), dev, lo=tc(c1)))
         if tc(c1):
             E.split_lo(P8)
-        c8 = 3 * D4 + D8
-        G8 = ar.act("G8", (B, h8, w8, 3 * c8), dev, lo=tc(pl["g8"].primary))
         t = c1(P8, ar.act("T8", (B, h8, w8, 3 * D4), dev, lo=tc(c2)))
         if tc(c2) and not tc(c1):
             E.split_lo(t)
         c2(t, G8.slice(0, 3 * D4), res=P8)
-        E.psm_cosine(f8.batch(0, B), f8.batch(B, 2 * B), D8, G8.slice(3 * D4, D8))
         self._hook("vol8", G8.slice(3 * D4, D8))
         pl["g8"].run(G8)                       # refreshes lo of x = G8[0:96] itself when its primary conv is tensor-core
         c1, c2 = pl["bb8"]

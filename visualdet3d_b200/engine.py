@@ -174,7 +174,7 @@ class ConvLayer:
         on_gpu = str(device).startswith("cuda")
         if eng == "tc16":      # fp16-split engine: any stride <= 4, Cin % 8 (zero-filled up to the 64-channel k-block), Cout % 4;
             # below 32 input channels the 64-channel k-block is mostly padding and the SIMT engine is faster
-            eligible = on_gpu and stride <= 4 and cin_p % 8 == 0 and cin_p >= 32 and Cout % 4 == 0 and Cout >= 24
+            eligible = on_gpu and stride <= 4 and cin_p % 8 == 0 and cin_p >= 32 and Cout % 4 == 0 and Cout >= 16
         else:
             eligible = on_gpu and stride == 1 and cin_p % 32 == 0 and Cout % 16 == 0
         self.engine = eng if (eng in ("tc", "tc1", "tc16") and eligible) else "simt"
@@ -364,6 +364,28 @@ def psm_cosine(left: Act, right: Act, D: int, out: Act):
     call("vd3d_psm_cosine_nhwc", left.ptr, right.ptr, left.B, left.H, left.W, left.C, left.cs, left.co, D,
          out.ptr, out.cs, out.co, _stream())
     return out
+
+
+def psm_engine_default() -> str:
+    """'tc' = tensor-core PSMCosine on the fp16 (hi, lo) feature planes when they exist (default), 'simt' = fp32 SIMT kernels"""
+    import os
+    return os.environ.get("VD3D_PSM_ENGINE", "tc")
+
+
+def psm_cosine_stereo(f: Act, B: int, D: int, out: Act, planes_fresh: bool):
+    """PSMCosine between the left (batch [0, B)) and right (batch [B, 2B)) halves of one feature tensor.  Uses the tensor-core
+    kernel when `f` carries fp16 (hi, lo) planes (refreshing them first if the producer was not a tensor-core conv).
+    Returns True if it refreshed the planes of `f`."""
+    assert f.B == 2 * B and out.C == D
+    if f.h16 and psm_engine_default() == "tc" and f.C % 64 == 0 and D % 4 == 0 and D <= 32:
+        if not planes_fresh:
+            split_lo(f)
+        hi, lo = f.lo[0], f.lo[1]
+        call("vd3d_psm_cosine_h16", hi[:B].data_ptr(), lo[:B].data_ptr(), hi[B:].data_ptr(), lo[B:].data_ptr(), B * f.H * f.W, f.W, f.C,
+             f.cs, f.co, D, out.ptr, out.cs, out.co, _stream())
+        return not planes_fresh
+    psm_cosine(f.batch(0, B), f.batch(B, 2 * B), D, out)
+    return False
 
 
 def anchor_mask(anchors: torch.Tensor, means_z: torch.Tensor, P2: torch.Tensor, mask: torch.Tensor,
