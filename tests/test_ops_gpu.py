@@ -231,14 +231,26 @@ def test_conv2d_tc_3xtf32_vs_fp32(case):
     assert torch.equal(got_lo, val - _trunc13(val))
 
 
-@pytest.mark.parametrize("halo", [2, 1, 0])
+TC16_MODES = {"persistent": ("0", "1", "1"), "pair": ("0", "1", "2"), "tile": ("0", "0", "1"), "halo2": ("2", "1", "1"), "halo1": ("1", "1", "1")}
+
+
+def _tc16_mode(monkeypatch, mode):
+    """persistent: one CTA per SM looping over tiles (default); pair: persistent CTA pairs (cta_group::2, UMMA M = 256);
+    tile: one CTA per output tile (round-1 kernel); halo2 / halo1: 3x3 convs stage the input halo once per channel chunk."""
+    halo, persist, cg = TC16_MODES[mode]
+    monkeypatch.setenv("VD3D_TC_HALO", halo)
+    monkeypatch.setenv("VD3D_TC_PERSIST", persist)
+    monkeypatch.setenv("VD3D_TC_CG", cg)
+
+
+@pytest.mark.parametrize("mode", list(TC16_MODES))
 @pytest.mark.parametrize("case", TC_CASES)
-def test_conv2d_tc16_fp16split_vs_fp64(case, halo, monkeypatch):
+def test_conv2d_tc16_fp16split_vs_fp64(case, mode, monkeypatch):
     """fp16-split tensor-core conv (3 kind::f16 MMAs on (hi, lo) fp16 planes, 22 significant bits): same accuracy bar as the
     3xTF32 form, checked against an fp64 convolution; also checks the fp16 planes the epilogue writes for the next layer.
     halo = 2 / 1: 3x3 convs stage the input halo once per channel chunk (full / vertical reuse); 0: generic per-tap boxes."""
     E = _E()
-    monkeypatch.setenv("VD3D_TC_HALO", str(halo))
+    _tc16_mode(monkeypatch, mode)
     B, Cin, H, W, Cout, k, p, d, has_b, has_r, relu = case
     g = torch.Generator().manual_seed(sum(case[:6]) + 1)
     x = torch.randn(B, Cin, H, W, generator=g)
@@ -297,11 +309,13 @@ TC16_EXTRA = [
 ]
 
 
+@pytest.mark.parametrize("mode", ["persistent", "pair", "tile"])
 @pytest.mark.parametrize("case", TC16_EXTRA)
-def test_conv2d_tc16_strided_and_ragged_channels(case):
+def test_conv2d_tc16_strided_and_ragged_channels(case, mode, monkeypatch):
     """stride > 1 goes through the TMA traversal stride (every stride-th pixel lands densely in shared memory);
     channel counts that are not multiples of the 64-channel k-block / 16-column MMA granule are zero-filled / masked."""
     E = _E()
+    _tc16_mode(monkeypatch, mode)
     B, Cin, H, W, Cout, k, p, s_ = case
     g = torch.Generator().manual_seed(sum(case))
     x = torch.randn(B, Cin, H, W, generator=g)
@@ -321,6 +335,60 @@ def test_conv2d_tc16_strided_and_ragged_channels(case):
     assert err < 2e-5, err
     assert float(out.t[..., :4].min()) == 7.0 and float(out.t[..., 4 + Cout:].min()) == 7.0
     assert float(out.lo[..., :4].float().min()) == 7.0 and float(out.lo[..., 4 + Cout:].float().min()) == 7.0
+
+
+@pytest.mark.parametrize("mode", ["persistent", "pair"])
+def test_conv2d_tc16_persistent_many_tiles(mode, monkeypatch):
+    """more output tiles than SMs (every CTA loops several times, the TMA ring and the TMEM chunk buffers wrap across tiles),
+    an odd number of M tiles (the second CTA of the last pair is dead) and several N tiles; checked against the exact-fp32
+    SIMT engine of the same library."""
+    E = _E()
+    _tc16_mode(monkeypatch, mode)
+    g = torch.Generator().manual_seed(11)
+    for (B, Cin, H, W, Cout) in ((3, 64, 40, 112, 64), (1, 128, 24, 80, 384), (5, 64, 24, 48, 96)):
+        x = torch.randn(B, H, W, Cin, generator=g)
+        w = torch.randn(Cout, Cin, 3, 3, generator=g) / np.sqrt(Cin * 9)
+        b = torch.randn(Cout, generator=g)
+        r = torch.randn(B, H, W, Cout, generator=g)
+        tc = E.ConvLayer(w, b, None, pad=1, relu=True, device="cuda", engine="tc16")
+        simt = E.ConvLayer(w, b, None, pad=1, relu=True, device="cuda", engine="simt")
+        xa = E.split_lo(E.Act(x.cuda(), 0, None, torch.zeros(2, B, H, W, Cin, device="cuda", dtype=torch.float16)))
+        ra = E.Act(r.cuda())
+        ref = simt(E.Act(xa.t), E.Act(torch.empty(B, H, W, Cout, device="cuda")), res=ra).t
+        out = tc(xa, E.Act(torch.zeros(B, H, W, Cout, device="cuda"), 0, None, torch.zeros(2, B, H, W, Cout, device="cuda", dtype=torch.float16)), res=ra)
+        err = float((out.t - ref).abs().max())
+        print((B, Cin, H, W, Cout), mode, "max|tc16 - simt|", err)
+        assert err < 2e-5, err
+        hi = out.t.half()
+        assert torch.equal(out.lo[0], hi) and torch.equal(out.lo[1], (out.t - hi.float()).half())
+
+
+@pytest.mark.parametrize("mode", ["persistent", "pair"])
+@pytest.mark.parametrize("shape", [(2, 3, 64, 96), (1, 3, 37, 53), (3, 3, 96, 320)])
+def test_stem_tensor_core_vs_fp64(shape, mode, monkeypatch):
+    """conv1 7x7 stride 2 + BN + ReLU (R/backbones/resnet.py:120-122) through the row-window tensor-core path
+    (image -> zero-padded fp16 row planes -> KHx1 conv over 64 virtual channels) against an fp64 convolution."""
+    E = _E()
+    _tc16_mode(monkeypatch, mode)
+    B, C, H, W = shape
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.randn(B, C, H, W, generator=g) * 2.0
+    w = torch.randn(64, C, 7, 7, generator=g) / np.sqrt(C * 49)
+    bn = dict(weight=torch.rand(64, generator=g) + 0.5, bias=torch.randn(64, generator=g) * 0.1,
+              running_mean=torch.randn(64, generator=g) * 0.1, running_var=torch.rand(64, generator=g) + 0.5)
+    ref64 = F.relu(F.batch_norm(F.conv2d(x.double(), w.double(), None, stride=2, padding=3), bn["running_mean"].double(), bn["running_var"].double(),
+                                bn["weight"].double(), bn["bias"].double(), False, 0.0, 1e-5))
+    layer = E.StemLayer(w, bn, stride=2, pad=3, relu=True, device="cuda")
+    Ho, Wo = layer.out_hw(H, W)
+    assert (Ho, Wo) == tuple(ref64.shape[2:])
+    arena = E.Arena("h16")
+    out = E.Act(torch.full((B, Ho, Wo, 64 + 8), 7.0, device="cuda"), 4, 64)
+    for _ in range(2):                      # second call reuses the zero-bordered row planes
+        layer(x.cuda(), out, arena, "t")
+    err = float((out.to_nchw().cpu().double() - ref64).abs().max())
+    print(shape, mode, "stem max|err| vs fp64", err)
+    assert err < 2e-5, err
+    assert float(out.t[..., :4].min()) == 7.0 and float(out.t[..., 68:].min()) == 7.0
 
 
 @pytest.mark.parametrize("shape", [(2, 64, 6, 80, 24), (1, 128, 5, 37, 12), (3, 64, 3, 50, 32), (1, 64, 2, 20, 4), (2, 192, 4, 64, 8)])

@@ -33,6 +33,8 @@ struct TcParams {
     float out_scale;         // multiplies the accumulator (undoes the power-of-two weight scaling of the fp16 path)
     void* out_h16_hi; void* out_h16_lo;
     int tiles_w, tiles_h;
+    int stride_w, pad_w;     // W-direction stride / padding (the H direction uses stride / pad); equal to them for ordinary convs
+    int m_tiles, n_tiles;    // persistent kernel: tile counts along M (B * tiles_h * tiles_w) and N
     int out_cs, out_co, res_cs, res_co, relu;
     const float* bias; const float* res; float* out; float* out_lo;
     uint32_t idesc;
@@ -394,6 +396,234 @@ conv2d_tc_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
     }
 }
 
+// ----------------------------------------------------------------------------------------------------------------
+// Persistent kernel (fp16 hi/lo operands; the default engine).
+//
+// One CTA per SM (CG = 1) or one CTA pair per TPC (CG = 2: cta_group::2, UMMA M = 256, every CTA stages its own 128
+// pixels of A and HALF of the weight tile, so the tensor core of each SM reads 6 KB instead of 8 KB of operands per
+// MMA and the TMA writes 48 KB instead of 64 KB per k-block: the kernel is shared-memory-bandwidth bound).
+// Tiles are taken round-robin (M fastest, so concurrently running CTAs share one weight tile in L2).  The TMA->MMA
+// ring and the chunked TMEM promotion run across tile boundaries: while the eight epilogue warps write tile i to
+// global memory the MMA warp is already accumulating the first two chunks of tile i+1.
+// Warp roles: 0 = TMA producer, 1 = MMA issuer (leader CTA only) + TMEM owner, 2..9 = epilogue; epilogue warp e works
+// on TMEM lane quadrant (warp % 4) and on column half e / 4 of the BN accumulator columns.
+// ----------------------------------------------------------------------------------------------------------------
+constexpr int TCP_THREADS = 320;
+#ifndef VD3D_TC_CG_DEFAULT
+#define VD3D_TC_CG_DEFAULT 1
+#endif
+
+template <int NG16, int CG>   // NG16 = 16-column groups per epilogue thread (>= ceil(BN / 32)); CG = CTAs per MMA (1 or 2)
+__global__ void __launch_bounds__(TCP_THREADS, 1)
+conv2d_tcp_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapAlo,
+                  const __grid_constant__ CUtensorMap mapWhi, const __grid_constant__ CUtensorMap mapWlo, const TcParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t bnl = (uint32_t)p.BN / CG;                      // weight rows staged by this CTA
+    const uint32_t b_bytes = bnl * 128u;
+    const uint32_t stage_bytes = 2u * TC_A_BYTES + 2u * b_bytes;   // [A hi | A lo | W hi | W lo]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+    uint64_t* full = bars;                        // [stages]  TMA -> MMA (leader's copy is the live one when CG = 2)
+    uint64_t* empty = bars + p.stages;            // [stages]  MMA -> TMA (multicast to both CTAs)
+    uint64_t* tmem_full = bars + 2 * p.stages;    // [2]       MMA -> epilogue (multicast)
+    uint64_t* tmem_empty = tmem_full + 2;         // [2]       epilogue -> MMA (leader's copy, 8 * CG arrivals)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
+    const int cchunks = p.cin_pad / 64;
+    const int KB = p.KH * p.KW * cchunks;
+    const int NC = (KB + p.chunk - 1) / p.chunk;
+    const int mt_units = (p.m_tiles + CG - 1) / CG;            // scheduling units along M (tiles or tile pairs)
+    const int units = mt_units * p.n_tiles;
+    const int u0 = (int)blockIdx.x / CG, ustep = (int)gridDim.x / CG;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 8 * CG); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {   // TMEM allocation (whole warp; with CG = 2 the same warp of both CTAs)
+        if (CG == 2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (CG == 2) cluster_sync_all();      // the peer's barriers are initialised before anything arrives on them
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ================= TMA producer (both CTAs of a pair) =================
+            int it = 0;
+            for (int u = u0; u < units; u += ustep) {
+                const int mu = u % mt_units, nt = u / mt_units;
+                int mt = mu * CG + (int)rank;
+                const bool live = mt < p.m_tiles;
+                const int tw = mt % p.tiles_w; mt /= p.tiles_w;
+                const int th = mt % p.tiles_h; const int b = live ? mt / p.tiles_h : p.B;      // dead half of an odd pair: out-of-range batch -> zero fill
+                const int wi0 = tw * TC_TW * p.stride_w - p.pad_w, hi0 = th * TC_TH * p.stride - p.pad;
+                const int n0 = nt * p.BN + (int)(rank * bnl);
+                for (int kb = 0; kb < KB; ++kb, ++it) {
+                    const int s = it % p.stages, ph = (it / p.stages) & 1;
+                    mbar_wait(&empty[s], ph ^ 1);
+                    const int tap = kb / cchunks, c0 = (kb - tap * cchunks) * 64;
+                    const int kh = tap / p.KW, kw = tap - kh * p.KW;
+                    uint8_t* st = smem + (size_t)s * stage_bytes;
+                    const int wi = wi0 + kw * p.dil, hi = hi0 + kh * p.dil;
+                    const int kcol = tap * p.cin_pad + c0;
+                    if (CG == 2) {
+                        const uint32_t lbar = mapa_shared(smem_u32(&full[s]), 0);
+                        if (rank == 0) mbar_expect_tx(&full[s], 2u * stage_bytes);
+                        tma_load_4d_2sm(st, &mapA, lbar, c0, wi, hi, b);
+                        tma_load_4d_2sm(st + TC_A_BYTES, &mapAlo, lbar, c0, wi, hi, b);
+                        tma_load_2d_2sm(st + 2 * TC_A_BYTES, &mapWhi, lbar, kcol, n0);
+                        tma_load_2d_2sm(st + 2 * TC_A_BYTES + b_bytes, &mapWlo, lbar, kcol, n0);
+                    } else {
+                        mbar_expect_tx(&full[s], stage_bytes);
+                        tma_load_4d(st, &mapA, &full[s], c0, wi, hi, b);
+                        tma_load_4d(st + TC_A_BYTES, &mapAlo, &full[s], c0, wi, hi, b);
+                        tma_load_2d(st + 2 * TC_A_BYTES, &mapWhi, &full[s], kcol, n0);
+                        tma_load_2d(st + 2 * TC_A_BYTES + b_bytes, &mapWlo, &full[s], kcol, n0);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 0) {
+            // ================= MMA issuer (leader CTA) =================
+            int it = 0, cc = 0;
+            for (int u = u0; u < units; u += ustep) {
+                int kb = 0;
+                for (int ci = 0; ci < NC; ++ci, ++cc) {
+                    const int buf = cc & 1, use = cc >> 1;
+                    mbar_wait(&tmem_empty[buf], (use & 1) ^ 1);          // every epilogue warp has promoted this buffer's previous chunk
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.BN);
+                    const int kend = min(KB, kb + p.chunk);
+                    for (bool first = true; kb < kend; ++kb, ++it) {
+                        const int s = it % p.stages, ph = (it / p.stages) & 1;
+                        mbar_wait(&full[s], ph);
+                        tc_fence_after();
+                        const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+                        const uint64_t dA = make_sdesc(sa), dAlo = make_sdesc(sa + TC_A_BYTES);
+                        const uint64_t dB = make_sdesc(sa + 2 * TC_A_BYTES), dBlo = make_sdesc(sa + 2 * TC_A_BYTES + b_bytes);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t off = (uint64_t)((k * 32) >> 4);     // one MMA K-step = 16 fp16 = 32 bytes inside the swizzle row
+                            if (CG == 2) {
+                                umma_f16_2sm(d_tmem, dAlo + off, dB + off, p.idesc, first ? 0u : 1u);      // small terms first, then the main product
+                                umma_f16_2sm(d_tmem, dA + off, dBlo + off, p.idesc, 1);
+                                umma_f16_2sm(d_tmem, dA + off, dB + off, p.idesc, 1);
+                            } else {
+                                umma_f16(d_tmem, dAlo + off, dB + off, p.idesc, first ? 0u : 1u);
+                                umma_f16(d_tmem, dA + off, dBlo + off, p.idesc, 1);
+                                umma_f16(d_tmem, dA + off, dB + off, p.idesc, 1);
+                            }
+                            first = false;
+                        }
+                        if (CG == 2) umma_commit_2sm(&empty[s]); else umma_commit(&empty[s]);       // frees the stage (in both CTAs)
+                    }
+                    if (CG == 2) umma_commit_2sm(&tmem_full[buf]); else umma_commit(&tmem_full[buf]);
+                }
+            }
+        }
+    } else {
+        // ================= epilogue warps =================
+        const int e = warp - 2, q = warp & 3, half = e >> 2;
+        const int half_cols = ((p.BN + 31) / 32) * 16;
+        const int cb = half * half_cols;                                 // first accumulator column of this thread
+        const int ncols = min(half_cols, p.BN - cb);                      // may be <= 0 for narrow tiles
+        const uint32_t te_local = smem_u32(&tmem_empty[0]);
+        const uint32_t te_leader = CG == 2 ? mapa_shared(te_local, 0) : te_local;
+        const float osc = p.out_scale;
+        int cc = 0;
+        for (int u = u0; u < units; u += ustep) {
+            float acc[NG16][16];
+#pragma unroll
+            for (int g = 0; g < NG16; ++g)
+#pragma unroll
+                for (int i = 0; i < 16; ++i) acc[g][i] = 0.f;
+            for (int ci = 0; ci < NC; ++ci, ++cc) {
+                const int buf = cc & 1, use = cc >> 1;
+                mbar_wait(&tmem_full[buf], use & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int g = 0; g < NG16; ++g) {
+                    if (g * 16 < ncols) {
+                        uint32_t v[16];
+                        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.BN + cb + g * 16), v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) acc[g][i] += __uint_as_float(v[i]);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if (CG == 2) mbar_arrive_cluster(te_leader + (uint32_t)buf * 8u);
+                    else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(te_local + (uint32_t)buf * 8u) : "memory");
+                }
+            }
+            // ---- tile output: scale / bias / residual / ReLU, fp32 value + the fp16 (hi, lo) planes ----
+            const int mu = u % mt_units, nt = u / mt_units;
+            int mt = mu * CG + (int)rank;
+            const bool live = mt < p.m_tiles;
+            const int tw = mt % p.tiles_w; mt /= p.tiles_w;
+            const int th = mt % p.tiles_h; const int b = mt / p.tiles_h;
+            const int r = q * 32 + lane;
+            const int ho = th * TC_TH + r / TC_TW, wo = tw * TC_TW + r % TC_TW;
+            if (live && ho < p.Ho && wo < p.Wo) {
+                const long long pix = ((long long)b * p.Ho + ho) * p.Wo + wo;
+                float* op = p.out + pix * p.out_cs + p.out_co;
+                __half* oh = p.out_h16_hi ? reinterpret_cast<__half*>(p.out_h16_hi) + pix * p.out_cs + p.out_co : nullptr;
+                __half* ol16 = p.out_h16_lo ? reinterpret_cast<__half*>(p.out_h16_lo) + pix * p.out_cs + p.out_co : nullptr;
+                const float* rp = p.res ? p.res + pix * p.res_cs + p.res_co : nullptr;
+                const int nbase = nt * p.BN + cb;
+#pragma unroll
+                for (int g = 0; g < NG16; ++g) {
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4) {
+                        const int n = nbase + g * 16 + i;
+                        if (g * 16 + i < ncols && n < p.Cout) {          // Cout % 4 == 0
+                            float4 a = make_float4(acc[g][i] * osc, acc[g][i + 1] * osc, acc[g][i + 2] * osc, acc[g][i + 3] * osc);
+                            if (p.bias) { float4 bb = ldg4(p.bias + n); a.x += bb.x; a.y += bb.y; a.z += bb.z; a.w += bb.w; }
+                            if (rp) { float4 rr = ldg4(rp + n); a.x += rr.x; a.y += rr.y; a.z += rr.z; a.w += rr.w; }
+                            if (p.relu) { a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f); }
+                            *reinterpret_cast<float4*>(op + n) = a;
+                            if (oh) {      // fp16 hi/lo planes for the next fp16-split conv: hi = rn16(v), lo = rn16(v - hi)
+                                __half hx = __float2half_rn(a.x), hy = __float2half_rn(a.y), hz = __float2half_rn(a.z), hw = __float2half_rn(a.w);
+                                __half lx = __float2half_rn(a.x - __half2float(hx)), ly = __float2half_rn(a.y - __half2float(hy));
+                                __half lz = __float2half_rn(a.z - __half2float(hz)), lw = __float2half_rn(a.w - __half2float(hw));
+                                __half2 h01 = __halves2half2(hx, hy), h23 = __halves2half2(hz, hw), l01 = __halves2half2(lx, ly), l23 = __halves2half2(lz, lw);
+                                uint2 hv, lv;
+                                hv.x = *reinterpret_cast<uint32_t*>(&h01); hv.y = *reinterpret_cast<uint32_t*>(&h23);
+                                lv.x = *reinterpret_cast<uint32_t*>(&l01); lv.y = *reinterpret_cast<uint32_t*>(&l23);
+                                *reinterpret_cast<uint2*>(oh + n) = hv;
+                                *reinterpret_cast<uint2*>(ol16 + n) = lv;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (CG == 2) cluster_sync_all();      // no remote arrive / multicast commit may land in a CTA that has already exited
+    if (warp == 1) {
+        tc_fence_after();
+        if (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+    }
+}
+
 // lo = v - (v & 0xFFFFE000): the part of v the tf32 MMA does not see.  Elementwise, float4, channel-slice aware.
 __global__ void split_lo_kernel(const float* __restrict__ in, float* __restrict__ lo, long long npix, int C4, int cs, int co) {
     long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -474,6 +704,59 @@ extern "C" int vd3d_tc_pick_bn(int Cout) {
     return 128;
 }
 
+// launch of the persistent kernel: p.BN / p.idesc (for M = 128) / p.tmem_cols / p.chunk / tile counts are set by the caller,
+// the weight maps have BN / CG rows per box
+static int tcp_launch(TcParams& p, const CUtensorMap& mA, const CUtensorMap& mAlo, const CUtensorMap& mWhi, const CUtensorMap& mWlo, int CG, void* stream) {
+    const int BN = p.BN;
+    const size_t stage_bytes = 2 * (size_t)TC_A_BYTES + 2 * (size_t)(BN / CG) * 128;
+    int stages = (int)((227 * 1024 - 1024 - 512) / stage_bytes);
+    if (stages > 8) stages = 8;
+    VD3D_REQUIRE(stages >= 2, "conv2d_tc: tile too large for shared memory");
+    p.stages = stages;
+    if (CG == 2) p.idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+    const size_t smem = stages * stage_bytes + (2 * stages + 6) * sizeof(uint64_t) + 1024;
+    static bool pattr_set = false;
+    if (!pattr_set) {
+#define VD3D_TCP_ATTR(NG, C) VD3D_CUDA(cudaFuncSetAttribute(conv2d_tcp_kernel<NG, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024))
+        VD3D_TCP_ATTR(2, 1); VD3D_TCP_ATTR(4, 1); VD3D_TCP_ATTR(5, 1); VD3D_TCP_ATTR(8, 1);
+        VD3D_TCP_ATTR(2, 2); VD3D_TCP_ATTR(4, 2); VD3D_TCP_ATTR(5, 2); VD3D_TCP_ATTR(8, 2);
+#undef VD3D_TCP_ATTR
+        pattr_set = true;
+    }
+    const int units = cdiv(p.m_tiles, CG) * p.n_tiles;
+    const int nsm = kNumSMs / CG;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(CG * (units < nsm ? units : nsm)));
+    cfg.blockDim = dim3(TCP_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    const int ng = (BN + 31) / 32;
+    cudaError_t le;
+#define VD3D_TCP_LAUNCH(NG, C) le = cudaLaunchKernelEx(&cfg, conv2d_tcp_kernel<NG, C>, mA, mAlo, mWhi, mWlo, p)
+    if (CG == 2) {
+        if (ng <= 2) VD3D_TCP_LAUNCH(2, 2); else if (ng <= 4) VD3D_TCP_LAUNCH(4, 2); else if (ng == 5) VD3D_TCP_LAUNCH(5, 2); else VD3D_TCP_LAUNCH(8, 2);
+    } else {
+        if (ng <= 2) VD3D_TCP_LAUNCH(2, 1); else if (ng <= 4) VD3D_TCP_LAUNCH(4, 1); else if (ng == 5) VD3D_TCP_LAUNCH(5, 1); else VD3D_TCP_LAUNCH(8, 1);
+    }
+#undef VD3D_TCP_LAUNCH
+    if (le != cudaSuccess) { set_error("conv2d_tcp: launch failed: %s", cudaGetErrorString(le)); return VD3D_ECUDA; }
+    VD3D_CHECK_LAUNCH("conv2d_tcp");
+    return VD3D_OK;
+}
+
+static void tc_env(int& persist, int& cg) {
+    // engine switches (A/B timing in tools/prof_conv.py, test parametrisation): VD3D_TC_PERSIST (default 1), VD3D_TC_CG (1 | 2)
+    const char* e = getenv("VD3D_TC_PERSIST");
+    persist = e ? atoi(e) : 1;
+    e = getenv("VD3D_TC_CG");
+    cg = e ? atoi(e) : VD3D_TC_CG_DEFAULT;
+}
+
 static int conv2d_tc_launch(int f16, const void* in, const void* in_lo, int B, int H, int W, int Cin, int in_cs, int in_co,
                             const void* w_hi, const void* w_lo, float out_scale, const float* bias, int KH, int KW, int pad, int dil, int stride,
                             const float* res, int res_cs, int res_co, float* out, float* out_lo, void* out_h16_hi, void* out_h16_lo,
@@ -488,7 +771,10 @@ static int conv2d_tc_launch(int f16, const void* in, const void* in_lo, int B, i
     VD3D_REQUIRE(((uintptr_t)in & 15) == 0 && ((uintptr_t)w_hi & 15) == 0 && ((uintptr_t)out & 15) == 0, "conv2d_tc: pointers must be 16-byte aligned");
     VD3D_REQUIRE(!out_h16_hi || (out_h16_lo && out_cs % 4 == 0), "conv2d_tc: fp16 output planes come in (hi, lo) pairs");
     int BN = bn > 0 ? bn : vd3d_tc_pick_bn(Cout);
-    VD3D_REQUIRE(BN % 16 == 0 && BN >= 16 && BN <= 160, "conv2d_tc: BN must be a multiple of 16 in [16, 160]");
+    int persist, cg_env;
+    tc_env(persist, cg_env);
+    const bool use_p = f16 && passes == 3 && persist != 0;
+    VD3D_REQUIRE(BN % 16 == 0 && BN >= 16 && BN <= (use_p ? 256 : 160), "conv2d_tc: BN must be a multiple of 16 in [16, %d]", use_p ? 256 : 160);
     TcParams p;
     memset(&p, 0, sizeof(p));
     VD3D_REQUIRE(stride >= 1 && stride <= 4, "conv2d_tc: stride must be in [1, 4]");
@@ -497,6 +783,8 @@ static int conv2d_tc_launch(int f16, const void* in, const void* in_lo, int B, i
     VD3D_REQUIRE(p.Ho > 0 && p.Wo > 0, "conv2d_tc: empty output");
     p.Cout = Cout; p.BN = BN; p.passes = passes; p.f16 = f16; p.bk = bk; p.cin_pad = (Cin + bk - 1) / bk * bk; p.out_scale = out_scale;
     p.tiles_w = cdiv(p.Wo, TC_TW); p.tiles_h = cdiv(p.Ho, TC_TH);
+    p.stride_w = stride; p.pad_w = pad;
+    p.m_tiles = p.tiles_w * p.tiles_h * B; p.n_tiles = cdiv(Cout, BN);
     p.out_cs = out_cs; p.out_co = out_co; p.res_cs = res_cs; p.res_co = res_co; p.relu = relu;
     p.bias = bias; p.res = res; p.out = out; p.out_lo = out_lo; p.out_h16_hi = out_h16_hi; p.out_h16_lo = out_h16_lo;
     // instruction descriptor (cute::UMMA::InstrDescriptor): D = f32 (1 @4), A/B format @7/@10 (tf32 = 2, f16 = 0), K-major, N>>3 @17, M>>4 @24
@@ -513,6 +801,18 @@ static int conv2d_tc_launch(int f16, const void* in, const void* in_lo, int B, i
         const char* e = getenv("VD3D_TC_HALO");
         p.h_mode = e ? atoi(e) : 0;     // opt-in: measured no faster than the generic kernel (the bound is UMMA operand reads, not L2)
         if (!(f16 && passes == 3 && KH == 3 && KW == 3 && pad == 1 && dil == 1 && stride == 1 && BN <= 128) || p.h_mode < 0 || p.h_mode > 2) p.h_mode = 0;
+    }
+    if (use_p && !p.h_mode) {
+        // ---- persistent kernel (default) ----
+        const int CG = (cg_env == 2 && BN % 32 == 0) ? 2 : 1;
+        const int K = KH * KW * p.cin_pad;
+        CUtensorMap mA, mAlo, mWhi, mWlo;
+        int rc;
+        if ((rc = make_map_act(&mA, in, B, H, W, Cin, in_cs, in_co, 2, TC_TW, TC_TH, stride))) return rc;
+        if ((rc = make_map_act(&mAlo, in_lo, B, H, W, Cin, in_cs, in_co, 2, TC_TW, TC_TH, stride))) return rc;
+        if ((rc = make_map_wgt(&mWhi, w_hi, Cout, K, BN / CG, 2))) return rc;
+        if ((rc = make_map_wgt(&mWlo, w_lo, Cout, K, BN / CG, 2))) return rc;
+        return tcp_launch(p, mA, mAlo, mWhi, mWlo, CG, stream);
     }
     if (p.h_mode) {
         // ---- halo kernel: A staged once per 64-channel chunk and reused by the taps ----
@@ -591,6 +891,101 @@ extern "C" int vd3d_conv2d_tc16(const void* in_hi, const void* in_lo, int B, int
                                 void* stream) {
     return conv2d_tc_launch(1, in_hi, in_lo, B, H, W, Cin, in_cs, in_co, w_hi, w_lo, out_scale, bias, KH, KW, pad, dil, stride, res, res_cs, res_co,
                             out, nullptr, out_hi16, out_lo16, Cout, out_cs, out_co, relu, passes, bn, stream);
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// Few-channel KHxKW convolution (the 7x7 stride-2 stem) on the tensor cores, without im2col:
+// the image is kept as fp16 (hi, lo) planes [B][H][Wp][4] (<= 4 channels per pixel, `xoff` zero pixels on the left, zeros
+// on the right).  The KW*4 <= 64 values a filter row needs for output column wo are CONTIGUOUS in that layout, starting at
+// pixel wo*stride (= wo*stride - pad + xoff with xoff == pad).  A tensor map with the overlapping W' stride of `stride`
+// pixels therefore presents the image as a virtual NHWC tensor [B][H][Wo][64] and the conv becomes a KHx1 convolution with
+// 64 "channels" (kw*4 + c; weights zero beyond KW*4) and stride (stride, 1): exactly what conv2d_tcp_kernel runs.
+// ----------------------------------------------------------------------------------------------------------------
+__global__ void image_to_h16_rows_kernel(const float* __restrict__ in, __half* __restrict__ hi, __half* __restrict__ lo, int C, int H, int W,
+                                         long long total, int Wp, int xoff) {
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const long long HW = (long long)H * W;
+    const long long b = idx / HW, pq = idx - b * HW;
+    const int y = (int)(pq / W), x = (int)(pq - (long long)y * W);
+    const float* ip = in + b * C * HW + pq;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int c = 0; c < C; ++c) v[c] = __ldg(ip + (long long)c * HW);
+    __half h[4], l[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { h[c] = __float2half_rn(v[c]); l[c] = __float2half_rn(v[c] - __half2float(h[c])); }
+    const long long o = ((b * H + y) * Wp + x + xoff) * 4;
+    __half2 h01 = __halves2half2(h[0], h[1]), h23 = __halves2half2(h[2], h[3]), l01 = __halves2half2(l[0], l[1]), l23 = __halves2half2(l[2], l[3]);
+    uint2 hv, lv;
+    hv.x = *reinterpret_cast<uint32_t*>(&h01); hv.y = *reinterpret_cast<uint32_t*>(&h23);
+    lv.x = *reinterpret_cast<uint32_t*>(&l01); lv.y = *reinterpret_cast<uint32_t*>(&l23);
+    *reinterpret_cast<uint2*>(hi + o) = hv;
+    *reinterpret_cast<uint2*>(lo + o) = lv;
+}
+
+extern "C" int vd3d_image_to_h16_rows(const float* img, int B, int C, int H, int W, void* hi16, void* lo16, int Wp, int xoff, void* stream) {
+    VD3D_REQUIRE(img && hi16 && lo16 && B > 0 && C >= 1 && C <= 4 && H > 0 && W > 0 && xoff >= 0 && Wp >= W + xoff, "image_to_h16_rows: bad args");
+    const long long total = (long long)B * H * W;
+    image_to_h16_rows_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(img, (__half*)hi16, (__half*)lo16, C, H, W, total, Wp, xoff);
+    VD3D_CHECK_LAUNCH("image_to_h16_rows");
+    return VD3D_OK;
+}
+
+extern "C" int vd3d_stem_row_pitch(int W, int KW, int stride, int pad) {
+    // pixels per padded row: left pad `pad`, the image, and enough zeros for the 16-pixel window of the last output column; even
+    const int Wo = (W + 2 * pad - KW) / stride + 1;
+    int need = stride * (Wo - 1) + 16;
+    if (need < W + pad) need = W + pad;
+    return (need + 1) / 2 * 2;
+}
+
+extern "C" int vd3d_conv2d_tc16_stem(const void* in_hi, const void* in_lo, int B, int H, int W, int Wp, int KH, int KW, int stride, int pad,
+                                     const void* w_hi, const void* w_lo, float out_scale, const float* bias,
+                                     float* out, void* out_hi16, void* out_lo16, int Cout, int out_cs, int out_co, int relu, void* stream) {
+    VD3D_REQUIRE(in_hi && in_lo && w_hi && w_lo && out, "conv2d_tc16_stem: null pointer");
+    VD3D_REQUIRE(KW >= 1 && KW <= 16 && KH >= 1 && stride >= 2 && stride <= 4 && stride % 2 == 0, "conv2d_tc16_stem: KW <= 16 and an even stride are required (got KW=%d stride=%d)", KW, stride);
+    VD3D_REQUIRE(Wp == vd3d_stem_row_pitch(W, KW, stride, pad), "conv2d_tc16_stem: row pitch %d != vd3d_stem_row_pitch() = %d", Wp, vd3d_stem_row_pitch(W, KW, stride, pad));
+    VD3D_REQUIRE(Cout % 16 == 0 && Cout <= 256 && out_cs % 4 == 0 && out_co % 4 == 0, "conv2d_tc16_stem: Cout must be a multiple of 16, <= 256");
+    VD3D_REQUIRE(((uintptr_t)in_hi & 15) == 0 && ((uintptr_t)in_lo & 15) == 0 && ((uintptr_t)w_hi & 15) == 0 && ((uintptr_t)out & 15) == 0, "conv2d_tc16_stem: pointers must be 16-byte aligned");
+    VD3D_REQUIRE(!out_hi16 || out_lo16, "conv2d_tc16_stem: fp16 output planes come in (hi, lo) pairs");
+    TcParams p;
+    memset(&p, 0, sizeof(p));
+    p.B = B; p.H = H; p.W = W; p.Cin = 64; p.KH = KH; p.KW = 1; p.pad = pad; p.dil = 1; p.stride = stride;
+    p.stride_w = 1; p.pad_w = 0;
+    p.Ho = (H + 2 * pad - KH) / stride + 1; p.Wo = (W + 2 * pad - KW) / stride + 1;
+    VD3D_REQUIRE(p.Ho > 0 && p.Wo > 0, "conv2d_tc16_stem: empty output");
+    const int BN = Cout;
+    p.Cout = Cout; p.BN = BN; p.passes = 3; p.f16 = 1; p.bk = 64; p.cin_pad = 64; p.out_scale = out_scale;
+    p.tiles_w = cdiv(p.Wo, TC_TW); p.tiles_h = cdiv(p.Ho, TC_TH);
+    p.m_tiles = p.tiles_w * p.tiles_h * B; p.n_tiles = 1;
+    p.out_cs = out_cs; p.out_co = out_co; p.relu = relu;
+    p.bias = bias; p.out = out; p.out_h16_hi = out_hi16; p.out_h16_lo = out_lo16;
+    p.idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    uint32_t cols = 32; while (cols < (uint32_t)(2 * BN)) cols <<= 1;
+    p.tmem_cols = cols;
+    p.chunk = 4;
+    int persist, cg_env;
+    tc_env(persist, cg_env);
+    const int CG = (cg_env == 2 && BN % 32 == 0) ? 2 : 1;
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { set_error("conv2d_tc16_stem: cuTensorMapEncodeTiled unavailable"); return VD3D_ECUDA; }
+    CUtensorMap mA, mAlo, mWhi, mWlo;
+    {
+        // virtual [B][H][Wo][64] view with overlapping W' stride (stride pixels = stride * 8 bytes)
+        cuuint64_t dims[4] = {64, (cuuint64_t)p.Wo, (cuuint64_t)H, (cuuint64_t)B};
+        cuuint64_t strides[3] = {(cuuint64_t)stride * 8, (cuuint64_t)Wp * 8, (cuuint64_t)H * Wp * 8};
+        cuuint32_t box[4] = {64, (cuuint32_t)TC_TW, (cuuint32_t)(TC_TH * stride), 1};
+        cuuint32_t es[4] = {1, 1, (cuuint32_t)stride, 1};
+        for (int i = 0; i < 2; ++i) {
+            CUresult r = enc(i ? &mAlo : &mA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)(i ? in_lo : in_hi), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) { set_error("conv2d_tc16_stem: cuTensorMapEncodeTiled(image) failed: %d", (int)r); return VD3D_ECUDA; }
+        }
+    }
+    int rc;
+    if ((rc = make_map_wgt(&mWhi, w_hi, Cout, KH * 64, BN / CG, 2))) return rc;
+    if ((rc = make_map_wgt(&mWlo, w_lo, Cout, KH * 64, BN / CG, 2))) return rc;
+    return tcp_launch(p, mA, mAlo, mWhi, mWlo, CG, stream);
 }
 
 extern "C" int vd3d_split_lo_nhwc(const float* in, float* lo, long long npix, int C, int cs, int co, void* stream) {

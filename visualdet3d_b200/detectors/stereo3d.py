@@ -30,6 +30,11 @@ class ResNetRunner:
     def __init__(self, p: M.ResNetP, device):
         self.p = p
         self.stem = E.ConvLayer(p.conv1.weight, None, E.bn_dict(p.bn1), stride=2, pad=3, relu=True, device=device, cin_pad=4)
+        # tensor-core stem (default with the fp16-split engine): image -> fp16 row planes -> KHx1 conv over 64 virtual channels
+        import os
+        self.stem_tc = None
+        if E.conv_engine_default() == "tc16" and os.environ.get("VD3D_STEM_TC", "1") != "0" and str(device).startswith("cuda"):
+            self.stem_tc = E.StemLayer(p.conv1.weight, E.bn_dict(p.bn1), stride=2, pad=3, relu=True, device=device)
         self.stages = []
         for i in range(p.num_stages):
             blocks = []
@@ -54,10 +59,13 @@ class ResNetRunner:
         L2-resident (the stereo plan launches the cost-volume kernel of that scale from it)."""
         dev = img_nchw.device
         B, _, H, W = img_nchw.shape
-        x0 = arena.act(tag + ".in4", (B, H, W, 4), dev, zero=True)
-        E.nchw_to_nhwc(img_nchw, x0)
         Hs, Ws = self.stem.out_hw(H, W)
-        x = self.stem(x0, arena.act(tag + ".stem", (B, Hs, Ws, 64), dev))
+        if self.stem_tc is not None:
+            x = self.stem_tc(img_nchw, arena.act(tag + ".stem", (B, Hs, Ws, 64), dev), arena, tag)
+        else:
+            x0 = arena.act(tag + ".in4", (B, H, W, 4), dev, zero=True)
+            E.nchw_to_nhwc(img_nchw, x0)
+            x = self.stem(x0, arena.act(tag + ".stem", (B, Hs, Ws, 64), dev))
         Hp, Wp = (Hs + 2 - 3) // 2 + 1, (Ws + 2 - 3) // 2 + 1
         outs = []
         self.out_lo_stale = []             # per returned feature map: True if its tensor-core companion is not up to date

@@ -241,6 +241,44 @@ class ConvLayer:
         return out
 
 
+class StemLayer:
+    """Few-channel KxK strided stem conv (conv1 7x7 s2 + BN + ReLU, R/backbones/resnet.py:120-122,186-188) on the tensor cores:
+    the NCHW image is converted straight into zero-padded fp16 (hi, lo) row planes and the conv runs as a KHx1 convolution
+    over 64 virtual channels (see conv2d_tc.cu, vd3d_conv2d_tc16_stem)."""
+
+    def __init__(self, weight, bn=None, stride=2, pad=3, relu=True, device="cuda"):
+        w, b = fold_bn(weight, None, bn)
+        Cout, Cin, KH, KW = w.shape
+        assert Cin <= 4 and KW <= 16 and stride % 2 == 0 and Cout % 16 == 0 and Cout <= 256
+        self.Cin, self.Cout, self.KH, self.KW, self.stride, self.pad, self.relu = Cin, Cout, KH, KW, stride, pad, relu
+        wk = torch.zeros(Cout, KH, 16, 4, dtype=torch.float64)
+        wk[:, :, :KW, :Cin] = w.permute(0, 2, 3, 1)
+        wmax = float(wk.abs().max())
+        k = int(np.floor(np.log2(16384.0 / wmax))) if wmax > 0 else 0
+        k = max(-24, min(24, k))
+        self.out_scale = float(2.0 ** (-k))
+        hi, lo = fp16_split(wk.reshape(Cout, KH * 64) * (2.0 ** k))
+        self.w_hi, self.w_lo = hi.to(device), lo.to(device)
+        self.b = b.float().to(device)
+
+    def out_hw(self, H, W):
+        return (H + 2 * self.pad - self.KH) // self.stride + 1, (W + 2 * self.pad - self.KW) // self.stride + 1
+
+    def __call__(self, img_nchw: torch.Tensor, out: Act, arena: "Arena", name: str):
+        _require_cuda(img_nchw, "stem")
+        x = img_nchw.contiguous().float()
+        B, C, H, W = x.shape
+        assert C == self.Cin and out.C == self.Cout
+        Wp = int(_lib.load().vd3d_stem_row_pitch(W, self.KW, self.stride, self.pad))
+        planes = arena.get(name + ".rows#h16", (2, B, H, Wp, 4), x.device, dtype=torch.float16, zero=True)   # borders stay zero
+        call("vd3d_image_to_h16_rows", x.data_ptr(), B, C, H, W, planes[0].data_ptr(), planes[1].data_ptr(), Wp, self.pad, _stream())
+        oh, ol = out.h16_ptrs
+        call("vd3d_conv2d_tc16_stem", planes[0].data_ptr(), planes[1].data_ptr(), B, H, W, Wp, self.KH, self.KW, self.stride, self.pad,
+             self.w_hi.data_ptr(), self.w_lo.data_ptr(), self.out_scale, self.b.data_ptr(), out.ptr, oh, ol, self.Cout, out.cs, out.co,
+             1 if self.relu else 0, _stream())
+        return out
+
+
 class DeformConvLayer:
     """ModulatedDeformConvPack (R/lib/ops/dcn/deform_conv.py:408-466) [+ folded BN] [+ ReLU] on NHWC activations:
     3x3 offset/mask conv (conv engine) -> deformable im2col with the mask sigmoid fused -> ONE tcgen05 1x1 GEMM over
