@@ -64,6 +64,9 @@ int vd3d_conv2d_nhwc(const float* in, int B, int H, int W, int Cin, int in_cs, i
  *   bn           : output-channel tile (multiple of 16, <= 256); 0 = vd3d_tc_pick_bn(Cout)
  * passes == 1 is plain single-pass TF32 (diagnostics only: ~1e-3 relative error, not parity-grade). */
 int vd3d_tc_pick_bn(int Cout);
+/* tile width of the persistent fp16-split engine (default of vd3d_conv2d_tc16 when bn == 0): Cout split evenly into
+ * ceil(Cout / 256) tiles of 16-column granules; tiles wider than 128 run as CTA pairs (cta_group::2, UMMA M = 256) */
+int vd3d_tc_pick_bn_persistent(int Cout);
 int vd3d_conv2d_tc(const float* in, const float* in_lo, int B, int H, int W, int Cin, int in_cs, int in_co,
                    const float* w_hi, const float* w_lo, const float* bias, int KH, int KW, int pad, int dil,
                    const float* res, int res_cs, int res_co,

@@ -231,11 +231,11 @@ def test_conv2d_tc_3xtf32_vs_fp32(case):
     assert torch.equal(got_lo, val - _trunc13(val))
 
 
-TC16_MODES = {"persistent": ("0", "1", "1"), "pair": ("0", "1", "2"), "tile": ("0", "0", "1"), "halo2": ("2", "1", "1"), "halo1": ("1", "1", "1")}
+TC16_MODES = {"auto": ("0", "1", "0"), "persistent": ("0", "1", "1"), "pair": ("0", "1", "2"), "tile": ("0", "0", "1"), "halo2": ("2", "1", "1"), "halo1": ("1", "1", "1")}
 
 
 def _tc16_mode(monkeypatch, mode):
-    """persistent: one CTA per SM looping over tiles (default); pair: persistent CTA pairs (cta_group::2, UMMA M = 256);
+    """auto (default): persistent kernel, CTA pairs for tiles wider than 128 columns; persistent: one CTA per SM looping over tiles; pair: persistent CTA pairs (cta_group::2, UMMA M = 256);
     tile: one CTA per output tile (round-1 kernel); halo2 / halo1: 3x3 convs stage the input halo once per channel chunk."""
     halo, persist, cg = TC16_MODES[mode]
     monkeypatch.setenv("VD3D_TC_HALO", halo)
@@ -309,7 +309,7 @@ TC16_EXTRA = [
 ]
 
 
-@pytest.mark.parametrize("mode", ["persistent", "pair", "tile"])
+@pytest.mark.parametrize("mode", ["auto", "persistent", "pair", "tile"])
 @pytest.mark.parametrize("case", TC16_EXTRA)
 def test_conv2d_tc16_strided_and_ragged_channels(case, mode, monkeypatch):
     """stride > 1 goes through the TMA traversal stride (every stride-th pixel lands densely in shared memory);
@@ -337,7 +337,7 @@ def test_conv2d_tc16_strided_and_ragged_channels(case, mode, monkeypatch):
     assert float(out.lo[..., :4].float().min()) == 7.0 and float(out.lo[..., 4 + Cout:].float().min()) == 7.0
 
 
-@pytest.mark.parametrize("mode", ["persistent", "pair"])
+@pytest.mark.parametrize("mode", ["auto", "persistent", "pair"])
 def test_conv2d_tc16_persistent_many_tiles(mode, monkeypatch):
     """more output tiles than SMs (every CTA loops several times, the TMA ring and the TMEM chunk buffers wrap across tiles),
     an odd number of M tiles (the second CTA of the last pair is dead) and several N tiles; checked against the exact-fp32
@@ -345,7 +345,9 @@ def test_conv2d_tc16_persistent_many_tiles(mode, monkeypatch):
     E = _E()
     _tc16_mode(monkeypatch, mode)
     g = torch.Generator().manual_seed(11)
-    for (B, Cin, H, W, Cout) in ((3, 64, 40, 112, 64), (1, 128, 24, 80, 384), (5, 64, 24, 48, 96)):
+    # Cout = 608 -> three tiles of 208 columns, the last one ragged (192 valid); 1408 -> six tiles of 240 (last 208): the head shape
+    for (B, Cin, H, W, Cout) in ((3, 64, 40, 112, 64), (1, 128, 24, 80, 384), (5, 64, 24, 48, 96), (3, 64, 24, 48, 608), (1, 64, 24, 80, 1408),
+                                 (1, 64, 17, 23, 100)):
         x = torch.randn(B, H, W, Cin, generator=g)
         w = torch.randn(Cout, Cin, 3, 3, generator=g) / np.sqrt(Cin * 9)
         b = torch.randn(Cout, generator=g)

@@ -236,3 +236,27 @@ def test_device_record_block_matches_results(det_bundle):
     if max(len(r[0]) for r in ref) > 1:
         with pytest.raises(RuntimeError):
             parallel.unpack_records(small.cpu())
+
+
+def test_streamed_pipeline_matches_forward_batch(det_bundle):
+    """visualdet3d_b200.pipeline.StreamedInference (pinned host batches, copy stream, async D2H of the record block): three
+    different batches in flight give exactly the detections of `forward_batch` on the same inputs, in submission order."""
+    from visualdet3d_b200 import synth
+    from visualdet3d_b200.pipeline import StreamedInference
+    det = det_bundle[0]
+    B, H, W = 2, 96, 320
+    pipe = StreamedInference(det, B, H, W, kmax=512)
+    batches = [synth.synth_stereo_inputs(B, H, W, seed=20 + i) for i in range(3)]
+    pinned = [(l.pin_memory(), r.pin_memory(), p.pin_memory()) for (l, r, p, _) in batches]
+    tickets = [pipe.submit(*pinned[0]), pipe.submit(*pinned[1])]
+    got = [pipe.collect(tickets[0])]
+    tickets.append(pipe.submit(*pinned[2]))
+    got += [pipe.collect(tickets[1]), pipe.collect(tickets[2])]
+    for (l, r, p, _), g in zip(batches, got):
+        with torch.no_grad():
+            ref = det.forward_batch(l.cuda(), r.cuda(), p.cuda())
+        assert len(g) == B
+        for (s, bx, c), (rs, rb, rc) in zip(g, ref):
+            assert torch.equal(s, rs.cpu()) and torch.equal(bx, rb.cpu()) and torch.equal(c, rc.cpu())
+    with pytest.raises(ValueError):
+        pipe.submit(batches[0][0], batches[0][1], batches[0][2])          # not pinned

@@ -12,7 +12,8 @@ reps = int(sys.argv[1]) if len(sys.argv) > 1 else 5
 configs = [tuple(int(v) for v in c.split(":")) for c in (sys.argv[2] if len(sys.argv) > 2 else "0:1:0,1:1:0,1:2:0").split(",")]
 SHAPES = [("head 1408->1408 @24x80 B8", 8, 24, 80, 1408, 1408, 1), ("layer1 64->64 @96x320 B16", 16, 96, 320, 64, 64, 1),
           ("layer2 128->128 @48x160 B16", 16, 48, 160, 128, 128, 1), ("layer3 256->256 @24x80 B16", 16, 24, 80, 256, 256, 1),
-          ("layer2.0 64->128 s2 @96x320 B16", 16, 96, 320, 64, 128, 2), ("odd 72->72 @47x79 B3", 3, 47, 79, 72, 72, 1)]
+          ("layer2.0 64->128 s2 @96x320 B16", 16, 96, 320, 64, 128, 2), ("odd 72->72 @47x79 B3", 3, 47, 79, 72, 72, 1),
+          ("head5 1408->1280 @24x80 B8", 8, 24, 80, 1408, 1280, 1)]
 if os.environ.get("PROF_SHAPES"):
     keep = [int(i) for i in os.environ["PROF_SHAPES"].split(",")]
     SHAPES = [SHAPES[i] for i in keep]
@@ -29,11 +30,11 @@ for name, B, H, W, Cin, Cout, stride in SHAPES:
     res = E.Act(torch.randn(B, Ho, Wo, Cout, generator=g).cuda())
     ref = ref_layer(E.Act(x.t), E.Act(torch.empty(B, Ho, Wo, Cout, device="cuda")), res=res).t
     torch.cuda.synchronize()
-    cases.append((name, B, Ho, Wo, Cin, Cout, layer, layer.bn_tile, x, res, ref))
+    cases.append((name, B, Ho, Wo, Cin, Cout, layer, 0, x, res, ref))
 for persist, cg, bn in configs:          # configs outermost: a trapping experimental config cannot hide the results of the safe ones
     os.environ["VD3D_TC_PERSIST"], os.environ["VD3D_TC_CG"] = str(persist), str(cg)
     for name, B, Ho, Wo, Cin, Cout, layer, bn0, x, res, ref in cases:
-        layer.bn_tile = bn if (bn and Cout % bn == 0) else bn0
+        layer.bn_tile = bn if bn else bn0
         out = E.Act(torch.zeros(B, Ho, Wo, Cout, device="cuda"), 0, None, torch.zeros(2, B, Ho, Wo, Cout, device="cuda", dtype=torch.float16))
         try:
             layer(x, out, res=res)
@@ -60,7 +61,7 @@ for persist, cg, bn in configs:          # configs outermost: a trapping experim
                 e1.record()
                 torch.cuda.synchronize()
                 c = smp.stop()
-                clk = f"  sustained {e0.elapsed_time(e1) / n * 1e3:8.1f} us @ {c['sm_mhz']} MHz {c['reasons']}"
+                clk = f"  sustained {e0.elapsed_time(e1) / n * 1e3:8.1f} us @ {c['sm_mhz']} MHz {c.get('power_w')} W {c['reasons']}"
             fl = 2.0 * B * Ho * Wo * Cin * Cout * 9
             print(f"{name:34s} persist={persist} cg={cg} bn={layer.bn_tile:3d}  {ms*1e3:8.1f} us  {3*fl/ms/1e9:7.1f} TF/s(x3)  max|err|={err:.2e}  planes={hl:.1e}{clk}", flush=True)
         except Exception as ex:

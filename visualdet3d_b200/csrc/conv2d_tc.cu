@@ -35,6 +35,9 @@ struct TcParams {
     int tiles_w, tiles_h;
     int stride_w, pad_w;     // W-direction stride / padding (the H direction uses stride / pad); equal to them for ordinary convs
     int m_tiles, n_tiles;    // persistent kernel: tile counts along M (B * tiles_h * tiles_w) and N
+    int cout_pad;            // Cout rounded up to 16 (ragged last N tile = cout_pad - (n_tiles - 1) * BN columns)
+    int v8;                  // output / residual / bias slices are 32-byte aligned: 256-bit global accesses
+    int dbg;                 // timing experiments only (VD3D_TC_DEBUG; results are wrong): bit 0 = one MMA per k-step, bit 1 = skip the lo-plane loads
     int out_cs, out_co, res_cs, res_co, relu;
     const float* bias; const float* res; float* out; float* out_lo;
     uint32_t idesc;
@@ -408,9 +411,37 @@ conv2d_tc_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
 // Warp roles: 0 = TMA producer, 1 = MMA issuer (leader CTA only) + TMEM owner, 2..9 = epilogue; epilogue warp e works
 // on TMEM lane quadrant (warp % 4) and on column half e / 4 of the BN accumulator columns.
 // ----------------------------------------------------------------------------------------------------------------
+// 8 consecutive channels: 256-bit global accesses when the slice is 32-byte aligned (`v8`), else two 128-bit ones
+__device__ __forceinline__ void ld8(const float* ptr, bool v8, float (&v)[8]) {
+    if (v8) {
+        asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(ptr));
+    } else {
+        const float4 a = ldg4(ptr), b = ldg4(ptr + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+}
+__device__ __forceinline__ void st8(float* ptr, bool v8, const float (&v)[8]) {
+    if (v8) {
+        asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(ptr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]),
+                     "f"(v[6]), "f"(v[7]) : "memory");
+    } else {
+        *reinterpret_cast<float4*>(ptr) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(ptr + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    }
+}
+__device__ __forceinline__ uint32_t pack_h2(__half a, __half b) { __half2 h = __halves2half2(a, b); return *reinterpret_cast<uint32_t*>(&h); }
+// fp16 (hi, lo) planes of 4 values: hi = rn16(v), lo = rn16(v - hi)
+__device__ __forceinline__ void split4(const float* v, uint2& hv, uint2& lv) {
+    __half h0 = __float2half_rn(v[0]), h1 = __float2half_rn(v[1]), h2 = __float2half_rn(v[2]), h3 = __float2half_rn(v[3]);
+    hv.x = pack_h2(h0, h1); hv.y = pack_h2(h2, h3);
+    lv.x = pack_h2(__float2half_rn(v[0] - __half2float(h0)), __float2half_rn(v[1] - __half2float(h1)));
+    lv.y = pack_h2(__float2half_rn(v[2] - __half2float(h2)), __float2half_rn(v[3] - __half2float(h3)));
+}
+
 constexpr int TCP_THREADS = 320;
 #ifndef VD3D_TC_CG_DEFAULT
-#define VD3D_TC_CG_DEFAULT 1
+#define VD3D_TC_CG_DEFAULT 0
 #endif
 
 template <int NG16, int CG>   // NG16 = 16-column groups per epilogue thread (>= ceil(BN / 32)); CG = CTAs per MMA (1 or 2)
@@ -469,7 +500,8 @@ conv2d_tcp_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                 const int tw = mt % p.tiles_w; mt /= p.tiles_w;
                 const int th = mt % p.tiles_h; const int b = live ? mt / p.tiles_h : p.B;      // dead half of an odd pair: out-of-range batch -> zero fill
                 const int wi0 = tw * TC_TW * p.stride_w - p.pad_w, hi0 = th * TC_TH * p.stride - p.pad;
-                const int n0 = nt * p.BN + (int)(rank * bnl);
+                const int nvalid = min(p.BN, p.cout_pad - nt * p.BN);                  // ragged last N tile (multiple of 16)
+                const int n0 = nt * p.BN + (int)rank * (nvalid / CG);                  // this CTA's weight rows start here (the box holds BN / CG rows)
                 for (int kb = 0; kb < KB; ++kb, ++it) {
                     const int s = it % p.stages, ph = (it / p.stages) & 1;
                     mbar_wait(&empty[s], ph ^ 1);
@@ -478,19 +510,21 @@ conv2d_tcp_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                     uint8_t* st = smem + (size_t)s * stage_bytes;
                     const int wi = wi0 + kw * p.dil, hi = hi0 + kh * p.dil;
                     const int kcol = tap * p.cin_pad + c0;
+                    const bool lo_too = !(p.dbg & 2);
+                    const uint32_t tx = lo_too ? stage_bytes : stage_bytes / 2;
                     if (CG == 2) {
                         const uint32_t lbar = mapa_shared(smem_u32(&full[s]), 0);
-                        if (rank == 0) mbar_expect_tx(&full[s], 2u * stage_bytes);
+                        if (rank == 0) mbar_expect_tx(&full[s], 2u * tx);
                         tma_load_4d_2sm(st, &mapA, lbar, c0, wi, hi, b);
-                        tma_load_4d_2sm(st + TC_A_BYTES, &mapAlo, lbar, c0, wi, hi, b);
+                        if (lo_too) tma_load_4d_2sm(st + TC_A_BYTES, &mapAlo, lbar, c0, wi, hi, b);
                         tma_load_2d_2sm(st + 2 * TC_A_BYTES, &mapWhi, lbar, kcol, n0);
-                        tma_load_2d_2sm(st + 2 * TC_A_BYTES + b_bytes, &mapWlo, lbar, kcol, n0);
+                        if (lo_too) tma_load_2d_2sm(st + 2 * TC_A_BYTES + b_bytes, &mapWlo, lbar, kcol, n0);
                     } else {
-                        mbar_expect_tx(&full[s], stage_bytes);
+                        mbar_expect_tx(&full[s], tx);
                         tma_load_4d(st, &mapA, &full[s], c0, wi, hi, b);
-                        tma_load_4d(st + TC_A_BYTES, &mapAlo, &full[s], c0, wi, hi, b);
+                        if (lo_too) tma_load_4d(st + TC_A_BYTES, &mapAlo, &full[s], c0, wi, hi, b);
                         tma_load_2d(st + 2 * TC_A_BYTES, &mapWhi, &full[s], kcol, n0);
-                        tma_load_2d(st + 2 * TC_A_BYTES + b_bytes, &mapWlo, &full[s], kcol, n0);
+                        if (lo_too) tma_load_2d(st + 2 * TC_A_BYTES + b_bytes, &mapWlo, &full[s], kcol, n0);
                     }
                 }
             }
@@ -501,6 +535,8 @@ conv2d_tcp_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             int it = 0, cc = 0;
             for (int u = u0; u < units; u += ustep) {
                 int kb = 0;
+                const int nvalid = min(p.BN, p.cout_pad - (u / mt_units) * p.BN);
+                const uint32_t idesc = (p.idesc & ~(0x3Fu << 17)) | ((uint32_t)(nvalid >> 3) << 17);      // MMA N = valid columns of this tile
                 for (int ci = 0; ci < NC; ++ci, ++cc) {
                     const int buf = cc & 1, use = cc >> 1;
                     mbar_wait(&tmem_empty[buf], (use & 1) ^ 1);          // every epilogue warp has promoted this buffer's previous chunk
@@ -517,14 +553,17 @@ conv2d_tcp_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
                             const uint64_t off = (uint64_t)((k * 32) >> 4);     // one MMA K-step = 16 fp16 = 32 bytes inside the swizzle row
-                            if (CG == 2) {
-                                umma_f16_2sm(d_tmem, dAlo + off, dB + off, p.idesc, first ? 0u : 1u);      // small terms first, then the main product
-                                umma_f16_2sm(d_tmem, dA + off, dBlo + off, p.idesc, 1);
-                                umma_f16_2sm(d_tmem, dA + off, dB + off, p.idesc, 1);
+                            if (p.dbg & 1) {
+                                if (CG == 2) umma_f16_2sm(d_tmem, dA + off, dB + off, idesc, first ? 0u : 1u);
+                                else umma_f16(d_tmem, dA + off, dB + off, idesc, first ? 0u : 1u);
+                            } else if (CG == 2) {
+                                umma_f16_2sm(d_tmem, dAlo + off, dB + off, idesc, first ? 0u : 1u);      // small terms first, then the main product
+                                umma_f16_2sm(d_tmem, dA + off, dBlo + off, idesc, 1);
+                                umma_f16_2sm(d_tmem, dA + off, dB + off, idesc, 1);
                             } else {
-                                umma_f16(d_tmem, dAlo + off, dB + off, p.idesc, first ? 0u : 1u);
-                                umma_f16(d_tmem, dA + off, dBlo + off, p.idesc, 1);
-                                umma_f16(d_tmem, dA + off, dB + off, p.idesc, 1);
+                                umma_f16(d_tmem, dAlo + off, dB + off, idesc, first ? 0u : 1u);
+                                umma_f16(d_tmem, dA + off, dBlo + off, idesc, 1);
+                                umma_f16(d_tmem, dA + off, dB + off, idesc, 1);
                             }
                             first = false;
                         }
@@ -539,12 +578,12 @@ conv2d_tcp_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         const int e = warp - 2, q = warp & 3, half = e >> 2;
         const int half_cols = ((p.BN + 31) / 32) * 16;
         const int cb = half * half_cols;                                 // first accumulator column of this thread
-        const int ncols = min(half_cols, p.BN - cb);                      // may be <= 0 for narrow tiles
         const uint32_t te_local = smem_u32(&tmem_empty[0]);
         const uint32_t te_leader = CG == 2 ? mapa_shared(te_local, 0) : te_local;
         const float osc = p.out_scale;
         int cc = 0;
         for (int u = u0; u < units; u += ustep) {
+            const int ncols = min(half_cols, min(p.BN, p.cout_pad - (u / mt_units) * p.BN) - cb);      // valid columns of this thread in this tile (<= 0: none)
             float acc[NG16][16];
 #pragma unroll
             for (int g = 0; g < NG16; ++g)
@@ -586,27 +625,69 @@ conv2d_tcp_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                 __half* ol16 = p.out_h16_lo ? reinterpret_cast<__half*>(p.out_h16_lo) + pix * p.out_cs + p.out_co : nullptr;
                 const float* rp = p.res ? p.res + pix * p.res_cs + p.res_co : nullptr;
                 const int nbase = nt * p.BN + cb;
+                const bool v8 = p.v8 != 0;
+                // batches of 16 * GB columns: all residual loads of a batch are issued before its arithmetic and stores
+                constexpr int GB = NG16 >= 8 ? 1 : 2;         // 16-column groups per batch (register budget of the widest variant)
 #pragma unroll
-                for (int g = 0; g < NG16; ++g) {
+                for (int bt = 0; bt < NG16; bt += GB) {
+                    float rr[2 * GB][8];
 #pragma unroll
-                    for (int i = 0; i < 16; i += 4) {
-                        const int n = nbase + g * 16 + i;
-                        if (g * 16 + i < ncols && n < p.Cout) {          // Cout % 4 == 0
-                            float4 a = make_float4(acc[g][i] * osc, acc[g][i + 1] * osc, acc[g][i + 2] * osc, acc[g][i + 3] * osc);
-                            if (p.bias) { float4 bb = ldg4(p.bias + n); a.x += bb.x; a.y += bb.y; a.z += bb.z; a.w += bb.w; }
-                            if (rp) { float4 rr = ldg4(rp + n); a.x += rr.x; a.y += rr.y; a.z += rr.z; a.w += rr.w; }
-                            if (p.relu) { a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f); }
-                            *reinterpret_cast<float4*>(op + n) = a;
-                            if (oh) {      // fp16 hi/lo planes for the next fp16-split conv: hi = rn16(v), lo = rn16(v - hi)
-                                __half hx = __float2half_rn(a.x), hy = __float2half_rn(a.y), hz = __float2half_rn(a.z), hw = __float2half_rn(a.w);
-                                __half lx = __float2half_rn(a.x - __half2float(hx)), ly = __float2half_rn(a.y - __half2float(hy));
-                                __half lz = __float2half_rn(a.z - __half2float(hz)), lw = __float2half_rn(a.w - __half2float(hw));
-                                __half2 h01 = __halves2half2(hx, hy), h23 = __halves2half2(hz, hw), l01 = __halves2half2(lx, ly), l23 = __halves2half2(lz, lw);
-                                uint2 hv, lv;
-                                hv.x = *reinterpret_cast<uint32_t*>(&h01); hv.y = *reinterpret_cast<uint32_t*>(&h23);
-                                lv.x = *reinterpret_cast<uint32_t*>(&l01); lv.y = *reinterpret_cast<uint32_t*>(&l23);
-                                *reinterpret_cast<uint2*>(oh + n) = hv;
-                                *reinterpret_cast<uint2*>(ol16 + n) = lv;
+                    for (int j = 0; j < 2 * GB; ++j) {
+                        const int col = bt * 16 + j * 8, n = nbase + col;
+                        if (bt + j / 2 < NG16 && rp && col < ncols && n + 8 <= p.Cout) ld8(rp + n, v8, rr[j]);
+                        else {
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) rr[j][k] = 0.f;
+                            if (bt + j / 2 < NG16 && rp && col < ncols && n + 4 <= p.Cout) {      // Cout % 8 == 4 tail
+                                const float4 t4 = ldg4(rp + n);
+                                rr[j][0] = t4.x; rr[j][1] = t4.y; rr[j][2] = t4.z; rr[j][3] = t4.w;
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 2 * GB; ++j) {
+                        if (bt + j / 2 < NG16) {
+                            const int g = bt + j / 2, i0 = (j & 1) * 8;
+                            const int col = bt * 16 + j * 8, n = nbase + col;
+                            if (col < ncols && n + 4 <= p.Cout) {
+                                const bool full8 = n + 8 <= p.Cout;
+                                float a[8];
+#pragma unroll
+                                for (int k = 0; k < 8; ++k) a[k] = acc[g][i0 + k] * osc + rr[j][k];
+                                if (p.bias) {
+                                    if (full8) {
+                                        float bb[8];
+                                        ld8(p.bias + n, v8, bb);
+#pragma unroll
+                                        for (int k = 0; k < 8; ++k) a[k] += bb[k];
+                                    } else {
+                                        const float4 b4 = ldg4(p.bias + n);
+                                        a[0] += b4.x; a[1] += b4.y; a[2] += b4.z; a[3] += b4.w;
+                                    }
+                                }
+                                if (p.relu) {
+#pragma unroll
+                                    for (int k = 0; k < 8; ++k) a[k] = fmaxf(a[k], 0.f);
+                                }
+                                if (full8) st8(op + n, v8, a);
+                                else *reinterpret_cast<float4*>(op + n) = make_float4(a[0], a[1], a[2], a[3]);
+                                if (oh) {      // fp16 hi/lo planes for the next fp16-split conv
+                                    uint2 h0, l0, h1, l1;
+                                    split4(a, h0, l0);
+                                    if (full8) {
+                                        split4(a + 4, h1, l1);
+                                        if (v8) {
+                                            *reinterpret_cast<uint4*>(oh + n) = make_uint4(h0.x, h0.y, h1.x, h1.y);
+                                            *reinterpret_cast<uint4*>(ol16 + n) = make_uint4(l0.x, l0.y, l1.x, l1.y);
+                                        } else {
+                                            *reinterpret_cast<uint2*>(oh + n) = h0; *reinterpret_cast<uint2*>(oh + n + 4) = h1;
+                                            *reinterpret_cast<uint2*>(ol16 + n) = l0; *reinterpret_cast<uint2*>(ol16 + n + 4) = l1;
+                                        }
+                                    } else {
+                                        *reinterpret_cast<uint2*>(oh + n) = h0;
+                                        *reinterpret_cast<uint2*>(ol16 + n) = l0;
+                                    }
+                                }
                             }
                         }
                     }
@@ -692,6 +773,14 @@ static int make_map_wgt(CUtensorMap* m, const void* base, int Cout, int K, int B
 
 using namespace vd3d;
 
+// persistent fp16 engine: the widest tile (<= 256) that splits Cout evenly into ceil(Cout / 256) tiles of 16-column granules;
+// tiles wider than 128 columns run as CTA pairs (cta_group::2) so that three operand stages still fit in shared memory
+extern "C" int vd3d_tc_pick_bn_persistent(int Cout) {
+    const int cp = (Cout + 15) / 16 * 16;
+    const int nt = (cp + 255) / 256;
+    return ((cp + nt - 1) / nt + 15) / 16 * 16;
+}
+
 extern "C" int vd3d_tc_pick_bn(int Cout) {
     // largest tile <= 128 that divides Cout evenly into 16-multiples; otherwise the single-tile / 64 fallbacks
     if (Cout % 128 == 0) return 128;
@@ -708,6 +797,7 @@ extern "C" int vd3d_tc_pick_bn(int Cout) {
 // the weight maps have BN / CG rows per box
 static int tcp_launch(TcParams& p, const CUtensorMap& mA, const CUtensorMap& mAlo, const CUtensorMap& mWhi, const CUtensorMap& mWlo, int CG, void* stream) {
     const int BN = p.BN;
+    { const char* e = getenv("VD3D_TC_DEBUG"); p.dbg = e ? atoi(e) : 0; }
     const size_t stage_bytes = 2 * (size_t)TC_A_BYTES + 2 * (size_t)(BN / CG) * 128;
     int stages = (int)((227 * 1024 - 1024 - 512) / stage_bytes);
     if (stages > 8) stages = 8;
@@ -770,9 +860,9 @@ static int conv2d_tc_launch(int f16, const void* in, const void* in_lo, int B, i
     VD3D_REQUIRE(!res || (res_cs % 4 == 0 && res_co % 4 == 0), "conv2d_tc: residual pitch/offset must be multiples of 4");
     VD3D_REQUIRE(((uintptr_t)in & 15) == 0 && ((uintptr_t)w_hi & 15) == 0 && ((uintptr_t)out & 15) == 0, "conv2d_tc: pointers must be 16-byte aligned");
     VD3D_REQUIRE(!out_h16_hi || (out_h16_lo && out_cs % 4 == 0), "conv2d_tc: fp16 output planes come in (hi, lo) pairs");
-    int BN = bn > 0 ? bn : vd3d_tc_pick_bn(Cout);
     int persist, cg_env;
     tc_env(persist, cg_env);
+    int BN = bn > 0 ? bn : ((f16 && passes == 3 && persist != 0) ? vd3d_tc_pick_bn_persistent(Cout) : vd3d_tc_pick_bn(Cout));
     const bool use_p = f16 && passes == 3 && persist != 0;
     VD3D_REQUIRE(BN % 16 == 0 && BN >= 16 && BN <= (use_p ? 256 : 160), "conv2d_tc: BN must be a multiple of 16 in [16, %d]", use_p ? 256 : 160);
     TcParams p;
@@ -784,7 +874,11 @@ static int conv2d_tc_launch(int f16, const void* in, const void* in_lo, int B, i
     p.Cout = Cout; p.BN = BN; p.passes = passes; p.f16 = f16; p.bk = bk; p.cin_pad = (Cin + bk - 1) / bk * bk; p.out_scale = out_scale;
     p.tiles_w = cdiv(p.Wo, TC_TW); p.tiles_h = cdiv(p.Ho, TC_TH);
     p.stride_w = stride; p.pad_w = pad;
-    p.m_tiles = p.tiles_w * p.tiles_h * B; p.n_tiles = cdiv(Cout, BN);
+    p.cout_pad = (Cout + 15) / 16 * 16;
+    p.m_tiles = p.tiles_w * p.tiles_h * B; p.n_tiles = cdiv(p.cout_pad, BN);
+    p.v8 = (out_cs % 8 == 0 && out_co % 8 == 0 && ((uintptr_t)out & 31) == 0 && (!bias || ((uintptr_t)bias & 31) == 0) &&
+            (!res || (res_cs % 8 == 0 && res_co % 8 == 0 && ((uintptr_t)res & 31) == 0)) &&
+            (!out_h16_hi || ((((uintptr_t)out_h16_hi | (uintptr_t)out_h16_lo) & 15) == 0))) ? 1 : 0;
     p.out_cs = out_cs; p.out_co = out_co; p.res_cs = res_cs; p.res_co = res_co; p.relu = relu;
     p.bias = bias; p.res = res; p.out = out; p.out_lo = out_lo; p.out_h16_hi = out_h16_hi; p.out_h16_lo = out_h16_lo;
     // instruction descriptor (cute::UMMA::InstrDescriptor): D = f32 (1 @4), A/B format @7/@10 (tf32 = 2, f16 = 0), K-major, N>>3 @17, M>>4 @24
@@ -804,7 +898,7 @@ static int conv2d_tc_launch(int f16, const void* in, const void* in_lo, int B, i
     }
     if (use_p && !p.h_mode) {
         // ---- persistent kernel (default) ----
-        const int CG = (cg_env == 2 && BN % 32 == 0) ? 2 : 1;
+        const int CG = (cg_env == 2 || (cg_env == 0 && BN > 128)) ? 2 : 1;        // VD3D_TC_CG: 0 = auto (pairs for wide tiles), 1, 2
         const int K = KH * KW * p.cin_pad;
         CUtensorMap mA, mAlo, mWhi, mWlo;
         int rc;
@@ -957,7 +1051,10 @@ extern "C" int vd3d_conv2d_tc16_stem(const void* in_hi, const void* in_lo, int B
     const int BN = Cout;
     p.Cout = Cout; p.BN = BN; p.passes = 3; p.f16 = 1; p.bk = 64; p.cin_pad = 64; p.out_scale = out_scale;
     p.tiles_w = cdiv(p.Wo, TC_TW); p.tiles_h = cdiv(p.Ho, TC_TH);
+    p.cout_pad = Cout;
     p.m_tiles = p.tiles_w * p.tiles_h * B; p.n_tiles = 1;
+    p.v8 = (out_cs % 8 == 0 && out_co % 8 == 0 && ((uintptr_t)out & 31) == 0 && (!bias || ((uintptr_t)bias & 31) == 0) &&
+            (!out_hi16 || ((((uintptr_t)out_hi16 | (uintptr_t)out_lo16) & 15) == 0))) ? 1 : 0;
     p.out_cs = out_cs; p.out_co = out_co; p.relu = relu;
     p.bias = bias; p.out = out; p.out_h16_hi = out_hi16; p.out_h16_lo = out_lo16;
     p.idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -966,7 +1063,7 @@ extern "C" int vd3d_conv2d_tc16_stem(const void* in_hi, const void* in_lo, int B
     p.chunk = 4;
     int persist, cg_env;
     tc_env(persist, cg_env);
-    const int CG = (cg_env == 2 && BN % 32 == 0) ? 2 : 1;
+    const int CG = (cg_env == 2 || (cg_env == 0 && BN > 128)) ? 2 : 1;
     EncodeTiledFn enc = get_encode();
     if (!enc) { set_error("conv2d_tc16_stem: cuTensorMapEncodeTiled unavailable"); return VD3D_ECUDA; }
     CUtensorMap mA, mAlo, mWhi, mWlo;

@@ -193,7 +193,7 @@ class ConvLayer:
             self.out_scale = float(2.0 ** (-k))
             hi, lo = fp16_split(wk.reshape(Cout, KH * KW * cin64) * (2.0 ** k))
             self.w_hi, self.w_lo = hi.to(device), lo.to(device)
-            self.bn_tile = int(_lib.load().vd3d_tc_pick_bn(Cout))
+            self.bn_tile = 0          # 0 = the library's policy for the engine in use (vd3d_tc_pick_bn_persistent / vd3d_tc_pick_bn)
         else:
             wk = w.permute(0, 2, 3, 1).reshape(Cout, KH * KW * cin_p).contiguous().float()
             hi, lo = tf32_split(wk)
