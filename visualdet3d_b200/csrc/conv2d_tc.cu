@@ -399,18 +399,6 @@ conv2d_tc_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
     }
 }
 
-// ----------------------------------------------------------------------------------------------------------------
-// Persistent kernel (fp16 hi/lo operands; the default engine).
-//
-// One CTA per SM (CG = 1) or one CTA pair per TPC (CG = 2: cta_group::2, UMMA M = 256, every CTA stages its own 128
-// pixels of A and HALF of the weight tile, so the tensor core of each SM reads 6 KB instead of 8 KB of operands per
-// MMA and the TMA writes 48 KB instead of 64 KB per k-block: the kernel is shared-memory-bandwidth bound).
-// Tiles are taken round-robin (M fastest, so concurrently running CTAs share one weight tile in L2).  The TMA->MMA
-// ring and the chunked TMEM promotion run across tile boundaries: while the eight epilogue warps write tile i to
-// global memory the MMA warp is already accumulating the first two chunks of tile i+1.
-// Warp roles: 0 = TMA producer, 1 = MMA issuer (leader CTA only) + TMEM owner, 2..9 = epilogue; epilogue warp e works
-// on TMEM lane quadrant (warp % 4) and on column half e / 4 of the BN accumulator columns.
-// ----------------------------------------------------------------------------------------------------------------
 // 8 consecutive channels: 256-bit global accesses when the slice is 32-byte aligned (`v8`), else two 128-bit ones
 __device__ __forceinline__ void ld8(const float* ptr, bool v8, float (&v)[8]) {
     if (v8) {
@@ -444,6 +432,146 @@ constexpr int TCP_THREADS = 320;
 #define VD3D_TC_CG_DEFAULT 0
 #endif
 
+// epilogue warps of the persistent kernels (warps 2..9): epilogue warp e owns TMEM lane quadrant (warp % 4) and column half e / 4.
+// Per tile: promote every accumulated chunk into registers (tcgen05.ld + round-to-nearest add), then scale / bias / residual /
+// ReLU and write the fp32 value plus the fp16 (hi, lo) planes the next tensor-core conv reads.
+template <int NG16, int CG>
+__device__ __forceinline__ void tcp_epilogue(const TcParams& p, uint32_t tmem_base, uint64_t* tmem_full, uint64_t* tmem_empty, int warp, int lane,
+                                             uint32_t rank, int NC, int u0, int ustep, int units, int mt_units) {
+    // ================= epilogue warps =================
+    const int e = warp - 2, q = warp & 3, half = e >> 2;
+    const int half_cols = ((p.BN + 31) / 32) * 16;
+    const int cb = half * half_cols;                                 // first accumulator column of this thread
+    const uint32_t te_local = smem_u32(&tmem_empty[0]);
+    const uint32_t te_leader = CG == 2 ? mapa_shared(te_local, 0) : te_local;
+    const float osc = p.out_scale;
+    int cc = 0;
+    for (int u = u0; u < units; u += ustep) {
+        const int ncols = min(half_cols, min(p.BN, p.cout_pad - (u / mt_units) * p.BN) - cb);      // valid columns of this thread in this tile (<= 0: none)
+        float acc[NG16][16];
+#pragma unroll
+        for (int g = 0; g < NG16; ++g)
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[g][i] = 0.f;
+        for (int ci = 0; ci < NC; ++ci, ++cc) {
+            const int buf = cc & 1, use = cc >> 1;
+            mbar_wait(&tmem_full[buf], use & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int g = 0; g < NG16; ++g) {
+                if (g * 16 < ncols) {
+                    uint32_t v[16];
+                    tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.BN + cb + g * 16), v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) acc[g][i] += __uint_as_float(v[i]);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if (CG == 2) mbar_arrive_cluster(te_leader + (uint32_t)buf * 8u);
+                else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(te_local + (uint32_t)buf * 8u) : "memory");
+            }
+        }
+        // ---- tile output: scale / bias / residual / ReLU, fp32 value + the fp16 (hi, lo) planes ----
+        const int mu = u % mt_units, nt = u / mt_units;
+        int mt = mu * CG + (int)rank;
+        const bool live = mt < p.m_tiles;
+        const int tw = mt % p.tiles_w; mt /= p.tiles_w;
+        const int th = mt % p.tiles_h; const int b = mt / p.tiles_h;
+        const int r = q * 32 + lane;
+        const int ho = th * TC_TH + r / TC_TW, wo = tw * TC_TW + r % TC_TW;
+        if (live && ho < p.Ho && wo < p.Wo) {
+            const long long pix = ((long long)b * p.Ho + ho) * p.Wo + wo;
+            float* op = p.out + pix * p.out_cs + p.out_co;
+            __half* oh = p.out_h16_hi ? reinterpret_cast<__half*>(p.out_h16_hi) + pix * p.out_cs + p.out_co : nullptr;
+            __half* ol16 = p.out_h16_lo ? reinterpret_cast<__half*>(p.out_h16_lo) + pix * p.out_cs + p.out_co : nullptr;
+            const float* rp = p.res ? p.res + pix * p.res_cs + p.res_co : nullptr;
+            const int nbase = nt * p.BN + cb;
+            const bool v8 = p.v8 != 0;
+            // batches of 16 * GB columns: all residual loads of a batch are issued before its arithmetic and stores
+            constexpr int GB = NG16 >= 8 ? 1 : 2;         // 16-column groups per batch (register budget of the widest variant)
+#pragma unroll
+            for (int bt = 0; bt < NG16; bt += GB) {
+                float rr[2 * GB][8];
+#pragma unroll
+                for (int j = 0; j < 2 * GB; ++j) {
+                    const int col = bt * 16 + j * 8, n = nbase + col;
+                    if (bt + j / 2 < NG16 && rp && col < ncols && n + 8 <= p.Cout) ld8(rp + n, v8, rr[j]);
+                    else {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) rr[j][k] = 0.f;
+                        if (bt + j / 2 < NG16 && rp && col < ncols && n + 4 <= p.Cout) {      // Cout % 8 == 4 tail
+                            const float4 t4 = ldg4(rp + n);
+                            rr[j][0] = t4.x; rr[j][1] = t4.y; rr[j][2] = t4.z; rr[j][3] = t4.w;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 2 * GB; ++j) {
+                    if (bt + j / 2 < NG16) {
+                        const int g = bt + j / 2, i0 = (j & 1) * 8;
+                        const int col = bt * 16 + j * 8, n = nbase + col;
+                        if (col < ncols && n + 4 <= p.Cout) {
+                            const bool full8 = n + 8 <= p.Cout;
+                            float a[8];
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) a[k] = acc[g][i0 + k] * osc + rr[j][k];
+                            if (p.bias) {
+                                if (full8) {
+                                    float bb[8];
+                                    ld8(p.bias + n, v8, bb);
+#pragma unroll
+                                    for (int k = 0; k < 8; ++k) a[k] += bb[k];
+                                } else {
+                                    const float4 b4 = ldg4(p.bias + n);
+                                    a[0] += b4.x; a[1] += b4.y; a[2] += b4.z; a[3] += b4.w;
+                                }
+                            }
+                            if (p.relu) {
+#pragma unroll
+                                for (int k = 0; k < 8; ++k) a[k] = fmaxf(a[k], 0.f);
+                            }
+                            if (full8) st8(op + n, v8, a);
+                            else *reinterpret_cast<float4*>(op + n) = make_float4(a[0], a[1], a[2], a[3]);
+                            if (oh) {      // fp16 hi/lo planes for the next fp16-split conv
+                                uint2 h0, l0, h1, l1;
+                                split4(a, h0, l0);
+                                if (full8) {
+                                    split4(a + 4, h1, l1);
+                                    if (v8) {
+                                        *reinterpret_cast<uint4*>(oh + n) = make_uint4(h0.x, h0.y, h1.x, h1.y);
+                                        *reinterpret_cast<uint4*>(ol16 + n) = make_uint4(l0.x, l0.y, l1.x, l1.y);
+                                    } else {
+                                        *reinterpret_cast<uint2*>(oh + n) = h0; *reinterpret_cast<uint2*>(oh + n + 4) = h1;
+                                        *reinterpret_cast<uint2*>(ol16 + n) = l0; *reinterpret_cast<uint2*>(ol16 + n + 4) = l1;
+                                    }
+                                } else {
+                                    *reinterpret_cast<uint2*>(oh + n) = h0;
+                                    *reinterpret_cast<uint2*>(ol16 + n) = l0;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// Persistent kernel (fp16 hi/lo operands; the default engine).
+//
+// One CTA per SM (CG = 1) or one CTA pair per TPC (CG = 2: cta_group::2, UMMA M = 256, every CTA stages its own 128
+// pixels of A and HALF of the weight tile, so the tensor core of each SM reads 6 KB instead of 8 KB of operands per
+// MMA and the TMA writes 48 KB instead of 64 KB per k-block: the kernel is shared-memory-bandwidth bound).
+// Tiles are taken round-robin (M fastest, so concurrently running CTAs share one weight tile in L2).  The TMA->MMA
+// ring and the chunked TMEM promotion run across tile boundaries: while the eight epilogue warps write tile i to
+// global memory the MMA warp is already accumulating the first two chunks of tile i+1.
+// Warp roles: 0 = TMA producer, 1 = MMA issuer (leader CTA only) + TMEM owner, 2..9 = epilogue; epilogue warp e works
+// on TMEM lane quadrant (warp % 4) and on column half e / 4 of the BN accumulator columns.
+// ----------------------------------------------------------------------------------------------------------------
 template <int NG16, int CG>   // NG16 = 16-column groups per epilogue thread (>= ceil(BN / 32)); CG = CTAs per MMA (1 or 2)
 __global__ void __launch_bounds__(TCP_THREADS, 1)
 conv2d_tcp_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapAlo,
@@ -574,130 +702,201 @@ conv2d_tcp_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             }
         }
     } else {
-        // ================= epilogue warps =================
-        const int e = warp - 2, q = warp & 3, half = e >> 2;
-        const int half_cols = ((p.BN + 31) / 32) * 16;
-        const int cb = half * half_cols;                                 // first accumulator column of this thread
-        const uint32_t te_local = smem_u32(&tmem_empty[0]);
-        const uint32_t te_leader = CG == 2 ? mapa_shared(te_local, 0) : te_local;
-        const float osc = p.out_scale;
-        int cc = 0;
-        for (int u = u0; u < units; u += ustep) {
-            const int ncols = min(half_cols, min(p.BN, p.cout_pad - (u / mt_units) * p.BN) - cb);      // valid columns of this thread in this tile (<= 0: none)
-            float acc[NG16][16];
-#pragma unroll
-            for (int g = 0; g < NG16; ++g)
-#pragma unroll
-                for (int i = 0; i < 16; ++i) acc[g][i] = 0.f;
-            for (int ci = 0; ci < NC; ++ci, ++cc) {
-                const int buf = cc & 1, use = cc >> 1;
-                mbar_wait(&tmem_full[buf], use & 1);
-                tc_fence_after();
-#pragma unroll
-                for (int g = 0; g < NG16; ++g) {
-                    if (g * 16 < ncols) {
-                        uint32_t v[16];
-                        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.BN + cb + g * 16), v);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) acc[g][i] += __uint_as_float(v[i]);
-                    }
-                }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) {
-                    if (CG == 2) mbar_arrive_cluster(te_leader + (uint32_t)buf * 8u);
-                    else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(te_local + (uint32_t)buf * 8u) : "memory");
-                }
-            }
-            // ---- tile output: scale / bias / residual / ReLU, fp32 value + the fp16 (hi, lo) planes ----
-            const int mu = u % mt_units, nt = u / mt_units;
-            int mt = mu * CG + (int)rank;
-            const bool live = mt < p.m_tiles;
-            const int tw = mt % p.tiles_w; mt /= p.tiles_w;
-            const int th = mt % p.tiles_h; const int b = mt / p.tiles_h;
-            const int r = q * 32 + lane;
-            const int ho = th * TC_TH + r / TC_TW, wo = tw * TC_TW + r % TC_TW;
-            if (live && ho < p.Ho && wo < p.Wo) {
-                const long long pix = ((long long)b * p.Ho + ho) * p.Wo + wo;
-                float* op = p.out + pix * p.out_cs + p.out_co;
-                __half* oh = p.out_h16_hi ? reinterpret_cast<__half*>(p.out_h16_hi) + pix * p.out_cs + p.out_co : nullptr;
-                __half* ol16 = p.out_h16_lo ? reinterpret_cast<__half*>(p.out_h16_lo) + pix * p.out_cs + p.out_co : nullptr;
-                const float* rp = p.res ? p.res + pix * p.res_cs + p.res_co : nullptr;
-                const int nbase = nt * p.BN + cb;
-                const bool v8 = p.v8 != 0;
-                // batches of 16 * GB columns: all residual loads of a batch are issued before its arithmetic and stores
-                constexpr int GB = NG16 >= 8 ? 1 : 2;         // 16-column groups per batch (register budget of the widest variant)
-#pragma unroll
-                for (int bt = 0; bt < NG16; bt += GB) {
-                    float rr[2 * GB][8];
-#pragma unroll
-                    for (int j = 0; j < 2 * GB; ++j) {
-                        const int col = bt * 16 + j * 8, n = nbase + col;
-                        if (bt + j / 2 < NG16 && rp && col < ncols && n + 8 <= p.Cout) ld8(rp + n, v8, rr[j]);
-                        else {
-#pragma unroll
-                            for (int k = 0; k < 8; ++k) rr[j][k] = 0.f;
-                            if (bt + j / 2 < NG16 && rp && col < ncols && n + 4 <= p.Cout) {      // Cout % 8 == 4 tail
-                                const float4 t4 = ldg4(rp + n);
-                                rr[j][0] = t4.x; rr[j][1] = t4.y; rr[j][2] = t4.z; rr[j][3] = t4.w;
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int j = 0; j < 2 * GB; ++j) {
-                        if (bt + j / 2 < NG16) {
-                            const int g = bt + j / 2, i0 = (j & 1) * 8;
-                            const int col = bt * 16 + j * 8, n = nbase + col;
-                            if (col < ncols && n + 4 <= p.Cout) {
-                                const bool full8 = n + 8 <= p.Cout;
-                                float a[8];
-#pragma unroll
-                                for (int k = 0; k < 8; ++k) a[k] = acc[g][i0 + k] * osc + rr[j][k];
-                                if (p.bias) {
-                                    if (full8) {
-                                        float bb[8];
-                                        ld8(p.bias + n, v8, bb);
-#pragma unroll
-                                        for (int k = 0; k < 8; ++k) a[k] += bb[k];
-                                    } else {
-                                        const float4 b4 = ldg4(p.bias + n);
-                                        a[0] += b4.x; a[1] += b4.y; a[2] += b4.z; a[3] += b4.w;
-                                    }
-                                }
-                                if (p.relu) {
-#pragma unroll
-                                    for (int k = 0; k < 8; ++k) a[k] = fmaxf(a[k], 0.f);
-                                }
-                                if (full8) st8(op + n, v8, a);
-                                else *reinterpret_cast<float4*>(op + n) = make_float4(a[0], a[1], a[2], a[3]);
-                                if (oh) {      // fp16 hi/lo planes for the next fp16-split conv
-                                    uint2 h0, l0, h1, l1;
-                                    split4(a, h0, l0);
-                                    if (full8) {
-                                        split4(a + 4, h1, l1);
-                                        if (v8) {
-                                            *reinterpret_cast<uint4*>(oh + n) = make_uint4(h0.x, h0.y, h1.x, h1.y);
-                                            *reinterpret_cast<uint4*>(ol16 + n) = make_uint4(l0.x, l0.y, l1.x, l1.y);
-                                        } else {
-                                            *reinterpret_cast<uint2*>(oh + n) = h0; *reinterpret_cast<uint2*>(oh + n + 4) = h1;
-                                            *reinterpret_cast<uint2*>(ol16 + n) = l0; *reinterpret_cast<uint2*>(ol16 + n + 4) = l1;
-                                        }
-                                    } else {
-                                        *reinterpret_cast<uint2*>(oh + n) = h0;
-                                        *reinterpret_cast<uint2*>(ol16 + n) = l0;
-                                    }
-                                }
-                            }
-                        }
-                    }
-                }
-            }
-        }
+        tcp_epilogue<NG16, CG>(p, tmem_base, tmem_full, tmem_empty, warp, lane, rank, NC, u0, ustep, units, mt_units);
         tc_fence_before();
     }
     __syncthreads();
     if (CG == 2) cluster_sync_all();      // no remote arrive / multicast commit may land in a CTA that has already exited
+    if (warp == 1) {
+        tc_fence_after();
+        if (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// Persistent halo kernel: 3x3 / stride 1 / pad 1 / dilation 1 convolutions (most of the network) with the A operand
+// staged ONCE per 64-channel chunk and reused by the nine taps (layout and descriptor arithmetic of conv2d_tc_halo_kernel,
+// h_mode 2), inside the persistent / paired structure of conv2d_tcp_kernel.
+//   A item  = [hi plane | lo plane], plane = [10 halo rows][2 half rows][10 px][128 B]; (row r, half g) is one TMA box
+//             {64 c, 10 w, 1 h} at pixel (w0 - 1 + 8g, h0 - 1 + r).  Tap (ky, kx) reads it through a descriptor that starts
+//             at ky*2560 + kx*128 and steps 1280 B per 8-pixel group.  200 px per chunk instead of 9 x 128.
+//   B stage = [W hi | W lo] of one (chunk, tap): BN / CG rows x 128 B each, own ring (warp 10 is its producer).
+// Operand bytes per 128 x 128 x 64 x 9-tap unit of work: 51 KB (A) + 9 x 32 KB / (CG * BN / 128) (W), against 9 x 64 KB.
+// ----------------------------------------------------------------------------------------------------------------
+constexpr int TCPH_THREADS = 352;            // warps: 0 = A producer, 1 = MMA, 2..9 = epilogue, 10 = W producer
+constexpr int TCPH_PLANE = 25600;
+constexpr int TCPH_ITEM = 2 * TCPH_PLANE;
+
+template <int NG16, int CG>
+__global__ void __launch_bounds__(TCPH_THREADS, 1)
+conv2d_tcph_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapAlo,
+                   const __grid_constant__ CUtensorMap mapWhi, const __grid_constant__ CUtensorMap mapWlo, const TcParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t bnl = (uint32_t)p.BN / CG;
+    const uint32_t b_bytes = bnl * 128u;
+    const uint32_t b_stage = 2u * b_bytes;
+    uint8_t* smemA = smem;
+    uint8_t* smemB = smem + (size_t)p.h_sa * TCPH_ITEM;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smemB + (size_t)p.h_sb * b_stage);
+    uint64_t* fullA = bars;
+    uint64_t* emptyA = fullA + p.h_sa;
+    uint64_t* fullB = emptyA + p.h_sa;
+    uint64_t* emptyB = fullB + p.h_sb;
+    uint64_t* tmem_full = emptyB + p.h_sb;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
+    const int cchunks = p.cin_pad / 64;
+    const int KB = 9 * cchunks;
+    const int NC = (KB + p.chunk - 1) / p.chunk;
+    const int mt_units = (p.m_tiles + CG - 1) / CG;
+    const int units = mt_units * p.n_tiles;
+    const int u0 = (int)blockIdx.x / CG, ustep = (int)gridDim.x / CG;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.h_sa; ++s) { mbar_init(&fullA[s], 1); mbar_init(&emptyA[s], 1); }
+        for (int s = 0; s < p.h_sb; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 8 * CG); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        if (CG == 2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (CG == 2) cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ================= A producer: one halo item per (tile, 64-channel chunk) =================
+            int it = 0;
+            for (int u = u0; u < units; u += ustep) {
+                const int mu = u % mt_units;
+                int mt = mu * CG + (int)rank;
+                const bool live = mt < p.m_tiles;
+                const int tw = mt % p.tiles_w; mt /= p.tiles_w;
+                const int th = mt % p.tiles_h; const int b = live ? mt / p.tiles_h : p.B;
+                const int w0 = tw * TC_TW, h0 = th * TC_TH;
+                for (int ch = 0; ch < cchunks; ++ch, ++it) {
+                    const int s = it % p.h_sa, ph = (it / p.h_sa) & 1;
+                    mbar_wait(&emptyA[s], ph ^ 1);
+                    uint8_t* st = smemA + (size_t)s * TCPH_ITEM;
+                    const int c0 = ch * 64;
+                    if (CG == 2) {
+                        const uint32_t lbar = mapa_shared(smem_u32(&fullA[s]), 0);
+                        if (rank == 0) mbar_expect_tx(&fullA[s], 2u * TCPH_ITEM);
+                        for (int r = 0; r < 10; ++r)
+                            for (int g = 0; g < 2; ++g) {
+                                const uint32_t off = (uint32_t)r * 2560u + (uint32_t)g * 1280u;
+                                tma_load_4d_2sm(st + off, &mapA, lbar, c0, w0 - 1 + 8 * g, h0 - 1 + r, b);
+                                tma_load_4d_2sm(st + TCPH_PLANE + off, &mapAlo, lbar, c0, w0 - 1 + 8 * g, h0 - 1 + r, b);
+                            }
+                    } else {
+                        mbar_expect_tx(&fullA[s], TCPH_ITEM);
+                        for (int r = 0; r < 10; ++r)
+                            for (int g = 0; g < 2; ++g) {
+                                const uint32_t off = (uint32_t)r * 2560u + (uint32_t)g * 1280u;
+                                tma_load_4d(st + off, &mapA, &fullA[s], c0, w0 - 1 + 8 * g, h0 - 1 + r, b);
+                                tma_load_4d(st + TCPH_PLANE + off, &mapAlo, &fullA[s], c0, w0 - 1 + 8 * g, h0 - 1 + r, b);
+                            }
+                    }
+                }
+            }
+        }
+    } else if (warp == 10) {
+        if (lane == 0) {
+            // ================= W producer: one (chunk, tap) weight block per k-block =================
+            int it = 0;
+            for (int u = u0; u < units; u += ustep) {
+                const int nt = u / mt_units;
+                const int nvalid = min(p.BN, p.cout_pad - nt * p.BN);
+                const int n0 = nt * p.BN + (int)rank * (nvalid / CG);
+                for (int kb = 0; kb < KB; ++kb, ++it) {
+                    const int s = it % p.h_sb, ph = (it / p.h_sb) & 1;
+                    mbar_wait(&emptyB[s], ph ^ 1);
+                    const int ch = kb / 9, tap = kb - ch * 9;
+                    const int kcol = tap * p.cin_pad + ch * 64;
+                    uint8_t* st = smemB + (size_t)s * b_stage;
+                    if (CG == 2) {
+                        const uint32_t lbar = mapa_shared(smem_u32(&fullB[s]), 0);
+                        if (rank == 0) mbar_expect_tx(&fullB[s], 2u * b_stage);
+                        tma_load_2d_2sm(st, &mapWhi, lbar, kcol, n0);
+                        tma_load_2d_2sm(st + b_bytes, &mapWlo, lbar, kcol, n0);
+                    } else {
+                        mbar_expect_tx(&fullB[s], b_stage);
+                        tma_load_2d(st, &mapWhi, &fullB[s], kcol, n0);
+                        tma_load_2d(st + b_bytes, &mapWlo, &fullB[s], kcol, n0);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 0) {
+            // ================= MMA issuer (leader CTA) =================
+            int ita = 0, itb = 0, cc = 0;
+            for (int u = u0; u < units; u += ustep) {
+                const int nvalid = min(p.BN, p.cout_pad - (u / mt_units) * p.BN);
+                const uint32_t idesc = (p.idesc & ~(0x3Fu << 17)) | ((uint32_t)(nvalid >> 3) << 17);
+                bool first = true;
+                for (int kb = 0; kb < KB; ++kb, ++itb) {
+                    const int ci = kb / p.chunk;
+                    const int buf = (cc + ci) & 1;
+                    if (kb - ci * p.chunk == 0) {
+                        mbar_wait(&tmem_empty[buf], (((cc + ci) >> 1) & 1) ^ 1);
+                        tc_fence_after();
+                        first = true;
+                    }
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.BN);
+                    const int ch = kb / 9, t = kb - ch * 9;
+                    const int sa = (ita + ch) % p.h_sa, sb = itb % p.h_sb;
+                    if (t == 0) mbar_wait(&fullA[sa], ((ita + ch) / p.h_sa) & 1);
+                    mbar_wait(&fullB[sb], (itb / p.h_sb) & 1);
+                    tc_fence_after();
+                    const int ky = t / 3, kx = t - ky * 3;
+                    const uint32_t a0 = smem_u32(smemA + (size_t)sa * TCPH_ITEM) + (uint32_t)ky * 2560u + (uint32_t)kx * 128u;
+                    const uint32_t b0 = smem_u32(smemB + (size_t)sb * b_stage);
+                    const uint64_t dA = make_sdesc(a0, 1280), dAlo = make_sdesc(a0 + TCPH_PLANE, 1280);
+                    const uint64_t dB = make_sdesc(b0), dBlo = make_sdesc(b0 + b_bytes);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint64_t off = (uint64_t)((k * 32) >> 4);
+                        if (CG == 2) {
+                            umma_f16_2sm(d_tmem, dAlo + off, dB + off, idesc, first ? 0u : 1u);
+                            umma_f16_2sm(d_tmem, dA + off, dBlo + off, idesc, 1);
+                            umma_f16_2sm(d_tmem, dA + off, dB + off, idesc, 1);
+                        } else {
+                            umma_f16(d_tmem, dAlo + off, dB + off, idesc, first ? 0u : 1u);
+                            umma_f16(d_tmem, dA + off, dBlo + off, idesc, 1);
+                            umma_f16(d_tmem, dA + off, dB + off, idesc, 1);
+                        }
+                        first = false;
+                    }
+                    if (CG == 2) umma_commit_2sm(&emptyB[sb]); else umma_commit(&emptyB[sb]);
+                    if (t == 8) { if (CG == 2) umma_commit_2sm(&emptyA[sa]); else umma_commit(&emptyA[sa]); }
+                    if (kb - ci * p.chunk == p.chunk - 1 || kb == KB - 1) { if (CG == 2) umma_commit_2sm(&tmem_full[buf]); else umma_commit(&tmem_full[buf]); }
+                }
+                ita += cchunks;
+                cc += NC;
+            }
+        }
+    } else {
+        tcp_epilogue<NG16, CG>(p, tmem_base, tmem_full, tmem_empty, warp, lane, rank, NC, u0, ustep, units, mt_units);
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (CG == 2) cluster_sync_all();
     if (warp == 1) {
         tc_fence_after();
         if (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
@@ -839,6 +1038,52 @@ static int tcp_launch(TcParams& p, const CUtensorMap& mA, const CUtensorMap& mAl
     return VD3D_OK;
 }
 
+// launch of the persistent halo kernel (3x3, stride 1, pad 1, dilation 1); same contract as tcp_launch, activation maps have box {64 c, 10 w, 1 h}
+static int tcph_launch(TcParams& p, const CUtensorMap& mA, const CUtensorMap& mAlo, const CUtensorMap& mWhi, const CUtensorMap& mWlo, int CG, void* stream) {
+    const int BN = p.BN;
+    { const char* e = getenv("VD3D_TC_DEBUG"); p.dbg = e ? atoi(e) : 0; }
+    const size_t b_stage = 2 * (size_t)(BN / CG) * 128;
+    p.h_sa = 2;
+    const size_t budget = 227 * 1024 - 1024 - 512 - (size_t)p.h_sa * TCPH_ITEM;
+    p.h_sb = (int)(budget / b_stage);
+    if (p.h_sb > 8) p.h_sb = 8;
+    VD3D_REQUIRE(p.h_sb >= 2, "conv2d_tc: halo tile too large for shared memory");
+    if (CG == 2) p.idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+    const size_t smem = (size_t)p.h_sa * TCPH_ITEM + (size_t)p.h_sb * b_stage + (2 * p.h_sa + 2 * p.h_sb + 6) * sizeof(uint64_t) + 1024;
+    static bool hattr_set = false;
+    if (!hattr_set) {
+#define VD3D_TCPH_ATTR(NG, C) VD3D_CUDA(cudaFuncSetAttribute(conv2d_tcph_kernel<NG, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024))
+        VD3D_TCPH_ATTR(2, 1); VD3D_TCPH_ATTR(4, 1); VD3D_TCPH_ATTR(5, 1); VD3D_TCPH_ATTR(8, 1);
+        VD3D_TCPH_ATTR(2, 2); VD3D_TCPH_ATTR(4, 2); VD3D_TCPH_ATTR(5, 2); VD3D_TCPH_ATTR(8, 2);
+#undef VD3D_TCPH_ATTR
+        hattr_set = true;
+    }
+    const int units = cdiv(p.m_tiles, CG) * p.n_tiles;
+    const int nsm = kNumSMs / CG;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(CG * (units < nsm ? units : nsm)));
+    cfg.blockDim = dim3(TCPH_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    const int ng = (BN + 31) / 32;
+    cudaError_t le;
+#define VD3D_TCPH_LAUNCH(NG, C) le = cudaLaunchKernelEx(&cfg, conv2d_tcph_kernel<NG, C>, mA, mAlo, mWhi, mWlo, p)
+    if (CG == 2) {
+        if (ng <= 2) VD3D_TCPH_LAUNCH(2, 2); else if (ng <= 4) VD3D_TCPH_LAUNCH(4, 2); else if (ng == 5) VD3D_TCPH_LAUNCH(5, 2); else VD3D_TCPH_LAUNCH(8, 2);
+    } else {
+        if (ng <= 2) VD3D_TCPH_LAUNCH(2, 1); else if (ng <= 4) VD3D_TCPH_LAUNCH(4, 1); else if (ng == 5) VD3D_TCPH_LAUNCH(5, 1); else VD3D_TCPH_LAUNCH(8, 1);
+    }
+#undef VD3D_TCPH_LAUNCH
+    if (le != cudaSuccess) { set_error("conv2d_tcph: launch failed: %s", cudaGetErrorString(le)); return VD3D_ECUDA; }
+    VD3D_CHECK_LAUNCH("conv2d_tcph");
+    return VD3D_OK;
+}
+
 static void tc_env(int& persist, int& cg) {
     // engine switches (A/B timing in tools/prof_conv.py, test parametrisation): VD3D_TC_PERSIST (default 1), VD3D_TC_CG (1 | 2)
     const char* e = getenv("VD3D_TC_PERSIST");
@@ -902,10 +1147,19 @@ static int conv2d_tc_launch(int f16, const void* in, const void* in_lo, int B, i
         const int K = KH * KW * p.cin_pad;
         CUtensorMap mA, mAlo, mWhi, mWlo;
         int rc;
-        if ((rc = make_map_act(&mA, in, B, H, W, Cin, in_cs, in_co, 2, TC_TW, TC_TH, stride))) return rc;
-        if ((rc = make_map_act(&mAlo, in_lo, B, H, W, Cin, in_cs, in_co, 2, TC_TW, TC_TH, stride))) return rc;
         if ((rc = make_map_wgt(&mWhi, w_hi, Cout, K, BN / CG, 2))) return rc;
         if ((rc = make_map_wgt(&mWlo, w_lo, Cout, K, BN / CG, 2))) return rc;
+        // VD3D_TC_PHALO=1 (opt-in): 3x3 stride-1 convs reuse the staged input halo across the nine taps.  Measured on B200: no faster
+        // than per-tap boxes (the pipeline is bound by TMA latency per stage and shared-memory bandwidth, not by L2 -> SM bytes).
+        const char* eh = getenv("VD3D_TC_PHALO");
+        const bool halo_fits = 227 * 1024 - 1024 - 512 - 2 * (size_t)TCPH_ITEM >= 2 * (2 * (size_t)(BN / CG) * 128);
+        if ((eh ? atoi(eh) : 0) != 0 && halo_fits && KH == 3 && KW == 3 && pad == 1 && dil == 1 && stride == 1) {
+            if ((rc = make_map_act(&mA, in, B, H, W, Cin, in_cs, in_co, 2, 10, 1))) return rc;
+            if ((rc = make_map_act(&mAlo, in_lo, B, H, W, Cin, in_cs, in_co, 2, 10, 1))) return rc;
+            return tcph_launch(p, mA, mAlo, mWhi, mWlo, CG, stream);
+        }
+        if ((rc = make_map_act(&mA, in, B, H, W, Cin, in_cs, in_co, 2, TC_TW, TC_TH, stride))) return rc;
+        if ((rc = make_map_act(&mAlo, in_lo, B, H, W, Cin, in_cs, in_co, 2, TC_TW, TC_TH, stride))) return rc;
         return tcp_launch(p, mA, mAlo, mWhi, mWlo, CG, stream);
     }
     if (p.h_mode) {
