@@ -94,6 +94,9 @@ int vd3d_image_to_h16_rows(const float* img_nchw, int B, int C, int H, int W, vo
 int vd3d_conv2d_tc16_stem(const void* in_hi, const void* in_lo, int B, int H, int W, int Wp, int KH, int KW, int stride, int pad,
                           const void* w_hi, const void* w_lo, float out_scale, const float* bias,
                           float* out, void* out_hi16, void* out_lo16, int Cout, int out_cs, int out_co, int relu, void* stream);
+/* Diagnostics: when set, CTA 0 of every persistent tensor-core conv writes clock64 stamps per k-block into a [5][n] int64 device
+ * buffer (0 stage free / 1 loads issued / 2 MMA thread waits / 3 stage landed / 4 MMAs issued); NULL disables (tools/trace_conv.py). */
+void vd3d_tc_set_trace(void* dev_i64, int n);
 /* fp32 channel slice -> fp16 (hi, lo) planes (producers that are not tensor-core convs). */
 int vd3d_split_h16_nhwc(const float* in, void* hi16, void* lo16, long long npix, int C, int cs, int co, void* stream);
 /* lo[pix][c] = in[pix][c] - (in[pix][c] & 0xFFFFE000) on a channel slice (producers that are not tensor-core convs). */

@@ -49,6 +49,7 @@ _SIGS = {
     "vd3d_psm_cosine_nhwc": (I, [P, P, I, I, I, I, I, I, I, P, I, I, P]),
     "vd3d_psm_cosine_nchw": (I, [P, P, I, I, I, I, I, P, P]),
     "vd3d_concat_volume_conv3d": (I, [P, P, I, I, I, I, I, P, P, P, P, P, P, I, I, P]),
+    "vd3d_tc_set_trace": (None, [P, I]),
     "vd3d_tc_pick_bn": (I, [I]),
     "vd3d_tc_pick_bn_persistent": (I, [I]),
     "vd3d_conv2d_tc": (I, [P, P, I, I, I, I, I, I, P, P, P, I, I, I, I, P, I, I, P, P, I, I, I, I, I, I, P]),

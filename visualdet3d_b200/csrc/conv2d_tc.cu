@@ -37,6 +37,7 @@ struct TcParams {
     int m_tiles, n_tiles;    // persistent kernel: tile counts along M (B * tiles_h * tiles_w) and N
     int cout_pad;            // Cout rounded up to 16 (ragged last N tile = cout_pad - (n_tiles - 1) * BN columns)
     int v8;                  // output / residual / bias slices are 32-byte aligned: 256-bit global accesses
+    long long* trace; int trace_n;   // VD3D diagnostics (vd3d_tc_set_trace): per-k-block clock64 stamps of CTA 0, [5][trace_n]
     int dbg;                 // timing experiments only (VD3D_TC_DEBUG; results are wrong): bit 0 = one MMA per k-step, bit 1 = skip the lo-plane loads
     int out_cs, out_co, res_cs, res_co, relu;
     const float* bias; const float* res; float* out; float* out_lo;
@@ -615,12 +616,14 @@ conv2d_tcp_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     __syncthreads();
     if (CG == 2) cluster_sync_all();      // the peer's barriers are initialised before anything arrives on them
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    // REDUX puts the (identical) value in a uniform register: the MMA issue loop then needs no per-instruction lane-broadcast of the
+    // accumulator address (measured: ~90 -> ~25 clk of issue time per tcgen05.mma)
+    const uint32_t tmem_base = __reduce_or_sync(0xffffffffu, *tmem_slot);
 
     if (warp == 0) {
-        if (lane == 0) {
-            // ================= TMA producer (both CTAs of a pair) =================
-            int it = 0;
+        {
+            // ================= TMA producer (both CTAs of a pair): the whole warp walks the ring, one elected lane issues =================
+            int it = 0, s = 0, ph = 0;
             for (int u = u0; u < units; u += ustep) {
                 const int mu = u % mt_units, nt = u / mt_units;
                 int mt = mu * CG + (int)rank;
@@ -630,11 +633,12 @@ conv2d_tcp_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                 const int wi0 = tw * TC_TW * p.stride_w - p.pad_w, hi0 = th * TC_TH * p.stride - p.pad;
                 const int nvalid = min(p.BN, p.cout_pad - nt * p.BN);                  // ragged last N tile (multiple of 16)
                 const int n0 = nt * p.BN + (int)rank * (nvalid / CG);                  // this CTA's weight rows start here (the box holds BN / CG rows)
+                int tap = 0, kh = 0, kw = 0, c0 = 0;
                 for (int kb = 0; kb < KB; ++kb, ++it) {
-                    const int s = it % p.stages, ph = (it / p.stages) & 1;
                     mbar_wait(&empty[s], ph ^ 1);
-                    const int tap = kb / cchunks, c0 = (kb - tap * cchunks) * 64;
-                    const int kh = tap / p.KW, kw = tap - kh * p.KW;
+                    const bool tr = p.trace && blockIdx.x == 0 && it < p.trace_n;
+                    if (elect_one()) {
+                    if (tr) p.trace[it] = clock64();                                          // [0] stage free, about to issue the loads
                     uint8_t* st = smem + (size_t)s * stage_bytes;
                     const int wi = wi0 + kw * p.dil, hi = hi0 + kh * p.dil;
                     const int kcol = tap * p.cin_pad + c0;
@@ -654,13 +658,19 @@ conv2d_tcp_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                         tma_load_2d(st + 2 * TC_A_BYTES, &mapWhi, &full[s], kcol, n0);
                         if (lo_too) tma_load_2d(st + 2 * TC_A_BYTES + b_bytes, &mapWlo, &full[s], kcol, n0);
                     }
+                    if (tr) p.trace[p.trace_n + it] = clock64();                              // [1] loads issued
+                    }
+                    __syncwarp();
+                    if (++s == p.stages) { s = 0; ph ^= 1; }
+                    c0 += 64;
+                    if (c0 == p.cin_pad) { c0 = 0; ++tap; if (++kw == p.KW) { kw = 0; ++kh; } }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0 && rank == 0) {
-            // ================= MMA issuer (leader CTA) =================
-            int it = 0, cc = 0;
+        if (rank == 0) {
+            // ================= MMA issuer (leader CTA): the whole warp walks the pipeline, one elected lane issues ==================
+            int it = 0, cc = 0, s = 0, ph = 0;
             for (int u = u0; u < units; u += ustep) {
                 int kb = 0;
                 const int nvalid = min(p.BN, p.cout_pad - (u / mt_units) * p.BN);
@@ -672,32 +682,41 @@ conv2d_tcp_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                     const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.BN);
                     const int kend = min(KB, kb + p.chunk);
                     for (bool first = true; kb < kend; ++kb, ++it) {
-                        const int s = it % p.stages, ph = (it / p.stages) & 1;
+                        const bool tr = p.trace && blockIdx.x == 0 && it < p.trace_n;
+                        if (tr && lane == 0) p.trace[2 * p.trace_n + it] = clock64();         // [2] MMA thread starts waiting for the stage
                         mbar_wait(&full[s], ph);
                         tc_fence_after();
+                        if (tr && lane == 0) p.trace[3 * p.trace_n + it] = clock64();         // [3] stage landed (seen by the MMA thread)
+                        if (elect_one()) {
                         const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
                         const uint64_t dA = make_sdesc(sa), dAlo = make_sdesc(sa + TC_A_BYTES);
                         const uint64_t dB = make_sdesc(sa + 2 * TC_A_BYTES), dBlo = make_sdesc(sa + 2 * TC_A_BYTES + b_bytes);
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
                             const uint64_t off = (uint64_t)((k * 32) >> 4);     // one MMA K-step = 16 fp16 = 32 bytes inside the swizzle row
+                            const uint32_t acc0 = (first && k == 0) ? 0u : 1u;  // the first MMA of a chunk overwrites the accumulator
                             if (p.dbg & 1) {
-                                if (CG == 2) umma_f16_2sm(d_tmem, dA + off, dB + off, idesc, first ? 0u : 1u);
-                                else umma_f16(d_tmem, dA + off, dB + off, idesc, first ? 0u : 1u);
+                                if (CG == 2) umma_f16_2sm(d_tmem, dA + off, dB + off, idesc, acc0);
+                                else umma_f16(d_tmem, dA + off, dB + off, idesc, acc0);
                             } else if (CG == 2) {
-                                umma_f16_2sm(d_tmem, dAlo + off, dB + off, idesc, first ? 0u : 1u);      // small terms first, then the main product
+                                umma_f16_2sm(d_tmem, dAlo + off, dB + off, idesc, acc0);      // small terms first, then the main product
                                 umma_f16_2sm(d_tmem, dA + off, dBlo + off, idesc, 1);
                                 umma_f16_2sm(d_tmem, dA + off, dB + off, idesc, 1);
                             } else {
-                                umma_f16(d_tmem, dAlo + off, dB + off, idesc, first ? 0u : 1u);
+                                umma_f16(d_tmem, dAlo + off, dB + off, idesc, acc0);
                                 umma_f16(d_tmem, dA + off, dBlo + off, idesc, 1);
                                 umma_f16(d_tmem, dA + off, dB + off, idesc, 1);
                             }
-                            first = false;
                         }
                         if (CG == 2) umma_commit_2sm(&empty[s]); else umma_commit(&empty[s]);       // frees the stage (in both CTAs)
+                        if (tr) p.trace[4 * p.trace_n + it] = clock64();                  // [4] MMAs + commit issued
+                        }
+                        __syncwarp();
+                        first = false;
+                        if (++s == p.stages) { s = 0; ph ^= 1; }
                     }
-                    if (CG == 2) umma_commit_2sm(&tmem_full[buf]); else umma_commit(&tmem_full[buf]);
+                    if (elect_one()) { if (CG == 2) umma_commit_2sm(&tmem_full[buf]); else umma_commit(&tmem_full[buf]); }
+                    __syncwarp();
                 }
             }
         }
@@ -776,7 +795,7 @@ conv2d_tcph_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     __syncthreads();
     if (CG == 2) cluster_sync_all();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __reduce_or_sync(0xffffffffu, *tmem_slot);      // uniform register (see conv2d_tcp_kernel)
 
     if (warp == 0) {
         if (lane == 0) {
@@ -992,11 +1011,17 @@ extern "C" int vd3d_tc_pick_bn(int Cout) {
     return 128;
 }
 
+// diagnostics: clock64 stamps of the TMA / MMA pipeline of CTA 0 ([5][n] int64 device buffer; NULL disables)
+static long long* g_trace = nullptr;
+static int g_trace_n = 0;
+extern "C" void vd3d_tc_set_trace(void* dev_i64, int n) { g_trace = (long long*)dev_i64; g_trace_n = n; }
+
 // launch of the persistent kernel: p.BN / p.idesc (for M = 128) / p.tmem_cols / p.chunk / tile counts are set by the caller,
 // the weight maps have BN / CG rows per box
 static int tcp_launch(TcParams& p, const CUtensorMap& mA, const CUtensorMap& mAlo, const CUtensorMap& mWhi, const CUtensorMap& mWlo, int CG, void* stream) {
     const int BN = p.BN;
     { const char* e = getenv("VD3D_TC_DEBUG"); p.dbg = e ? atoi(e) : 0; }
+    p.trace = g_trace; p.trace_n = g_trace_n;
     const size_t stage_bytes = 2 * (size_t)TC_A_BYTES + 2 * (size_t)(BN / CG) * 128;
     int stages = (int)((227 * 1024 - 1024 - 512) / stage_bytes);
     if (stages > 8) stages = 8;

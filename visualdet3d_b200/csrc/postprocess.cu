@@ -109,7 +109,7 @@ __global__ void decode_candidates_kernel(const float* __restrict__ cls, const fl
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// stage 2 (one CTA per image): bitonic sort of (key, slot) in shared memory, greedy NMS, ordered write-out.
+// stage 2 (one CTA per image): bitonic sort of (key, slot) in shared memory, greedy NMS by 64-row bit-matrix blocks, ordered write-out.
 // torchvision CPU nms: areas = (x2-x1)*(y2-y1); inter = max(0, xx2-xx1)*max(0, yy2-yy1);
 //                      ovr = inter / (area_i + area_j - inter); suppress j if ovr > thr.
 // ---------------------------------------------------------------------------------------------------------
@@ -121,25 +121,28 @@ __global__ void __launch_bounds__(NMS_THREADS) sort_nms_kernel(DecodeWs ws, int 
                                                                 int32_t* __restrict__ out_count, int32_t* __restrict__ out_ncand) {
     extern __shared__ __align__(16) unsigned char sm_raw[];
     unsigned long long* skey = reinterpret_cast<unsigned long long*>(sm_raw);            // [cap_pow2]
-    int* sslot = reinterpret_cast<int*>(skey + cap_pow2);                                // [cap_pow2]
-    float4* sbox = reinterpret_cast<float4*>(sslot + cap_pow2);                          // [cap_pow2]
-    float* sarea = reinterpret_cast<float*>(sbox + cap_pow2);                            // [cap_pow2]
-    unsigned char* ssup = reinterpret_cast<unsigned char*>(sarea + cap_pow2);            // [cap_pow2]
+    unsigned long long* smask = skey + cap_pow2;                                         // [64][cap_pow2 / 64]: suppression bits of one 64-row block
+    float4* sbox = reinterpret_cast<float4*>(smask + cap_pow2);                          // [cap_pow2]
+    int* sslot = reinterpret_cast<int*>(sbox + cap_pow2);                                // [cap_pow2]
+    float* sarea = reinterpret_cast<float*>(sslot + cap_pow2);                           // [cap_pow2]
+    int* skeep = reinterpret_cast<int*>(sarea + cap_pow2);                               // [cap_pow2] sorted positions of the kept boxes
     __shared__ int s_nkeep;
     const int b = blockIdx.x, t = threadIdx.x;
-    int n = ws.ncand[b];
+    const int n = ws.ncand[b];
     if (t == 0) out_ncand[b] = n;
     if (n > cap) { if (t == 0) out_count[b] = -1; return; }
+    int np2 = 64;                                   // sort size: next power of two >= n (the padding keys ~0 sort to the end)
+    while (np2 < n) np2 <<= 1;
 
-    for (int i = t; i < cap_pow2; i += NMS_THREADS) {
+    for (int i = t; i < np2; i += NMS_THREADS) {
         skey[i] = (i < n) ? ws.keys[(long long)b * cap + i] : ~0ull;
         sslot[i] = i;
     }
     __syncthreads();
     // bitonic sort ascending on key
-    for (int k = 2; k <= cap_pow2; k <<= 1) {
+    for (int k = 2; k <= np2; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = t; i < cap_pow2; i += NMS_THREADS) {
+            for (int i = t; i < np2; i += NMS_THREADS) {
                 int ixj = i ^ j;
                 if (ixj > i) {
                     bool up = ((i & k) == 0);
@@ -158,41 +161,70 @@ __global__ void __launch_bounds__(NMS_THREADS) sort_nms_kernel(DecodeWs ws, int 
         float4 bx = make_float4(bp[0], bp[1], bp[2], bp[3]);
         sbox[i] = bx;
         sarea[i] = mul(sub(bx.z, bx.x), sub(bx.w, bx.y));
-        ssup[i] = 0;
     }
-    if (t == 0) s_nkeep = 0;
     __syncthreads();
-    // greedy sweep: i is kept iff not suppressed by an earlier kept box
-    for (int i = 0; i < n; ++i) {
-        if (ssup[i]) continue;                       // uniform branch (shared value, synced below)
-        float4 bi = sbox[i];
-        float ai = sarea[i];
-        for (int j = i + 1 + t; j < n; j += NMS_THREADS) {
-            if (ssup[j]) continue;
-            float4 bj = sbox[j];
-            float xx1 = fmaxf(bi.x, bj.x), yy1 = fmaxf(bi.y, bj.y);
-            float xx2 = fminf(bi.z, bj.z), yy2 = fminf(bi.w, bj.w);
-            float w = fmaxf(0.f, sub(xx2, xx1)), h = fmaxf(0.f, sub(yy2, yy1));
-            float inter = mul(w, h);
-            float ovr = __fdiv_rn(inter, sub(add(ai, sarea[j]), inter));
-            if ((double)ovr > iou_thr) ssup[j] = 1;   // torchvision compares the f32 IoU with a double threshold
+    // Greedy sweep (box i is kept iff no earlier KEPT box suppresses it), 64 rows at a time: all threads build the suppression bit
+    // matrix of the block (bit j of word w of row r: box 64w + j comes after row box i and IoU(i, 64w + j) > thr), then warp 0 walks
+    // the 64 rows in order with the removed-set held as one 64-bit word per lane.
+    const int nw = (n + 63) >> 6;                   // <= 32 words (cap <= 2048) ... or 64 for cap 4096: two words per lane
+    const int wpr = cap_pow2 >> 6;                  // words per mask row
+    unsigned long long removed0 = 0, removed1 = 0;  // warp 0: lane l holds words l and l + 32
+    int nkeep = 0;
+    const int warp = t >> 5, lane = t & 31;
+    for (int c = 0; c < nw; ++c) {
+        const int words = nw - c;
+        for (int e = t; e < 64 * words; e += NMS_THREADS) {
+            const int r = e & 63, w = c + (e >> 6);
+            const int i = c * 64 + r;
+            unsigned long long bits = 0;
+            if (i < n) {
+                const float4 bi = sbox[i];
+                const float ai = sarea[i];
+                const int j0 = w * 64;
+                const int jend = min(64, n - j0);
+                for (int j = (w == c ? r + 1 : 0); j < jend; ++j) {
+                    const float4 bj = sbox[j0 + j];
+                    float xx1 = fmaxf(bi.x, bj.x), yy1 = fmaxf(bi.y, bj.y);
+                    float xx2 = fminf(bi.z, bj.z), yy2 = fminf(bi.w, bj.w);
+                    float ww = fmaxf(0.f, sub(xx2, xx1)), hh = fmaxf(0.f, sub(yy2, yy1));
+                    float inter = mul(ww, hh);
+                    float ovr = __fdiv_rn(inter, sub(add(ai, sarea[j0 + j]), inter));
+                    if ((double)ovr > iou_thr) bits |= 1ull << j;    // torchvision compares the f32 IoU with a double threshold
+                }
+            }
+            smask[r * wpr + w] = bits;
         }
-        if (t == 0) {
-            int k = s_nkeep++;
-            int slot = sslot[i];
-            unsigned long long key = skey[i];
-            out_scores[(long long)b * cap + k] = __uint_as_float(~(unsigned int)(key >> 32));
-            out_anchor[(long long)b * cap + k] = (int)(unsigned int)(key & 0xffffffffu);
-            out_cls[(long long)b * cap + k] = (int64_t)ws.labels[(long long)b * cap + slot];
-            const float* bp = ws.boxes + ((long long)b * cap + slot) * 11;
-            float* op = out_boxes + ((long long)b * cap + k) * 11;
-#pragma unroll
-            for (int q = 0; q < 11; ++q) op[q] = bp[q];
+        __syncthreads();
+        if (warp == 0) {
+            const int rows = min(64, n - c * 64);
+            for (int r = 0; r < rows; ++r) {
+                const unsigned long long rc = c < 32 ? __shfl_sync(0xffffffffu, removed0, c) : __shfl_sync(0xffffffffu, removed1, c - 32);
+                if ((rc >> r) & 1ull) continue;                       // warp-uniform
+                if (lane == 0) skeep[nkeep] = c * 64 + r;
+                ++nkeep;
+                if (lane >= c && lane < nw) removed0 |= smask[r * wpr + lane];
+                if (lane + 32 >= c && lane + 32 < nw) removed1 |= smask[r * wpr + lane + 32];
+            }
         }
         __syncthreads();
     }
+    if (t == 0) s_nkeep = nkeep;
     __syncthreads();
-    if (t == 0) out_count[b] = s_nkeep;
+    nkeep = s_nkeep;
+    // ordered write-out of the kept boxes, all threads
+    for (int k = t; k < nkeep; k += NMS_THREADS) {
+        const int i = skeep[k];
+        const int slot = sslot[i];
+        const unsigned long long key = skey[i];
+        out_scores[(long long)b * cap + k] = __uint_as_float(~(unsigned int)(key >> 32));
+        out_anchor[(long long)b * cap + k] = (int)(unsigned int)(key & 0xffffffffu);
+        out_cls[(long long)b * cap + k] = (int64_t)ws.labels[(long long)b * cap + slot];
+        const float* bp = ws.boxes + ((long long)b * cap + slot) * 11;
+        float* op = out_boxes + ((long long)b * cap + k) * 11;
+#pragma unroll
+        for (int q = 0; q < 11; ++q) op[q] = bp[q];
+    }
+    if (t == 0) out_count[b] = nkeep;
 }
 
 // fixed-capacity detection record block for the multi-GPU all-gather: rec[b] = [count | kmax x (11 box floats, score, class)]
@@ -260,7 +292,8 @@ extern "C" int vd3d_decode_nms(const float* cls, const float* reg, const float* 
                                                                          score_thr, img_w, img_h, cap, ws);
     VD3D_CHECK_LAUNCH("decode_candidates");
     int cp2 = next_pow2(cap);
-    size_t smem = (size_t)cp2 * (8 + 4 + 16 + 4 + 1) + 16;
+    if (cp2 < 64) cp2 = 64;                      // the 64-row bit-matrix blocks of the NMS sweep
+    size_t smem = (size_t)cp2 * (8 + 8 + 16 + 4 + 4 + 4) + 16;
     VD3D_CUDA(cudaFuncSetAttribute(sort_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     sort_nms_kernel<<<B, NMS_THREADS, smem, st>>>(ws, cap, cp2, iou_thr, out_scores, out_boxes, out_cls, out_anchor, out_count, out_ncand);
     VD3D_CHECK_LAUNCH("sort_nms");
