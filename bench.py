@@ -32,6 +32,7 @@ METRIC = "synthetic_384x1280_stereo_pairs_per_sec"
 UNIT = "pairs/s"
 H, W = 384, 1280
 PSM4_BYTES_PER_PAIR = 4 * (H // 4) * (W // 4) * (2 * 64 + 24)   # 18,677,760 B
+PSM4_NCU_TRAFFIC_B8 = 137_400_000                                # DRAM bytes per launch of the scale-4 PSMCosine kernel at B = 8 (ncu)
 
 
 def measured_peaks():
@@ -354,7 +355,11 @@ def main():
                                 if (os.environ.get("VD3D_PSM_ENGINE", "tc") == "tc" and os.environ.get("VD3D_CONV_ENGINE", "tc16") == "tc16")
                                 else "psm_cosine_nhwc_v4_kernel<64> (scale-4 PSMCosine, SIMT)"), "bound": "hbm", "achieved": achieved, "peak": peak,
                      "peak_kind": peak_kind, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                     "avg_launch_ms": psm_avg_ms, "algorithmic_bytes_per_launch": PSM4_BYTES_PER_PAIR * B, "traffic": None},
+                     "avg_launch_ms": psm_avg_ms, "algorithmic_bytes_per_launch": PSM4_BYTES_PER_PAIR * B,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at B = 8 from the committed `ncu --set full` capture
+                     # (profiles/r01_ncu_psm_cosine_tc.txt: 125.9 MB read + 11.5 MB written, 27.6 us cold); null for other batch sizes
+                     "traffic": (PSM4_NCU_TRAFFIC_B8 if (B == 8 and os.environ.get("VD3D_PSM_ENGINE", "tc") == "tc") else None),
+                     "traffic_source": "ncu --set full, one launch, profiles/r01_ncu_psm_cosine_tc.txt"},
     }
     if not args.no_cpu_baseline:
         cores = pick_cpu_threads()

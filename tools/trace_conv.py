@@ -32,14 +32,14 @@ for si in sel:
         n = int((t[0] > 0).sum())
         t = t[:, :n]
         t0 = t[0, 0]
-        lat = t[3] - t[0]                  # stage free -> landed (upper bound on the load latency: includes the MMA thread's own lateness)
-        wait = t[3] - t[2]                 # MMA thread blocked on the stage
-        issue = t[4] - t[3]                # descriptor setup + 12 MMAs + commit issue time
+        lat = t[3] - t[0]                  # stage free -> its MMAs start
+        wait = t[2] - t[3]                 # issue start -> look-ahead wait for the next stage starts (= first half of the MMAs issued)
+        issue = t[4] - t[3]                # 12 MMAs + look-ahead (wait, fence, descriptors) + commit
         per = np.diff(t[4])
         sl = slice(20, min(n, 400))
-        print(f"{name:30s} cg={cg} bn={bn:3d} n={n}  period {np.median(per[sl]):7.0f}  free->landed {np.median(lat[sl]):7.0f}  "
-              f"issue-loads {np.median((t[1]-t[0])[sl]):5.0f}  mma-wait {np.median(wait[sl]):7.0f}  mma-issue {np.median(issue[sl]):6.0f} clk", flush=True)
+        print(f"{name:30s} cg={cg} bn={bn:3d} n={n}  period {np.median(per[sl]):7.0f}  free->mma-start {np.median(lat[sl]):7.0f}  "
+              f"issue-loads {np.median((t[1]-t[0])[sl]):5.0f}  half-issue {np.median(wait[sl]):7.0f}  mma-issue {np.median(issue[sl]):6.0f} clk", flush=True)
         k = 40
         print("   k-block:", " ".join(f"{int(v):6d}" for v in range(k, k + 8)))
-        for r, lab in enumerate(["free", "issued", "mwait", "landed", "mmadone"]):
+        for r, lab in enumerate(["free", "issued", "lookahd", "mmastart", "mmadone"]):
             print(f"   {lab:8s}", " ".join(f"{int(v - t0):6d}" for v in t[r, k:k + 8]))

@@ -668,58 +668,84 @@ conv2d_tcp_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             }
         }
     } else if (warp == 1) {
-        if (rank == 0) {
-            // ================= MMA issuer (leader CTA): the whole warp walks the pipeline, one elected lane issues ==================
-            int it = 0, cc = 0, s = 0, ph = 0;
-            for (int u = u0; u < units; u += ustep) {
-                int kb = 0;
+        if (rank == 0 && elect_one()) {
+            // ================= MMA issuer (leader CTA, one elected lane) =================
+            // Software-pipelined over the flat sequence of k-blocks of all tiles of this CTA: the barrier wait, fence and descriptor
+            // set-up of k-block g+1 sit BETWEEN the two halves of the MMAs of k-block g, where the tensor core still has queued work
+            // (issue is blocking and the queue is shallow: anything between the last MMA of g and the first of g+1 is a bubble).
+            const int my_units = (units - u0 + ustep - 1) / ustep;           // tiles of this CTA (>= 1: the grid never exceeds the tile count)
+            const long long total = (long long)my_units * KB;
+            int s = 0, ph = 0, cc = 0;
+            auto stage_desc = [&](int st, uint64_t& dA, uint64_t& dAlo, uint64_t& dB, uint64_t& dBlo) {
+                const uint32_t sa = smem_u32(smem + (size_t)st * stage_bytes);
+                dA = make_sdesc(sa); dAlo = make_sdesc(sa + TC_A_BYTES);
+                dB = make_sdesc(sa + 2 * TC_A_BYTES); dBlo = make_sdesc(sa + 2 * TC_A_BYTES + b_bytes);
+            };
+            auto tile_idesc = [&](int unit_local) {
+                const int u = u0 + unit_local * ustep;
                 const int nvalid = min(p.BN, p.cout_pad - (u / mt_units) * p.BN);
-                const uint32_t idesc = (p.idesc & ~(0x3Fu << 17)) | ((uint32_t)(nvalid >> 3) << 17);      // MMA N = valid columns of this tile
-                for (int ci = 0; ci < NC; ++ci, ++cc) {
-                    const int buf = cc & 1, use = cc >> 1;
-                    mbar_wait(&tmem_empty[buf], (use & 1) ^ 1);          // every epilogue warp has promoted this buffer's previous chunk
-                    tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.BN);
-                    const int kend = min(KB, kb + p.chunk);
-                    for (bool first = true; kb < kend; ++kb, ++it) {
-                        const bool tr = p.trace && blockIdx.x == 0 && it < p.trace_n;
-                        if (tr && lane == 0) p.trace[2 * p.trace_n + it] = clock64();         // [2] MMA thread starts waiting for the stage
-                        mbar_wait(&full[s], ph);
-                        tc_fence_after();
-                        if (tr && lane == 0) p.trace[3 * p.trace_n + it] = clock64();         // [3] stage landed (seen by the MMA thread)
-                        if (elect_one()) {
-                        const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
-                        const uint64_t dA = make_sdesc(sa), dAlo = make_sdesc(sa + TC_A_BYTES);
-                        const uint64_t dB = make_sdesc(sa + 2 * TC_A_BYTES), dBlo = make_sdesc(sa + 2 * TC_A_BYTES + b_bytes);
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const uint64_t off = (uint64_t)((k * 32) >> 4);     // one MMA K-step = 16 fp16 = 32 bytes inside the swizzle row
-                            const uint32_t acc0 = (first && k == 0) ? 0u : 1u;  // the first MMA of a chunk overwrites the accumulator
-                            if (p.dbg & 1) {
-                                if (CG == 2) umma_f16_2sm(d_tmem, dA + off, dB + off, idesc, acc0);
-                                else umma_f16(d_tmem, dA + off, dB + off, idesc, acc0);
-                            } else if (CG == 2) {
-                                umma_f16_2sm(d_tmem, dAlo + off, dB + off, idesc, acc0);      // small terms first, then the main product
-                                umma_f16_2sm(d_tmem, dA + off, dBlo + off, idesc, 1);
-                                umma_f16_2sm(d_tmem, dA + off, dB + off, idesc, 1);
-                            } else {
-                                umma_f16(d_tmem, dAlo + off, dB + off, idesc, acc0);
-                                umma_f16(d_tmem, dA + off, dBlo + off, idesc, 1);
-                                umma_f16(d_tmem, dA + off, dB + off, idesc, 1);
-                            }
-                        }
-                        if (CG == 2) umma_commit_2sm(&empty[s]); else umma_commit(&empty[s]);       // frees the stage (in both CTAs)
-                        if (tr) p.trace[4 * p.trace_n + it] = clock64();                  // [4] MMAs + commit issued
-                        }
-                        __syncwarp();
-                        first = false;
-                        if (++s == p.stages) { s = 0; ph ^= 1; }
-                    }
-                    if (elect_one()) { if (CG == 2) umma_commit_2sm(&tmem_full[buf]); else umma_commit(&tmem_full[buf]); }
-                    __syncwarp();
+                return (p.idesc & ~(0x3Fu << 17)) | ((uint32_t)(nvalid >> 3) << 17);      // MMA N = valid columns of the tile
+            };
+            auto issue = [&](uint32_t d_tmem, uint32_t idesc, uint64_t dA, uint64_t dAlo, uint64_t dB, uint64_t dBlo, int k, uint32_t acc0) {
+                const uint64_t off = (uint64_t)((k * 32) >> 4);       // one MMA K-step = 16 fp16 = 32 bytes inside the swizzle row
+                if (p.dbg & 1) {
+                    if (CG == 2) umma_f16_2sm(d_tmem, dA + off, dB + off, idesc, acc0); else umma_f16(d_tmem, dA + off, dB + off, idesc, acc0);
+                } else if (CG == 2) {
+                    umma_f16_2sm(d_tmem, dAlo + off, dB + off, idesc, acc0);      // small terms first, then the main product
+                    umma_f16_2sm(d_tmem, dA + off, dBlo + off, idesc, 1);
+                    umma_f16_2sm(d_tmem, dA + off, dB + off, idesc, 1);
+                } else {
+                    umma_f16(d_tmem, dAlo + off, dB + off, idesc, acc0);
+                    umma_f16(d_tmem, dA + off, dBlo + off, idesc, 1);
+                    umma_f16(d_tmem, dA + off, dB + off, idesc, 1);
                 }
+            };
+            // prologue: first accumulator buffer and first stage
+            mbar_wait(&tmem_empty[0], 1);
+            mbar_wait(&full[0], 0);
+            tc_fence_after();
+            uint64_t dA, dAlo, dB, dBlo;
+            stage_desc(0, dA, dAlo, dB, dBlo);
+            uint32_t idesc = tile_idesc(0);
+            int kb = 0, unit_local = 0;
+            for (long long g = 0; g < total; ++g) {
+                const int buf = cc & 1;
+                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.BN);
+                const bool first_in_chunk = (kb % p.chunk) == 0;
+                const bool last_in_chunk = (kb % p.chunk) == p.chunk - 1 || kb == KB - 1;
+                const bool tr = p.trace && blockIdx.x == 0 && g < p.trace_n;
+                if (tr) p.trace[3 * p.trace_n + g] = clock64();                               // [3] about to issue k-block g
+                issue(d_tmem, idesc, dA, dAlo, dB, dBlo, 0, first_in_chunk ? 0u : 1u);
+                issue(d_tmem, idesc, dA, dAlo, dB, dBlo, 1, 1u);
+                // ---- look-ahead for k-block g+1 while the MMAs above are queued ----
+                const int s_cur = s;
+                uint64_t nA = 0, nAlo = 0, nB = 0, nBlo = 0;
+                const bool has_next = g + 1 < total;
+                if (has_next) {
+                    if (++s == p.stages) { s = 0; ph ^= 1; }
+                    if (tr) p.trace[2 * p.trace_n + g] = clock64();                           // [2] look-ahead wait starts
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after();
+                    stage_desc(s, nA, nAlo, nB, nBlo);
+                }
+                issue(d_tmem, idesc, dA, dAlo, dB, dBlo, 2, 1u);
+                issue(d_tmem, idesc, dA, dAlo, dB, dBlo, 3, 1u);
+                if (CG == 2) umma_commit_2sm(&empty[s_cur]); else umma_commit(&empty[s_cur]);       // frees the stage (in both CTAs)
+                if (tr) p.trace[4 * p.trace_n + g] = clock64();                               // [4] MMAs + commit issued
+                if (last_in_chunk) {
+                    if (CG == 2) umma_commit_2sm(&tmem_full[buf]); else umma_commit(&tmem_full[buf]);
+                    ++cc;
+                    if (has_next) {
+                        const int nbuf = cc & 1, use = cc >> 1;
+                        mbar_wait(&tmem_empty[nbuf], (use & 1) ^ 1);     // every epilogue warp has promoted this buffer's previous chunk
+                        tc_fence_after();
+                    }
+                }
+                if (++kb == KB) { kb = 0; ++unit_local; if (has_next) idesc = tile_idesc(unit_local); }
+                dA = nA; dAlo = nAlo; dB = nB; dBlo = nBlo;
             }
         }
+        __syncwarp();
     } else {
         tcp_epilogue<NG16, CG>(p, tmem_base, tmem_full, tmem_empty, warp, lane, rank, NC, u0, ustep, units, mt_units);
         tc_fence_before();
