@@ -213,6 +213,13 @@ int vd3d_deform_im2col_nhwc(const float* x, int B, int H, int W, int C, int x_cs
                             const float* msk, int msk_cs, int msk_co, int mask_sigmoid,
                             int KH, int KW, int stride, int pad, int dil, int deform_groups,
                             float* col, float* col_lo, int col_cs, void* stream);
+/* Same gather writing the fp16 (hi, lo) planes of the columns that vd3d_conv2d_tc16 reads (hi = rn16(v), lo = rn16(v - hi));
+ * col (the fp32 columns) may be NULL: the planes alone feed the GEMM (no vd3d_split_h16_nhwc pass over 9*C floats per pixel). */
+int vd3d_deform_im2col_h16(const float* x, int B, int H, int W, int C, int x_cs, int x_co,
+                           const float* off, int off_cs, int off_co,
+                           const float* msk, int msk_cs, int msk_co, int mask_sigmoid,
+                           int KH, int KW, int stride, int pad, int dil, int deform_groups,
+                           float* col, void* col_hi16, void* col_lo16, int col_cs, void* stream);
 
 /* ---- Ground-Aware Convolution sampling (LookGround.forward, R/lib/look_ground.py:24-71) ---------------------------
  * x NHWC [B][H][W] (stride-16 features), dconv = output of disp_create's 3x3 conv (channel d_co; tanh applied here),

@@ -1,6 +1,6 @@
 """Secondary measurements (BASELINE.json configs[2], configs[3] and the configs[0] plumbing case on the GPU): device-resident
 forward rate of the other detectors of the hot path, CUDA events, inputs larger than L2 or L2 flushed by the step itself.
-usage: python tools/bench_detectors.py [steps]   -> one JSON line per detector"""
+usage: python tools/bench_detectors.py [steps] [name,name]   -> one JSON line per detector"""
 import json, os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -8,6 +8,7 @@ from visualdet3d_b200 import synth, _lib
 from visualdet3d_b200.detectors import build_synthetic_mono3d, build_synthetic_monoflex
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 10
+only = set(sys.argv[2].split(",")) if len(sys.argv) > 2 else None
 CASES = [("Yolo3D", "configs[0] shape on the GPU: Yolo3D ResNet-18 (DCNv2 head)", 1, 288, 1280, lambda: build_synthetic_mono3d("Yolo3D", seed=0, depth=18)[0]),
          ("Yolo3D-b8", "Yolo3D ResNet-18 (DCNv2 head), batch 8", 8, 288, 1280, lambda: build_synthetic_mono3d("Yolo3D", seed=0, depth=18)[0]),
          ("GroundAwareYolo3D", "configs[2]: Ground-aware Mono3D (GAC head, ResNet-101), batch 8 mono 288x1280", 8, 288, 1280,
@@ -15,6 +16,8 @@ CASES = [("Yolo3D", "configs[0] shape on the GPU: Yolo3D ResNet-18 (DCNv2 head)"
          ("MonoFlex", "configs[3]: MonoFlex DLA-34 + DCNv2, batch 8, 384x1280", 8, 384, 1280, lambda: build_synthetic_monoflex(seed=0)[0]),
          ("KM3D", "configs[3]: KM3D DLA-34 + DCNv2, batch 8, 384x1280", 8, 384, 1280, lambda: build_synthetic_monoflex(seed=0, name="KM3D")[0])]
 for name, desc, B, H, W, mk in CASES:
+    if only and name not in only:
+        continue
     try:
         det = mk().cuda().eval()
         img, P2 = synth.synth_mono_inputs(B, H, W, seed=1)

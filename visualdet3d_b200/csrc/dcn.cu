@@ -9,6 +9,7 @@
 // computed once per (pixel, tap) and shared by all channels: one CTA = 32 pixels x all taps, threads sweep channel quads.
 // HBM-bound gather: reads x once (L2 serves the 9x tap reuse), writes KH*KW*C floats (+lo) per pixel.
 #include "common.cuh"
+#include <cuda_fp16.h>
 
 namespace vd3d {
 
@@ -20,6 +21,7 @@ struct DcnParams {
     int KH, KW, stride, pad, dil, dg;
     int Ho, Wo;
     float* col; float* col_lo; int col_cs;          // [B*Ho*Wo][col_cs], channels [0, KH*KW*C)
+    __half* col_h16_hi; __half* col_h16_lo;         // optional fp16 (hi, lo) planes of the columns (same pitch): what the fp16-split GEMM reads
 };
 
 constexpr int DCN_PIX = 32;       // pixels per CTA
@@ -95,7 +97,18 @@ __global__ void __launch_bounds__(DCN_THREADS) deform_im2col_kernel(const DcnPar
         float m = s_m[pl][k];
         acc.x *= m; acc.y *= m; acc.z *= m; acc.w *= m;
         long long o = pix * p.col_cs + (long long)k * p.C + c;
-        *reinterpret_cast<float4*>(p.col + o) = acc;
+        if (p.col) *reinterpret_cast<float4*>(p.col + o) = acc;
+        if (p.col_h16_hi) {     // hi = rn16(v), lo = rn16(v - hi): identical to vd3d_split_h16_nhwc on the fp32 columns
+            __half hx = __float2half_rn(acc.x), hy = __float2half_rn(acc.y), hz = __float2half_rn(acc.z), hw = __float2half_rn(acc.w);
+            __half2 h01 = __halves2half2(hx, hy), h23 = __halves2half2(hz, hw);
+            __half2 l01 = __halves2half2(__float2half_rn(acc.x - __half2float(hx)), __float2half_rn(acc.y - __half2float(hy)));
+            __half2 l23 = __halves2half2(__float2half_rn(acc.z - __half2float(hz)), __float2half_rn(acc.w - __half2float(hw)));
+            uint2 hv, lv;
+            hv.x = *reinterpret_cast<uint32_t*>(&h01); hv.y = *reinterpret_cast<uint32_t*>(&h23);
+            lv.x = *reinterpret_cast<uint32_t*>(&l01); lv.y = *reinterpret_cast<uint32_t*>(&l23);
+            *reinterpret_cast<uint2*>(p.col_h16_hi + o) = hv;
+            *reinterpret_cast<uint2*>(p.col_h16_lo + o) = lv;
+        }
         if (p.col_lo) {
             float4 l;
             l.x = acc.x - __uint_as_float(__float_as_uint(acc.x) & 0xFFFFE000u);
@@ -111,12 +124,13 @@ __global__ void __launch_bounds__(DCN_THREADS) deform_im2col_kernel(const DcnPar
 
 using namespace vd3d;
 
-extern "C" int vd3d_deform_im2col_nhwc(const float* x, int B, int H, int W, int C, int x_cs, int x_co,
-                                       const float* off, int off_cs, int off_co,
-                                       const float* msk, int msk_cs, int msk_co, int mask_sigmoid,
-                                       int KH, int KW, int stride, int pad, int dil, int deform_groups,
-                                       float* col, float* col_lo, int col_cs, void* stream) {
-    VD3D_REQUIRE(x && off && col, "deform_im2col: null pointer");
+static int deform_im2col_launch(const float* x, int B, int H, int W, int C, int x_cs, int x_co,
+                                const float* off, int off_cs, int off_co,
+                                const float* msk, int msk_cs, int msk_co, int mask_sigmoid,
+                                int KH, int KW, int stride, int pad, int dil, int deform_groups,
+                                float* col, float* col_lo, void* col_hi16, void* col_lo16, int col_cs, void* stream) {
+    VD3D_REQUIRE(x && off && (col || col_hi16), "deform_im2col: null pointer");
+    VD3D_REQUIRE(!col_hi16 || col_lo16, "deform_im2col: fp16 planes come in (hi, lo) pairs");
     VD3D_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && KH > 0 && KW > 0 && KH * KW <= DCN_MAXK, "deform_im2col: bad shape (<= 49 taps)");
     VD3D_REQUIRE(deform_groups >= 1 && C % deform_groups == 0 && (C / deform_groups) % 4 == 0, "deform_im2col: channels per deformable group must be a multiple of 4");
     VD3D_REQUIRE(x_cs % 4 == 0 && x_co % 4 == 0 && col_cs % 4 == 0 && col_cs >= KH * KW * C, "deform_im2col: pitches/offsets must be multiples of 4");
@@ -127,10 +141,30 @@ extern "C" int vd3d_deform_im2col_nhwc(const float* x, int B, int H, int W, int 
     p.Ho = (H + 2 * pad - (dil * (KH - 1) + 1)) / stride + 1;
     p.Wo = (W + 2 * pad - (dil * (KW - 1) + 1)) / stride + 1;
     VD3D_REQUIRE(p.Ho > 0 && p.Wo > 0, "deform_im2col: empty output");
-    p.col = col; p.col_lo = col_lo; p.col_cs = col_cs;
+    p.col = col; p.col_lo = col_lo; p.col_cs = col_cs; p.col_h16_hi = (__half*)col_hi16; p.col_h16_lo = (__half*)col_lo16;
     long long npix = (long long)B * p.Ho * p.Wo;
     dim3 grid(cdiv(npix, DCN_PIX), deform_groups);
     deform_im2col_kernel<<<grid, DCN_THREADS, 0, (cudaStream_t)stream>>>(p);
     VD3D_CHECK_LAUNCH("deform_im2col");
     return VD3D_OK;
+}
+
+extern "C" int vd3d_deform_im2col_nhwc(const float* x, int B, int H, int W, int C, int x_cs, int x_co,
+                                       const float* off, int off_cs, int off_co,
+                                       const float* msk, int msk_cs, int msk_co, int mask_sigmoid,
+                                       int KH, int KW, int stride, int pad, int dil, int deform_groups,
+                                       float* col, float* col_lo, int col_cs, void* stream) {
+    VD3D_REQUIRE(col, "deform_im2col: null pointer");
+    return deform_im2col_launch(x, B, H, W, C, x_cs, x_co, off, off_cs, off_co, msk, msk_cs, msk_co, mask_sigmoid, KH, KW, stride, pad, dil, deform_groups,
+                                col, col_lo, nullptr, nullptr, col_cs, stream);
+}
+
+extern "C" int vd3d_deform_im2col_h16(const float* x, int B, int H, int W, int C, int x_cs, int x_co,
+                                      const float* off, int off_cs, int off_co,
+                                      const float* msk, int msk_cs, int msk_co, int mask_sigmoid,
+                                      int KH, int KW, int stride, int pad, int dil, int deform_groups,
+                                      float* col, void* col_hi16, void* col_lo16, int col_cs, void* stream) {
+    VD3D_REQUIRE(col_hi16 && col_lo16, "deform_im2col_h16: null pointer");
+    return deform_im2col_launch(x, B, H, W, C, x_cs, x_co, off, off_cs, off_co, msk, msk_cs, msk_co, mask_sigmoid, KH, KW, stride, pad, dil, deform_groups,
+                                col, nullptr, col_hi16, col_lo16, col_cs, stream);
 }

@@ -312,12 +312,16 @@ class DeformConvLayer:
         Ho, Wo = self.out_hw(x.H, x.W)
         K = self.KH * self.KW
         om = self.off_conv(x, arena.act(name + ".om", (B, Ho, Wo, self.n_off_pad), dev))
-        cols = arena.act(name + ".cols", (B, Ho, Wo, K * self.C), dev, lo=self.main.engine != "simt")
-        call("vd3d_deform_im2col_nhwc", x.ptr, B, x.H, x.W, x.C, x.cs, x.co, om.ptr, om.cs, 0,
-             om.ptr, om.cs, 2 * K * self.dg, 1, self.KH, self.KW, self.stride, self.pad, self.dil, self.dg,
-             cols.ptr, cols.lo_ptr, cols.cs, _stream())
-        if cols.h16:
-            split_lo(cols)
+        cols = arena.act("dcn.cols", (B, Ho, Wo, K * self.C), dev, lo=self.main.engine != "simt")     # one buffer per shape, shared by all DCN layers
+        if cols.h16:      # the fp16-split GEMM reads only the planes: the gather writes them directly, the fp32 columns are never stored
+            ch, cl = cols.h16_ptrs
+            call("vd3d_deform_im2col_h16", x.ptr, B, x.H, x.W, x.C, x.cs, x.co, om.ptr, om.cs, 0,
+                 om.ptr, om.cs, 2 * K * self.dg, 1, self.KH, self.KW, self.stride, self.pad, self.dil, self.dg,
+                 cols.ptr if CHECK_LO else None, ch, cl, cols.cs, _stream())
+        else:
+            call("vd3d_deform_im2col_nhwc", x.ptr, B, x.H, x.W, x.C, x.cs, x.co, om.ptr, om.cs, 0,
+                 om.ptr, om.cs, 2 * K * self.dg, 1, self.KH, self.KW, self.stride, self.pad, self.dil, self.dg,
+                 cols.ptr, cols.lo_ptr, cols.cs, _stream())
         return self.main(cols, out, res=res)
 
 
