@@ -361,7 +361,7 @@ def main():
                      "traffic": (PSM4_NCU_TRAFFIC_B8 if (B == 8 and os.environ.get("VD3D_PSM_ENGINE", "tc") == "tc") else None),
                      "traffic_source": "ncu --set full, one launch, profiles/r01_ncu_psm_cosine_tc.txt"},
     }
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:          # the CPU arm is timed on rank 0 at N = 1 only (the driver runs --impl reference for every N)
         cores = pick_cpu_threads()
         v, sec = cpu_forward_rate(1, 3, cores)
         out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",

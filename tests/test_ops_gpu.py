@@ -232,14 +232,15 @@ def test_conv2d_tc_3xtf32_vs_fp32(case):
 
 
 # (VD3D_TC_HALO, VD3D_TC_PERSIST, VD3D_TC_CG, VD3D_TC_PHALO)
-TC16_MODES = {"auto": ("0", "1", "0", "1"), "persistent": ("0", "1", "1", "1"), "pair": ("0", "1", "2", "1"),
+TC16_MODES = {"default": ("0", "1", "0", "2"), "auto": ("0", "1", "0", "1"), "persistent": ("0", "1", "1", "1"), "pair": ("0", "1", "2", "1"),
               "auto-generic": ("0", "1", "0", "0"), "persistent-generic": ("0", "1", "1", "0"), "pair-generic": ("0", "1", "2", "0"),
               "tile": ("0", "0", "1", "0"), "halo2": ("2", "1", "1", "0"), "halo1": ("1", "1", "1", "0")}
 
 
 def _tc16_mode(monkeypatch, mode):
-    """auto (default): persistent kernel, CTA pairs (cta_group::2, UMMA M = 256) for tiles wider than 128 columns, 3x3 stride-1
-    convs reuse the staged input halo across their nine taps; persistent / pair: one CTA per SM / CTA pairs everywhere;
+    """default: persistent kernel, CTA pairs (cta_group::2, UMMA M = 256) for tiles wider than 128 columns and input-halo reuse
+    (A staged once per channel chunk for the nine taps) for those paired 3x3 stride-1 convs; auto / persistent / pair: halo reuse
+    for every 3x3 stride-1 conv with automatic pairing / one CTA per SM / CTA pairs everywhere;
     *-generic: per-tap input boxes for every conv (no halo reuse); tile: one CTA per output tile (round-1 kernel);
     halo2 / halo1: round-1 halo kernels."""
     halo, persist, cg, phalo = TC16_MODES[mode]
@@ -343,7 +344,7 @@ def test_conv2d_tc16_strided_and_ragged_channels(case, mode, monkeypatch):
     assert float(out.lo[..., :4].float().min()) == 7.0 and float(out.lo[..., 4 + Cout:].float().min()) == 7.0
 
 
-@pytest.mark.parametrize("mode", ["auto", "persistent", "pair", "auto-generic", "persistent-generic", "pair-generic"])
+@pytest.mark.parametrize("mode", ["default", "auto", "persistent", "pair", "auto-generic", "persistent-generic", "pair-generic"])
 def test_conv2d_tc16_persistent_many_tiles(mode, monkeypatch):
     """more output tiles than SMs (every CTA loops several times, the TMA ring and the TMEM chunk buffers wrap across tiles),
     an odd number of M tiles (the second CTA of the last pair is dead) and several N tiles; checked against the exact-fp32

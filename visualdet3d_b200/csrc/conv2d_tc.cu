@@ -824,8 +824,8 @@ conv2d_tcph_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     const uint32_t tmem_base = __reduce_or_sync(0xffffffffu, *tmem_slot);      // uniform register (see conv2d_tcp_kernel)
 
     if (warp == 0) {
-        if (lane == 0) {
-            // ================= A producer: one halo item per (tile, 64-channel chunk) =================
+        if (elect_one()) {
+            // ================= A producer (one elected lane): one halo item per (tile, 64-channel chunk) =================
             int it = 0;
             for (int u = u0; u < units; u += ustep) {
                 const int mu = u % mt_units;
@@ -860,9 +860,10 @@ conv2d_tcph_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
                 }
             }
         }
+        __syncwarp();
     } else if (warp == 10) {
-        if (lane == 0) {
-            // ================= W producer: one (chunk, tap) weight block per k-block =================
+        if (elect_one()) {
+            // ================= W producer (one elected lane): one (chunk, tap) weight block per k-block =================
             int it = 0;
             for (int u = u0; u < units; u += ustep) {
                 const int nt = u / mt_units;
@@ -887,9 +888,10 @@ conv2d_tcph_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
                 }
             }
         }
+        __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0 && rank == 0) {
-            // ================= MMA issuer (leader CTA) =================
+        if (rank == 0 && elect_one()) {
+            // ================= MMA issuer (leader CTA, one elected lane) =================
             int ita = 0, itb = 0, cc = 0;
             for (int u = u0; u < units; u += ustep) {
                 const int nvalid = min(p.BN, p.cout_pad - (u / mt_units) * p.BN);
@@ -936,6 +938,7 @@ conv2d_tcph_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
                 cc += NC;
             }
         }
+        __syncwarp();
     } else {
         tcp_epilogue<NG16, CG>(p, tmem_base, tmem_full, tmem_empty, warp, lane, rank, NC, u0, ustep, units, mt_units);
         tc_fence_before();
@@ -1200,11 +1203,12 @@ static int conv2d_tc_launch(int f16, const void* in, const void* in_lo, int B, i
         int rc;
         if ((rc = make_map_wgt(&mWhi, w_hi, Cout, K, BN / CG, 2))) return rc;
         if ((rc = make_map_wgt(&mWlo, w_lo, Cout, K, BN / CG, 2))) return rc;
-        // VD3D_TC_PHALO=1 (opt-in): 3x3 stride-1 convs reuse the staged input halo across the nine taps.  Measured on B200: no faster
-        // than per-tap boxes (the pipeline is bound by TMA latency per stage and shared-memory bandwidth, not by L2 -> SM bytes).
+        // Input-halo reuse for 3x3 stride-1 convs (A staged once per 64-channel chunk, nine taps read it): VD3D_TC_PHALO = 2 (default):
+        // for the wide, paired tiles only (measured: head conv -8 %, layer3 -2 %; the narrow-tile layers are 3..5 % slower with it), 1: always, 0: never
         const char* eh = getenv("VD3D_TC_PHALO");
+        const int phalo = eh ? atoi(eh) : 2;
         const bool halo_fits = 227 * 1024 - 1024 - 512 - 2 * (size_t)TCPH_ITEM >= 2 * (2 * (size_t)(BN / CG) * 128);
-        if ((eh ? atoi(eh) : 0) != 0 && halo_fits && KH == 3 && KW == 3 && pad == 1 && dil == 1 && stride == 1) {
+        if ((phalo == 1 || (phalo == 2 && CG == 2)) && halo_fits && KH == 3 && KW == 3 && pad == 1 && dil == 1 && stride == 1) {
             if ((rc = make_map_act(&mA, in, B, H, W, Cin, in_cs, in_co, 2, 10, 1))) return rc;
             if ((rc = make_map_act(&mAlo, in_lo, B, H, W, Cin, in_cs, in_co, 2, 10, 1))) return rc;
             return tcph_launch(p, mA, mAlo, mWhi, mWlo, CG, stream);
