@@ -87,11 +87,12 @@ int vd3d_conv2d_tc16(const void* in_hi, const void* in_lo, int B, int H, int W, 
 /* Few-channel KHxKW convolution (the ResNet / DLA stem: conv1 7x7 stride 2, R/backbones/resnet.py:120,186) on the tensor cores.
  * The image is held as fp16 (hi, lo) planes [B][H][Wp][4] (pixel x at column x + pad, zeros elsewhere: the buffer must be
  * zero-initialised once); Wp = vd3d_stem_row_pitch(W, KW, stride, pad).  vd3d_image_to_h16_rows fills the planes from an
- * NCHW fp32 image (C <= 4; xoff = pad).  Weights: fp16 (hi, lo) [Cout][KH][64] with column kw*4 + c (zero beyond KW*4 and for
- * c >= C), scaled by a power of two like vd3d_conv2d_tc16; even stride, KW <= 16, Cout % 16 == 0, Cout <= 256. */
+ * NCHW fp32 image (C <= 4; xoff = pad).  `win` = window elements per filter row (32: 8 pixels, 64-byte swizzle rows; 64: 16 pixels,
+ * 128-byte rows), win >= 4 * KW.  Weights: fp16 (hi, lo) [Cout][KH][win] with column kw*4 + c (zero beyond KW*4 and for c >= C),
+ * scaled by a power of two like vd3d_conv2d_tc16; even stride, Cout % 16 == 0, Cout <= 256. */
 int vd3d_stem_row_pitch(int W, int KW, int stride, int pad);
 int vd3d_image_to_h16_rows(const float* img_nchw, int B, int C, int H, int W, void* hi16, void* lo16, int Wp, int xoff, void* stream);
-int vd3d_conv2d_tc16_stem(const void* in_hi, const void* in_lo, int B, int H, int W, int Wp, int KH, int KW, int stride, int pad,
+int vd3d_conv2d_tc16_stem(const void* in_hi, const void* in_lo, int B, int H, int W, int Wp, int KH, int KW, int stride, int pad, int win,
                           const void* w_hi, const void* w_lo, float out_scale, const float* bias,
                           float* out, void* out_hi16, void* out_lo16, int Cout, int out_cs, int out_co, int relu, void* stream);
 /* Diagnostics: when set, CTA 0 of every persistent tensor-core conv writes clock64 stamps per k-block into a [5][n] int64 device

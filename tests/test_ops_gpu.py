@@ -372,13 +372,15 @@ def test_conv2d_tc16_persistent_many_tiles(mode, monkeypatch):
         assert torch.equal(out.lo[0], hi) and torch.equal(out.lo[1], (out.t - hi.float()).half())
 
 
+@pytest.mark.parametrize("win", ["32", "64"])
 @pytest.mark.parametrize("mode", ["persistent", "pair"])
 @pytest.mark.parametrize("shape", [(2, 3, 64, 96), (1, 3, 37, 53), (3, 3, 96, 320)])
-def test_stem_tensor_core_vs_fp64(shape, mode, monkeypatch):
+def test_stem_tensor_core_vs_fp64(shape, mode, win, monkeypatch):
     """conv1 7x7 stride 2 + BN + ReLU (R/backbones/resnet.py:120-122) through the row-window tensor-core path
     (image -> zero-padded fp16 row planes -> KHx1 conv over 64 virtual channels) against an fp64 convolution."""
     E = _E()
     _tc16_mode(monkeypatch, mode)
+    monkeypatch.setenv("VD3D_STEM_WIN", win)          # 32: 8-pixel windows on 64-byte swizzle rows (default), 64: 16-pixel windows on 128-byte rows
     B, C, H, W = shape
     g = torch.Generator().manual_seed(sum(shape))
     x = torch.randn(B, C, H, W, generator=g) * 2.0

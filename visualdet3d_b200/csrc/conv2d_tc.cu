@@ -35,6 +35,7 @@ struct TcParams {
     int tiles_w, tiles_h;
     int stride_w, pad_w;     // W-direction stride / padding (the H direction uses stride / pad); equal to them for ordinary convs
     int m_tiles, n_tiles;    // persistent kernel: tile counts along M (B * tiles_h * tiles_w) and N
+    int rowb;                // bytes per operand row in shared memory = K bytes per k-block: 128 (64 channels, SWIZZLE_128B) or 64 (32, SWIZZLE_64B)
     int cout_pad;            // Cout rounded up to 16 (ragged last N tile = cout_pad - (n_tiles - 1) * BN columns)
     int v8;                  // output / residual / bias slices are 32-byte aligned: 256-bit global accesses
     long long* trace; int trace_n;   // VD3D diagnostics (vd3d_tc_set_trace): per-k-block clock64 stamps of CTA 0, [5][trace_n]
@@ -580,8 +581,11 @@ conv2d_tcp_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t bnl = (uint32_t)p.BN / CG;                      // weight rows staged by this CTA
-    const uint32_t b_bytes = bnl * 128u;
-    const uint32_t stage_bytes = 2u * TC_A_BYTES + 2u * b_bytes;   // [A hi | A lo | W hi | W lo]
+    const uint32_t rowb = (uint32_t)p.rowb;                        // 128 (SWIZZLE_128B, 64 channels per k-block) or 64 (SWIZZLE_64B, 32)
+    const uint32_t a_bytes = 128u * rowb;                          // one A plane of a stage: 128 pixel rows
+    const uint32_t b_bytes = bnl * rowb;
+    const uint32_t stage_bytes = 2u * a_bytes + 2u * b_bytes;      // [A hi | A lo | W hi | W lo]
+    const int kbc = (int)rowb / 2;                                 // channels per k-block
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
     uint64_t* full = bars;                        // [stages]  TMA -> MMA (leader's copy is the live one when CG = 2)
     uint64_t* empty = bars + p.stages;            // [stages]  MMA -> TMA (multicast to both CTAs)
@@ -591,7 +595,7 @@ conv2d_tcp_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
-    const int cchunks = p.cin_pad / 64;
+    const int cchunks = p.cin_pad / kbc;
     const int KB = p.KH * p.KW * cchunks;
     const int NC = (KB + p.chunk - 1) / p.chunk;
     const int mt_units = (p.m_tiles + CG - 1) / CG;            // scheduling units along M (tiles or tile pairs)
@@ -648,21 +652,21 @@ conv2d_tcp_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                         const uint32_t lbar = mapa_shared(smem_u32(&full[s]), 0);
                         if (rank == 0) mbar_expect_tx(&full[s], 2u * tx);
                         tma_load_4d_2sm(st, &mapA, lbar, c0, wi, hi, b);
-                        if (lo_too) tma_load_4d_2sm(st + TC_A_BYTES, &mapAlo, lbar, c0, wi, hi, b);
-                        tma_load_2d_2sm(st + 2 * TC_A_BYTES, &mapWhi, lbar, kcol, n0);
-                        if (lo_too) tma_load_2d_2sm(st + 2 * TC_A_BYTES + b_bytes, &mapWlo, lbar, kcol, n0);
+                        if (lo_too) tma_load_4d_2sm(st + a_bytes, &mapAlo, lbar, c0, wi, hi, b);
+                        tma_load_2d_2sm(st + 2 * a_bytes, &mapWhi, lbar, kcol, n0);
+                        if (lo_too) tma_load_2d_2sm(st + 2 * a_bytes + b_bytes, &mapWlo, lbar, kcol, n0);
                     } else {
                         mbar_expect_tx(&full[s], tx);
                         tma_load_4d(st, &mapA, &full[s], c0, wi, hi, b);
-                        if (lo_too) tma_load_4d(st + TC_A_BYTES, &mapAlo, &full[s], c0, wi, hi, b);
-                        tma_load_2d(st + 2 * TC_A_BYTES, &mapWhi, &full[s], kcol, n0);
-                        if (lo_too) tma_load_2d(st + 2 * TC_A_BYTES + b_bytes, &mapWlo, &full[s], kcol, n0);
+                        if (lo_too) tma_load_4d(st + a_bytes, &mapAlo, &full[s], c0, wi, hi, b);
+                        tma_load_2d(st + 2 * a_bytes, &mapWhi, &full[s], kcol, n0);
+                        if (lo_too) tma_load_2d(st + 2 * a_bytes + b_bytes, &mapWlo, &full[s], kcol, n0);
                     }
                     if (tr) p.trace[p.trace_n + it] = clock64();                              // [1] loads issued
                     }
                     __syncwarp();
                     if (++s == p.stages) { s = 0; ph ^= 1; }
-                    c0 += 64;
+                    c0 += kbc;
                     if (c0 == p.cin_pad) { c0 = 0; ++tap; if (++kw == p.KW) { kw = 0; ++kh; } }
                 }
             }
@@ -678,8 +682,9 @@ conv2d_tcp_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             int s = 0, ph = 0, cc = 0;
             auto stage_desc = [&](int st, uint64_t& dA, uint64_t& dAlo, uint64_t& dB, uint64_t& dBlo) {
                 const uint32_t sa = smem_u32(smem + (size_t)st * stage_bytes);
-                dA = make_sdesc(sa); dAlo = make_sdesc(sa + TC_A_BYTES);
-                dB = make_sdesc(sa + 2 * TC_A_BYTES); dBlo = make_sdesc(sa + 2 * TC_A_BYTES + b_bytes);
+                const uint32_t sbo = 8u * rowb, lay = rowb == 128u ? 2u : 4u;
+                dA = make_sdesc(sa, sbo, lay); dAlo = make_sdesc(sa + a_bytes, sbo, lay);
+                dB = make_sdesc(sa + 2 * a_bytes, sbo, lay); dBlo = make_sdesc(sa + 2 * a_bytes + b_bytes, sbo, lay);
             };
             auto tile_idesc = [&](int unit_local) {
                 const int u = u0 + unit_local * ustep;
@@ -716,7 +721,7 @@ conv2d_tcp_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                 const bool tr = p.trace && blockIdx.x == 0 && g < p.trace_n;
                 if (tr) p.trace[3 * p.trace_n + g] = clock64();                               // [3] about to issue k-block g
                 issue(d_tmem, idesc, dA, dAlo, dB, dBlo, 0, first_in_chunk ? 0u : 1u);
-                issue(d_tmem, idesc, dA, dAlo, dB, dBlo, 1, 1u);
+                if (rowb == 128u) issue(d_tmem, idesc, dA, dAlo, dB, dBlo, 1, 1u);
                 // ---- look-ahead for k-block g+1 while the MMAs above are queued ----
                 const int s_cur = s;
                 uint64_t nA = 0, nAlo = 0, nB = 0, nBlo = 0;
@@ -728,8 +733,12 @@ conv2d_tcp_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                     tc_fence_after();
                     stage_desc(s, nA, nAlo, nB, nBlo);
                 }
-                issue(d_tmem, idesc, dA, dAlo, dB, dBlo, 2, 1u);
-                issue(d_tmem, idesc, dA, dAlo, dB, dBlo, 3, 1u);
+                if (rowb == 128u) {
+                    issue(d_tmem, idesc, dA, dAlo, dB, dBlo, 2, 1u);
+                    issue(d_tmem, idesc, dA, dAlo, dB, dBlo, 3, 1u);
+                } else {
+                    issue(d_tmem, idesc, dA, dAlo, dB, dBlo, 1, 1u);      // 64-byte rows: two K steps per k-block
+                }
                 if (CG == 2) umma_commit_2sm(&empty[s_cur]); else umma_commit(&empty[s_cur]);       // frees the stage (in both CTAs)
                 if (tr) p.trace[4 * p.trace_n + g] = clock64();                               // [4] MMAs + commit issued
                 if (last_in_chunk) {
@@ -1003,15 +1012,15 @@ static int make_map_act(CUtensorMap* m, const void* base_v, int B, int H, int W,
     return VD3D_OK;
 }
 
-static int make_map_wgt(CUtensorMap* m, const void* base, int Cout, int K, int BN, int esize = 4) {
+static int make_map_wgt(CUtensorMap* m, const void* base, int Cout, int K, int BN, int esize = 4, int rowb = 128) {
     EncodeTiledFn enc = get_encode();
     if (!enc) { set_error("conv2d_tc: cuTensorMapEncodeTiled unavailable"); return VD3D_ECUDA; }
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)Cout};
     cuuint64_t strides[1] = {(cuuint64_t)K * esize};
-    cuuint32_t box[2] = {(cuuint32_t)(128 / esize), (cuuint32_t)BN};
+    cuuint32_t box[2] = {(cuuint32_t)(rowb / esize), (cuuint32_t)BN};
     cuuint32_t es[2] = {1, 1};
     CUresult r = enc(m, esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     rowb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("conv2d_tc: cuTensorMapEncodeTiled(weights) failed: %d", (int)r); return VD3D_ECUDA; }
     return VD3D_OK;
 }
@@ -1051,7 +1060,8 @@ static int tcp_launch(TcParams& p, const CUtensorMap& mA, const CUtensorMap& mAl
     const int BN = p.BN;
     { const char* e = getenv("VD3D_TC_DEBUG"); p.dbg = e ? atoi(e) : 0; }
     p.trace = g_trace; p.trace_n = g_trace_n;
-    const size_t stage_bytes = 2 * (size_t)TC_A_BYTES + 2 * (size_t)(BN / CG) * 128;
+    if (p.rowb == 0) p.rowb = 128;
+    const size_t stage_bytes = 2 * (size_t)128 * p.rowb + 2 * (size_t)(BN / CG) * p.rowb;
     int stages = (int)((227 * 1024 - 1024 - 512) / stage_bytes);
     if (stages > 8) stages = 8;
     VD3D_REQUIRE(stages >= 2, "conv2d_tc: tile too large for shared memory");
@@ -1342,23 +1352,24 @@ extern "C" int vd3d_stem_row_pitch(int W, int KW, int stride, int pad) {
     return (need + 1) / 2 * 2;
 }
 
-extern "C" int vd3d_conv2d_tc16_stem(const void* in_hi, const void* in_lo, int B, int H, int W, int Wp, int KH, int KW, int stride, int pad,
+extern "C" int vd3d_conv2d_tc16_stem(const void* in_hi, const void* in_lo, int B, int H, int W, int Wp, int KH, int KW, int stride, int pad, int win,
                                      const void* w_hi, const void* w_lo, float out_scale, const float* bias,
                                      float* out, void* out_hi16, void* out_lo16, int Cout, int out_cs, int out_co, int relu, void* stream) {
     VD3D_REQUIRE(in_hi && in_lo && w_hi && w_lo && out, "conv2d_tc16_stem: null pointer");
-    VD3D_REQUIRE(KW >= 1 && KW <= 16 && KH >= 1 && stride >= 2 && stride <= 4 && stride % 2 == 0, "conv2d_tc16_stem: KW <= 16 and an even stride are required (got KW=%d stride=%d)", KW, stride);
+    VD3D_REQUIRE((win == 64 || win == 32) && KW >= 1 && KW * 4 <= win && KH >= 1 && stride >= 2 && stride <= 4 && stride % 2 == 0,
+                 "conv2d_tc16_stem: window of 32 or 64 elements >= 4 * KW and an even stride are required (got KW=%d win=%d stride=%d)", KW, win, stride);
     VD3D_REQUIRE(Wp == vd3d_stem_row_pitch(W, KW, stride, pad), "conv2d_tc16_stem: row pitch %d != vd3d_stem_row_pitch() = %d", Wp, vd3d_stem_row_pitch(W, KW, stride, pad));
     VD3D_REQUIRE(Cout % 16 == 0 && Cout <= 256 && out_cs % 4 == 0 && out_co % 4 == 0, "conv2d_tc16_stem: Cout must be a multiple of 16, <= 256");
     VD3D_REQUIRE(((uintptr_t)in_hi & 15) == 0 && ((uintptr_t)in_lo & 15) == 0 && ((uintptr_t)w_hi & 15) == 0 && ((uintptr_t)out & 15) == 0, "conv2d_tc16_stem: pointers must be 16-byte aligned");
     VD3D_REQUIRE(!out_hi16 || out_lo16, "conv2d_tc16_stem: fp16 output planes come in (hi, lo) pairs");
     TcParams p;
     memset(&p, 0, sizeof(p));
-    p.B = B; p.H = H; p.W = W; p.Cin = 64; p.KH = KH; p.KW = 1; p.pad = pad; p.dil = 1; p.stride = stride;
+    p.B = B; p.H = H; p.W = W; p.Cin = win; p.KH = KH; p.KW = 1; p.pad = pad; p.dil = 1; p.stride = stride;
     p.stride_w = 1; p.pad_w = 0;
     p.Ho = (H + 2 * pad - KH) / stride + 1; p.Wo = (W + 2 * pad - KW) / stride + 1;
     VD3D_REQUIRE(p.Ho > 0 && p.Wo > 0, "conv2d_tc16_stem: empty output");
     const int BN = Cout;
-    p.Cout = Cout; p.BN = BN; p.passes = 3; p.f16 = 1; p.bk = 64; p.cin_pad = 64; p.out_scale = out_scale;
+    p.Cout = Cout; p.BN = BN; p.passes = 3; p.f16 = 1; p.bk = win; p.cin_pad = win; p.rowb = 2 * win; p.out_scale = out_scale;
     p.tiles_w = cdiv(p.Wo, TC_TW); p.tiles_h = cdiv(p.Ho, TC_TH);
     p.cout_pad = Cout;
     p.m_tiles = p.tiles_w * p.tiles_h * B; p.n_tiles = 1;
@@ -1377,20 +1388,20 @@ extern "C" int vd3d_conv2d_tc16_stem(const void* in_hi, const void* in_lo, int B
     if (!enc) { set_error("conv2d_tc16_stem: cuTensorMapEncodeTiled unavailable"); return VD3D_ECUDA; }
     CUtensorMap mA, mAlo, mWhi, mWlo;
     {
-        // virtual [B][H][Wo][64] view with overlapping W' stride (stride pixels = stride * 8 bytes)
-        cuuint64_t dims[4] = {64, (cuuint64_t)p.Wo, (cuuint64_t)H, (cuuint64_t)B};
+        // virtual [B][H][Wo][win] view with overlapping W' stride (stride pixels = stride * 8 bytes)
+        cuuint64_t dims[4] = {(cuuint64_t)win, (cuuint64_t)p.Wo, (cuuint64_t)H, (cuuint64_t)B};
         cuuint64_t strides[3] = {(cuuint64_t)stride * 8, (cuuint64_t)Wp * 8, (cuuint64_t)H * Wp * 8};
-        cuuint32_t box[4] = {64, (cuuint32_t)TC_TW, (cuuint32_t)(TC_TH * stride), 1};
+        cuuint32_t box[4] = {(cuuint32_t)win, (cuuint32_t)TC_TW, (cuuint32_t)(TC_TH * stride), 1};
         cuuint32_t es[4] = {1, 1, (cuuint32_t)stride, 1};
         for (int i = 0; i < 2; ++i) {
             CUresult r = enc(i ? &mAlo : &mA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)(i ? in_lo : in_hi), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                             win == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) { set_error("conv2d_tc16_stem: cuTensorMapEncodeTiled(image) failed: %d", (int)r); return VD3D_ECUDA; }
         }
     }
     int rc;
-    if ((rc = make_map_wgt(&mWhi, w_hi, Cout, KH * 64, BN / CG, 2))) return rc;
-    if ((rc = make_map_wgt(&mWlo, w_lo, Cout, KH * 64, BN / CG, 2))) return rc;
+    if ((rc = make_map_wgt(&mWhi, w_hi, Cout, KH * win, BN / CG, 2, 2 * win))) return rc;
+    if ((rc = make_map_wgt(&mWlo, w_lo, Cout, KH * win, BN / CG, 2, 2 * win))) return rc;
     return tcp_launch(p, mA, mAlo, mWhi, mWlo, CG, stream);
 }
 

@@ -90,13 +90,14 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
 // shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor layout)
-__device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr, uint32_t sbo = 1024) {
+// `layout`: cute::UMMA::LayoutType, 2 = SWIZZLE_128B (128-byte rows, 8-row groups 1024 B apart), 4 = SWIZZLE_64B (64-byte rows, 512 B)
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr, uint32_t sbo = 1024, uint32_t layout = 2) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr >> 4) & 0x3FFF);        // start address
     d |= (uint64_t)0 << 16;                          // leading byte offset (unused for swizzled K-major)
-    d |= (uint64_t)(sbo >> 4) << 32;                 // stride byte offset between 8-row groups (1024 = dense 8 rows * 128 B)
+    d |= (uint64_t)(sbo >> 4) << 32;                 // stride byte offset between 8-row groups (dense: 8 rows * row bytes)
     d |= (uint64_t)1 << 46;                          // descriptor version (Blackwell)
-    d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
+    d |= (uint64_t)layout << 61;
     return d;
 }
 __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {

@@ -251,13 +251,15 @@ class StemLayer:
         Cout, Cin, KH, KW = w.shape
         assert Cin <= 4 and KW <= 16 and stride % 2 == 0 and Cout % 16 == 0 and Cout <= 256
         self.Cin, self.Cout, self.KH, self.KW, self.stride, self.pad, self.relu = Cin, Cout, KH, KW, stride, pad, relu
-        wk = torch.zeros(Cout, KH, 16, 4, dtype=torch.float64)
+        import os
+        self.win = 32 if (KW <= 8 and os.environ.get("VD3D_STEM_WIN", "32") != "64") else 64     # window elements per filter row (8 or 16 pixels x 4)
+        wk = torch.zeros(Cout, KH, self.win // 4, 4, dtype=torch.float64)
         wk[:, :, :KW, :Cin] = w.permute(0, 2, 3, 1)
         wmax = float(wk.abs().max())
         k = int(np.floor(np.log2(16384.0 / wmax))) if wmax > 0 else 0
         k = max(-24, min(24, k))
         self.out_scale = float(2.0 ** (-k))
-        hi, lo = fp16_split(wk.reshape(Cout, KH * 64) * (2.0 ** k))
+        hi, lo = fp16_split(wk.reshape(Cout, KH * self.win) * (2.0 ** k))
         self.w_hi, self.w_lo = hi.to(device), lo.to(device)
         self.b = b.float().to(device)
 
@@ -273,7 +275,7 @@ class StemLayer:
         planes = arena.get(name + ".rows#h16", (2, B, H, Wp, 4), x.device, dtype=torch.float16, zero=True)   # borders stay zero
         call("vd3d_image_to_h16_rows", x.data_ptr(), B, C, H, W, planes[0].data_ptr(), planes[1].data_ptr(), Wp, self.pad, _stream())
         oh, ol = out.h16_ptrs
-        call("vd3d_conv2d_tc16_stem", planes[0].data_ptr(), planes[1].data_ptr(), B, H, W, Wp, self.KH, self.KW, self.stride, self.pad,
+        call("vd3d_conv2d_tc16_stem", planes[0].data_ptr(), planes[1].data_ptr(), B, H, W, Wp, self.KH, self.KW, self.stride, self.pad, self.win,
              self.w_hi.data_ptr(), self.w_lo.data_ptr(), self.out_scale, self.b.data_ptr(), out.ptr, oh, ol, self.Cout, out.cs, out.co,
              1 if self.relu else 0, _stream())
         return out
