@@ -372,6 +372,29 @@ def test_conv2d_tc16_persistent_many_tiles(mode, monkeypatch):
         assert torch.equal(out.lo[0], hi) and torch.equal(out.lo[1], (out.t - hi.float()).half())
 
 
+def test_conv2d_tc16_tile_policies_are_bit_identical(monkeypatch):
+    """The tile policy depends on the problem size (tile width, CTA pairs, input-halo reuse), so the same layer may run through
+    different kernels at different batch sizes: every persistent variant must accumulate in the same order and give
+    bit-identical results (batch invariance of the detectors rests on this)."""
+    E = _E()
+    g = torch.Generator().manual_seed(3)
+    B, Cin, H, W, Cout = 2, 128, 24, 80, 384
+    x = torch.randn(B, H, W, Cin, generator=g)
+    w = torch.randn(Cout, Cin, 3, 3, generator=g) / np.sqrt(Cin * 9)
+    b = torch.randn(Cout, generator=g)
+    layer = E.ConvLayer(w, b, None, pad=1, relu=True, device="cuda", engine="tc16")
+    xa = E.split_lo(E.Act(x.cuda(), 0, None, torch.zeros(2, B, H, W, Cin, device="cuda", dtype=torch.float16)))
+    outs = {}
+    for mode in ("default", "auto", "persistent", "pair", "auto-generic", "persistent-generic", "pair-generic"):
+        _tc16_mode(monkeypatch, mode)
+        for bn in (0, 96, 128, 192):
+            layer.bn_tile = bn
+            outs[(mode, bn)] = layer(xa, E.Act(torch.zeros(B, H, W, Cout, device="cuda"))).t.clone()
+    ref = outs[("default", 0)]
+    for k, v in outs.items():
+        assert torch.equal(v, ref), k
+
+
 @pytest.mark.parametrize("win", ["32", "64"])
 @pytest.mark.parametrize("mode", ["persistent", "pair"])
 @pytest.mark.parametrize("shape", [(2, 3, 64, 96), (1, 3, 37, 53), (3, 3, 96, 320)])

@@ -39,7 +39,7 @@ struct TcParams {
     int cout_pad;            // Cout rounded up to 16 (ragged last N tile = cout_pad - (n_tiles - 1) * BN columns)
     int v8;                  // output / residual / bias slices are 32-byte aligned: 256-bit global accesses
     long long* trace; int trace_n;   // VD3D diagnostics (vd3d_tc_set_trace): per-k-block clock64 stamps of CTA 0, [5][trace_n]
-    int dbg;                 // timing experiments only (VD3D_TC_DEBUG; results are wrong): bit 0 = one MMA per k-step, bit 1 = skip the lo-plane loads
+    int dbg;                 // timing experiments only (VD3D_TC_DEBUG; results are wrong): bit 0 = one MMA per k-step, bit 1 = skip the lo-plane loads, bit 3 = tap-major k-block order
     int out_cs, out_co, res_cs, res_co, relu;
     const float* bias; const float* res; float* out; float* out_lo;
     uint32_t idesc;
@@ -666,8 +666,16 @@ conv2d_tcp_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                     }
                     __syncwarp();
                     if (++s == p.stages) { s = 0; ph ^= 1; }
-                    c0 += kbc;
-                    if (c0 == p.cin_pad) { c0 = 0; ++tap; if (++kw == p.KW) { kw = 0; ++kh; } }
+                    // k-block order: channel chunk outermost, taps inside (the same order as the halo kernel, so both accumulate
+                    // identically and a layer gives bit-identical results whichever of the two the tile policy picks)
+                    if (p.dbg & 8) {          // timing experiment: taps outermost (the results then differ from the halo kernel's in the last bit)
+                        c0 += kbc;
+                        if (c0 == p.cin_pad) { c0 = 0; ++tap; if (++kw == p.KW) { kw = 0; ++kh; } }
+                    } else {
+                        ++tap;
+                        if (++kw == p.KW) { kw = 0; ++kh; }
+                        if (tap == p.KH * p.KW) { tap = 0; kh = 0; kw = 0; c0 += kbc; }
+                    }
                 }
             }
         }
@@ -1037,6 +1045,26 @@ extern "C" int vd3d_tc_pick_bn_persistent(int Cout) {
     return ((cp + nt - 1) / nt + 15) / 16 * 16;
 }
 
+// Tile width for a given problem: minimise  rounds x (BN + 64)  over 16-column granules, where rounds = ceil(tiles / SMs (pairs)) and the
+// constant stands for the per-k-block cost that does not scale with the tile width (barrier / commit / issue gaps); tiles wider than 128
+// columns run as CTA pairs.  E.g. Cout = 1152 at 120 M tiles: 5 x 240 needs 5 rounds (300 pair tiles on 74 pairs), 6 x 192 also 5 rounds
+// of narrower tiles: -16 %; Cout = 1408 keeps 6 x 240 (360 pair tiles, 4.86 rounds).
+static int pick_bn_cost(int Cout, int m_tiles) {
+    const int cp = (Cout + 15) / 16 * 16;
+    if (cp <= 128) return cp;
+    int best = vd3d_tc_pick_bn_persistent(Cout);
+    long long best_cost = -1;
+    for (int bn = 96; bn <= 256; bn += 16) {
+        const int cg = bn > 128 ? 2 : 1;
+        const long long units = (long long)((m_tiles + cg - 1) / cg) * ((cp + bn - 1) / bn);
+        const long long slots = kNumSMs / cg;
+        const long long rounds = (units + slots - 1) / slots;
+        const long long cost = rounds * (bn + 64);
+        if (best_cost < 0 || cost < best_cost || (cost == best_cost && bn > best)) { best_cost = cost; best = bn; }
+    }
+    return best;
+}
+
 extern "C" int vd3d_tc_pick_bn(int Cout) {
     // largest tile <= 128 that divides Cout evenly into 16-multiples; otherwise the single-tile / 64 fallbacks
     if (Cout % 128 == 0) return 128;
@@ -1171,7 +1199,13 @@ static int conv2d_tc_launch(int f16, const void* in, const void* in_lo, int B, i
     VD3D_REQUIRE(!out_h16_hi || (out_h16_lo && out_cs % 4 == 0), "conv2d_tc: fp16 output planes come in (hi, lo) pairs");
     int persist, cg_env;
     tc_env(persist, cg_env);
-    int BN = bn > 0 ? bn : ((f16 && passes == 3 && persist != 0) ? vd3d_tc_pick_bn_persistent(Cout) : vd3d_tc_pick_bn(Cout));
+    int BN = bn;
+    if (BN <= 0) {
+        if (f16 && passes == 3 && persist != 0) {
+            const int Ho_ = (H + 2 * pad - dil * (KH - 1) - 1) / stride + 1, Wo_ = (W + 2 * pad - dil * (KW - 1) - 1) / stride + 1;
+            BN = pick_bn_cost(Cout, cdiv(Wo_, TC_TW) * cdiv(Ho_, TC_TH) * B);
+        } else BN = vd3d_tc_pick_bn(Cout);
+    }
     const bool use_p = f16 && passes == 3 && persist != 0;
     VD3D_REQUIRE(BN % 16 == 0 && BN >= 16 && BN <= (use_p ? 256 : 160), "conv2d_tc: BN must be a multiple of 16 in [16, %d]", use_p ? 256 : 160);
     TcParams p;
