@@ -39,7 +39,7 @@ struct TcParams {
     int cout_pad;            // Cout rounded up to 16 (ragged last N tile = cout_pad - (n_tiles - 1) * BN columns)
     int v8;                  // output / residual / bias slices are 32-byte aligned: 256-bit global accesses
     long long* trace; int trace_n;   // VD3D diagnostics (vd3d_tc_set_trace): per-k-block clock64 stamps of CTA 0, [5][trace_n]
-    int dbg;                 // timing experiments only (VD3D_TC_DEBUG; results are wrong): bit 0 = one MMA per k-step, bit 1 = skip the lo-plane loads, bit 3 = tap-major k-block order
+    int dbg;                 // timing experiments only (VD3D_TC_DEBUG; results are wrong): bit 0 = one MMA per k-step, bit 1 = skip the lo-plane loads, bit 3 = tap-major k-block order, bit 4 = no epilogue output, bit 5 = no residual loads
     int out_cs, out_co, res_cs, res_co, relu;
     const float* bias; const float* res; float* out; float* out_lo;
     uint32_t idesc;
@@ -47,6 +47,8 @@ struct TcParams {
     // halo kernel (3x3, pad 1, dil 1, fp16 operands): one A item in shared memory serves `h_taps` taps
     int h_mode;              // 2: full halo (10 rows x 2 half-rows of 10 px, 9 taps / item), 1: vertical halo (16 px x 10 rows per kx, 3 taps / item)
     int h_taps, h_sa, h_sb;  // taps per A item, A stages, B stages
+    int nbuf;                // persistent kernels: TMEM accumulator (chunk) buffers, 2..4 = min(4, 512 / BN): how many chunks the MMA warp may run ahead of the epilogue
+    int w_res;               // persistent halo kernel: all weight blocks of the (single) N tile stay resident in shared memory
     uint32_t h_rp, h_sbo;    // bytes per halo row, bytes between 8-pixel groups (UMMA stride byte offset)
 };
 
@@ -89,7 +91,7 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint32_t tmem_bas
     __half* oh = p.out_h16_hi ? reinterpret_cast<__half*>(p.out_h16_hi) + pix * p.out_cs + p.out_co : nullptr;
     __half* ol16 = p.out_h16_lo ? reinterpret_cast<__half*>(p.out_h16_lo) + pix * p.out_cs + p.out_co : nullptr;
     const float osc = p.out_scale;
-    const float* rp = p.res ? p.res + pix * p.res_cs + p.res_co : nullptr;
+    const float* rp = (p.res && !(p.dbg & 32)) ? p.res + pix * p.res_cs + p.res_co : nullptr;
     if (ok) {
 #pragma unroll
         for (int g = 0; g < NG; ++g) {
@@ -456,7 +458,7 @@ __device__ __forceinline__ void tcp_epilogue(const TcParams& p, uint32_t tmem_ba
 #pragma unroll
             for (int i = 0; i < 16; ++i) acc[g][i] = 0.f;
         for (int ci = 0; ci < NC; ++ci, ++cc) {
-            const int buf = cc & 1, use = cc >> 1;
+            const int buf = cc % p.nbuf, use = cc / p.nbuf;
             mbar_wait(&tmem_full[buf], use & 1);
             tc_fence_after();
 #pragma unroll
@@ -484,12 +486,12 @@ __device__ __forceinline__ void tcp_epilogue(const TcParams& p, uint32_t tmem_ba
         const int th = mt % p.tiles_h; const int b = mt / p.tiles_h;
         const int r = q * 32 + lane;
         const int ho = th * TC_TH + r / TC_TW, wo = tw * TC_TW + r % TC_TW;
-        if (live && ho < p.Ho && wo < p.Wo) {
+        if (live && ho < p.Ho && wo < p.Wo && !(p.dbg & 16)) {
             const long long pix = ((long long)b * p.Ho + ho) * p.Wo + wo;
             float* op = p.out + pix * p.out_cs + p.out_co;
             __half* oh = p.out_h16_hi ? reinterpret_cast<__half*>(p.out_h16_hi) + pix * p.out_cs + p.out_co : nullptr;
             __half* ol16 = p.out_h16_lo ? reinterpret_cast<__half*>(p.out_h16_lo) + pix * p.out_cs + p.out_co : nullptr;
-            const float* rp = p.res ? p.res + pix * p.res_cs + p.res_co : nullptr;
+            const float* rp = (p.res && !(p.dbg & 32)) ? p.res + pix * p.res_cs + p.res_co : nullptr;
             const int nbase = nt * p.BN + cb;
             const bool v8 = p.v8 != 0;
             // batches of 16 * GB columns: all residual loads of a batch are issued before its arithmetic and stores
@@ -590,8 +592,8 @@ conv2d_tcp_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     uint64_t* full = bars;                        // [stages]  TMA -> MMA (leader's copy is the live one when CG = 2)
     uint64_t* empty = bars + p.stages;            // [stages]  MMA -> TMA (multicast to both CTAs)
     uint64_t* tmem_full = bars + 2 * p.stages;    // [2]       MMA -> epilogue (multicast)
-    uint64_t* tmem_empty = tmem_full + 2;         // [2]       epilogue -> MMA (leader's copy, 8 * CG arrivals)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    uint64_t* tmem_empty = tmem_full + 4;         // [nbuf <= 4] epilogue -> MMA (leader's copy, 8 * CG arrivals)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
@@ -604,7 +606,7 @@ conv2d_tcp_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 8 * CG); }
+        for (int i = 0; i < 4; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 8 * CG); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {   // TMEM allocation (whole warp; with CG = 2 the same warp of both CTAs)
@@ -722,7 +724,7 @@ conv2d_tcp_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             uint32_t idesc = tile_idesc(0);
             int kb = 0, unit_local = 0;
             for (long long g = 0; g < total; ++g) {
-                const int buf = cc & 1;
+                const int buf = cc % p.nbuf;
                 const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.BN);
                 const bool first_in_chunk = (kb % p.chunk) == 0;
                 const bool last_in_chunk = (kb % p.chunk) == p.chunk - 1 || kb == KB - 1;
@@ -753,7 +755,7 @@ conv2d_tcp_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                     if (CG == 2) umma_commit_2sm(&tmem_full[buf]); else umma_commit(&tmem_full[buf]);
                     ++cc;
                     if (has_next) {
-                        const int nbuf = cc & 1, use = cc >> 1;
+                        const int nbuf = cc % p.nbuf, use = cc / p.nbuf;
                         mbar_wait(&tmem_empty[nbuf], (use & 1) ^ 1);     // every epilogue warp has promoted this buffer's previous chunk
                         tc_fence_after();
                     }
@@ -807,8 +809,8 @@ conv2d_tcph_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     uint64_t* fullB = emptyA + p.h_sa;
     uint64_t* emptyB = fullB + p.h_sb;
     uint64_t* tmem_full = emptyB + p.h_sb;
-    uint64_t* tmem_empty = tmem_full + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    uint64_t* tmem_empty = tmem_full + 4;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
@@ -822,7 +824,7 @@ conv2d_tcph_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.h_sa; ++s) { mbar_init(&fullA[s], 1); mbar_init(&emptyA[s], 1); }
         for (int s = 0; s < p.h_sb; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 8 * CG); }
+        for (int i = 0; i < 4; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 8 * CG); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -882,6 +884,19 @@ conv2d_tcph_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
         if (elect_one()) {
             // ================= W producer (one elected lane): one (chunk, tap) weight block per k-block =================
             int it = 0;
+            if (p.w_res) {
+                // weight-resident mode (one N tile, 9 * cchunks weight blocks fit next to the two A items): every block is loaded ONCE per CTA
+                const int n0 = (int)rank * (min(p.BN, p.cout_pad) / CG);
+                const uint32_t lbar = CG == 2 ? mapa_shared(smem_u32(&fullB[0]), 0) : 0u;
+                if (rank == 0) mbar_expect_tx(&fullB[0], (uint32_t)CG * (uint32_t)KB * b_stage);
+                for (int kb = 0; kb < KB; ++kb) {
+                    const int ch = kb / 9, tap = kb - ch * 9;
+                    const int kcol = tap * p.cin_pad + ch * 64;
+                    uint8_t* st = smemB + (size_t)kb * b_stage;
+                    if (CG == 2) { tma_load_2d_2sm(st, &mapWhi, lbar, kcol, n0); tma_load_2d_2sm(st + b_bytes, &mapWlo, lbar, kcol, n0); }
+                    else { tma_load_2d(st, &mapWhi, &fullB[0], kcol, n0); tma_load_2d(st + b_bytes, &mapWlo, &fullB[0], kcol, n0); }
+                }
+            } else
             for (int u = u0; u < units; u += ustep) {
                 const int nt = u / mt_units;
                 const int nvalid = min(p.BN, p.cout_pad - nt * p.BN);
@@ -910,23 +925,24 @@ conv2d_tcph_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
         if (rank == 0 && elect_one()) {
             // ================= MMA issuer (leader CTA, one elected lane) =================
             int ita = 0, itb = 0, cc = 0;
+            if (p.w_res) { mbar_wait(&fullB[0], 0); tc_fence_after(); }
             for (int u = u0; u < units; u += ustep) {
                 const int nvalid = min(p.BN, p.cout_pad - (u / mt_units) * p.BN);
                 const uint32_t idesc = (p.idesc & ~(0x3Fu << 17)) | ((uint32_t)(nvalid >> 3) << 17);
                 bool first = true;
                 for (int kb = 0; kb < KB; ++kb, ++itb) {
                     const int ci = kb / p.chunk;
-                    const int buf = (cc + ci) & 1;
+                    const int buf = (cc + ci) % p.nbuf;
                     if (kb - ci * p.chunk == 0) {
-                        mbar_wait(&tmem_empty[buf], (((cc + ci) >> 1) & 1) ^ 1);
+                        mbar_wait(&tmem_empty[buf], (((cc + ci) / p.nbuf) & 1) ^ 1);
                         tc_fence_after();
                         first = true;
                     }
                     const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.BN);
                     const int ch = kb / 9, t = kb - ch * 9;
-                    const int sa = (ita + ch) % p.h_sa, sb = itb % p.h_sb;
+                    const int sa = (ita + ch) % p.h_sa, sb = p.w_res ? kb : itb % p.h_sb;
                     if (t == 0) mbar_wait(&fullA[sa], ((ita + ch) / p.h_sa) & 1);
-                    mbar_wait(&fullB[sb], (itb / p.h_sb) & 1);
+                    if (!p.w_res) mbar_wait(&fullB[sb], (itb / p.h_sb) & 1);
                     tc_fence_after();
                     const int ky = t / 3, kx = t - ky * 3;
                     const uint32_t a0 = smem_u32(smemA + (size_t)sa * TCPH_ITEM) + (uint32_t)ky * 2560u + (uint32_t)kx * 128u;
@@ -947,7 +963,7 @@ conv2d_tcph_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
                         }
                         first = false;
                     }
-                    if (CG == 2) umma_commit_2sm(&emptyB[sb]); else umma_commit(&emptyB[sb]);
+                    if (!p.w_res) { if (CG == 2) umma_commit_2sm(&emptyB[sb]); else umma_commit(&emptyB[sb]); }
                     if (t == 8) { if (CG == 2) umma_commit_2sm(&emptyA[sa]); else umma_commit(&emptyA[sa]); }
                     if (kb - ci * p.chunk == p.chunk - 1 || kb == KB - 1) { if (CG == 2) umma_commit_2sm(&tmem_full[buf]); else umma_commit(&tmem_full[buf]); }
                 }
@@ -1077,6 +1093,21 @@ extern "C" int vd3d_tc_pick_bn(int Cout) {
     return 128;
 }
 
+// TMEM accumulator buffers of the persistent kernels: as many BN-column chunk buffers as fit in the 512 columns, at most 4
+// (VD3D_TC_NBUF overrides).  With 2 buffers the MMA warp can run 2 chunks (8 k-blocks) ahead of the epilogue; 4 buffers let it
+// finish most of the next tile of a short-K layer while the epilogue warps are still writing the previous tile to global memory.
+static void tcp_set_accumulators(TcParams& p) {
+    int nb = 512 / p.BN;
+    if (nb > 4) nb = 4;
+    if (nb < 2) nb = 2;
+    const char* e = getenv("VD3D_TC_NBUF");
+    if (e && atoi(e) >= 2 && atoi(e) <= nb) nb = atoi(e);
+    p.nbuf = nb;
+    uint32_t cols = 32;
+    while (cols < (uint32_t)(nb * p.BN)) cols <<= 1;
+    p.tmem_cols = cols;
+}
+
 // diagnostics: clock64 stamps of the TMA / MMA pipeline of CTA 0 ([5][n] int64 device buffer; NULL disables)
 static long long* g_trace = nullptr;
 static int g_trace_n = 0;
@@ -1088,6 +1119,7 @@ static int tcp_launch(TcParams& p, const CUtensorMap& mA, const CUtensorMap& mAl
     const int BN = p.BN;
     { const char* e = getenv("VD3D_TC_DEBUG"); p.dbg = e ? atoi(e) : 0; }
     p.trace = g_trace; p.trace_n = g_trace_n;
+    tcp_set_accumulators(p);
     if (p.rowb == 0) p.rowb = 128;
     const size_t stage_bytes = 2 * (size_t)128 * p.rowb + 2 * (size_t)(BN / CG) * p.rowb;
     int stages = (int)((227 * 1024 - 1024 - 512) / stage_bytes);
@@ -1095,7 +1127,7 @@ static int tcp_launch(TcParams& p, const CUtensorMap& mA, const CUtensorMap& mAl
     VD3D_REQUIRE(stages >= 2, "conv2d_tc: tile too large for shared memory");
     p.stages = stages;
     if (CG == 2) p.idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
-    const size_t smem = stages * stage_bytes + (2 * stages + 6) * sizeof(uint64_t) + 1024;
+    const size_t smem = stages * stage_bytes + (2 * stages + 10) * sizeof(uint64_t) + 1024;
     static bool pattr_set = false;
     if (!pattr_set) {
 #define VD3D_TCP_ATTR(NG, C) VD3D_CUDA(cudaFuncSetAttribute(conv2d_tcp_kernel<NG, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024))
@@ -1134,14 +1166,17 @@ static int tcp_launch(TcParams& p, const CUtensorMap& mA, const CUtensorMap& mAl
 static int tcph_launch(TcParams& p, const CUtensorMap& mA, const CUtensorMap& mAlo, const CUtensorMap& mWhi, const CUtensorMap& mWlo, int CG, void* stream) {
     const int BN = p.BN;
     { const char* e = getenv("VD3D_TC_DEBUG"); p.dbg = e ? atoi(e) : 0; }
+    tcp_set_accumulators(p);
     const size_t b_stage = 2 * (size_t)(BN / CG) * 128;
     p.h_sa = 2;
     const size_t budget = 227 * 1024 - 1024 - 512 - (size_t)p.h_sa * TCPH_ITEM;
-    p.h_sb = (int)(budget / b_stage);
-    if (p.h_sb > 8) p.h_sb = 8;
+    const int KBtot = 9 * (p.cin_pad / 64);
+    p.w_res = (p.n_tiles == 1 && (size_t)KBtot * b_stage <= budget) ? 1 : 0;
+    p.h_sb = p.w_res ? KBtot : (int)(budget / b_stage);
+    if (!p.w_res && p.h_sb > 8) p.h_sb = 8;
     VD3D_REQUIRE(p.h_sb >= 2, "conv2d_tc: halo tile too large for shared memory");
     if (CG == 2) p.idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
-    const size_t smem = (size_t)p.h_sa * TCPH_ITEM + (size_t)p.h_sb * b_stage + (2 * p.h_sa + 2 * p.h_sb + 6) * sizeof(uint64_t) + 1024;
+    const size_t smem = (size_t)p.h_sa * TCPH_ITEM + (size_t)p.h_sb * b_stage + (2 * p.h_sa + 2 * p.h_sb + 10) * sizeof(uint64_t) + 1024;
     static bool hattr_set = false;
     if (!hattr_set) {
 #define VD3D_TCPH_ATTR(NG, C) VD3D_CUDA(cudaFuncSetAttribute(conv2d_tcph_kernel<NG, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024))
@@ -1241,7 +1276,14 @@ static int conv2d_tc_launch(int f16, const void* in, const void* in_lo, int B, i
     }
     if (use_p && !p.h_mode) {
         // ---- persistent kernel (default) ----
-        const int CG = (cg_env == 2 || (cg_env == 0 && BN > 128)) ? 2 : 1;        // VD3D_TC_CG: 0 = auto (pairs for wide tiles), 1, 2
+        int CG = (cg_env == 2 || (cg_env == 0 && BN > 128)) ? 2 : 1;        // VD3D_TC_CG: 0 = auto (pairs for wide tiles), 1, 2
+        const bool s1_3x3 = KH == 3 && KW == 3 && pad == 1 && dil == 1 && stride == 1;
+        // one narrow N tile whose 9 * cchunks weight blocks fit beside the two input-halo items when split over a CTA pair (64 -> 64 layers):
+        // paired halo kernel with the weights resident in shared memory (only the input halo is streamed)
+        const char* ewr = getenv("VD3D_TC_WRES");
+        const bool wres_pair = (ewr ? atoi(ewr) : 1) != 0 && cg_env == 0 && s1_3x3 && p.n_tiles == 1 && BN % 16 == 0 &&
+                               (size_t)9 * (p.cin_pad / 64) * BN * 128 <= (size_t)(227 * 1024 - 1024 - 512) - 2 * (size_t)TCPH_ITEM;
+        if (wres_pair) CG = 2;
         const int K = KH * KW * p.cin_pad;
         CUtensorMap mA, mAlo, mWhi, mWlo;
         int rc;
@@ -1252,7 +1294,7 @@ static int conv2d_tc_launch(int f16, const void* in, const void* in_lo, int B, i
         const char* eh = getenv("VD3D_TC_PHALO");
         const int phalo = eh ? atoi(eh) : 2;
         const bool halo_fits = 227 * 1024 - 1024 - 512 - 2 * (size_t)TCPH_ITEM >= 2 * (2 * (size_t)(BN / CG) * 128);
-        if ((phalo == 1 || (phalo == 2 && CG == 2)) && halo_fits && KH == 3 && KW == 3 && pad == 1 && dil == 1 && stride == 1) {
+        if ((phalo == 1 || (phalo == 2 && CG == 2)) && halo_fits && s1_3x3) {
             if ((rc = make_map_act(&mA, in, B, H, W, Cin, in_cs, in_co, 2, 10, 1))) return rc;
             if ((rc = make_map_act(&mAlo, in_lo, B, H, W, Cin, in_cs, in_co, 2, 10, 1))) return rc;
             return tcph_launch(p, mA, mAlo, mWhi, mWlo, CG, stream);
