@@ -109,3 +109,25 @@ def test_monoflex_registered_and_state_dict_keys_match_reference(kind):
     ref = json.load(open(os.path.join(GOLDEN, f"{kind.lower()}_keys.json")))
     mine = {k: list(v.shape) for k, v in det.state_dict().items()}
     assert list(mine.keys()) == list(ref.keys()) and mine == ref
+
+
+def test_host_side_tile_and_layout_helpers():
+    """Pure host entries of the C ABI (no GPU): the persistent conv engine's default tile width and the stem's padded row pitch."""
+    from visualdet3d_b200 import _lib
+    lib = _lib.load()
+    for cout in (16, 24, 64, 72, 128, 144, 256, 288, 384, 608, 1152, 1408, 2048):
+        bn = lib.vd3d_tc_pick_bn_persistent(cout)
+        cp = (cout + 15) // 16 * 16
+        assert bn % 16 == 0 and 16 <= bn <= 256
+        n_tiles = (cp + bn - 1) // bn
+        assert n_tiles == (cp + 255) // 256                      # as few tiles as 256 accumulator columns allow ...
+        assert n_tiles * bn - cp < 16 * n_tiles                  # ... split evenly (less than one 16-column granule of padding per tile)
+    assert lib.vd3d_tc_pick_bn_persistent(1408) == 240 and lib.vd3d_tc_pick_bn_persistent(64) == 64
+    # stem rows: `pad` zero pixels on the left, the image, and the 16-pixel window of the last output column; even pixel count
+    for (W, KW, s, pad) in ((1280, 7, 2, 3), (320, 7, 2, 3), (53, 7, 2, 3), (96, 3, 2, 1)):
+        Wp = lib.vd3d_stem_row_pitch(W, KW, s, pad)
+        Wo = (W + 2 * pad - KW) // s + 1
+        assert Wp % 2 == 0 and Wp >= W + pad and Wp >= s * (Wo - 1) + 16
+    # the null-pointer / bad-argument paths return an error code and a message instead of launching anything
+    assert lib.vd3d_conv2d_tc16_stem(None, None, 1, 8, 8, 16, 7, 7, 2, 3, 32, None, None, 1.0, None, None, None, None, 64, 64, 0, 1, None) != 0
+    assert b"null pointer" in lib.vd3d_last_error()
