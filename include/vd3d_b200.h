@@ -200,6 +200,19 @@ int vd3d_km3d_decode(const float* heads, int B, int H, int W, int ncls, int cs, 
                      int out_cap, float* out_scores, float* out_boxes, long long* out_cls, int* out_index, int* out_count,
                      int* out_ncand, void* stream);
 
+/* ---- post-optimisation of the yaw by hill climbing (R/lib/fast_utils/hill_climbing.py:24-122; caller detection_3d_head.py:294-308) ----
+ * For each detection the yaw ry is moved in +-step_r steps (halved when neither direction improves, until step_r <= r_lim) to maximise
+ * the IoU between the detected 2-D box and the hull of the projected 3-D box (clipped to img_w x img_h; the reference hard-codes 1280 x 288).
+ * vd3d_post_opt_host runs on the HOST (float64, the reference's numba arithmetic): p2 / p2_inv row-major 4x4, box2d [n][4] f32,
+ * (cx, cy) projected centre in pixels, z / w / h / l / theta0 as float32 values; theta_out [n] (wrapped like the reference), iou_out [n] or NULL.
+ * vd3d_post_opt is the same routine as one CUDA thread per detection on the fixed-capacity NMS output (boxes [B][cap][11], cls [B][cap] i64,
+ * count [B] i32, P2 [B][3][4] of KITTI shape), rewriting alpha in place for rows with cls == label and z > min_depth; no host round trip. */
+int vd3d_post_opt_host(const double* p2, const double* p2_inv, int n, const float* box2d, const double* cx, const double* cy,
+                       const float* z, const float* w, const float* h, const float* l, const float* theta0,
+                       double img_w, double img_h, double step_r_init, double r_lim, double* theta_out, double* iou_out);
+int vd3d_post_opt(float* boxes, const long long* cls, const int* count, const float* P2, int B, int cap,
+                  float img_w, float img_h, float step_r_init, float r_lim, float min_depth, int label, void* stream);
+
 /* ---- deformable convolution (R/lib/ops/dcn, make.sh) ----------------------------------------------------------
  * Deformable / modulated-deformable im2col on NHWC activations; the GEMM that the reference runs per image with cuBLAS
  * (deform_conv_cuda.cpp:540-556) is then ONE batched 1x1 convolution on vd3d_conv2d_tc over K = KH*KW*C.

@@ -39,7 +39,7 @@ class Anchor3DDetector(nn.Module):
         self.prior_mean, self.prior_std = load_priors(head["preprocessed_path"], acfg.get("obj_types", self.obj_types),
                                                       n_rows, len(acfg["ratios"]))
         if self.test_cfg.get("post_optimization", False):
-            # R/heads/detection_3d_head.py:294-308 (CPU numba hill climbing) is a "next" row
+            # R/heads/detection_3d_head.py:294-308 (hill climbing on the yaw): applied in `results` (postopt.py)
             self.post_optimization = True
         else:
             self.post_optimization = False
@@ -106,11 +106,21 @@ class Anchor3DDetector(nn.Module):
         dec.run(cls.t.view(B, N, self.num_cls_output), reg.t.view(B, N, 12), tab.anchors, tab.mean_std, mask,
                 self.num_classes, self.test_cfg.get("score_thr", 0.5), self.test_cfg.get("nms_iou_thr", 0.5), W, H)
         self._last_decoder = dec
+        dec.post_opt_P2 = P2 if self.post_optimization else None      # `results` refines the yaw of the kept rows (head.test_cfg.post_optimization)
         return dec
 
     @staticmethod
     def results(dec: E.DecodeNms):
-        return [(s.clone(), b.clone(), c.clone()) for (s, b, c) in dec.results()]
+        """Per-image (scores, bboxes, cls) triples.  With `test_cfg.post_optimization` the kept car boxes deeper than 3 m get their yaw
+        refined by hill climbing (R/heads/detection_3d_head.py:294-308) on the host, on the rows this call has just synchronised on:
+        K <= a few hundred rows, float64 search in `vd3d_post_opt_host` (the reference also runs it on the CPU, one `.item()` per box)."""
+        res = [(s.clone(), b.clone(), c.clone()) for (s, b, c) in dec.results()]
+        P2 = getattr(dec, "post_opt_P2", None)
+        if P2 is not None:
+            from .. import postopt
+            P2h = P2.detach().cpu().numpy()
+            res = [(s, postopt.post_process(b, c, P2h[i]).to(b.device), c) if len(s) else (s, b, c) for i, (s, b, c) in enumerate(res)]
+        return res
 
     def train_forward(self, *a, **k):
         raise NotImplementedError("training forward is out of scope of the B200 inference path (SURVEY.md section 2)")

@@ -62,9 +62,6 @@ class _Mono3DBase(Anchor3DDetector):
         super().__init__(network_cfg)
         self.bbox_head = self.head_cls(**self.head_kwargs)
         self.core = M.YoloMono3DCoreP(dict(network_cfg["backbone"]))
-        if self.post_optimization:
-            raise NotImplementedError("test_cfg.post_optimization=True (CPU hill climbing, detection_3d_head.py:294-308) is not "
-                                      "implemented on the B200 path yet; set it to False")
 
     def reg_plan(self, dev) -> dict:  # pragma: no cover
         raise NotImplementedError

@@ -28,6 +28,10 @@ class StreamedInference:
         self.ev_free = [torch.cuda.Event() for _ in range(depth)]
         self.ev_done = [torch.cuda.Event() for _ in range(depth)]
         self.submitted = 0
+        self.post_opt = bool(getattr(detector, "post_optimization", False))
+        if self.post_opt and world > 1:
+            raise NotImplementedError("post_optimization with the multi-GPU record all-gather needs the device kernel (vd3d_post_opt) on every rank: round 2")
+        self.host_P2 = [None] * depth
         self.h2d_bytes = 4 * (2 * batch * 3 * height * width + batch * 12)
         self.d2h_bytes = 4 * world * batch * (1 + kmax * parallel.REC)
 
@@ -55,6 +59,7 @@ class StreamedInference:
         rec = parallel.all_gather_records(parallel.pack_records_device(dec, self.kmax))     # the single collective of the path
         self.host_rec[k].copy_(rec, non_blocking=True)
         self.ev_done[k].record(cur)
+        self.host_P2[k] = P2
         self.submitted += 1
         return i
 
@@ -62,4 +67,9 @@ class StreamedInference:
         """Block until batch `ticket` is on the host; returns the per-image (scores, boxes, classes) of the GLOBAL batch."""
         k = ticket % self.depth
         self.ev_done[k].synchronize()
-        return parallel.unpack_records(self.host_rec[k])
+        res = parallel.unpack_records(self.host_rec[k])
+        if self.post_opt:            # yaw refinement of the kept rows on the host (detectors.base.Anchor3DDetector.results does the same)
+            from . import postopt
+            P2h = self.host_P2[k].numpy()
+            res = [(s, postopt.post_process(b, c, P2h[i]), c) if len(s) else (s, b, c) for i, (s, b, c) in enumerate(res)]
+        return res
