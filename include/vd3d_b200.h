@@ -200,6 +200,18 @@ int vd3d_km3d_decode(const float* heads, int B, int H, int W, int ncls, int cs, 
                      int out_cap, float* out_scores, float* out_boxes, long long* out_cls, int* out_index, int* out_count,
                      int* out_ncand, void* stream);
 
+/* ---- input pipeline (R/data/pipeline/stereo_augmentator.py:29-134,213-258: ConvertToFloat, CropTop, Resize, Normalize) -------------------
+ * uint8 HWC frame -> rows [crop_top, H) -> cv2.resize(INTER_LINEAR, float32) to height Ho with the aspect ratio preserved -> cropped / zero
+ * padded on the right to Wo -> (v / 255 - mean[c]) / std[c] -> [C][Ho][Wo] float32.  vd3d_preprocess_host runs on the HOST (parity against the
+ * reference's cv2 / numpy pipeline); vd3d_preprocess is the batched CUDA form: `descs_dev` = B records of vd3d_preprocess_desc_bytes() bytes
+ * each, filled on the host by vd3d_preprocess_describe (frames of different sizes in one batch; src = DEVICE pointer to the uploaded frame),
+ * out = [B][C][Ho][Wo].  The calibration update of CropTop / Resize is host arithmetic (visualdet3d_b200/preprocess.py). */
+int vd3d_preprocess_host(const unsigned char* src, int H, int W, int C, int pitch, int crop_top, int Ho, int Wo,
+                         const float* mean, const float* stdv, float* out);
+int vd3d_preprocess_desc_bytes(void);
+int vd3d_preprocess_describe(void* desc_host, const unsigned char* src_dev, int H, int W, int C, int pitch, int crop_top, int Ho, int Wo);
+int vd3d_preprocess(const void* descs_dev, int B, int C, int Ho, int Wo, const float* mean, const float* stdv, float* out, void* stream);
+
 /* ---- post-optimisation of the yaw by hill climbing (R/lib/fast_utils/hill_climbing.py:24-122; caller detection_3d_head.py:294-308) ----
  * For each detection the yaw ry is moved in +-step_r steps (halved when neither direction improves, until step_r <= r_lim) to maximise
  * the IoU between the detected 2-D box and the hull of the projected 3-D box (clipped to img_w x img_h; the reference hard-codes 1280 x 288).

@@ -1,4 +1,5 @@
-"""-m gpu (runs last): `test_cfg.post_optimization` on the detector path, and the CUDA form of the hill climbing against its host form."""
+"""-m gpu (runs last): the SURVEY 8(f) "next" rows on the GPU — `test_cfg.post_optimization` on the detector path, the CUDA form of the
+hill climbing and of the input pipeline against their host forms (which tests/test_postopt_cpu.py / test_preprocess_cpu.py pin to the reference)."""
 import ctypes
 
 import numpy as np
@@ -57,3 +58,19 @@ def test_device_hill_climbing_matches_host():
     d = torch.minimum(d, (d - 2 * np.pi).abs())
     print("device vs host hill climbing: max |d alpha|", float(d.max()), " rows within 1e-5:", int((d < 1e-5).sum()), "/", K)
     assert int((d < 1e-5).sum()) >= int(0.97 * K)
+
+
+def test_device_input_pipeline_matches_host():
+    """vd3d_preprocess (batched CUDA form, frames of two different sizes in one batch) vs vd3d_preprocess_host on the same frames."""
+    import os
+    import sys
+    from conftest import GOLDEN
+    sys.path.insert(0, GOLDEN)
+    from make_golden_preprocess import frame
+    from visualdet3d_b200 import preprocess as pp
+    frames = [frame(0, 375, 1242), frame(1, 370, 1224)]
+    want = np.stack([pp.preprocess_host(f, 100, (288, 1280)) for f in frames])
+    got = pp.preprocess_batch(frames, 100, (288, 1280)).cpu().numpy()
+    d = float(np.abs(got - want).max())
+    print("device vs host input pipeline: max |diff|", d)
+    assert got.shape == (2, 3, 288, 1280) and d < 1e-5

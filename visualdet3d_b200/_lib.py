@@ -70,6 +70,10 @@ _SIGS = {
     "vd3d_monoflex_decode": (I, [P, I, I, I, I, I, I, I, I, I, I, I, I, I, I, P, F, c_double, I, F, F, F, F, I, P, I, P, P, P, P, P, P, P]),
     "vd3d_km3d_decode_workspace": (c_longlong, [I, I, I]),
     "vd3d_km3d_decode": (I, [P, I, I, I, I, I, I, I, I, I, I, I, I, I, I, P, F, c_double, I, F, F, I, I, P, I, P, P, P, P, P, P, P]),
+    "vd3d_preprocess_host": (I, [P, I, I, I, I, I, I, I, P, P, P]),
+    "vd3d_preprocess_desc_bytes": (I, []),
+    "vd3d_preprocess_describe": (I, [P, P, I, I, I, I, I, I, I]),
+    "vd3d_preprocess": (I, [P, I, I, I, I, P, P, P, P]),
     "vd3d_post_opt_host": (I, [P, P, I, P, P, P, P, P, P, P, P, c_double, c_double, c_double, c_double, P, P]),
     "vd3d_post_opt": (I, [P, P, P, P, I, I, F, F, F, F, F, I, P]),
     "vd3d_pack_records": (I, [P, P, P, P, I, I, I, P, P]),
