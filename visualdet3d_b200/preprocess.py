@@ -35,7 +35,8 @@ def _f32(v: Sequence[float]) -> np.ndarray:
 
 
 def preprocess_host(frame: np.ndarray, crop_top: int, size: Tuple[int, int], mean=RGB_MEAN, std=RGB_STD) -> np.ndarray:
-    """uint8 [H, W, C] -> float32 [C, size[0], size[1]] on the host (the checker of the CUDA form; also usable without a GPU)."""
+    """uint8 [H, W, C] -> float32 [C, size[0], size[1]] on the host: the parity checker of the CUDA form (`preprocess_batch` is the product
+    path; tests pin this routine to the reference and the kernel to this routine)."""
     assert frame.dtype == np.uint8 and frame.ndim == 3
     frame = np.ascontiguousarray(frame)
     H, W, C = frame.shape
