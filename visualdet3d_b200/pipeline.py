@@ -32,6 +32,7 @@ class StreamedInference:
         if self.post_opt and world > 1:
             raise NotImplementedError("post_optimization with the multi-GPU record all-gather needs the device kernel (vd3d_post_opt) on every rank: round 2")
         self.host_P2 = [None] * depth
+        self._uncollected = [False] * depth        # slot holds a batch whose records have not been collected yet
         self.h2d_bytes = 4 * (2 * batch * 3 * height * width + batch * 12)
         self.d2h_bytes = 4 * world * batch * (1 + kmax * parallel.REC)
 
@@ -43,6 +44,8 @@ class StreamedInference:
                 raise ValueError("StreamedInference.submit expects pinned host tensors")
         i = self.submitted
         k = i % self.depth
+        if self._uncollected[k]:
+            raise RuntimeError(f"StreamedInference: batch {i - self.depth} has not been collected; at most {self.depth} batches may be in flight")
         cur = torch.cuda.current_stream(self.dev)
         with torch.cuda.stream(self.copy_stream):
             if i >= self.depth:
@@ -60,13 +63,17 @@ class StreamedInference:
         self.host_rec[k].copy_(rec, non_blocking=True)
         self.ev_done[k].record(cur)
         self.host_P2[k] = P2
+        self._uncollected[k] = True
         self.submitted += 1
         return i
 
     def collect(self, ticket: int) -> List:
         """Block until batch `ticket` is on the host; returns the per-image (scores, boxes, classes) of the GLOBAL batch."""
         k = ticket % self.depth
+        if not (self.submitted - self.depth <= ticket < self.submitted) or not self._uncollected[k]:
+            raise RuntimeError(f"StreamedInference: ticket {ticket} is not in flight")
         self.ev_done[k].synchronize()
+        self._uncollected[k] = False
         res = parallel.unpack_records(self.host_rec[k])
         if self.post_opt:            # yaw refinement of the kept rows on the host (detectors.base.Anchor3DDetector.results does the same)
             from . import postopt
