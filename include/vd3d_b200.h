@@ -172,8 +172,15 @@ int vd3d_decode_nms(const float* cls, const float* reg, const float* anchors, co
                     float* out_scores, float* out_boxes, int64_t* out_cls, int32_t* out_anchor,
                     int32_t* out_count, int32_t* out_ncand, void* stream);
 
+/* fp16-range guard of the fp16-split tensor-core engine.  Activations travel between tensor-core convs as two fp16 planes (hi, lo) of
+ * the UNSCALED fp32 value (the reference's fp32 path has no such limit): |v| >= 65520 would become hi = inf.  Every kernel that writes
+ * such planes (conv epilogues, vd3d_split_h16_nhwc, vd3d_image_to_h16_rows, vd3d_deform_im2col_h16) ORs a per-device word when it meets
+ * such a value; vd3d_fp16_range_check reads it (synchronises `stream`), optionally clears it, and the record kernels report it as
+ * count = -2 so that no result computed from an overflowed plane is ever returned silently. */
+int vd3d_fp16_range_check(int* overflow_out, int reset, void* stream);
+
 /* Record block for the multi-GPU all-gather: rec [B][1 + kmax*13] f32 = count, then kmax rows of
- * (11 box floats, score, class); count = -1 flags an overflow.  Built on the device from the vd3d_decode_nms outputs. */
+ * (11 box floats, score, class); count = -1 flags a capacity overflow, -2 the fp16-range guard.  Built on the device from the vd3d_decode_nms outputs. */
 int vd3d_pack_records(const float* scores, const float* boxes, const int64_t* cls, const int32_t* count, int B, int cap, int kmax,
                       float* rec, void* stream);
 
@@ -224,6 +231,21 @@ int vd3d_post_opt_host(const double* p2, const double* p2_inv, int n, const floa
                        double img_w, double img_h, double step_r_init, double r_lim, double* theta_out, double* iou_out);
 int vd3d_post_opt(float* boxes, const long long* cls, const int* count, const float* P2, int B, int cap,
                   float img_w, float img_h, float step_r_init, float r_lim, float min_depth, int label, void* stream);
+
+/* ---- post-forward geometry (`test_one`, R/networks/pipelines/evaluators.py:112-131) -------------------------------
+ * On the fixed-capacity NMS output (boxes [B][cap][11] = x1, y1, x2, y2, cx, cy, z, w, h, l, alpha; count [B]; P2 [B][3][4]):
+ *   box3d [B][cap][7]  = BackProjection (R/networks/utils/utils.py:256-278): (x, y, z, w, h, l, alpha) in the camera frame,
+ *   theta [B][cap]     = alpha2theta_3d (visualDet3D/utils/utils.py:47-62) as BBox3dProjector returns it (R/networks/utils/utils.py:229),
+ *   box2d [B][cap][4]  = the 2-D box shifted / scaled to the pixels of the original frame through original_P [B][3][4]
+ *                        (evaluators.py:118-127); original_P == NULL copies the boxes,
+ *   corners / homo [B][cap][8][3] (optional, NULL to skip) = BBox3dProjector's camera-frame and image-plane corners (:230-253).
+ * float32 in the reference's operation order (x, y, box2d bit-identical to the reference's tensors); rows past count[b] are zero-filled.
+ * vd3d_pack_records_geo builds the all-gather record block with these columns appended: rec [B][1 + kmax*20] =
+ * count, then kmax rows of (11 box floats, score, class, x3d, y3d, theta, 4 rescaled box floats). */
+int vd3d_post_forward(const float* boxes, const int32_t* count, const float* P2, const float* original_P, int B, int cap,
+                      float* box3d, float* theta, float* box2d, float* corners, float* homo, void* stream);
+int vd3d_pack_records_geo(const float* scores, const float* boxes, const int64_t* cls, const int32_t* count, const float* box3d,
+                          const float* theta, const float* box2d, int B, int cap, int kmax, float* rec, void* stream);
 
 /* ---- deformable convolution (R/lib/ops/dcn, make.sh) ----------------------------------------------------------
  * Deformable / modulated-deformable im2col on NHWC activations; the GEMM that the reference runs per image with cuBLAS

@@ -21,6 +21,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(HERE)), "oracle"))
 import refload  # noqa: E402
 from visualdet3d_b200 import synth  # noqa: E402
 
@@ -249,15 +250,19 @@ if __name__ == "__main__":
     if "stereo3d" in which:
         gen_stereo3d()
         gen_stereo3d(H=192, W=640, B=1, tag="stereo3d_192x640")
+        gen_stereo3d(H=384, W=1280, B=1, tag="stereo3d_384x1280")      # BASELINE.json configs[1] shape
     if "yolo3d" in which:
         gen_mono3d("Yolo3D", 96, 320, 2)
         gen_mono3d("Yolo3D", 288, 1280, 1)       # BASELINE.json configs[0]
     if "km3d" in which:
         gen_monoflex(96, 320, 2, kind="KM3D")
         gen_monoflex(192, 640, 1, kind="KM3D")
+        gen_monoflex(384, 1280, 1, kind="KM3D")     # BASELINE.json configs[3] shape
     if "monoflex" in which:
         gen_monoflex(96, 320, 2)
         gen_monoflex(192, 640, 1)
+        gen_monoflex(384, 1280, 1)                  # BASELINE.json configs[3] shape
     if "gac" in which:
         gen_mono3d("GroundAwareYolo3D", 96, 320, 2)
         gen_mono3d("GroundAwareYolo3D", 288, 640, 1)
+        gen_mono3d("GroundAwareYolo3D", 288, 1280, 1)   # BASELINE.json configs[2] shape

@@ -10,6 +10,7 @@ import torch
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(HERE)), "oracle"))
 import refload  # noqa: E402
 
 P2 = np.array([[5.02790613e+02, 0.0, 4.29568996e+02, 3.25392427e+01], [0.0, 5.02790613e+02, 5.72491378e+01, -5.99834524e-01],

@@ -67,3 +67,53 @@ def test_stem_weight_layout():
         assert float((rec[:, :, :7, :3] - w.permute(0, 2, 3, 1).double()).abs().max()) < float(w.abs().max()) * 2.0 ** -20
         assert float(rec[:, :, 7:, :].abs().max()) == 0.0 and float(rec[:, :, :, 3].abs().max()) == 0.0      # zero beyond KW pixels / 3 channels
         assert layer.out_hw(384, 1280) == (192, 640)
+
+
+def test_dcn_weight_cache_is_keyed_on_the_tensor_object():
+    """ops.dcn packs tensor-core weights once per weight tensor.  The cache must never serve an entry to ANOTHER tensor that happens to
+    live at the same address with the same shape and version (a freed model followed by a new one): entries are keyed on the object and
+    die with it; in-place updates re-pack."""
+    import gc
+    from visualdet3d_b200.ops import dcn
+    c = dcn._WeightCache()
+    g = torch.Generator().manual_seed(0)
+    w = torch.randn(8, 4, 3, 3, generator=g)
+    h1, l1 = c.get(w)
+    assert c.get(w)[0] is h1 and len(c) == 1
+    want = w.permute(0, 2, 3, 1).reshape(8, 36).clone()
+    assert float((h1 + l1 - want).abs().max()) < 4e-6               # tf32 (hi, lo): 21 significant bits
+    w.mul_(2.0)                                            # in-place change -> re-packed
+    h2, l2 = c.get(w)
+    assert h2 is not h1 and float((h2 + l2 - 2 * want).abs().max()) < 8e-6
+    ptr = w.data_ptr()
+    del w
+    gc.collect()
+    assert len(c) == 0                                     # the entry died with its tensor
+    # a different tensor, same shape / version / (very likely) the same address: gets its own packing
+    w2 = torch.randn(8, 4, 3, 3, generator=g)
+    h3, l3 = c.get(w2)
+    assert float((h3 + l3 - w2.permute(0, 2, 3, 1).reshape(8, 36)).abs().max()) < 4e-6
+    print("same address reused:", w2.data_ptr() == ptr)
+
+
+def test_anchor_config_is_honoured_or_refused(tmp_path):
+    """Every argument the reference's Anchors / head take (R/heads/anchors.py:11-14, detection_3d_head.py:30) is either honoured
+    (filter thresholds) or refused loudly (prior channels != 6, read_precompute_anchor=False) -- never silently ignored."""
+    import pytest
+    from visualdet3d_b200 import synth
+    from visualdet3d_b200.detectors import Stereo3D
+    obj_types = ["Car", "Pedestrian"]
+    pm, ps = synth.synth_priors(16, 3, obj_types)
+    synth.write_priors(str(tmp_path), pm, ps, obj_types)
+    cfg = synth.stereo3d_cfg(str(tmp_path), obj_types)
+    assert Stereo3D(cfg).anchor_filter == (-0.5, 1.8, 40.0)
+    cfg["head"]["anchors_cfg"]["filter_y_threshold_min_max"] = (-0.3, 1.5)
+    cfg["head"]["anchors_cfg"]["filter_x_threshold"] = 30.0
+    assert Stereo3D(cfg).anchor_filter == (-0.3, 1.5, 30.0)
+    cfg["head"]["anchors_cfg"]["anchor_prior_channel"] = 7
+    with pytest.raises(ValueError):
+        Stereo3D(cfg)
+    cfg["head"]["anchors_cfg"]["anchor_prior_channel"] = 6
+    cfg["head"]["read_precompute_anchor"] = False
+    with pytest.raises(ValueError):
+        Stereo3D(cfg)

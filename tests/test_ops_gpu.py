@@ -305,6 +305,55 @@ def test_tc16_large_and_tiny_magnitudes():
         assert rel < 4e-6, (wscale, xscale, rel)
 
 
+def test_fp16_range_guard():
+    """The fp16-split engine keeps activations UNSCALED as fp16 (hi, lo) planes: |v| >= 65520 cannot be represented (hi = inf).  Every
+    kernel that writes such planes raises a device flag instead of silently producing inf / NaN: the splitter, the conv epilogue
+    (output planes), and -- end to end -- the detector (`Vd3dError` from `results()` and from the streamed pipeline's record block)."""
+    E = _E()
+    from visualdet3d_b200._lib import Vd3dError
+    g = torch.Generator().manual_seed(7)
+    assert not E.fp16_range_overflowed()
+    planes = lambda *s: torch.zeros(2, *s, device="cuda", dtype=torch.float16)
+    # (a) splitter: 65519 still rounds to the largest finite fp16, 65520 does not
+    x = torch.randn(1, 64, 16, 24, generator=g)
+    x[0, 3, 2, 5] = 65519.0
+    E.split_lo(E.Act(nhwc(x).cuda(), 0, None, planes(1, 16, 24, 64)))
+    assert not E.fp16_range_overflowed()
+    x[0, 3, 2, 5] = -65520.0
+    xa = E.split_lo(E.Act(nhwc(x).cuda(), 0, None, planes(1, 16, 24, 64)))
+    assert E.fp16_range_overflowed() and not E.fp16_range_overflowed()           # reading clears it
+    assert bool(torch.isinf(xa.lo[0].float()).any())
+    # (b) conv epilogue: in-range inputs, an output beyond the range; without output planes nothing is flagged (fp32 output is exact)
+    x = torch.randn(1, 64, 16, 24, generator=g) * 1000
+    w = torch.randn(32, 64, 3, 3, generator=g)
+    layer = E.ConvLayer(w, None, None, pad=1, relu=False, device="cuda", engine="tc16")
+    xa = E.split_lo(E.Act(nhwc(x).cuda(), 0, None, planes(1, 16, 24, 64)))
+    assert not E.fp16_range_overflowed()
+    out32 = layer(xa, E.Act(torch.empty(1, 16, 24, 32, device="cuda")))
+    assert float(out32.t.abs().max()) > 65520 and not E.fp16_range_overflowed()
+    layer(xa, E.Act(torch.empty(1, 16, 24, 32, device="cuda"), 0, None, planes(1, 16, 24, 32)))
+    assert E.fp16_range_overflowed()
+    # (c) end to end: a frame scaled out of range makes the detector raise instead of returning detections; the next forward is clean
+    from visualdet3d_b200 import synth
+    from visualdet3d_b200.detectors import build_synthetic_stereo3d
+    from visualdet3d_b200.pipeline import StreamedInference
+    det, *_ = build_synthetic_stereo3d(seed=0)
+    det = det.cuda().eval()
+    left, right, P2, _ = synth.synth_stereo_inputs(1, 96, 320, seed=1)
+    with torch.no_grad():
+        with pytest.raises(Vd3dError, match="fp16 range"):
+            det.forward_batch(left.cuda() * 1e6, right.cuda() * 1e6, P2.cuda())
+        good = det.forward_batch(left.cuda(), right.cuda(), P2.cuda())
+        assert len(good[0][0]) > 0
+    pipe = StreamedInference(det, 1, 96, 320, kmax=64)
+    t = pipe.submit((left * 1e6).pin_memory(), (right * 1e6).pin_memory(), P2.pin_memory())
+    with pytest.raises(Vd3dError, match="fp16 range"):
+        pipe.collect(t)
+    t = pipe.submit(left.pin_memory(), right.pin_memory(), P2.pin_memory())
+    got = pipe.collect(t)
+    assert torch.equal(got[0][0], good[0][0].cpu())
+
+
 TC16_EXTRA = [
     # B, Cin, H, W, Cout, k, pad, stride
     (2, 64, 24, 40, 128, 3, 1, 2),       # ResNet stage entry: 3x3 stride 2

@@ -62,3 +62,31 @@ def test_all_gather_detections_gloo_world2():
     res = [q.get(timeout=120) for _ in ps]
     [p.join(60) for p in ps]
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_geometry_records_and_guard_flags():
+    """The 20-column record form (post-forward columns appended by vd3d_pack_records_geo) unpacks into the plain triples plus
+    (box3d, theta, box2d); count == -1 (capacity) and -2 (fp16-range guard of the tensor-core engine) raise instead of returning rows."""
+    from visualdet3d_b200._lib import Vd3dError
+    g = torch.Generator().manual_seed(3)
+    kmax, R = 4, parallel.REC_GEO
+    buf = torch.zeros(2, 1 + kmax * R)
+    rows = torch.randn(3, R, generator=g)
+    rows[:, 12] = torch.tensor([0.0, 2.0, 1.0])
+    buf[0, 0] = 3
+    buf[0, 1:1 + 3 * R] = rows.reshape(-1)
+    geo = []
+    out = parallel.unpack_records(buf, R, geo)
+    assert len(out) == 2 and len(geo) == 2 and out[1][0].shape == (0,) and geo[1][0].shape == (0, 7)
+    s, b, c = out[0]
+    assert torch.equal(s, rows[:, 11]) and torch.equal(b, rows[:, :11]) and c.tolist() == [0, 2, 1]
+    box3d, theta, box2d = geo[0]
+    assert torch.equal(box3d[:, :2], rows[:, 13:15]) and torch.equal(box3d[:, 2:], rows[:, 6:11])
+    assert torch.equal(theta, rows[:, 15]) and torch.equal(box2d, rows[:, 16:20])
+    assert [tuple(t.shape) for t in parallel.unpack_records(buf, R)[0]] == [(3,), (3, 11), (3,)]     # geometry list optional
+    buf[1, 0] = -1
+    with pytest.raises(RuntimeError):
+        parallel.unpack_records(buf, R)
+    buf[1, 0] = -2
+    with pytest.raises(Vd3dError, match="fp16 range"):
+        parallel.unpack_records(buf, R)

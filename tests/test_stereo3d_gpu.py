@@ -62,7 +62,7 @@ def run_with_stages(det, left, right, P2):
     return res, st
 
 
-@pytest.mark.parametrize("tag", ["stereo3d_96x320", "stereo3d_192x640"])
+@pytest.mark.parametrize("tag", ["stereo3d_96x320", "stereo3d_192x640", "stereo3d_384x1280"])    # the last one = BASELINE configs[1] shape
 def test_against_reference_fixture(det_bundle, tag):
     from visualdet3d_b200 import synth
     det, sd, cfg, (pm, ps) = det_bundle
@@ -142,9 +142,9 @@ def test_decode_nms_exact_on_oracle_predictions(det_bundle):
         np.testing.assert_allclose(out[b][1].cpu().numpy(), rb.numpy(), atol=1e-4)
 
 
-def test_full_size_batch8_properties(det_bundle):
-    """BASELINE config[1] shape (batch 8, 384x1280): batch invariance (image b of the batched run == the same pair run
-    alone), determinism, and one full-size image checked against the oracle."""
+def test_full_size_batch8_all_images_vs_oracle(det_bundle):
+    """BASELINE config[1] shape (batch 8, 384x1280): determinism, batch invariance (image b of the batched run == the same pair
+    run alone), and EVERY image of the batch against the oracle (kept anchor sets, order, values within 1e-3)."""
     from visualdet3d_b200 import synth
     det, sd, cfg, (pm, ps) = det_bundle
     B, H, W = 8, 384, 1280
@@ -152,16 +152,16 @@ def test_full_size_batch8_properties(det_bundle):
     l, r, p = left.cuda(), right.cuda(), P2.cuda()
     with torch.no_grad():
         res = det.forward_batch(l, r, p)
+        anchors = [det._last_decoder.anchor[b, :len(res[b][0])].clone() for b in range(B)]
         res2 = det.forward_batch(l, r, p)
         single = det([l[5:6], r[5:6], p[5:6], None])
     for a, b in zip(res, res2):
         assert all(torch.equal(x, y) for x, y in zip(a, b))
     assert all(torch.equal(x, y) for x, y in zip(res[5], single))
     assert sum(len(x[0]) for x in res) > 8
-    ref = tp.stereo3d_forward(sd, left[5:6], right[5:6], P2[5:6], cfg, pm, ps)[0]
-    k = len(single[0])
-    swaps = assert_dets_match(single, ref, det._last_decoder.anchor[0, :k])
-    print("full-size image: detections", k, "score-tied order swaps", swaps)
+    ref = tp.stereo3d_forward(sd, left, right, P2, cfg, pm, ps)
+    swaps = [assert_dets_match(res[b], ref[b], anchors[b]) for b in range(B)]
+    print("full-size batch: detections per image", [len(x[0]) for x in res], "score-tied order swaps", swaps)
 
 
 def test_reference_list_protocol_and_empty_result(det_bundle):
@@ -213,9 +213,19 @@ def test_engines_agree(det_bundle):
             bres = det2.forward_batch(left.cuda(), right.cuda(), P2.cuda())
             anchors_b = [det2._last_decoder.anchor[b, :len(bres[b][0])].cpu() for b in range(2)]
         for b in range(2):
-            assert torch.equal(torch.sort(anchors_a[b])[0], torch.sort(anchors_b[b])[0]), eng
-            if torch.equal(anchors_a[b], anchors_b[b]) and len(a[b][0]):
-                assert float((a[b][1] - bres[b][1]).abs().max()) < 1e-3, eng
+            assert len(a[b][0]) > 3
+            sa, ia = torch.sort(anchors_a[b])
+            sb, ib = torch.sort(anchors_b[b])
+            assert torch.equal(sa, sb), eng                                    # same kept anchors ...
+            for j in (0, 1, 2):                                                # ... and, row for row after aligning on the anchor index,
+                va, vb = a[b][j][ia.cuda()], bres[b][j][ib.cuda()]            # the same scores / boxes / classes
+                if j == 2:
+                    assert torch.equal(va, vb), eng
+                else:
+                    assert float((va - vb).abs().max()) < 1e-3, (eng, j, float((va - vb).abs().max()))
+            moved = (anchors_a[b] != anchors_b[b]).nonzero()[:, 0].tolist()    # order may differ only between score-tied rows
+            for i in moved:
+                assert abs(float(a[b][0][i]) - float(bres[b][0][i])) < 1e-5, eng
 
 
 def test_device_record_block_matches_results(det_bundle):

@@ -9,9 +9,15 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def test_detector_flag_applies_host_post_optimisation():
-    """Yolo3D with head.test_cfg.post_optimization=True == the same forward without it, followed by postopt.post_process per image."""
-    from visualdet3d_b200 import synth, postopt
+def wrapped_abs_diff(a, b):
+    d = (a - b).abs()
+    return torch.minimum(d, (d - 2 * np.pi).abs())
+
+
+def test_detector_flag_runs_device_post_optimisation():
+    """Yolo3D with head.test_cfg.post_optimization=True: the yaw refinement runs as a kernel after the NMS (no host pass) and equals the
+    same forward without it followed by the host form `postopt.post_process` (which tests/test_postopt_cpu.py pins to the reference)."""
+    from visualdet3d_b200 import synth, postopt, _lib
     from visualdet3d_b200.detectors import build_synthetic_mono3d
     det, sd, cfg, _ = build_synthetic_mono3d("Yolo3D", seed=0)
     det = det.cuda().eval()
@@ -20,44 +26,157 @@ def test_detector_flag_applies_host_post_optimisation():
         plain = det.forward_batch(img.cuda(), P2.cuda())
         det.post_optimization = True
         try:
-            refined = det.forward_batch(img.cuda(), P2.cuda())
+            n0 = _lib.launch_count()
+            dec = det.launch(img.cuda(), P2.cuda())
+            assert _lib.launch_count() > n0
+            refined = det.results(dec)
         finally:
             det.post_optimization = False
+    changed = 0
     for b, ((s, bx, c), (rs, rb, rc)) in enumerate(zip(plain, refined)):
         assert torch.equal(s, rs) and torch.equal(c, rc) and rb.device == bx.device
         want = postopt.post_process(bx, c, P2[b].numpy()) if len(s) else bx.cpu()
-        assert torch.equal(rb.cpu(), want)
+        assert torch.equal(rb.cpu()[:, :10], want[:, :10])
+        if len(s):
+            assert float(wrapped_abs_diff(rb.cpu()[:, 10], want[:, 10]).max()) < 1e-5
+            changed += int((rb.cpu()[:, 10] != bx.cpu()[:, 10]).sum())
+    assert changed > 0
 
 
-def test_device_hill_climbing_matches_host():
-    """vd3d_post_opt (one thread per detection, in place on the fixed-capacity NMS layout) vs vd3d_post_opt_host on the same rows:
-    same search, float64; the float32 alpha <-> yaw conversions use device atan2f instead of numpy's, so equality is to 1e-5 rad."""
+def test_device_hill_climbing_matches_reference():
+    """vd3d_post_opt (one thread per detection, in place on the fixed-capacity NMS layout) against the UNMODIFIED reference's own outputs
+    (tests/golden/postopt.npz: `post_opt` of R/lib/fast_utils/hill_climbing.py run through numba) and against the host form.  Same
+    float64 search compiled without FMA contraction; the only differences are last-bit ones of cos / sin / atan2 between the device
+    and the host libm, which can move the result by an ulp of float32 but must not change a branch: every row within 1e-5 rad."""
     import os
     from conftest import GOLDEN
     from visualdet3d_b200 import postopt, _lib
     fx = np.load(os.path.join(GOLDEN, "postopt.npz"))
     P2 = fx["P2"]
-    b = torch.from_numpy(fx["c2_in"])
-    labels = torch.from_numpy(fx["c2_labels"]).long()
-    want = postopt.post_process(b, labels, P2)
-    K = b.shape[0]
-    cap = 256
-    boxes = torch.zeros(1, cap, 11)
-    boxes[0, :K] = b
-    cls = torch.zeros(1, cap, dtype=torch.int64)
-    cls[0, :K] = labels
-    boxes, cls = boxes.cuda(), cls.cuda()
-    count = torch.tensor([K], dtype=torch.int32, device="cuda")
     P2d = torch.from_numpy(P2).view(1, 3, 4).cuda().contiguous()
-    _lib.call("vd3d_post_opt", boxes.data_ptr(), cls.data_ptr(), count.data_ptr(), P2d.data_ptr(), 1, cap, 1280.0, 288.0, 0.4, 0.01, 3.0, 0,
-              torch.cuda.current_stream().cuda_stream)
-    got = boxes[0, :K].cpu()
-    assert torch.equal(got[:, :10], want[:, :10])
-    assert float(boxes[0, K:].abs().max()) == 0.0                       # rows beyond the count untouched
-    d = (got[:, 10] - want[:, 10]).abs()
-    d = torch.minimum(d, (d - 2 * np.pi).abs())
-    print("device vs host hill climbing: max |d alpha|", float(d.max()), " rows within 1e-5:", int((d < 1e-5).sum()), "/", K)
-    assert int((d < 1e-5).sum()) >= int(0.97 * K)
+    n_cases = len([k for k in fx.files if k.endswith("_in")])
+    for ci in range(n_cases):
+        b = torch.from_numpy(fx[f"c{ci}_in"])
+        labels = torch.from_numpy(fx[f"c{ci}_labels"]).long()
+        ref = torch.from_numpy(fx[f"c{ci}_out"])
+        host = postopt.post_process(b, labels, P2)
+        K = b.shape[0]
+        cap = 256
+        boxes = torch.zeros(1, cap, 11)
+        boxes[0, :K] = b
+        cls = torch.zeros(1, cap, dtype=torch.int64)
+        cls[0, :K] = labels
+        boxes, cls = boxes.cuda(), cls.cuda()
+        count = torch.tensor([K], dtype=torch.int32, device="cuda")
+        _lib.call("vd3d_post_opt", boxes.data_ptr(), cls.data_ptr(), count.data_ptr(), P2d.data_ptr(), 1, cap, 1280.0, 288.0, 0.4, 0.01, 3.0, 0,
+                  torch.cuda.current_stream().cuda_stream)
+        got = boxes[0, :K].cpu()
+        assert torch.equal(got[:, :10], ref[:, :10])
+        assert float(boxes[0, K:].abs().max()) == 0.0                       # rows beyond the count untouched
+        sel = (b[:, 6] > 3) & (labels == 0)
+        assert torch.equal(got[~sel], b[~sel])                              # unselected rows untouched
+        d_ref, d_host = wrapped_abs_diff(got[:, 10], ref[:, 10]), wrapped_abs_diff(got[:, 10], host[:, 10])
+        print(f"case {ci}: {int(sel.sum())} refined rows; vs reference: max |d alpha| {float(d_ref.max()):.3g}, bit-identical "
+              f"{int((got[sel, 10] == ref[sel, 10]).sum())}; vs host form: max {float(d_host.max()):.3g}")
+        assert float(d_host.max()) < 1e-5, d_host
+        # the host form itself is bit-identical to the reference on >= 98 % of rows (a last-bit IoU tie can flip a decision in numba's
+        # own code path, test_postopt_cpu.py); rows where host == reference must also match the reference on the device
+        same = host[:, 10] == ref[:, 10]
+        assert float(d_ref[same].max()) < 1e-5
+
+
+def test_device_post_forward_matches_reference():
+    """vd3d_post_forward against the UNMODIFIED reference's BackProjection / BBox3dProjector / 2-D rescale outputs
+    (tests/golden/postforward.npz): x, y and the rescaled boxes bit-exact (float32 +,-,*,/ in the reference's order), theta / corners
+    through atan2 / cos / sin within float32 rounding."""
+    import os
+    from conftest import GOLDEN
+    from visualdet3d_b200 import engine as E
+    fx = np.load(os.path.join(GOLDEN, "postforward.npz"))
+    n = len({k.split("_")[0] for k in fx.files})
+    seen = 0
+    for ci in range(n):
+        c = {k[len(f"c{ci}_"):]: fx[k] for k in fx.files if k.startswith(f"c{ci}_")}
+        K = len(c["scores"])
+        cap = 256
+        dec = E.DecodeNms(2, cap, "cuda")                                   # image 0 = the case, image 1 = empty
+        dec.boxes.zero_(), dec.scores.zero_(), dec.cls.zero_()
+        dec.boxes[0, :K] = torch.from_numpy(c["bbox"]).cuda()
+        dec.count.copy_(torch.tensor([K, 0], dtype=torch.int32))
+        P2 = torch.from_numpy(np.stack([c["P2"], c["P2"]])).cuda().contiguous()
+        oP = torch.from_numpy(np.stack([c["oP"], c["oP"]])).cuda().contiguous()
+        dec.post_forward(P2, oP, corners=True)
+        assert np.array_equal(dec.box3d[0, :K].cpu().numpy(), c["box3d"]), ci
+        assert np.array_equal(dec.box2d[0, :K].cpu().numpy(), c["box2d"]), ci
+        if K:
+            np.testing.assert_allclose(dec.theta[0, :K].cpu().numpy(), c["thetas"], atol=1e-6, rtol=0)
+            np.testing.assert_allclose(dec.corners[0, :K].cpu().numpy(), c["corners"], atol=2e-5, rtol=1e-6)
+            np.testing.assert_allclose(dec.homo[0, :K].cpu().numpy(), c["homo"], atol=2e-3, rtol=2e-5)
+            seen += K
+        assert float(dec.box3d[0, K:].abs().max()) == 0.0 and float(dec.box3d[1].abs().max()) == 0.0
+        dec.post_forward(P2, None)                                          # no original_P: boxes copied
+        assert torch.equal(dec.box2d[0, :K], dec.boxes[0, :K, :4])
+    assert seen > 200
+
+
+def test_streamed_pipeline_mono_with_post_opt_geometry_and_frames():
+    """StreamedInference on a mono detector with `post_optimization` (the GAC config, BASELINE configs[2]): (a) float32 inputs with the
+    device geometry columns == `forward_batch` + the host post-forward functions; (b) uint8 frames through the device input pipeline ==
+    the same frames preprocessed by `preprocess_batch` and run through `forward_batch`."""
+    import os
+    import sys
+    from conftest import GOLDEN
+    sys.path.insert(0, GOLDEN)
+    from make_golden_preprocess import frame
+    from visualdet3d_b200 import synth, postforward as pf, preprocess as pp
+    from visualdet3d_b200.detectors import build_synthetic_mono3d
+    from visualdet3d_b200.pipeline import StreamedInference
+    det, sd, cfg, _ = build_synthetic_mono3d("Yolo3D", seed=0)
+    det = det.cuda().eval()
+    det.post_optimization = True
+    B, H, W = 2, 96, 320
+    img, P2 = synth.synth_mono_inputs(B, H, W, seed=4)
+    oP = P2.clone()
+    oP[:, :2] *= 1.25
+    pipe = StreamedInference(det, B, H, W, kmax=256, geometry=True)
+    t = pipe.submit(img.pin_memory(), P2.pin_memory(), original_P=oP.pin_memory())
+    pipe.wait_copied(t)
+    got = pipe.collect(t)
+    with torch.no_grad():
+        ref = det.forward_batch(img.cuda(), P2.cuda())
+    n = 0
+    for b in range(B):
+        for x, y in zip(got[b], ref[b]):
+            assert torch.equal(x, y.cpu())
+        box3d, theta, box2d = pipe.last_geometry[b]
+        bx = ref[b][1].cpu()
+        want3 = pf.back_projection(bx[:, 4:], P2[b].numpy())
+        assert torch.equal(box3d, want3)
+        assert torch.equal(box2d, pf.rescale_boxes_2d(bx[:, :4], P2[b].numpy(), oP[b].numpy()))
+        if len(bx):
+            np.testing.assert_allclose(theta.numpy(), pf.alpha_to_theta(want3[:, 6], want3[:, 0], want3[:, 2], P2[b].numpy()).numpy(), atol=1e-6)
+        n += len(bx)
+    assert n > 0
+    texts = pipe.kitti_text(got, ["Car", "Pedestrian", "Cyclist"], threshold=0.0)
+    assert sum(tx.count("\n") for tx in texts) == n
+    with pytest.raises(TypeError):
+        pipe.submit(img.pin_memory(), img.pin_memory(), P2.pin_memory())     # a mono detector takes one image per sample
+    # (b) uint8 frames: 375 x 1242 camera frames -> crop 100 -> 288 x 1280 (the reference's test-time augmentation of the mono configs)
+    det.post_optimization = False
+    frames = [frame(0, 375, 1242), frame(1, 375, 1242)]
+    Hn, Wn = 288, 1280
+    pipe2 = StreamedInference(det, 2, Hn, Wn, kmax=256, frame_hw=(375, 1242), crop_top=100)
+    _, P2n = synth.synth_mono_inputs(2, Hn, Wn, seed=2)
+    fr = torch.from_numpy(np.stack(frames)).pin_memory()
+    t = pipe2.submit_frames(fr, P2n.pin_memory())
+    got = pipe2.collect(t)
+    with torch.no_grad():
+        x = pp.preprocess_batch(frames, 100, (Hn, Wn))
+        ref = det.forward_batch(x, P2n.cuda())
+    for b in range(2):
+        for a, r in zip(got[b], ref[b]):
+            assert torch.equal(a, r.cpu())
+    assert pipe2.h2d_bytes_frames < pipe2.h2d_bytes / 3.5
 
 
 def test_device_input_pipeline_matches_host():

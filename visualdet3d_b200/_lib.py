@@ -76,7 +76,10 @@ _SIGS = {
     "vd3d_preprocess": (I, [P, I, I, I, I, P, P, P, P]),
     "vd3d_post_opt_host": (I, [P, P, I, P, P, P, P, P, P, P, P, c_double, c_double, c_double, c_double, P, P]),
     "vd3d_post_opt": (I, [P, P, P, P, I, I, F, F, F, F, F, I, P]),
+    "vd3d_fp16_range_check": (I, [P, I, P]),
     "vd3d_pack_records": (I, [P, P, P, P, I, I, I, P, P]),
+    "vd3d_post_forward": (I, [P, P, P, P, I, I, P, P, P, P, P, P]),
+    "vd3d_pack_records_geo": (I, [P, P, P, P, P, P, P, I, I, I, P, P]),
     "vd3d_look_ground_sample": (I, [P, I, I, I, I, I, I, P, I, I, P, F, F, P, P, I, P]),
     "vd3d_anchor_mask": (I, [P, P, P, I, I, I, F, F, F, P, P]),
     "vd3d_decode_nms_workspace": (c_longlong, [I, I]),

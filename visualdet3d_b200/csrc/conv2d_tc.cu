@@ -32,6 +32,7 @@ struct TcParams {
     int cin_pad;             // weight K layout: per-tap channel count rounded up to bk
     float out_scale;         // multiplies the accumulator (undoes the power-of-two weight scaling of the fp16 path)
     void* out_h16_hi; void* out_h16_lo;
+    int* range_flag;         // fp16-range guard (common.cuh): ORed to 1 when a value written to the fp16 planes is beyond the fp16 range
     int tiles_w, tiles_h;
     int stride_w, pad_w;     // W-direction stride / padding (the H direction uses stride / pad); equal to them for ordinary convs
     int m_tiles, n_tiles;    // persistent kernel: tile counts along M (B * tiles_h * tiles_w) and N
@@ -92,6 +93,7 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint32_t tmem_bas
     __half* ol16 = p.out_h16_lo ? reinterpret_cast<__half*>(p.out_h16_lo) + pix * p.out_cs + p.out_co : nullptr;
     const float osc = p.out_scale;
     const float* rp = (p.res && !(p.dbg & 32)) ? p.res + pix * p.res_cs + p.res_co : nullptr;
+    float amax = 0.f;
     if (ok) {
 #pragma unroll
         for (int g = 0; g < NG; ++g) {
@@ -113,6 +115,7 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint32_t tmem_bas
                         *reinterpret_cast<float4*>(olo + n) = l;
                     }
                     if (oh) {      // fp16 hi/lo planes for the next fp16-split conv: hi = rn16(v), lo = rn16(v - hi)
+                        amax = amax4(amax, a);
                         __half hx = __float2half_rn(a.x), hy = __float2half_rn(a.y), hz = __float2half_rn(a.z), hw = __float2half_rn(a.w);
                         __half lx = __float2half_rn(a.x - __half2float(hx)), ly = __float2half_rn(a.y - __half2float(hy));
                         __half lz = __float2half_rn(a.z - __half2float(hz)), lw = __float2half_rn(a.w - __half2float(hw));
@@ -127,6 +130,7 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint32_t tmem_bas
             }
         }
     }
+    note_fp16_range(amax, p.range_flag);
 }
 
 // ----------------------------------------------------------------------------------------------------------------
@@ -449,6 +453,7 @@ __device__ __forceinline__ void tcp_epilogue(const TcParams& p, uint32_t tmem_ba
     const uint32_t te_local = smem_u32(&tmem_empty[0]);
     const uint32_t te_leader = CG == 2 ? mapa_shared(te_local, 0) : te_local;
     const float osc = p.out_scale;
+    float amax = 0.f;                                               // fp16-range guard: largest magnitude written to the fp16 planes
     int cc = 0;
     for (int u = u0; u < units; u += ustep) {
         const int ncols = min(half_cols, min(p.BN, p.cout_pad - (u / mt_units) * p.BN) - cb);      // valid columns of this thread in this tile (<= 0: none)
@@ -541,6 +546,8 @@ __device__ __forceinline__ void tcp_epilogue(const TcParams& p, uint32_t tmem_ba
                             else *reinterpret_cast<float4*>(op + n) = make_float4(a[0], a[1], a[2], a[3]);
                             if (oh) {      // fp16 hi/lo planes for the next fp16-split conv
                                 uint2 h0, l0, h1, l1;
+#pragma unroll
+                                for (int k = 0; k < 8; ++k) amax = fmaxf(amax, fabsf(a[k]));     // (in the Cout % 8 == 4 tail a[4..7] belong to zero-weight padding columns)
                                 split4(a, h0, l0);
                                 if (full8) {
                                     split4(a + 4, h1, l1);
@@ -562,6 +569,7 @@ __device__ __forceinline__ void tcp_epilogue(const TcParams& p, uint32_t tmem_ba
             }
         }
     }
+    note_fp16_range(amax, p.range_flag);
 }
 
 // ----------------------------------------------------------------------------------------------------------------
@@ -1000,11 +1008,13 @@ __global__ void split_lo_kernel(const float* __restrict__ in, float* __restrict_
 }
 
 // fp32 -> fp16 (hi, lo) planes: hi = rn16(v), lo = rn16(v - hi).  Elementwise, channel-slice aware (planes share the fp32 pitch).
-__global__ void split_h16_kernel(const float* __restrict__ in, __half* __restrict__ hi, __half* __restrict__ lo, long long npix, int C4, int cs, int co) {
+__global__ void split_h16_kernel(const float* __restrict__ in, __half* __restrict__ hi, __half* __restrict__ lo, long long npix, int C4, int cs, int co,
+                                 int* __restrict__ range_flag) {
     long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= npix * C4) return;
     int c4 = (int)(idx % C4); long long pix = idx / C4;
     float4 a = ldg4(in + pix * cs + co + 4 * c4);
+    note_fp16_range(amax4(0.f, a), range_flag);
     __half hx = __float2half_rn(a.x), hy = __float2half_rn(a.y), hz = __float2half_rn(a.z), hw = __float2half_rn(a.w);
     __half2 h01 = __halves2half2(hx, hy), h23 = __halves2half2(hz, hw);
     __half2 l01 = __halves2half2(__float2half_rn(a.x - __half2float(hx)), __float2half_rn(a.y - __half2float(hy)));
@@ -1259,6 +1269,7 @@ static int conv2d_tc_launch(int f16, const void* in, const void* in_lo, int B, i
             (!out_h16_hi || ((((uintptr_t)out_h16_hi | (uintptr_t)out_h16_lo) & 15) == 0))) ? 1 : 0;
     p.out_cs = out_cs; p.out_co = out_co; p.res_cs = res_cs; p.res_co = res_co; p.relu = relu;
     p.bias = bias; p.res = res; p.out = out; p.out_lo = out_lo; p.out_h16_hi = out_h16_hi; p.out_h16_lo = out_h16_lo;
+    p.range_flag = out_h16_hi ? fp16_range_flag() : nullptr;
     // instruction descriptor (cute::UMMA::InstrDescriptor): D = f32 (1 @4), A/B format @7/@10 (tf32 = 2, f16 = 0), K-major, N>>3 @17, M>>4 @24
     const uint32_t fmt = f16 ? 0u : 2u;
     p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -1391,7 +1402,7 @@ extern "C" int vd3d_conv2d_tc16(const void* in_hi, const void* in_lo, int B, int
 // 64 "channels" (kw*4 + c; weights zero beyond KW*4) and stride (stride, 1): exactly what conv2d_tcp_kernel runs.
 // ----------------------------------------------------------------------------------------------------------------
 __global__ void image_to_h16_rows_kernel(const float* __restrict__ in, __half* __restrict__ hi, __half* __restrict__ lo, int C, int H, int W,
-                                         long long total, int Wp, int xoff) {
+                                         long long total, int Wp, int xoff, int* __restrict__ range_flag) {
     long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
     const long long HW = (long long)H * W;
@@ -1400,6 +1411,7 @@ __global__ void image_to_h16_rows_kernel(const float* __restrict__ in, __half* _
     const float* ip = in + b * C * HW + pq;
     float v[4] = {0.f, 0.f, 0.f, 0.f};
     for (int c = 0; c < C; ++c) v[c] = __ldg(ip + (long long)c * HW);
+    note_fp16_range(fmaxf(fmaxf(fabsf(v[0]), fabsf(v[1])), fmaxf(fabsf(v[2]), fabsf(v[3]))), range_flag);
     __half h[4], l[4];
 #pragma unroll
     for (int c = 0; c < 4; ++c) { h[c] = __float2half_rn(v[c]); l[c] = __float2half_rn(v[c] - __half2float(h[c])); }
@@ -1415,7 +1427,7 @@ __global__ void image_to_h16_rows_kernel(const float* __restrict__ in, __half* _
 extern "C" int vd3d_image_to_h16_rows(const float* img, int B, int C, int H, int W, void* hi16, void* lo16, int Wp, int xoff, void* stream) {
     VD3D_REQUIRE(img && hi16 && lo16 && B > 0 && C >= 1 && C <= 4 && H > 0 && W > 0 && xoff >= 0 && Wp >= W + xoff, "image_to_h16_rows: bad args");
     const long long total = (long long)B * H * W;
-    image_to_h16_rows_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(img, (__half*)hi16, (__half*)lo16, C, H, W, total, Wp, xoff);
+    image_to_h16_rows_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(img, (__half*)hi16, (__half*)lo16, C, H, W, total, Wp, xoff, fp16_range_flag());
     VD3D_CHECK_LAUNCH("image_to_h16_rows");
     return VD3D_OK;
 }
@@ -1453,6 +1465,7 @@ extern "C" int vd3d_conv2d_tc16_stem(const void* in_hi, const void* in_lo, int B
             (!out_hi16 || ((((uintptr_t)out_hi16 | (uintptr_t)out_lo16) & 15) == 0))) ? 1 : 0;
     p.out_cs = out_cs; p.out_co = out_co; p.relu = relu;
     p.bias = bias; p.out = out; p.out_h16_hi = out_hi16; p.out_h16_lo = out_lo16;
+    p.range_flag = out_hi16 ? fp16_range_flag() : nullptr;
     p.idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     uint32_t cols = 32; while (cols < (uint32_t)(2 * BN)) cols <<= 1;
     p.tmem_cols = cols;
@@ -1492,7 +1505,7 @@ extern "C" int vd3d_split_lo_nhwc(const float* in, float* lo, long long npix, in
 extern "C" int vd3d_split_h16_nhwc(const float* in, void* hi16, void* lo16, long long npix, int C, int cs, int co, void* stream) {
     VD3D_REQUIRE(in && hi16 && lo16 && C % 4 == 0 && cs % 4 == 0 && co % 4 == 0, "split_h16: bad args");
     long long total = npix * (C / 4);
-    split_h16_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(in, (__half*)hi16, (__half*)lo16, npix, C / 4, cs, co);
+    split_h16_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(in, (__half*)hi16, (__half*)lo16, npix, C / 4, cs, co, fp16_range_flag());
     VD3D_CHECK_LAUNCH("split_h16");
     return VD3D_OK;
 }

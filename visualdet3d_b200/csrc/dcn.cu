@@ -22,6 +22,7 @@ struct DcnParams {
     int Ho, Wo;
     float* col; float* col_lo; int col_cs;          // [B*Ho*Wo][col_cs], channels [0, KH*KW*C)
     __half* col_h16_hi; __half* col_h16_lo;         // optional fp16 (hi, lo) planes of the columns (same pitch): what the fp16-split GEMM reads
+    int* range_flag;                                // fp16-range guard (common.cuh)
 };
 
 constexpr int DCN_PIX = 32;       // pixels per CTA
@@ -99,6 +100,7 @@ __global__ void __launch_bounds__(DCN_THREADS) deform_im2col_kernel(const DcnPar
         long long o = pix * p.col_cs + (long long)k * p.C + c;
         if (p.col) *reinterpret_cast<float4*>(p.col + o) = acc;
         if (p.col_h16_hi) {     // hi = rn16(v), lo = rn16(v - hi): identical to vd3d_split_h16_nhwc on the fp32 columns
+            note_fp16_range(amax4(0.f, acc), p.range_flag);
             __half hx = __float2half_rn(acc.x), hy = __float2half_rn(acc.y), hz = __float2half_rn(acc.z), hw = __float2half_rn(acc.w);
             __half2 h01 = __halves2half2(hx, hy), h23 = __halves2half2(hz, hw);
             __half2 l01 = __halves2half2(__float2half_rn(acc.x - __half2float(hx)), __float2half_rn(acc.y - __half2float(hy)));
@@ -142,6 +144,7 @@ static int deform_im2col_launch(const float* x, int B, int H, int W, int C, int 
     p.Wo = (W + 2 * pad - (dil * (KW - 1) + 1)) / stride + 1;
     VD3D_REQUIRE(p.Ho > 0 && p.Wo > 0, "deform_im2col: empty output");
     p.col = col; p.col_lo = col_lo; p.col_cs = col_cs; p.col_h16_hi = (__half*)col_hi16; p.col_h16_lo = (__half*)col_lo16;
+    p.range_flag = col_hi16 ? fp16_range_flag() : nullptr;
     long long npix = (long long)B * p.Ho * p.Wo;
     dim3 grid(cdiv(npix, DCN_PIX), deform_groups);
     deform_im2col_kernel<<<grid, DCN_THREADS, 0, (cudaStream_t)stream>>>(p);

@@ -18,6 +18,21 @@ void set_error(const char* fmt, ...) {
 }
 void count_launch(int n) { g_launches += n; }
 
+static std::mutex g_flag_mu;
+static int* g_range_flag[64] = {nullptr};
+int* fp16_range_flag() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lk(g_flag_mu);
+    if (!g_range_flag[dev]) {
+        int* p = nullptr;
+        if (cudaMalloc(&p, sizeof(int)) != cudaSuccess) return nullptr;
+        if (cudaMemset(p, 0, sizeof(int)) != cudaSuccess) { cudaFree(p); return nullptr; }
+        g_range_flag[dev] = p;
+    }
+    return g_range_flag[dev];
+}
+
 // ---------------------------------------------------------------------------------------------------------
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int HW, int out_cs, int out_co) {
     // block: 32 pixels x 8 lanes... simple tiled transpose through smem: tile 32 (pixels) x 32 (channels)
@@ -194,6 +209,19 @@ __global__ void copy_channels_kernel(const float* __restrict__ in, float* __rest
 }  // namespace vd3d
 
 using namespace vd3d;
+
+extern "C" int vd3d_fp16_range_check(int* overflow_out, int reset, void* stream) {
+    VD3D_REQUIRE(overflow_out, "fp16_range_check: null output");
+    int* f = fp16_range_flag();
+    VD3D_REQUIRE(f, "fp16_range_check: could not allocate the device flag");
+    cudaStream_t st = (cudaStream_t)stream;
+    int v = 0;
+    VD3D_CUDA(cudaMemcpyAsync(&v, f, sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (reset) VD3D_CUDA(cudaMemsetAsync(f, 0, sizeof(int), st));
+    VD3D_CUDA(cudaStreamSynchronize(st));
+    *overflow_out = v;
+    return VD3D_OK;
+}
 
 extern "C" const char* vd3d_last_error(void) { return g_err; }
 extern "C" int vd3d_version(void) { return 100; }

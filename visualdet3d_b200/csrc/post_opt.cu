@@ -6,7 +6,9 @@
 //
 // One routine, float64 like the reference's numba code, compiled for the host (vd3d_post_opt_host: what Mono3D detectors call on the
 // few kept rows after the result copy; the reference does the same on the CPU with a D2H `.item()` per detection) and for the device
-// (post_opt_kernel / vd3d_post_opt: one thread per detection on the fixed-capacity NMS output, no host round trip).
+// (post_opt_kernel / vd3d_post_opt: one thread per detection on the fixed-capacity NMS output, no host round trip).  This translation unit
+// is compiled with -fmad=false (__graft_entry__.py): the device then evaluates every a * b + c of the search in two IEEE roundings like the
+// host compiler and the reference's numba code do, so the discrete accept / halve decisions agree.
 #include "common.cuh"
 #include <math.h>
 
@@ -101,7 +103,8 @@ __global__ void post_opt_kernel(float* __restrict__ boxes, const long long* __re
     const float cx = bx[4], cy = bx[5], z = bx[6];
     // depth test on the back-projected z (BackProjection keeps z): detection_3d_head.py:303
     if (!(z > min_depth)) return;
-    const float off = atan2f(cx - P[2], P[0]);
+    // float32 atan2 of the reference's numpy call (convertAlpha2Rot): evaluated in double and rounded once == a correctly rounded atan2f
+    const float off = (float)atan2((double)(cx - P[2]), (double)P[0]);
     float th0 = bx[10] + off;
     if (th0 > 3.14159274f) th0 -= 6.28318548f;
     if (th0 <= -3.14159274f) th0 += 6.28318548f;

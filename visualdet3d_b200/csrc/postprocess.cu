@@ -229,9 +229,10 @@ __global__ void __launch_bounds__(NMS_THREADS) sort_nms_kernel(DecodeWs ws, int 
 
 // fixed-capacity detection record block for the multi-GPU all-gather: rec[b] = [count | kmax x (11 box floats, score, class)]
 __global__ void pack_records_kernel(const float* __restrict__ scores, const float* __restrict__ boxes, const int64_t* __restrict__ cls,
-                                    const int32_t* __restrict__ count, int cap, int kmax, float* __restrict__ rec) {
+                                    const int32_t* __restrict__ count, int cap, int kmax, float* __restrict__ rec, const int* __restrict__ range_flag) {
     const int b = blockIdx.x;
-    const int n = count[b];
+    int n = count[b];
+    if (range_flag && *range_flag) n = -2;                            // -2: an activation left the fp16 range of the tensor-core engine (results invalid)
     float* r = rec + (long long)b * (1 + kmax * 13);
     if (threadIdx.x == 0) r[0] = (n > kmax) ? -1.0f : (float)n;       // -1: capacity overflow (also n == -1 from the decode stage)
     const int m = n < 0 ? 0 : (n > kmax ? 0 : n);
@@ -250,7 +251,7 @@ using namespace vd3d;
 extern "C" int vd3d_pack_records(const float* scores, const float* boxes, const int64_t* cls, const int32_t* count, int B, int cap, int kmax,
                                  float* rec, void* stream) {
     VD3D_REQUIRE(scores && boxes && cls && count && rec && B > 0 && cap > 0 && kmax > 0, "pack_records: bad args");
-    pack_records_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(scores, boxes, cls, count, cap, kmax, rec);
+    pack_records_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(scores, boxes, cls, count, cap, kmax, rec, fp16_range_flag());
     VD3D_CHECK_LAUNCH("pack_records");
     return VD3D_OK;
 }

@@ -22,6 +22,17 @@ class Anchor3DDetector(nn.Module):
         head = network_cfg["head"]
         acfg = head["anchors_cfg"]
         self.anchors_cfg = {k: acfg[k] for k in ("pyramid_levels", "strides", "sizes", "ratios", "scales")}
+        # the remaining arguments of the reference's Anchors (R/heads/anchors.py:11-14) and of the head (detection_3d_head.py:30): honoured
+        # or refused, never silently ignored
+        y_mm = acfg.get("filter_y_threshold_min_max", (-0.5, 1.8))
+        x_thr = acfg.get("filter_x_threshold", 40.0)
+        if y_mm is None or x_thr is None:
+            raise ValueError("anchors_cfg.filter_y_threshold_min_max / filter_x_threshold must be numbers (set test_cfg.filter_anchor=False to disable the filter)")
+        self.anchor_filter = (float(y_mm[0]), float(y_mm[1]), float(x_thr))
+        if int(acfg.get("anchor_prior_channel", 6)) != 6:
+            raise ValueError("anchors_cfg.anchor_prior_channel must be 6 (z, sin2a, cos2a, w, h, l: the decode layout of detection_3d_head.py:218-263)")
+        if not bool(head.get("read_precompute_anchor", True)):
+            raise ValueError("head.read_precompute_anchor=False is not supported: the 3-D decode needs the precomputed anchor priors")
         self.num_anchors = len(acfg["pyramid_levels"]) * len(acfg["ratios"]) * len(acfg["scales"])
         self.num_classes = head["num_classes"]
         self.test_cfg = dict(head.get("test_cfg", {}))
@@ -38,11 +49,8 @@ class Anchor3DDetector(nn.Module):
         n_rows = len(acfg["scales"]) * len(acfg["pyramid_levels"])
         self.prior_mean, self.prior_std = load_priors(head["preprocessed_path"], acfg.get("obj_types", self.obj_types),
                                                       n_rows, len(acfg["ratios"]))
-        if self.test_cfg.get("post_optimization", False):
-            # R/heads/detection_3d_head.py:294-308 (hill climbing on the yaw): applied in `results` (postopt.py)
-            self.post_optimization = True
-        else:
-            self.post_optimization = False
+        # R/heads/detection_3d_head.py:294-308 (hill climbing on the yaw): device kernel after the NMS (`decode`)
+        self.post_optimization = bool(self.test_cfg.get("post_optimization", False))
         self.max_detections = int(self.test_cfg.get("max_candidates", 2048))   # fixed capacity of the decode / NMS stage
         self._plan = None
         self._plan_version = None
@@ -95,7 +103,7 @@ class Anchor3DDetector(nn.Module):
         assert cls.co == 0 and reg.co == 0 and cls.cs == cls.C and reg.cs == reg.C
         mask = self._arena.get("mask", (B, N), dev, dtype=torch.uint8)
         if self.filter_anchor:
-            E.anchor_mask(tab.anchors, tab.means_z, P2, mask)
+            E.anchor_mask(tab.anchors, tab.means_z, P2, mask, *self.anchor_filter)
         else:
             mask.fill_(1)
         self._hook("mask", mask)
@@ -105,22 +113,17 @@ class Anchor3DDetector(nn.Module):
         dec = self._decoders[key]
         dec.run(cls.t.view(B, N, self.num_cls_output), reg.t.view(B, N, 12), tab.anchors, tab.mean_std, mask,
                 self.num_classes, self.test_cfg.get("score_thr", 0.5), self.test_cfg.get("nms_iou_thr", 0.5), W, H)
+        if self.post_optimization:
+            # head.test_cfg.post_optimization (R/heads/detection_3d_head.py:294-308): yaw hill climbing of the kept car boxes deeper than
+            # 3 m, in place on the fixed-capacity NMS output, stream-ordered (the reference searches on the CPU with one `.item()` per box)
+            dec.post_opt(P2)
         self._last_decoder = dec
-        dec.post_opt_P2 = P2 if self.post_optimization else None      # `results` refines the yaw of the kept rows (head.test_cfg.post_optimization)
         return dec
 
     @staticmethod
     def results(dec: E.DecodeNms):
-        """Per-image (scores, bboxes, cls) triples.  With `test_cfg.post_optimization` the kept car boxes deeper than 3 m get their yaw
-        refined by hill climbing (R/heads/detection_3d_head.py:294-308) on the host, on the rows this call has just synchronised on:
-        K <= a few hundred rows, float64 search in `vd3d_post_opt_host` (the reference also runs it on the CPU, one `.item()` per box)."""
-        res = [(s.clone(), b.clone(), c.clone()) for (s, b, c) in dec.results()]
-        P2 = getattr(dec, "post_opt_P2", None)
-        if P2 is not None:
-            from .. import postopt
-            P2h = P2.detach().cpu().numpy()
-            res = [(s, postopt.post_process(b, c, P2h[i]).to(b.device), c) if len(s) else (s, b, c) for i, (s, b, c) in enumerate(res)]
-        return res
+        """Per-image (scores, bboxes, cls) triples (one D2H read of the counts)."""
+        return [(s.clone(), b.clone(), c.clone()) for (s, b, c) in dec.results()]
 
     def train_forward(self, *a, **k):
         raise NotImplementedError("training forward is out of scope of the B200 inference path (SURVEY.md section 2)")

@@ -67,6 +67,7 @@ class KM3DHeadP(M.Holder):
 
 class _CenterNetBase(nn.Module):
     WITH_POSITION_LOSS = False
+    N_IMAGES = 1          # images per sample of `launch` (pipeline.StreamedInference)
 
     def __init__(self, network_cfg):
         super().__init__()
@@ -168,14 +169,18 @@ class MonoFlex(_CenterNetBase):
         for t, nm in ((images, "image"), (P2, "P2")):
             E._require_cuda(t, nm)
         images, P2 = images.float().contiguous(), P2.float().contiguous()
-        B, _, H, W = images.shape
-        out = self.network(images)
-        pl = self._plan
+        _, _, H, W = images.shape
+        return self.decode_maps(self.network(images), P2, H, W)
+
+    def decode_maps(self, out: E.Act, P2: torch.Tensor, H: int, W: int):
+        """MonoFlexHead.get_bboxes (R/heads/monoflex_head.py:114-179) on the head maps `out` ([B, H/4, W/4, out_channels], the
+        channel offsets of `prepare()`); split from `launch` so that tests can feed the decode with the oracle's maps."""
+        pl = self.prepare()
         off = pl["offsets"]
         missing = [k for k in self.REQUIRED if k not in off]
         if missing:
             raise Vd3dError(f"MonoFlex head_dict lacks {missing}")
-        dev = images.device
+        B, dev = out.B, out.t.device
         key = (B, str(dev))
         if key not in self._decoders:
             d = E.DecodeNms(B, 128, dev)
@@ -206,15 +211,18 @@ class KM3D(_CenterNetBase):
         for t, nm in ((images, "image"), (P2, "P2")):
             E._require_cuda(t, nm)
         images, P2 = images.float().contiguous(), P2.float().contiguous()
-        B, _, H, W = images.shape
-        out = self.network(images)
-        off = self._plan["offsets"]
+        _, _, H, W = images.shape
+        return self.decode_maps(self.network(images), P2, H, W)
+
+    def decode_maps(self, out: E.Act, P2: torch.Tensor, H: int, W: int):
+        """KM3DHead.get_bboxes/_decode + gen_position on the head maps `out` (see MonoFlex.decode_maps)."""
+        off = self.prepare()["offsets"]
         missing = [k for k in self.REQUIRED if k not in off]
         if missing:
             raise Vd3dError(f"KM3D head_dict lacks {missing}")
         if self.bbox_head.head_dict["hps"] != 18 or self.bbox_head.head_dict["hm_hp"] != 9:
             raise Vd3dError("KM3D decode expects 9 keypoints (hps = 18, hm_hp = 9)")
-        dev = images.device
+        B, dev = out.B, out.t.device
         key = (B, str(dev))
         if key not in self._decoders:
             d = E.DecodeNms(B, 128, dev)

@@ -58,6 +58,8 @@ class LookGroundRunner:
 class _Mono3DBase(Anchor3DDetector):
     head_cls = None
 
+    N_IMAGES = 1          # images per sample of `launch` (pipeline.StreamedInference)
+
     def __init__(self, network_cfg):
         super().__init__(network_cfg)
         self.bbox_head = self.head_cls(**self.head_kwargs)

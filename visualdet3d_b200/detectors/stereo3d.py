@@ -54,17 +54,24 @@ class ResNetRunner:
                 blocks.append(d)
             self.stages.append(blocks)
 
-    def run(self, img_nchw: torch.Tensor, arena: E.Arena, tag: str = "bb", on_output=None) -> List[E.Act]:
-        """on_output(act, lo_stale) -> lo_stale: called as soon as a returned feature map exists, i.e. while it is still
+    def run(self, img_nchw, arena: E.Arena, tag: str = "bb", on_output=None) -> List[E.Act]:
+        """`img_nchw`: [B, 3, H, W], or a list of such tensors forming the batch in order (stereo: [left, right]; the parts are read in
+        place, the reference's `torch.cat([left, right])` copy does not exist).
+        on_output(act, lo_stale) -> lo_stale: called as soon as a returned feature map exists, i.e. while it is still
         L2-resident (the stereo plan launches the cost-volume kernel of that scale from it)."""
-        dev = img_nchw.device
-        B, _, H, W = img_nchw.shape
+        parts = list(img_nchw) if isinstance(img_nchw, (list, tuple)) else [img_nchw]
+        dev = parts[0].device
+        _, _, H, W = parts[0].shape
+        B = sum(int(p.shape[0]) for p in parts)
         Hs, Ws = self.stem.out_hw(H, W)
         if self.stem_tc is not None:
-            x = self.stem_tc(img_nchw, arena.act(tag + ".stem", (B, Hs, Ws, 64), dev), arena, tag)
+            x = self.stem_tc(parts, arena.act(tag + ".stem", (B, Hs, Ws, 64), dev), arena, tag)
         else:
             x0 = arena.act(tag + ".in4", (B, H, W, 4), dev, zero=True)
-            E.nchw_to_nhwc(img_nchw, x0)
+            b0 = 0
+            for p in parts:
+                E.nchw_to_nhwc(p, x0.batch(b0, b0 + int(p.shape[0])))
+                b0 += int(p.shape[0])
             x = self.stem(x0, arena.act(tag + ".stem", (B, Hs, Ws, 64), dev))
         Hp, Wp = (Hs + 2 - 3) // 2 + 1, (Ws + 2 - 3) // 2 + 1
         outs = []
@@ -176,6 +183,7 @@ def basic_block_runner(blk: M.BasicBlockP, device):
 @DETECTOR_DICT.register_module
 class Stereo3D(Anchor3DDetector):
     """YOLOStereo3D detector (inference).  `network_cfg` is the reference's `cfg.detector` (R/config/Stereo3D_example:111-167)."""
+    N_IMAGES = 2          # images per sample of `launch` (left, right): what pipeline.StreamedInference stages per batch
 
     def __init__(self, network_cfg):
         super().__init__(network_cfg)
@@ -214,9 +222,8 @@ class Stereo3D(Anchor3DDetector):
         B, _, H, W = left.shape
         if H % 16 or W % 16:
             raise Vd3dError(f"Stereo3D: image size {H}x{W} must be a multiple of 16")
-        imgs = ar.get("imgs", (2 * B, 3, H, W), dev)
-        imgs[:B].copy_(left)
-        imgs[B:].copy_(right)
+        if right.shape != left.shape:
+            raise Vd3dError(f"Stereo3D: left {tuple(left.shape)} and right {tuple(right.shape)} images differ in shape")
         neck = self.core.neck
         D4, D8, D16 = neck.cost_volume_0.depth_channel, neck.cost_volume_1.depth_channel, neck.cost_volume_2.depth_channel
         h4, w4, h8, w8, h16, w16 = H // 4, W // 4, H // 8, W // 8, H // 16, W // 16
@@ -242,7 +249,7 @@ class Stereo3D(Anchor3DDetector):
                 return lo_stale and not refreshed
             return lo_stale
 
-        f4, f8, f16 = pl["backbone"].run(imgs, ar, on_output=cost_volume_early)
+        f4, f8, f16 = pl["backbone"].run([left, right], ar, on_output=cost_volume_early)      # one [2B] batch: left = [0, B), right = [B, 2B)
         self._hook("feat4", f4), self._hook("feat8", f8), self._hook("feat16", f16)
         self._hook("vol4", G4.slice(0, D4))
         pl["g4"].run(G4)

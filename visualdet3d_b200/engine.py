@@ -266,14 +266,25 @@ class StemLayer:
     def out_hw(self, H, W):
         return (H + 2 * self.pad - self.KH) // self.stride + 1, (W + 2 * self.pad - self.KW) // self.stride + 1
 
-    def __call__(self, img_nchw: torch.Tensor, out: Act, arena: "Arena", name: str):
-        _require_cuda(img_nchw, "stem")
-        x = img_nchw.contiguous().float()
-        B, C, H, W = x.shape
-        assert C == self.Cin and out.C == self.Cout
+    def __call__(self, img_nchw, out: Act, arena: "Arena", name: str):
+        """`img_nchw`: one [B, C, H, W] tensor, or a list of such tensors that together form the batch (the stereo plan passes
+        [left, right]: each part is converted straight into its batch range of the row planes, no concatenated copy exists)."""
+        parts = list(img_nchw) if isinstance(img_nchw, (list, tuple)) else [img_nchw]
+        parts = [p.contiguous().float() for p in parts]
+        for p in parts:
+            _require_cuda(p, "stem")
+        _, C, H, W = parts[0].shape
+        B = sum(int(p.shape[0]) for p in parts)
+        assert all(tuple(p.shape[1:]) == (C, H, W) for p in parts)
+        assert C == self.Cin and out.C == self.Cout and out.B == B
         Wp = int(_lib.load().vd3d_stem_row_pitch(W, self.KW, self.stride, self.pad))
-        planes = arena.get(name + ".rows#h16", (2, B, H, Wp, 4), x.device, dtype=torch.float16, zero=True)   # borders stay zero
-        call("vd3d_image_to_h16_rows", x.data_ptr(), B, C, H, W, planes[0].data_ptr(), planes[1].data_ptr(), Wp, self.pad, _stream())
+        planes = arena.get(name + ".rows#h16", (2, B, H, Wp, 4), parts[0].device, dtype=torch.float16, zero=True)   # borders stay zero
+        b0 = 0
+        for p in parts:
+            nb = int(p.shape[0])
+            call("vd3d_image_to_h16_rows", p.data_ptr(), nb, C, H, W, planes[0, b0:b0 + nb].data_ptr(), planes[1, b0:b0 + nb].data_ptr(),
+                 Wp, self.pad, _stream())
+            b0 += nb
         oh, ol = out.h16_ptrs
         call("vd3d_conv2d_tc16_stem", planes[0].data_ptr(), planes[1].data_ptr(), B, H, W, Wp, self.KH, self.KW, self.stride, self.pad, self.win,
              self.w_hi.data_ptr(), self.w_lo.data_ptr(), self.out_scale, self.b.data_ptr(), out.ptr, oh, ol, self.Cout, out.cs, out.co,
@@ -440,6 +451,18 @@ def anchor_mask(anchors: torch.Tensor, means_z: torch.Tensor, P2: torch.Tensor, 
     return mask
 
 
+RANGE_MSG = ("an activation left the fp16 range (|v| >= 65520) in front of a tensor-core conv: the fp16-split engine keeps activations "
+             "unscaled as fp16 (hi, lo) planes.  Results of this forward are invalid; run with VD3D_CONV_ENGINE=tc (3xTF32) or simt.")
+
+
+def fp16_range_overflowed(reset: bool = True) -> bool:
+    """Read (and by default clear) the device-side fp16-range flag; synchronises the current stream."""
+    import ctypes
+    v = ctypes.c_int(0)
+    call("vd3d_fp16_range_check", ctypes.byref(v), 1 if reset else 0, _stream())
+    return bool(v.value)
+
+
 class DecodeNms:
     """Fixed-capacity decode + NMS outputs for a batch (buffers are reused across calls)."""
 
@@ -462,9 +485,38 @@ class DecodeNms:
              self.cap, self.ws.data_ptr(), self.scores.data_ptr(), self.boxes.data_ptr(), self.cls.data_ptr(),
              self.anchor.data_ptr(), self.count.data_ptr(), self.ncand.data_ptr(), _stream())
 
+    def post_opt(self, P2: torch.Tensor, img_w: float = 1280.0, img_h: float = 288.0, step_r_init: float = 0.4, r_lim: float = 0.01,
+                 min_depth: float = 3.0, label: int = 0):
+        """`post_optimization` of the anchor heads (R/heads/detection_3d_head.py:294-308 -> R/lib/fast_utils/hill_climbing.py): the yaw of
+        every kept row with class `label` deeper than `min_depth` is refined in place by hill climbing, one thread per row, stream-ordered
+        after the NMS (no host round trip; the reference reads one `.item()` per box and searches on the CPU).  The hull of the projected
+        box is clipped to 1280 x 288 like the reference's hard-coded constants (hill_climbing.py:98-103)."""
+        call("vd3d_post_opt", self.boxes.data_ptr(), self.cls.data_ptr(), self.count.data_ptr(), P2.data_ptr(), self.B, self.cap,
+             float(img_w), float(img_h), float(step_r_init), float(r_lim), float(min_depth), int(label), _stream())
+
+    def post_forward(self, P2: torch.Tensor, original_P: Optional[torch.Tensor] = None, corners: bool = False):
+        """Post-forward geometry of `test_one` (R/pipelines/evaluators.py:112-131) on the kept rows, on the device: back-projected box
+        (x, y, z, w, h, l, alpha), rotation theta, 2-D boxes in the pixels of the original frame.  Results stay in fixed-capacity
+        buffers (`self.box3d [B, cap, 7]`, `self.theta [B, cap]`, `self.box2d [B, cap, 4]`, optionally `self.corners / self.homo`)."""
+        dev = self.scores.device
+        if getattr(self, "box3d", None) is None:
+            self.box3d = torch.empty(self.B, self.cap, 7, dtype=torch.float32, device=dev)
+            self.theta = torch.empty(self.B, self.cap, dtype=torch.float32, device=dev)
+            self.box2d = torch.empty(self.B, self.cap, 4, dtype=torch.float32, device=dev)
+            self.corners = self.homo = None
+        if corners and self.corners is None:
+            self.corners = torch.empty(self.B, self.cap, 8, 3, dtype=torch.float32, device=dev)
+            self.homo = torch.empty(self.B, self.cap, 8, 3, dtype=torch.float32, device=dev)
+        call("vd3d_post_forward", self.boxes.data_ptr(), self.count.data_ptr(), P2.data_ptr(),
+             original_P.data_ptr() if original_P is not None else None, self.B, self.cap, self.box3d.data_ptr(), self.theta.data_ptr(),
+             self.box2d.data_ptr(), self.corners.data_ptr() if corners else None, self.homo.data_ptr() if corners else None, _stream())
+        return self
+
     def results(self):
         """One D2H read of the counts (the only host sync of the forward), then per-image views."""
         counts = self.count.tolist()
+        if fp16_range_overflowed():
+            raise _lib.Vd3dError(RANGE_MSG)
         out = []
         for b, k in enumerate(counts):
             if k < 0:

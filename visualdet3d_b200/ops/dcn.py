@@ -28,23 +28,32 @@ from .._lib import call
 
 
 class _WeightCache:
-    """packed (hi, lo) tensor-core weights per weight tensor, re-packed when the tensor changes in place"""
+    """Packed (hi, lo) tensor-core weights per weight TENSOR OBJECT: entries are keyed by `id(weight)` and hold a weak reference to the
+    tensor, so an entry can never be served to a different tensor that the allocator later places at the same address (a freed model's
+    weights followed by a new model of the same shape); it is re-packed when the tensor changes in place (`_version`) or is re-pointed
+    (`data_ptr`, e.g. after `.data = ...` / `load_state_dict` on a fresh storage) and dropped when the tensor dies."""
 
     def __init__(self):
         self._d = {}
 
     def get(self, weight: torch.Tensor):
-        key = (weight.data_ptr(), tuple(weight.shape))
+        import weakref
+        key = id(weight)
         ent = self._d.get(key)
-        if ent is None or ent[0] != weight._version:
+        if ent is not None and (ent[0]() is not weight or ent[1] != (weight._version, weight.data_ptr(), tuple(weight.shape))):
+            ent = None
+        if ent is None:
             Cout, C, KH, KW = weight.shape
             wk = weight.detach().permute(0, 2, 3, 1).reshape(Cout, KH * KW * C).contiguous().float()
             hi, lo = E.tf32_split(wk)
-            ent = (weight._version, hi, lo)
-            if len(self._d) > 256:
-                self._d.clear()
+            d = self._d
+            ref = weakref.ref(weight, lambda _r, key=key, d=d: d.pop(key, None))
+            ent = (ref, (weight._version, weight.data_ptr(), tuple(weight.shape)), hi, lo)
             self._d[key] = ent
-        return ent[1], ent[2]
+        return ent[2], ent[3]
+
+    def __len__(self):
+        return len(self._d)
 
 
 _wcache = _WeightCache()
