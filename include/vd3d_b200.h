@@ -84,6 +84,14 @@ int vd3d_conv2d_tc16(const void* in_hi, const void* in_lo, int B, int H, int W, 
                      int stride, const float* res, int res_cs, int res_co,
                      float* out, void* out_hi16, void* out_lo16, int Cout, int out_cs, int out_co, int relu, int passes, int bn,
                      void* stream);
+/* Planes-only form of vd3d_conv2d_tc16 (3 passes, persistent engine): between two tensor-core convs an activation is consumed as its
+ * fp16 (hi, lo) planes only, so the fp32 copy need not exist at all.  `out` may be NULL (only out_hi16 / out_lo16 are written: half the
+ * output bytes of a layer), and the residual may be given as planes (res_hi16 / res_lo16, value = hi + lo, exact to 2^-22 relative: the
+ * planes ARE the tensor) instead of an fp32 tensor `res`; pitch / offset res_cs / res_co apply to whichever form is passed. */
+int vd3d_conv2d_tc16_planes(const void* in_hi, const void* in_lo, int B, int H, int W, int Cin, int in_cs, int in_co,
+                            const void* w_hi, const void* w_lo, float out_scale, const float* bias, int KH, int KW, int pad, int dil,
+                            int stride, const float* res, const void* res_hi16, const void* res_lo16, int res_cs, int res_co,
+                            float* out, void* out_hi16, void* out_lo16, int Cout, int out_cs, int out_co, int relu, int bn, void* stream);
 /* Few-channel KHxKW convolution (the ResNet / DLA stem: conv1 7x7 stride 2, R/backbones/resnet.py:120,186) on the tensor cores.
  * The image is held as fp16 (hi, lo) planes [B][H][Wp][4] (pixel x at column x + pad, zeros elsewhere: the buffer must be
  * zero-initialised once); Wp = vd3d_stem_row_pitch(W, KW, stride, pad).  vd3d_image_to_h16_rows fills the planes from an

@@ -43,6 +43,7 @@ struct TcParams {
     int dbg;                 // timing experiments only (VD3D_TC_DEBUG; results are wrong): bit 0 = one MMA per k-step, bit 1 = skip the lo-plane loads, bit 3 = tap-major k-block order, bit 4 = no epilogue output, bit 5 = no residual loads
     int out_cs, out_co, res_cs, res_co, relu;
     const float* bias; const float* res; float* out; float* out_lo;
+    const void* res_h16_hi; const void* res_h16_lo;   // residual given as fp16 (hi, lo) planes (value = hi + lo) instead of an fp32 tensor (`res`)
     uint32_t idesc;
     uint32_t tmem_cols;
     // halo kernel (3x3, pad 1, dil 1, fp16 operands): one A item in shared memory serves `h_taps` taps
@@ -417,6 +418,32 @@ __device__ __forceinline__ void ld8(const float* ptr, bool v8, float (&v)[8]) {
         v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
     }
 }
+// 8 consecutive channels of a tensor kept as fp16 (hi, lo) planes: value = hi + lo (exact in fp32: |lo| <= ulp16(hi) / 2)
+__device__ __forceinline__ void ld8_planes(const __half* hp, const __half* lp, bool v8, float (&v)[8]) {
+    uint32_t h[4], l[4];
+    if (v8) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(hp)), b = __ldg(reinterpret_cast<const uint4*>(lp));
+        h[0] = a.x; h[1] = a.y; h[2] = a.z; h[3] = a.w; l[0] = b.x; l[1] = b.y; l[2] = b.z; l[3] = b.w;
+    } else {
+        const uint2 a0 = __ldg(reinterpret_cast<const uint2*>(hp)), a1 = __ldg(reinterpret_cast<const uint2*>(hp + 4));
+        const uint2 b0 = __ldg(reinterpret_cast<const uint2*>(lp)), b1 = __ldg(reinterpret_cast<const uint2*>(lp + 4));
+        h[0] = a0.x; h[1] = a0.y; h[2] = a1.x; h[3] = a1.y; l[0] = b0.x; l[1] = b0.y; l[2] = b1.x; l[3] = b1.y;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 fh = __half22float2(*reinterpret_cast<const __half2*>(&h[i])), fl = __half22float2(*reinterpret_cast<const __half2*>(&l[i]));
+        v[2 * i] = fh.x + fl.x; v[2 * i + 1] = fh.y + fl.y;
+    }
+}
+__device__ __forceinline__ void ld4_planes(const __half* hp, const __half* lp, float (&v)[8]) {
+    const uint2 a = __ldg(reinterpret_cast<const uint2*>(hp)), b = __ldg(reinterpret_cast<const uint2*>(lp));
+    const uint32_t h[2] = {a.x, a.y}, l[2] = {b.x, b.y};
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float2 fh = __half22float2(*reinterpret_cast<const __half2*>(&h[i])), fl = __half22float2(*reinterpret_cast<const __half2*>(&l[i]));
+        v[2 * i] = fh.x + fl.x; v[2 * i + 1] = fh.y + fl.y;
+    }
+}
 __device__ __forceinline__ void st8(float* ptr, bool v8, const float (&v)[8]) {
     if (v8) {
         asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(ptr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]),
@@ -443,7 +470,7 @@ constexpr int TCP_THREADS = 320;
 // epilogue warps of the persistent kernels (warps 2..9): epilogue warp e owns TMEM lane quadrant (warp % 4) and column half e / 4.
 // Per tile: promote every accumulated chunk into registers (tcgen05.ld + round-to-nearest add), then scale / bias / residual /
 // ReLU and write the fp32 value plus the fp16 (hi, lo) planes the next tensor-core conv reads.
-template <int NG16, int CG>
+template <int NG16, int CG, int PL>   // PL = 1: "planes" mode (fp32 output optional, residual as fp32 tensor or as fp16 planes); PL = 0: fp32 output + fp32 residual only
 __device__ __forceinline__ void tcp_epilogue(const TcParams& p, uint32_t tmem_base, uint64_t* tmem_full, uint64_t* tmem_empty, int warp, int lane,
                                              uint32_t rank, int NC, int u0, int ustep, int units, int mt_units) {
     // ================= epilogue warps =================
@@ -493,10 +520,13 @@ __device__ __forceinline__ void tcp_epilogue(const TcParams& p, uint32_t tmem_ba
         const int ho = th * TC_TH + r / TC_TW, wo = tw * TC_TW + r % TC_TW;
         if (live && ho < p.Ho && wo < p.Wo && !(p.dbg & 16)) {
             const long long pix = ((long long)b * p.Ho + ho) * p.Wo + wo;
-            float* op = p.out + pix * p.out_cs + p.out_co;
+            float* op = (PL == 0 || p.out) ? p.out + pix * p.out_cs + p.out_co : nullptr;           // nullptr (PL = 1 only): planes-only output, no fp32 copy is written
             __half* oh = p.out_h16_hi ? reinterpret_cast<__half*>(p.out_h16_hi) + pix * p.out_cs + p.out_co : nullptr;
             __half* ol16 = p.out_h16_lo ? reinterpret_cast<__half*>(p.out_h16_lo) + pix * p.out_cs + p.out_co : nullptr;
             const float* rp = (p.res && !(p.dbg & 32)) ? p.res + pix * p.res_cs + p.res_co : nullptr;
+            const __half* rph = (PL == 1 && p.res_h16_hi && !(p.dbg & 32)) ? reinterpret_cast<const __half*>(p.res_h16_hi) + pix * p.res_cs + p.res_co : nullptr;
+            const __half* rpl = (PL == 1 && rph) ? reinterpret_cast<const __half*>(p.res_h16_lo) + pix * p.res_cs + p.res_co : nullptr;
+            const bool has_res = rp || (PL == 1 && rph);
             const int nbase = nt * p.BN + cb;
             const bool v8 = p.v8 != 0;
             // batches of 16 * GB columns: all residual loads of a batch are issued before its arithmetic and stores
@@ -507,13 +537,16 @@ __device__ __forceinline__ void tcp_epilogue(const TcParams& p, uint32_t tmem_ba
 #pragma unroll
                 for (int j = 0; j < 2 * GB; ++j) {
                     const int col = bt * 16 + j * 8, n = nbase + col;
-                    if (bt + j / 2 < NG16 && rp && col < ncols && n + 8 <= p.Cout) ld8(rp + n, v8, rr[j]);
-                    else {
+                    if (bt + j / 2 < NG16 && has_res && col < ncols && n + 8 <= p.Cout) {
+                        if (PL == 0 || rp) ld8(rp + n, v8, rr[j]); else ld8_planes(rph + n, rpl + n, v8, rr[j]);
+                    } else {
 #pragma unroll
                         for (int k = 0; k < 8; ++k) rr[j][k] = 0.f;
-                        if (bt + j / 2 < NG16 && rp && col < ncols && n + 4 <= p.Cout) {      // Cout % 8 == 4 tail
-                            const float4 t4 = ldg4(rp + n);
-                            rr[j][0] = t4.x; rr[j][1] = t4.y; rr[j][2] = t4.z; rr[j][3] = t4.w;
+                        if (bt + j / 2 < NG16 && has_res && col < ncols && n + 4 <= p.Cout) {      // Cout % 8 == 4 tail
+                            if (PL == 0 || rp) {
+                                const float4 t4 = ldg4(rp + n);
+                                rr[j][0] = t4.x; rr[j][1] = t4.y; rr[j][2] = t4.z; rr[j][3] = t4.w;
+                            } else ld4_planes(rph + n, rpl + n, rr[j]);
                         }
                     }
                 }
@@ -542,8 +575,10 @@ __device__ __forceinline__ void tcp_epilogue(const TcParams& p, uint32_t tmem_ba
 #pragma unroll
                                 for (int k = 0; k < 8; ++k) a[k] = fmaxf(a[k], 0.f);
                             }
-                            if (full8) st8(op + n, v8, a);
-                            else *reinterpret_cast<float4*>(op + n) = make_float4(a[0], a[1], a[2], a[3]);
+                            if (PL == 0 || op) {
+                                if (full8) st8(op + n, v8, a);
+                                else *reinterpret_cast<float4*>(op + n) = make_float4(a[0], a[1], a[2], a[3]);
+                            }
                             if (oh) {      // fp16 hi/lo planes for the next fp16-split conv
                                 uint2 h0, l0, h1, l1;
 #pragma unroll
@@ -584,7 +619,7 @@ __device__ __forceinline__ void tcp_epilogue(const TcParams& p, uint32_t tmem_ba
 // Warp roles: 0 = TMA producer, 1 = MMA issuer (leader CTA only) + TMEM owner, 2..9 = epilogue; epilogue warp e works
 // on TMEM lane quadrant (warp % 4) and on column half e / 4 of the BN accumulator columns.
 // ----------------------------------------------------------------------------------------------------------------
-template <int NG16, int CG>   // NG16 = 16-column groups per epilogue thread (>= ceil(BN / 32)); CG = CTAs per MMA (1 or 2)
+template <int NG16, int CG, int PL>   // NG16 = 16-column groups per epilogue thread (>= ceil(BN / 32)); CG = CTAs per MMA (1 or 2); PL: see tcp_epilogue
 __global__ void __launch_bounds__(TCP_THREADS, 1)
 conv2d_tcp_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapAlo,
                   const __grid_constant__ CUtensorMap mapWhi, const __grid_constant__ CUtensorMap mapWlo, const TcParams p) {
@@ -774,7 +809,7 @@ conv2d_tcp_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         }
         __syncwarp();
     } else {
-        tcp_epilogue<NG16, CG>(p, tmem_base, tmem_full, tmem_empty, warp, lane, rank, NC, u0, ustep, units, mt_units);
+        tcp_epilogue<NG16, CG, PL>(p, tmem_base, tmem_full, tmem_empty, warp, lane, rank, NC, u0, ustep, units, mt_units);
         tc_fence_before();
     }
     __syncthreads();
@@ -800,7 +835,7 @@ constexpr int TCPH_THREADS = 352;            // warps: 0 = A producer, 1 = MMA, 
 constexpr int TCPH_PLANE = 25600;
 constexpr int TCPH_ITEM = 2 * TCPH_PLANE;
 
-template <int NG16, int CG>
+template <int NG16, int CG, int PL>
 __global__ void __launch_bounds__(TCPH_THREADS, 1)
 conv2d_tcph_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapAlo,
                    const __grid_constant__ CUtensorMap mapWhi, const __grid_constant__ CUtensorMap mapWlo, const TcParams p) {
@@ -981,7 +1016,7 @@ conv2d_tcph_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
         }
         __syncwarp();
     } else {
-        tcp_epilogue<NG16, CG>(p, tmem_base, tmem_full, tmem_empty, warp, lane, rank, NC, u0, ustep, units, mt_units);
+        tcp_epilogue<NG16, CG, PL>(p, tmem_base, tmem_full, tmem_empty, warp, lane, rank, NC, u0, ustep, units, mt_units);
         tc_fence_before();
     }
     __syncthreads();
@@ -1140,7 +1175,8 @@ static int tcp_launch(TcParams& p, const CUtensorMap& mA, const CUtensorMap& mAl
     const size_t smem = stages * stage_bytes + (2 * stages + 10) * sizeof(uint64_t) + 1024;
     static bool pattr_set = false;
     if (!pattr_set) {
-#define VD3D_TCP_ATTR(NG, C) VD3D_CUDA(cudaFuncSetAttribute(conv2d_tcp_kernel<NG, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024))
+#define VD3D_TCP_ATTR(NG, C) VD3D_CUDA(cudaFuncSetAttribute(conv2d_tcp_kernel<NG, C, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+                             VD3D_CUDA(cudaFuncSetAttribute(conv2d_tcp_kernel<NG, C, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024))
         VD3D_TCP_ATTR(2, 1); VD3D_TCP_ATTR(4, 1); VD3D_TCP_ATTR(5, 1); VD3D_TCP_ATTR(8, 1);
         VD3D_TCP_ATTR(2, 2); VD3D_TCP_ATTR(4, 2); VD3D_TCP_ATTR(5, 2); VD3D_TCP_ATTR(8, 2);
 #undef VD3D_TCP_ATTR
@@ -1160,7 +1196,9 @@ static int tcp_launch(TcParams& p, const CUtensorMap& mA, const CUtensorMap& mAl
     cfg.attrs = attr; cfg.numAttrs = 1;
     const int ng = (BN + 31) / 32;
     cudaError_t le;
-#define VD3D_TCP_LAUNCH(NG, C) le = cudaLaunchKernelEx(&cfg, conv2d_tcp_kernel<NG, C>, mA, mAlo, mWhi, mWlo, p)
+    const bool pl = p.out == nullptr || p.res_h16_hi != nullptr;
+#define VD3D_TCP_LAUNCH(NG, C) le = pl ? cudaLaunchKernelEx(&cfg, conv2d_tcp_kernel<NG, C, 1>, mA, mAlo, mWhi, mWlo, p) \
+                                       : cudaLaunchKernelEx(&cfg, conv2d_tcp_kernel<NG, C, 0>, mA, mAlo, mWhi, mWlo, p)
     if (CG == 2) {
         if (ng <= 2) VD3D_TCP_LAUNCH(2, 2); else if (ng <= 4) VD3D_TCP_LAUNCH(4, 2); else if (ng == 5) VD3D_TCP_LAUNCH(5, 2); else VD3D_TCP_LAUNCH(8, 2);
     } else {
@@ -1189,7 +1227,8 @@ static int tcph_launch(TcParams& p, const CUtensorMap& mA, const CUtensorMap& mA
     const size_t smem = (size_t)p.h_sa * TCPH_ITEM + (size_t)p.h_sb * b_stage + (2 * p.h_sa + 2 * p.h_sb + 10) * sizeof(uint64_t) + 1024;
     static bool hattr_set = false;
     if (!hattr_set) {
-#define VD3D_TCPH_ATTR(NG, C) VD3D_CUDA(cudaFuncSetAttribute(conv2d_tcph_kernel<NG, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024))
+#define VD3D_TCPH_ATTR(NG, C) VD3D_CUDA(cudaFuncSetAttribute(conv2d_tcph_kernel<NG, C, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+                              VD3D_CUDA(cudaFuncSetAttribute(conv2d_tcph_kernel<NG, C, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024))
         VD3D_TCPH_ATTR(2, 1); VD3D_TCPH_ATTR(4, 1); VD3D_TCPH_ATTR(5, 1); VD3D_TCPH_ATTR(8, 1);
         VD3D_TCPH_ATTR(2, 2); VD3D_TCPH_ATTR(4, 2); VD3D_TCPH_ATTR(5, 2); VD3D_TCPH_ATTR(8, 2);
 #undef VD3D_TCPH_ATTR
@@ -1209,7 +1248,9 @@ static int tcph_launch(TcParams& p, const CUtensorMap& mA, const CUtensorMap& mA
     cfg.attrs = attr; cfg.numAttrs = 1;
     const int ng = (BN + 31) / 32;
     cudaError_t le;
-#define VD3D_TCPH_LAUNCH(NG, C) le = cudaLaunchKernelEx(&cfg, conv2d_tcph_kernel<NG, C>, mA, mAlo, mWhi, mWlo, p)
+    const bool pl = p.out == nullptr || p.res_h16_hi != nullptr;
+#define VD3D_TCPH_LAUNCH(NG, C) le = pl ? cudaLaunchKernelEx(&cfg, conv2d_tcph_kernel<NG, C, 1>, mA, mAlo, mWhi, mWlo, p) \
+                                        : cudaLaunchKernelEx(&cfg, conv2d_tcph_kernel<NG, C, 0>, mA, mAlo, mWhi, mWlo, p)
     if (CG == 2) {
         if (ng <= 2) VD3D_TCPH_LAUNCH(2, 2); else if (ng <= 4) VD3D_TCPH_LAUNCH(4, 2); else if (ng == 5) VD3D_TCPH_LAUNCH(5, 2); else VD3D_TCPH_LAUNCH(8, 2);
     } else {
@@ -1232,15 +1273,18 @@ static void tc_env(int& persist, int& cg) {
 static int conv2d_tc_launch(int f16, const void* in, const void* in_lo, int B, int H, int W, int Cin, int in_cs, int in_co,
                             const void* w_hi, const void* w_lo, float out_scale, const float* bias, int KH, int KW, int pad, int dil, int stride,
                             const float* res, int res_cs, int res_co, float* out, float* out_lo, void* out_h16_hi, void* out_h16_lo,
-                            int Cout, int out_cs, int out_co, int relu, int passes, int bn, void* stream) {
-    VD3D_REQUIRE(in && w_hi && out, "conv2d_tc: null pointer");
+                            int Cout, int out_cs, int out_co, int relu, int passes, int bn, void* stream,
+                            const void* res_h16_hi = nullptr, const void* res_h16_lo = nullptr) {
+    VD3D_REQUIRE(in && w_hi && (out || out_h16_hi), "conv2d_tc: null pointer");
+    VD3D_REQUIRE(!(res && res_h16_hi) && (!res_h16_hi == !res_h16_lo), "conv2d_tc: the residual is either an fp32 tensor or an fp16 (hi, lo) plane pair");
     VD3D_REQUIRE(passes == 1 || passes == 3, "conv2d_tc: passes must be 1 or 3");
     VD3D_REQUIRE(passes == 1 || (in_lo && w_lo), "conv2d_tc: 3-pass mode needs the lo tensors");
     const int esize = f16 ? 2 : 4, bk = 128 / esize;
     VD3D_REQUIRE(f16 ? (Cin % 8 == 0) : (Cin % bk == 0), "conv2d_tc: Cin must be a multiple of %d (got %d)", f16 ? 8 : bk, Cin);
     VD3D_REQUIRE(in_cs % 8 == 0 && in_co % 8 == 0 && out_cs % 4 == 0 && out_co % 4 == 0 && Cout % 4 == 0, "conv2d_tc: pitches/offsets alignment");
-    VD3D_REQUIRE(!res || (res_cs % 4 == 0 && res_co % 4 == 0), "conv2d_tc: residual pitch/offset must be multiples of 4");
+    VD3D_REQUIRE(!(res || res_h16_hi) || (res_cs % 4 == 0 && res_co % 4 == 0), "conv2d_tc: residual pitch/offset must be multiples of 4");
     VD3D_REQUIRE(((uintptr_t)in & 15) == 0 && ((uintptr_t)w_hi & 15) == 0 && ((uintptr_t)out & 15) == 0, "conv2d_tc: pointers must be 16-byte aligned");
+    VD3D_REQUIRE(!res_h16_hi || ((((uintptr_t)res_h16_hi | (uintptr_t)res_h16_lo) & 7) == 0), "conv2d_tc: residual planes must be 8-byte aligned");
     VD3D_REQUIRE(!out_h16_hi || (out_h16_lo && out_cs % 4 == 0), "conv2d_tc: fp16 output planes come in (hi, lo) pairs");
     int persist, cg_env;
     tc_env(persist, cg_env);
@@ -1252,6 +1296,7 @@ static int conv2d_tc_launch(int f16, const void* in, const void* in_lo, int B, i
         } else BN = vd3d_tc_pick_bn(Cout);
     }
     const bool use_p = f16 && passes == 3 && persist != 0;
+    VD3D_REQUIRE(use_p || (out && !res_h16_hi), "conv2d_tc: planes-only output / plane residuals need the persistent fp16-split engine");
     VD3D_REQUIRE(BN % 16 == 0 && BN >= 16 && BN <= (use_p ? 256 : 160), "conv2d_tc: BN must be a multiple of 16 in [16, %d]", use_p ? 256 : 160);
     TcParams p;
     memset(&p, 0, sizeof(p));
@@ -1266,9 +1311,11 @@ static int conv2d_tc_launch(int f16, const void* in, const void* in_lo, int B, i
     p.m_tiles = p.tiles_w * p.tiles_h * B; p.n_tiles = cdiv(p.cout_pad, BN);
     p.v8 = (out_cs % 8 == 0 && out_co % 8 == 0 && ((uintptr_t)out & 31) == 0 && (!bias || ((uintptr_t)bias & 31) == 0) &&
             (!res || (res_cs % 8 == 0 && res_co % 8 == 0 && ((uintptr_t)res & 31) == 0)) &&
+            (!res_h16_hi || (res_cs % 8 == 0 && res_co % 8 == 0 && ((((uintptr_t)res_h16_hi | (uintptr_t)res_h16_lo) & 15) == 0))) &&
             (!out_h16_hi || ((((uintptr_t)out_h16_hi | (uintptr_t)out_h16_lo) & 15) == 0))) ? 1 : 0;
     p.out_cs = out_cs; p.out_co = out_co; p.res_cs = res_cs; p.res_co = res_co; p.relu = relu;
     p.bias = bias; p.res = res; p.out = out; p.out_lo = out_lo; p.out_h16_hi = out_h16_hi; p.out_h16_lo = out_h16_lo;
+    p.res_h16_hi = res_h16_hi; p.res_h16_lo = res_h16_lo;
     p.range_flag = out_h16_hi ? fp16_range_flag() : nullptr;
     // instruction descriptor (cute::UMMA::InstrDescriptor): D = f32 (1 @4), A/B format @7/@10 (tf32 = 2, f16 = 0), K-major, N>>3 @17, M>>4 @24
     const uint32_t fmt = f16 ? 0u : 2u;
@@ -1391,6 +1438,14 @@ extern "C" int vd3d_conv2d_tc16(const void* in_hi, const void* in_lo, int B, int
                                 void* stream) {
     return conv2d_tc_launch(1, in_hi, in_lo, B, H, W, Cin, in_cs, in_co, w_hi, w_lo, out_scale, bias, KH, KW, pad, dil, stride, res, res_cs, res_co,
                             out, nullptr, out_hi16, out_lo16, Cout, out_cs, out_co, relu, passes, bn, stream);
+}
+
+extern "C" int vd3d_conv2d_tc16_planes(const void* in_hi, const void* in_lo, int B, int H, int W, int Cin, int in_cs, int in_co,
+                                       const void* w_hi, const void* w_lo, float out_scale, const float* bias, int KH, int KW, int pad, int dil,
+                                       int stride, const float* res, const void* res_hi16, const void* res_lo16, int res_cs, int res_co,
+                                       float* out, void* out_hi16, void* out_lo16, int Cout, int out_cs, int out_co, int relu, int bn, void* stream) {
+    return conv2d_tc_launch(1, in_hi, in_lo, B, H, W, Cin, in_cs, in_co, w_hi, w_lo, out_scale, bias, KH, KW, pad, dil, stride, res, res_cs, res_co,
+                            out, nullptr, out_hi16, out_lo16, Cout, out_cs, out_co, relu, 3, bn, stream, res_hi16, res_lo16);
 }
 
 // ----------------------------------------------------------------------------------------------------------------

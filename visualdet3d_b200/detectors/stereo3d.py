@@ -54,9 +54,12 @@ class ResNetRunner:
                 blocks.append(d)
             self.stages.append(blocks)
 
-    def run(self, img_nchw, arena: E.Arena, tag: str = "bb", on_output=None) -> List[E.Act]:
+    def run(self, img_nchw, arena: E.Arena, tag: str = "bb", on_output=None, f32_outputs=None) -> List[E.Act]:
         """`img_nchw`: [B, 3, H, W], or a list of such tensors forming the batch in order (stereo: [left, right]; the parts are read in
         place, the reference's `torch.cat([left, right])` copy does not exist).
+        Inside the stages every activation lives as fp16 (hi, lo) planes only (`engine.planes_mode_ok`): a block's convs, its residual and
+        the tensor-core PSMCosine read planes, so no fp32 copy is written or re-read (half the activation traffic of the 64 / 128-channel
+        layers).  `f32_outputs[j]` says whether returned feature map j also needs its fp32 tensor (default: yes).
         on_output(act, lo_stale) -> lo_stale: called as soon as a returned feature map exists, i.e. while it is still
         L2-resident (the stereo plan launches the cost-volume kernel of that scale from it)."""
         parts = list(img_nchw) if isinstance(img_nchw, (list, tuple)) else [img_nchw]
@@ -81,6 +84,16 @@ class ResNetRunner:
             self.out_lo_stale.append(True)
         x = E.maxpool3x3s2(x, arena.act(tag + ".pool", (B, Hp, Wp, 64), dev, lo=True))
         fresh = True                       # x.lo is stale (x was written by a non-tensor-core kernel)
+        plm = E.planes_mode_ok()
+        n_ret = len(outs)                  # index of the next returned feature map
+
+        def want_f32(stage_idx, last_block, out_layer):
+            """fp32 copy of a block output: needed only if it is a returned map whose consumers read fp32 (or planes mode is off)"""
+            if not plm or out_layer.engine != "tc16":
+                return True
+            if last_block and stage_idx in self.p.out_indices:
+                return True if f32_outputs is None else bool(f32_outputs[n_ret])
+            return False
 
         def feed(layer, a, stale):
             """make sure `a` carries a valid lo companion if `layer` runs on the tensor cores"""
@@ -96,28 +109,29 @@ class ResNetRunner:
                     c1, c2 = d["c1"], d["c2"]
                     Ho, Wo = c1.out_hw(x.H, x.W)
                     fresh = feed(c1, x, fresh)
-                    t = c1(x, arena.act(name + ".t", (B, Ho, Wo, c1.Cout), dev, lo=True))
+                    t = c1(x, arena.act(name + ".t", (B, Ho, Wo, c1.Cout), dev, lo=True), f32_out=not (plm and c2.engine == "tc16"))
                     feed(c2, t, c1.engine == "simt")
                     r = x if "ds" not in d else d["ds"](x, arena.act(name + ".r", (B, Ho, Wo, c2.Cout), dev))
-                    x = c2(t, arena.act(name + ".o", (B, Ho, Wo, c2.Cout), dev, lo=True), res=r)
+                    x = c2(t, arena.act(name + ".o", (B, Ho, Wo, c2.Cout), dev, lo=True), res=r, f32_out=want_f32(i, j == len(blocks) - 1, c2))
                     fresh = c2.engine == "simt"
                 else:
                     c1, c2, c3 = d["c1"], d["c2"], d["c3"]
                     fresh = feed(c1, x, fresh)
-                    t1 = c1(x, arena.act(name + ".t1", (B, x.H, x.W, c1.Cout), dev, lo=True))
+                    t1 = c1(x, arena.act(name + ".t1", (B, x.H, x.W, c1.Cout), dev, lo=True), f32_out=not (plm and c2.engine == "tc16"))
                     Ho, Wo = c2.out_hw(x.H, x.W)
                     feed(c2, t1, c1.engine == "simt")
-                    t2 = c2(t1, arena.act(name + ".t2", (B, Ho, Wo, c2.Cout), dev, lo=True))
+                    t2 = c2(t1, arena.act(name + ".t2", (B, Ho, Wo, c2.Cout), dev, lo=True), f32_out=not (plm and c3.engine == "tc16"))
                     feed(c3, t2, c2.engine == "simt")
                     if "ds" in d:
                         fresh = feed(d["ds"], x, fresh)
                         r = d["ds"](x, arena.act(name + ".r", (B, Ho, Wo, c3.Cout), dev))
                     else:
                         r = x
-                    x = c3(t2, arena.act(name + ".o", (B, Ho, Wo, c3.Cout), dev, lo=True), res=r)
+                    x = c3(t2, arena.act(name + ".o", (B, Ho, Wo, c3.Cout), dev, lo=True), res=r, f32_out=want_f32(i, j == len(blocks) - 1, c3))
                     fresh = c3.engine == "simt"
             if i in self.p.out_indices:
                 outs.append(x)
+                n_ret += 1
                 if on_output is not None:
                     fresh = on_output(x, fresh)
                 self.out_lo_stale.append(fresh)
@@ -249,7 +263,11 @@ class Stereo3D(Anchor3DDetector):
                 return lo_stale and not refreshed
             return lo_stale
 
-        f4, f8, f16 = pl["backbone"].run([left, right], ar, on_output=cost_volume_early)      # one [2B] batch: left = [0, B), right = [B, 2B)
+        # one [2B] batch: left = [0, B), right = [B, 2B).  The scale-4 / scale-8 features feed only the tensor-core PSMCosine (planes);
+        # the scale-16 features are also read as fp32 (left-feature copy, 1x1 down-sample on the SIMT engine)
+        bbp = self.core.backbone
+        need = [not E.psm_tc_eligible(bbp.out_channels(0), D4), not E.psm_tc_eligible(bbp.out_channels(1), D8), True]
+        f4, f8, f16 = pl["backbone"].run([left, right], ar, on_output=cost_volume_early, f32_outputs=need)
         self._hook("feat4", f4), self._hook("feat8", f8), self._hook("feat16", f16)
         self._hook("vol4", G4.slice(0, D4))
         pl["g4"].run(G4)

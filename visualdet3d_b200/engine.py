@@ -32,11 +32,14 @@ class Act:
       * float16, shape [2, B, H, W, cs]: planes hi = rn16(t) and lo = rn16(t - hi) ("tc16" engine, the default).
     The tcgen05 conv engine consumes and produces these; other producers leave them stale and the plan calls `split_lo`
     before a tensor-core consumer."""
-    __slots__ = ("t", "co", "C", "lo")
+    __slots__ = ("t", "co", "C", "lo", "f32")
 
-    def __init__(self, t: torch.Tensor, co: int = 0, C: Optional[int] = None, lo: Optional[torch.Tensor] = None):
+    def __init__(self, t: torch.Tensor, co: int = 0, C: Optional[int] = None, lo: Optional[torch.Tensor] = None, f32: bool = True):
         assert t.dim() == 4 and t.dtype == torch.float32 and t.is_contiguous()
         self.t, self.co, self.lo = t, co, lo
+        # False: the fp32 tensor was NOT written by the producer (planes-only output of a tensor-core conv whose consumers are all
+        # tensor-core convs / plane residuals): the fp16 (hi, lo) planes are the tensor, `t` only carries the shape
+        self.f32 = f32
         self.C = (t.shape[3] - co) if C is None else C
         assert 0 <= co and co + self.C <= t.shape[3]
         assert lo is None or (lo.dtype == torch.float32 and lo.shape == t.shape) or \
@@ -48,11 +51,12 @@ class Act:
     cs = property(lambda s: s.t.shape[3])
 
     def slice(self, co: int, C: int) -> "Act":
-        return Act(self.t, self.co + co, C, self.lo)
+        return Act(self.t, self.co + co, C, self.lo, self.f32)
 
     def batch(self, b0: int, b1: int) -> "Act":
         # (a batch sub-range of the fp16 planes is not contiguous: such views drop the companion; they only feed non-TC kernels)
         lo = self.lo[b0:b1] if (self.lo is not None and self.lo.dtype == torch.float32) else None
+        need_f32(self, "Act.batch")
         return Act(self.t[b0:b1], self.co, self.C, lo)
 
     @property
@@ -74,9 +78,25 @@ class Act:
 
     def to_nchw(self) -> torch.Tensor:
         """Dense [B, C, H, W] copy (tests / NCHW-facing op mirrors)."""
+        if not self.f32:        # planes-only tensor: value = hi + lo (test / hook path: plain torch ops)
+            v = self.lo[0][..., self.co:self.co + self.C].float() + self.lo[1][..., self.co:self.co + self.C].float()
+            return v.permute(0, 3, 1, 2).contiguous()
         out = torch.empty(self.B, self.C, self.H, self.W, device=self.t.device, dtype=torch.float32)
         call("vd3d_nhwc_to_nchw", self.ptr, out.data_ptr(), self.B, self.C, self.H, self.W, self.cs, self.co, _stream())
         return out
+
+
+def need_f32(x: "Act", what: str):
+    """Plan check: `what` reads the fp32 tensor of `x`, which a planes-only producer did not write."""
+    if not x.f32:
+        raise _lib.Vd3dError(f"{what}: the activation exists only as fp16 (hi, lo) planes (plan bug: its producer was told no fp32 consumer follows)")
+
+
+def planes_mode_ok() -> bool:
+    """Planes-only activations between tensor-core convs (`vd3d_conv2d_tc16_planes`): default on with the persistent fp16-split engine;
+    VD3D_PLANES=0 restores the round-1 behaviour (every conv also writes the fp32 tensor)."""
+    import os
+    return conv_engine_default() == "tc16" and os.environ.get("VD3D_TC_PERSIST", "1") != "0" and os.environ.get("VD3D_PLANES", "1") != "0"
 
 
 class Arena:
@@ -205,13 +225,22 @@ class ConvLayer:
         Wo = (W + 2 * self.pad - self.dil * (self.KW - 1) - 1) // self.stride + 1
         return Ho, Wo
 
-    def __call__(self, x: Act, out: Act, res: Optional[Act] = None, relu: Optional[bool] = None):
+    def __call__(self, x: Act, out: Act, res: Optional[Act] = None, relu: Optional[bool] = None, f32_out: bool = True):
+        """f32_out=False (fp16-split engine only): write ONLY the fp16 (hi, lo) planes of the output; legal when every consumer is a
+        tensor-core conv, a plane residual or the tensor-core PSMCosine kernel.  A residual whose fp32 tensor is not valid is read
+        from its planes."""
         assert x.C == self.Cin, (x.C, self.Cin)
         assert out.C == self.Cout and out.B == x.B
         Ho, Wo = self.out_hw(x.H, x.W)
         assert (out.H, out.W) == (Ho, Wo), ((out.H, out.W), (Ho, Wo))
         r = self.relu if relu is None else relu
+        if self.engine != "tc16" or not out.h16:
+            f32_out = True
+        out.f32 = f32_out
+        if self.engine != "tc16" and res is not None:
+            need_f32(res, "conv residual")
         if self.engine == "simt":
+            need_f32(x, "SIMT conv")
             call("vd3d_conv2d_nhwc", x.ptr, x.B, x.H, x.W, x.C, x.cs, x.co, self.w.data_ptr(), self.b.data_ptr(),
                  self.KH, self.KW, self.stride, self.pad, self.dil,
                  res.ptr if res is not None else None, res.cs if res is not None else 0, res.co if res is not None else 0,
@@ -224,6 +253,17 @@ class ConvLayer:
                 check_lo(x)
             xh, xl = x.h16_ptrs
             oh, ol = out.h16_ptrs
+            res_planes = res is not None and not res.f32
+            if not f32_out or res_planes:
+                if res_planes and not res.h16:
+                    raise _lib.Vd3dError("conv residual: neither an fp32 tensor nor fp16 planes are valid")
+                rh, rl = res.h16_ptrs if res_planes else (None, None)
+                call("vd3d_conv2d_tc16_planes", xh, xl, x.B, x.H, x.W, x.C, x.cs, x.co, self.w_hi.data_ptr(), self.w_lo.data_ptr(), self.out_scale,
+                     self.b.data_ptr(), self.KH, self.KW, self.pad, self.dil, self.stride,
+                     res.ptr if (res is not None and not res_planes) else None, rh, rl,
+                     res.cs if res is not None else 0, res.co if res is not None else 0,
+                     out.ptr if f32_out else None, oh, ol, self.Cout, out.cs, out.co, 1 if r else 0, self.bn_tile, _stream())
+                return out
             call("vd3d_conv2d_tc16", xh, xl, x.B, x.H, x.W, x.C, x.cs, x.co, self.w_hi.data_ptr(), self.w_lo.data_ptr(), self.out_scale,
                  self.b.data_ptr(), self.KH, self.KW, self.pad, self.dil, self.stride,
                  res.ptr if res is not None else None, res.cs if res is not None else 0, res.co if res is not None else 0,
@@ -351,6 +391,7 @@ class DwConvLayer:
 
     def __call__(self, x: Act, out: Act):
         assert x.C == self.C and out.C == self.C
+        need_f32(x, "dwconv3x3")
         call("vd3d_dwconv3x3_nhwc", x.ptr, x.B, x.H, x.W, x.C, x.cs, x.co, self.w.data_ptr(), self.b.data_ptr(),
              out.ptr, out.cs, out.co, 1 if self.relu else 0, _stream())
         return out
@@ -367,6 +408,7 @@ def split_lo(x: Act) -> Act:
     """Refresh the `lo` companion of a channel slice written by a non-tensor-core producer."""
     if x.lo is None:
         return x
+    need_f32(x, "split_lo")
     if x.h16:
         h, l = x.h16_ptrs
         call("vd3d_split_h16_nhwc", x.ptr, h, l, x.B * x.H * x.W, x.C, x.cs, x.co, _stream())
@@ -377,6 +419,8 @@ def split_lo(x: Act) -> Act:
 
 def check_lo(x: Act):
     """Debug (VD3D_CHECK_LO=1): assert the companion of the slice a tensor-core conv is about to read is fresh."""
+    if not x.f32:
+        return                      # planes-only tensor: the planes are the tensor
     t = x.t[..., x.co:x.co + x.C]
     if x.h16:
         hi = t.half()
@@ -399,22 +443,26 @@ def nchw_to_nhwc(x: torch.Tensor, out: Act):
 
 
 def maxpool3x3s2(x: Act, out: Act):
+    need_f32(x, "maxpool3x3s2")
     call("vd3d_maxpool3x3s2_nhwc", x.ptr, x.B, x.H, x.W, x.C, x.cs, x.co, out.ptr, out.cs, out.co, _stream())
     return out
 
 
 def avgpool2(x: Act, out: Act):
+    need_f32(x, "avgpool2")
     call("vd3d_avgpool2_nhwc", x.ptr, x.B, x.H, x.W, x.C, x.cs, x.co, out.ptr, out.cs, out.co, _stream())
     return out
 
 
 def copy_channels(x: Act, out: Act):
+    need_f32(x, "copy_channels")
     assert x.C == out.C and x.B * x.H * x.W == out.B * out.H * out.W
     call("vd3d_copy_channels_nhwc", x.ptr, x.B * x.H * x.W, x.C, x.cs, x.co, out.ptr, out.cs, out.co, _stream())
     return out
 
 
 def psm_cosine(left: Act, right: Act, D: int, out: Act):
+    need_f32(left, "psm_cosine (SIMT)"), need_f32(right, "psm_cosine (SIMT)")
     assert (left.cs, left.co, left.C) == (right.cs, right.co, right.C) and out.C == D
     call("vd3d_psm_cosine_nhwc", left.ptr, right.ptr, left.B, left.H, left.W, left.C, left.cs, left.co, D,
          out.ptr, out.cs, out.co, _stream())
@@ -425,6 +473,11 @@ def psm_engine_default() -> str:
     """'tc' = tensor-core PSMCosine on the fp16 (hi, lo) feature planes when they exist (default), 'simt' = fp32 SIMT kernels"""
     import os
     return os.environ.get("VD3D_PSM_ENGINE", "tc")
+
+
+def psm_tc_eligible(C: int, D: int) -> bool:
+    """the tensor-core PSMCosine kernel takes this (channels, disparities) shape: it then reads the fp16 planes only"""
+    return psm_engine_default() == "tc" and lo_mode() == "h16" and C % 64 == 0 and D % 4 == 0 and D <= 32
 
 
 def psm_cosine_stereo(f: Act, B: int, D: int, out: Act, planes_fresh: bool):
