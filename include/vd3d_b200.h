@@ -287,6 +287,19 @@ int vd3d_look_ground_sample(const float* x, int B, int H, int W, int C, int x_cs
                             float baseline, float relative_elevation,
                             float* out, float* out_lo, int out_cs, void* stream);
 
+/* Backward of the deformable convolutions (training side): the reference's col2im + col2im_coord kernels
+ * (deform_conv_cuda_kernel.cu:635-767 modulated, :279-436 DCNv1) fused into one pass over the column gradients
+ *   colgrad [B*Ho*Wo][cg_cs], channel k*C + c  =  sum_o W[o, c, k] * grad_out[pix][o]     (a plain GEMM, done by the caller)
+ * writing grad_x (NHWC, ACCUMULATED into with 16-byte vector reductions: zero-fill it first), grad_off [pix][.. g*2K + 2k (+1)] and
+ * grad_msk [pix][.. g*K + k] (both ASSIGNED; grad_msk / msk NULL for DCNv1).  Any of the three outputs may be NULL.  `msk` holds the
+ * modulation values as used by the forward (after the sigmoid).  Same layout conventions as vd3d_deform_im2col_nhwc. */
+int vd3d_deform_col2im_nhwc(const float* x, int B, int H, int W, int C, int x_cs, int x_co,
+                            const float* off, int off_cs, int off_co, const float* msk, int msk_cs, int msk_co,
+                            int KH, int KW, int stride, int pad, int dil, int deform_groups,
+                            const float* colgrad, int cg_cs,
+                            float* grad_x, int gx_cs, int gx_co, float* grad_off, int go_cs, int go_co,
+                            float* grad_msk, int gm_cs, int gm_co, void* stream);
+
 /* ---- iou3d (R/lib/ops/iou3d, make.sh) ---------------------------------------------------------------------------
  * boxes [n][5] = (x1, y1, x2, y2, ry) f32.  Replace iou3d_cuda.boxes_overlap_bev_gpu / boxes_iou_bev_gpu (iou3d.cpp:31-71,
  * kernels iou3d_kernel.cu:223-248) and nms_gpu / nms_normal_gpu (iou3d.cpp:73-170, kernels :250-348).  NMS runs entirely on

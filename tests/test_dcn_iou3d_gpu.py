@@ -115,6 +115,57 @@ def test_modulated_deform_conv_vs_reference_extension(case):
     np.testing.assert_allclose(o1.cpu().numpy(), o2.cpu().numpy(), rtol=1e-4, atol=2e-5)
 
 
+@pytest.mark.parametrize("case", DCN_CASES)
+def test_deform_conv_backward_vs_reference_extension(case):
+    """the three backward entries of `deform_conv_ext` against the reference's own compiled kernels
+    (modulated col2im / col2im_coord, deform_conv_cuda_kernel.cu:635-767; DCNv1 :279-436) on the same tensors: grad_input, grad_offset,
+    grad_mask, grad_weight, grad_bias.  Sums run in a different order (one fused pass, fp32 atomics): rtol 1e-4 of the tensor's scale."""
+    from visualdet3d_b200.ops import dcn
+    B, C, H, W, Co, k, s, p, d, dg = case
+    g = torch.Generator().manual_seed(1000 + sum(case))
+    x = torch.randn(B, C, H, W, generator=g)
+    w = torch.randn(Co, C, k, k, generator=g) / np.sqrt(C * k * k)
+    bias = torch.randn(Co, generator=g)
+    Ho, Wo = (H + 2 * p - (d * (k - 1) + 1)) // s + 1, (W + 2 * p - (d * (k - 1) + 1)) // s + 1
+    off = torch.randn(B, 2 * k * k * dg, Ho, Wo, generator=g) * 2.0
+    off[0, :, 0, 0] = 50.0
+    mask = torch.sigmoid(torch.randn(B, k * k * dg, Ho, Wo, generator=g))
+    gout = torch.randn(B, Co, Ho, Wo, generator=g)
+    xc, wc, bc, oc, mc, gc = x.cuda(), w.cuda(), bias.cuda(), off.cuda(), mask.cuda(), gout.cuda()
+    ref = ref_ext("ref_deform_conv_ext")
+    e = lambda: xc.new_empty(0)
+
+    def close(a, b, what):
+        scale = float(b.abs().max()) + 1e-12
+        err = float((a - b).abs().max()) / scale
+        assert err < 1e-4, (what, err)
+        return err
+
+    # ---- DCNv2 ----
+    res = []
+    for ext in (dcn, ref):
+        gi, gw, gb = torch.zeros_like(xc), torch.zeros_like(wc), torch.zeros_like(bc)
+        go, gm = torch.zeros_like(oc), torch.zeros_like(mc)
+        ext.modulated_deform_conv_backward(xc, wc, bc, e(), oc, mc, e(), gi, gw, gb, go, gm, gc, k, k, s, s, p, p, d, d, 1, dg, True)
+        torch.cuda.synchronize()
+        res.append((gi, gw, gb, go, gm))
+    errs = [close(a, b, n) for a, b, n in zip(res[0], res[1], ("grad_input", "grad_weight", "grad_bias", "grad_offset", "grad_mask"))]
+    # accumulate-into contracts: a second call doubles grad_input / grad_weight / grad_bias, re-assigns grad_offset / grad_mask
+    gi, gw, gb, go, gm = [t.clone() for t in res[0]]
+    dcn.modulated_deform_conv_backward(xc, wc, bc, e(), oc, mc, e(), gi, gw, gb, go, gm, gc, k, k, s, s, p, p, d, d, 1, dg, True)
+    close(gi, 2 * res[1][0], "grad_input x2"), close(gw, 2 * res[1][1], "grad_weight x2"), close(go, res[1][3], "grad_offset again")
+    # ---- DCNv1 ----
+    r1 = []
+    for ext in (dcn, ref):
+        gi, go, gw = torch.zeros_like(xc), torch.zeros_like(oc), torch.zeros_like(wc)
+        assert ext.deform_conv_backward_input(xc, oc, gc, gi, go, wc, e(), k, k, s, s, p, p, d, d, 1, dg, B) == 1
+        assert ext.deform_conv_backward_parameters(xc, oc, gc, gw, e(), e(), k, k, s, s, p, p, d, d, 1, dg, 0.5, B) == 1
+        torch.cuda.synchronize()
+        r1.append((gi, go, gw))
+    errs += [close(a, b, n) for a, b, n in zip(r1[0], r1[1], ("v1 grad_input", "v1 grad_offset", "v1 grad_weight (scale 0.5)"))]
+    print(case, "max relative errors", ["%.1e" % v for v in errs])
+
+
 def test_dcn_error_behaviour_and_pack_module():
     from visualdet3d_b200.ops import dcn
     x = torch.randn(1, 32, 8, 8)
@@ -122,8 +173,10 @@ def test_dcn_error_behaviour_and_pack_module():
     with pytest.raises(RuntimeError):
         dcn.modulated_deform_conv_forward(x, w, None, x, torch.zeros(1, 18, 8, 8), torch.ones(1, 9, 8, 8), torch.empty(1, 16, 8, 8), x,
                                           3, 3, 1, 1, 1, 1, 1, 1, 1, 1, False)
-    with pytest.raises(NotImplementedError):
-        dcn.modulated_deform_conv_backward()
+    with pytest.raises(RuntimeError):       # backward entries mirror the forward's checks (CPU tensors are refused, not computed on the host)
+        dcn.modulated_deform_conv_backward(x, w, None, x, torch.zeros(1, 18, 8, 8), torch.ones(1, 9, 8, 8), x, torch.zeros_like(x), torch.zeros_like(w),
+                                           None, torch.zeros(1, 18, 8, 8), torch.zeros(1, 9, 8, 8), torch.zeros(1, 16, 8, 8),
+                                           3, 3, 1, 1, 1, 1, 1, 1, 1, 1, False)
     # module mirror vs the CPU restatement, conv_offset re-randomised (the reference zero-fills it)
     m = dcn.ModulatedDeformConvPack(64, 64, 3, padding=1)
     g = torch.Generator().manual_seed(0)

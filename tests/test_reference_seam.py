@@ -51,6 +51,7 @@ def test_reference_modules_and_pipelines_over_b200_ops():
     print(json.dumps(out, indent=1))
     # unmodified ModulatedDeformConvPack / DeformConvPack of the reference, running on visualdet3d_b200.ops.dcn vs on its own extension
     assert out["dcn_v2_rel_err"] < 1e-4 and out["dcn_v1_rel_err"] < 1e-4
+    assert out["dcn_v2_grad_rel_err"] < 1e-4 and out["dcn_v1_grad_rel_err"] < 1e-4      # the reference's autograd Functions over our backward entries
     assert out["iou3d_max_err"] < 1e-5 and out["iou3d_nms_equal"]
     # the reference's unmodified test pipelines driving the B200 detectors == the committed reference fixtures
     for k in ("stereo", "mono"):

@@ -52,6 +52,16 @@ def main():
             y_ref = m(x).clone()
             dc.deform_conv_ext = our_dcn
         out[key] = float((y_ours - y_ref).abs().max() / y_ref.abs().max())
+        # ... and its unmodified autograd Function (deform_conv.py:55-230) training through the B200 backward entries
+        grads = []
+        for ext in (our_dcn, ref_dcn):
+            dc.deform_conv_ext = ext
+            xg = x.clone().requires_grad_(True)
+            m.zero_grad()
+            (m(xg) * torch.linspace(-1, 1, 96, device="cuda").view(1, -1, 1, 1)).sum().backward()
+            grads.append([xg.grad.clone(), m.weight.grad.clone(), m.conv_offset.weight.grad.clone()])
+        dc.deform_conv_ext = our_dcn
+        out[key.replace("rel_err", "grad_rel_err")] = max(float((a - b).abs().max() / b.abs().max()) for a, b in zip(*grads))
     # ---- 2. the reference's unmodified iou3d.py on our extension module ---------------------------------------------------------------
     from visualDet3D.networks.lib.ops.iou3d import iou3d as ri
     a = torch.rand(40, 7, generator=g) * torch.tensor([20, 2, 40, 1, 1, 3, 6.28]) + torch.tensor([-10, 0, 2, 1.2, 1.4, 3.0, -3.14])

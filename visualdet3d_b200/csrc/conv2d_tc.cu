@@ -36,6 +36,7 @@ struct TcParams {
     int tiles_w, tiles_h;
     int stride_w, pad_w;     // W-direction stride / padding (the H direction uses stride / pad); equal to them for ordinary convs
     int m_tiles, n_tiles;    // persistent kernel: tile counts along M (B * tiles_h * tiles_w) and N
+    int mblock;              // persistent kernels: scheduling units (tiles / tile pairs) per M block of the L2-aware tile order (0: one block)
     int rowb;                // bytes per operand row in shared memory = K bytes per k-block: 128 (64 channels, SWIZZLE_128B) or 64 (32, SWIZZLE_64B)
     int cout_pad;            // Cout rounded up to 16 (ragged last N tile = cout_pad - (n_tiles - 1) * BN columns)
     int v8;                  // output / residual / bias slices are 32-byte aligned: 256-bit global accesses
@@ -462,6 +463,20 @@ __device__ __forceinline__ void split4(const float* v, uint2& hv, uint2& lv) {
     lv.y = pack_h2(__float2half_rn(v[2] - __half2float(h2)), __float2half_rn(v[3] - __half2float(h3)));
 }
 
+// Tile order of the persistent kernels.  Unit u -> (mu, nt): M fastest inside an M BLOCK of `mblock` units, then the N tiles, then the
+// next M block.  With one block (mblock == 0) every N tile streams the whole activation tensor again (1408-wide layers: 86 MB of
+// A per pass against ~63 MB of L2 that one SM's traffic can keep: 6 passes = 0.5 GB of DRAM reads); with blocks sized to stay L2-resident
+// the activations are read from DRAM once and the weights once per block.  Pure scheduling: every tile computes the same bits.
+__device__ __forceinline__ void unit_tile(const TcParams& p, int u, int mt_units, int& mu, int& nt) {
+    if (p.mblock <= 0 || p.mblock >= mt_units) { mu = u % mt_units; nt = u / mt_units; return; }
+    const int per = p.mblock * p.n_tiles;
+    const int blk = u / per, r = u - blk * per;
+    const int m0 = blk * p.mblock;
+    const int cur = min(p.mblock, mt_units - m0);
+    nt = r / cur; mu = m0 + (r - nt * cur);
+}
+__device__ __forceinline__ int unit_nt(const TcParams& p, int u, int mt_units) { int mu, nt; unit_tile(p, u, mt_units, mu, nt); return nt; }
+
 constexpr int TCP_THREADS = 320;
 #ifndef VD3D_TC_CG_DEFAULT
 #define VD3D_TC_CG_DEFAULT 0
@@ -483,7 +498,7 @@ __device__ __forceinline__ void tcp_epilogue(const TcParams& p, uint32_t tmem_ba
     float amax = 0.f;                                               // fp16-range guard: largest magnitude written to the fp16 planes
     int cc = 0;
     for (int u = u0; u < units; u += ustep) {
-        const int ncols = min(half_cols, min(p.BN, p.cout_pad - (u / mt_units) * p.BN) - cb);      // valid columns of this thread in this tile (<= 0: none)
+        const int ncols = min(half_cols, min(p.BN, p.cout_pad - unit_nt(p, u, mt_units) * p.BN) - cb);      // valid columns of this thread in this tile (<= 0: none)
         float acc[NG16][16];
 #pragma unroll
         for (int g = 0; g < NG16; ++g)
@@ -511,7 +526,8 @@ __device__ __forceinline__ void tcp_epilogue(const TcParams& p, uint32_t tmem_ba
             }
         }
         // ---- tile output: scale / bias / residual / ReLU, fp32 value + the fp16 (hi, lo) planes ----
-        const int mu = u % mt_units, nt = u / mt_units;
+        int mu, nt;
+        unit_tile(p, u, mt_units, mu, nt);
         int mt = mu * CG + (int)rank;
         const bool live = mt < p.m_tiles;
         const int tw = mt % p.tiles_w; mt /= p.tiles_w;
@@ -674,7 +690,8 @@ conv2d_tcp_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             // ================= TMA producer (both CTAs of a pair): the whole warp walks the ring, one elected lane issues =================
             int it = 0, s = 0, ph = 0;
             for (int u = u0; u < units; u += ustep) {
-                const int mu = u % mt_units, nt = u / mt_units;
+                int mu, nt;
+                unit_tile(p, u, mt_units, mu, nt);
                 int mt = mu * CG + (int)rank;
                 const bool live = mt < p.m_tiles;
                 const int tw = mt % p.tiles_w; mt /= p.tiles_w;
@@ -741,7 +758,7 @@ conv2d_tcp_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             };
             auto tile_idesc = [&](int unit_local) {
                 const int u = u0 + unit_local * ustep;
-                const int nvalid = min(p.BN, p.cout_pad - (u / mt_units) * p.BN);
+                const int nvalid = min(p.BN, p.cout_pad - unit_nt(p, u, mt_units) * p.BN);
                 return (p.idesc & ~(0x3Fu << 17)) | ((uint32_t)(nvalid >> 3) << 17);      // MMA N = valid columns of the tile
             };
             auto issue = [&](uint32_t d_tmem, uint32_t idesc, uint64_t dA, uint64_t dAlo, uint64_t dB, uint64_t dBlo, int k, uint32_t acc0) {
@@ -890,7 +907,8 @@ conv2d_tcph_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
             // ================= A producer (one elected lane): one halo item per (tile, 64-channel chunk) =================
             int it = 0;
             for (int u = u0; u < units; u += ustep) {
-                const int mu = u % mt_units;
+                int mu, nt_unused;
+                unit_tile(p, u, mt_units, mu, nt_unused);
                 int mt = mu * CG + (int)rank;
                 const bool live = mt < p.m_tiles;
                 const int tw = mt % p.tiles_w; mt /= p.tiles_w;
@@ -941,7 +959,7 @@ conv2d_tcph_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
                 }
             } else
             for (int u = u0; u < units; u += ustep) {
-                const int nt = u / mt_units;
+                const int nt = unit_nt(p, u, mt_units);
                 const int nvalid = min(p.BN, p.cout_pad - nt * p.BN);
                 const int n0 = nt * p.BN + (int)rank * (nvalid / CG);
                 for (int kb = 0; kb < KB; ++kb, ++it) {
@@ -970,7 +988,7 @@ conv2d_tcph_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
             int ita = 0, itb = 0, cc = 0;
             if (p.w_res) { mbar_wait(&fullB[0], 0); tc_fence_after(); }
             for (int u = u0; u < units; u += ustep) {
-                const int nvalid = min(p.BN, p.cout_pad - (u / mt_units) * p.BN);
+                const int nvalid = min(p.BN, p.cout_pad - unit_nt(p, u, mt_units) * p.BN);
                 const uint32_t idesc = (p.idesc & ~(0x3Fu << 17)) | ((uint32_t)(nvalid >> 3) << 17);
                 bool first = true;
                 for (int kb = 0; kb < KB; ++kb, ++itb) {
@@ -1309,6 +1327,25 @@ static int conv2d_tc_launch(int f16, const void* in, const void* in_lo, int B, i
     p.stride_w = stride; p.pad_w = pad;
     p.cout_pad = (Cout + 15) / 16 * 16;
     p.m_tiles = p.tiles_w * p.tiles_h * B; p.n_tiles = cdiv(p.cout_pad, BN);
+    {
+        // L2-aware tile order (unit_tile): M blocks whose activation slab (hi + lo planes of the block's input pixels, all channels) is about
+        // VD3D_TC_L2MB megabytes (default 28: a block plus one N tile of weights stays inside the share of the 126 MB L2 that survives the
+        // streaming of the rest); only when there is more than one N tile (otherwise A is read once anyway).  0 disables.
+        const char* e = getenv("VD3D_TC_L2MB");
+        const double l2mb = e ? atof(e) : 28.0;
+        p.mblock = 0;
+        if (f16 && p.n_tiles > 1 && l2mb > 0) {
+            const double a_bytes_per_tile = 128.0 * stride * stride * (double)p.cin_pad * 4.0;      // input pixels behind one 128-pixel output tile, 2 fp16 planes
+            const int cg_guess = BN > 128 ? 2 : 1;
+            int mb = (int)(l2mb * 1048576.0 / (a_bytes_per_tile * cg_guess));
+            const int mt_units = cdiv(p.m_tiles, cg_guess);
+            if (mb < 8) mb = 8;
+            if (mb < mt_units) {
+                const int nblk = cdiv(mt_units, mb);
+                p.mblock = cdiv(mt_units, nblk);       // equal blocks
+            }
+        }
+    }
     p.v8 = (out_cs % 8 == 0 && out_co % 8 == 0 && ((uintptr_t)out & 31) == 0 && (!bias || ((uintptr_t)bias & 31) == 0) &&
             (!res || (res_cs % 8 == 0 && res_co % 8 == 0 && ((uintptr_t)res & 31) == 0)) &&
             (!res_h16_hi || (res_cs % 8 == 0 && res_co % 8 == 0 && ((((uintptr_t)res_h16_hi | (uintptr_t)res_h16_lo) & 15) == 0))) &&

@@ -12,8 +12,9 @@ where they are re-bound locally (deform_conv_cuda.cpp:198-205,524-535) — are i
 Tensors are the reference's NCHW fp32 CUDA tensors.  Internally: NCHW -> NHWC, deformable im2col (one launch for the whole
 batch, not one per image), ONE tcgen05 1x1 GEMM over K = KH*KW*C with 3xTF32 accuracy, NHWC -> NCHW.
 Errors mirror the reference: CPU tensors -> RuntimeError("... not implemented on CPU"), non-contiguous input/weight and
-shape mismatches -> RuntimeError.  `group > 1` is not supported (no in-scope caller uses it); backward entries raise
-NotImplementedError (training is out of scope).
+shape mismatches -> RuntimeError.  `group > 1` is not supported (no in-scope caller uses it).  The three backward entries
+(deform_conv_ext.cpp:69-104,126-147) are implemented too: the reference's unmodified autograd Functions
+(deform_conv.py:55-152,154-230) then train through these ops.
 """
 from __future__ import annotations
 
@@ -135,11 +136,111 @@ def deform_conv_forward(input, weight, offset, output, columns, ones, kW, kH, dW
     return 1
 
 
-def deform_conv_backward_input(*a, **k):
-    raise NotImplementedError("deform conv backward is out of scope of the B200 inference path")
+# ---- backward (training side) ------------------------------------------------------------------------------------
+def _to_nhwc(t: torch.Tensor, pad_to: int = 4) -> E.Act:
+    B, C, H, W = t.shape
+    cs = (C + pad_to - 1) // pad_to * pad_to
+    a = E.Act(torch.zeros(B, H, W, cs, device=t.device) if cs != C else torch.empty(B, H, W, cs, device=t.device), 0, C)
+    call("vd3d_nchw_to_nhwc", t.contiguous().float().data_ptr(), a.ptr, B, C, H, W, cs, 0, E._stream())
+    return a
 
 
-deform_conv_backward_parameters = modulated_deform_conv_backward = deform_conv_backward_input
+def _from_nhwc(a: E.Act, C: int) -> torch.Tensor:
+    out = torch.empty(a.B, C, a.H, a.W, device=a.t.device)
+    call("vd3d_nhwc_to_nchw", a.ptr, out.data_ptr(), a.B, C, a.H, a.W, a.cs, 0, E._stream())
+    return out
+
+
+def _backward(input, weight, offset, mask, grad_output, grad_input, grad_offset, grad_mask, grad_weight, grad_bias,
+              kh, kw, stride, pad, dil, deformable_group, scale=1.0):
+    """Gradients of (modulated) deformable convolution, written into the caller's tensors with the reference's contracts
+    (deform_conv_cuda.cpp:573-690 / :262-488): grad_input is accumulated into (the reference's col2im atomically adds into the
+    zero-filled tensor), grad_offset / grad_mask are assigned, grad_weight / grad_bias are accumulated into (`addmm_`).
+    Plan: NCHW -> NHWC once; colgrad = grad_out . W as ONE GEMM for the whole batch (the reference loops over images);
+    `vd3d_deform_col2im_nhwc` = the reference's col2im + col2im_coord kernels fused into one pass; the weight gradient is one GEMM over
+    the forward gather's columns (`vd3d_deform_im2col_nhwc`).  The two dense GEMMs are library GEMMs like the reference's `addmm_`."""
+    B, C, H, W = input.shape
+    Cout = weight.shape[0]
+    K = kh * kw
+    Ho = (H + 2 * pad - (dil * (kh - 1) + 1)) // stride + 1
+    Wo = (W + 2 * pad - (dil * (kw - 1) + 1)) // stride + 1
+    if tuple(grad_output.shape) != (B, Cout, Ho, Wo):
+        raise RuntimeError(f"grad_output has shape {tuple(grad_output.shape)}, expected {(B, Cout, Ho, Wo)}")
+    st = E._stream()
+    dev = input.device
+    x = _to_nhwc(input)
+    n_off = 2 * K * deformable_group
+    n_msk = K * deformable_group if mask is not None else 0
+    om = E.Act(torch.zeros(B, Ho, Wo, (n_off + n_msk + 3) // 4 * 4, device=dev))
+    call("vd3d_nchw_to_nhwc", offset.contiguous().float().data_ptr(), om.ptr, B, n_off, Ho, Wo, om.cs, 0, st)
+    if mask is not None:
+        call("vd3d_nchw_to_nhwc", mask.contiguous().float().data_ptr(), om.ptr, B, n_msk, Ho, Wo, om.cs, n_off, st)
+    go = _to_nhwc(grad_output)                                       # [B, Ho, Wo, Cout (padded to 4)]
+    go2 = go.t.view(-1, go.cs)[:, :Cout]
+    wk = weight.detach().float().permute(0, 2, 3, 1).reshape(Cout, K * C)      # [Cout, k*C + c]: the column order of the gather
+    if grad_input is not None or grad_offset is not None or grad_mask is not None:
+        colgrad = torch.matmul(go2, wk).contiguous()                  # [npix, K*C]
+        gx = torch.zeros(B, H, W, x.cs, device=dev) if grad_input is not None else None
+        goff = torch.empty(B, Ho, Wo, (n_off + 3) // 4 * 4, device=dev)
+        gmsk = torch.empty(B, Ho, Wo, (n_msk + 3) // 4 * 4, device=dev) if mask is not None else None
+        call("vd3d_deform_col2im_nhwc", x.ptr, B, H, W, C, x.cs, 0, om.ptr, om.cs, 0,
+             om.ptr if mask is not None else None, om.cs, n_off, kh, kw, stride, pad, dil, deformable_group,
+             colgrad.data_ptr(), K * C, gx.data_ptr() if gx is not None else None, x.cs, 0, goff.data_ptr(), goff.shape[3], 0,
+             gmsk.data_ptr() if gmsk is not None else None, gmsk.shape[3] if gmsk is not None else 0, 0, st)
+        if grad_input is not None:
+            grad_input.add_(_from_nhwc(E.Act(gx), C).view_as(grad_input))
+        if grad_offset is not None:
+            grad_offset.copy_(_from_nhwc(E.Act(goff), n_off).view_as(grad_offset))
+        if grad_mask is not None and gmsk is not None:
+            grad_mask.copy_(_from_nhwc(E.Act(gmsk), n_msk).view_as(grad_mask))
+    if grad_weight is not None:
+        cols = torch.empty(B * Ho * Wo, K * C, device=dev)
+        call("vd3d_deform_im2col_nhwc", x.ptr, B, H, W, C, x.cs, 0, om.ptr, om.cs, 0,
+             om.ptr if mask is not None else None, om.cs, n_off, 0, kh, kw, stride, pad, dil, deformable_group,
+             cols.data_ptr(), None, K * C, st)
+        gw = torch.matmul(go2.t(), cols).view(Cout, K, C).permute(0, 2, 1).reshape(Cout, C, kh, kw)
+        grad_weight.add_(gw.view_as(grad_weight), alpha=float(scale))
+    if grad_bias is not None:
+        grad_bias.add_(go2.sum(dim=0).view_as(grad_bias))
+
+
+def _square(a, b, what):
+    if a != b:
+        raise RuntimeError(f"visualdet3d_b200 deform conv: only square {what} is supported")
+    return a
+
+
+def modulated_deform_conv_backward(input, weight, bias, ones, offset, mask, columns, grad_input, grad_weight, grad_bias, grad_offset, grad_mask,
+                                   grad_output, kernel_h, kernel_w, stride_h, stride_w, pad_h, pad_w, dilation_h, dilation_w, group,
+                                   deformable_group, with_bias) -> None:
+    """deform_conv_ext.cpp:126-147 (`columns` / `ones` are scratch in the reference and ignored here)."""
+    _check_inputs(input, weight, offset, kernel_h, kernel_w, group, deformable_group)
+    _backward(input, weight, offset, mask, grad_output, grad_input, grad_offset, grad_mask, grad_weight, grad_bias if with_bias else None,
+              kernel_h, kernel_w, _square(stride_h, stride_w, "stride"), _square(pad_h, pad_w, "padding"), _square(dilation_h, dilation_w, "dilation"),
+              deformable_group)
+
+
+def deform_conv_backward_input(input, offset, gradOutput, gradInput, gradOffset, weight, columns, kW, kH, dW, dH, padW, padH, dilationW, dilationH,
+                               group, deformable_group, im2col_step) -> int:
+    """deform_conv_ext.cpp:69-86: gradInput (accumulated), gradOffset (assigned)."""
+    _check_inputs(input, weight, offset, kH, kW, group, deformable_group)
+    _backward(input, weight, offset, None, gradOutput, gradInput, gradOffset, None, None, None, kH, kW, _square(dH, dW, "stride"),
+              _square(padH, padW, "padding"), _square(dilationH, dilationW, "dilation"), deformable_group)
+    return 1
+
+
+def deform_conv_backward_parameters(input, offset, gradOutput, gradWeight, columns, ones, kW, kH, dW, dH, padW, padH, dilationW, dilationH,
+                                    group, deformable_group, scale, im2col_step) -> int:
+    """deform_conv_ext.cpp:88-104: gradWeight += scale * dL/dW."""
+    if gradWeight.shape[2] != kH or gradWeight.shape[3] != kW:
+        raise RuntimeError("kernel size and gradWeight shape do not match")
+    if not input.is_cuda:
+        raise RuntimeError("deform conv is not implemented on CPU")
+    if group != 1:
+        raise RuntimeError("visualdet3d_b200 deform conv: group > 1 is not supported")
+    _backward(input, gradWeight, offset, None, gradOutput, None, None, None, gradWeight, None, kH, kW, _square(dH, dW, "stride"),
+              _square(padH, padW, "padding"), _square(dilationH, dilationW, "dilation"), deformable_group, scale=scale)
+    return 1
 
 
 # ---- functional + module mirrors (deform_conv.py:55-96,154-187,408-466) ------------------------------------------------
