@@ -287,6 +287,20 @@ int vd3d_look_ground_sample(const float* x, int B, int H, int W, int C, int x_cs
                             float baseline, float relative_elevation,
                             float* out, float* out_lo, int out_cs, void* stream);
 
+/* Fused (modulated) deformable convolution: the bilinear gather writes the fp16 (hi, lo) A operand of the tcgen05 GEMM straight into
+ * shared memory (SWIZZLE_128B K-major layout + fence.proxy.async), so the column tensor of the reference (deform_conv_cuda.cpp:539-556)
+ * never exists in HBM.  x: NHWC fp32; om: NHWC at output resolution holding the offsets (channel off_co + 2k = dh, + 1 = dw) and, when
+ * has_mask, the modulation (msk_co + k; mask_sigmoid applies the sigmoid of ModulatedDeformConvPack.forward); weights: the fp16 (hi, lo)
+ * [Cout][KH*KW*C] matrix of vd3d_conv2d_tc16 (k = tap*C + c) with its power-of-two out_scale; epilogue (bias, residual, ReLU, fp32 output and
+ * optional fp16 planes) as vd3d_conv2d_tc16.  One deformable group, KH*KW <= 9, C % 64 == 0.  Bit-identical to vd3d_deform_im2col_h16 followed
+ * by vd3d_conv2d_tc16 (same K order, same gather arithmetic). */
+int vd3d_deform_conv_fused(const float* x, int B, int H, int W, int C, int x_cs, int x_co,
+                           const float* om, int om_cs, int off_co, int msk_co, int has_mask, int mask_sigmoid,
+                           int KH, int KW, int stride, int pad, int dil,
+                           const void* w_hi, const void* w_lo, float out_scale, const float* bias,
+                           const float* res, int res_cs, int res_co,
+                           float* out, void* out_hi16, void* out_lo16, int Cout, int out_cs, int out_co, int relu, void* stream);
+
 /* Backward of the deformable convolutions (training side): the reference's col2im + col2im_coord kernels
  * (deform_conv_cuda_kernel.cu:635-767 modulated, :279-436 DCNv1) fused into one pass over the column gradients
  *   colgrad [B*Ho*Wo][cg_cs], channel k*C + c  =  sum_o W[o, c, k] * grad_out[pix][o]     (a plain GEMM, done by the caller)

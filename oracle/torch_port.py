@@ -350,7 +350,7 @@ def modulated_deform_conv(x, offset, mask, weight, bias=None, stride=1, padding=
 
 def modulated_deform_conv_pack(sd: SD, p: str, x, stride=1, padding=1, dilation=1):
     """ModulatedDeformConvPack.forward (R/lib/ops/dcn/deform_conv.py:459-466)."""
-    out = conv(sd, p + ".conv_offset", x, stride=stride, padding=padding)
+    out = conv(sd, p + ".conv_offset", x, stride=stride, padding=padding, dilation=dilation)      # conv_offset shares the dilation (:441-449)
     o1, o2, m = torch.chunk(out, 3, dim=1)
     return modulated_deform_conv(x, torch.cat((o1, o2), dim=1), torch.sigmoid(m), sd[p + ".weight"], sd.get(p + ".bias"),
                                  stride, padding, dilation)

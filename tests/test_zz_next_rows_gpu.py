@@ -176,7 +176,7 @@ def test_streamed_pipeline_mono_with_post_opt_geometry_and_frames():
     for b in range(2):
         for a, r in zip(got[b], ref[b]):
             assert torch.equal(a, r.cpu())
-    assert pipe2.h2d_bytes_frames < pipe2.h2d_bytes / 3.5
+    assert pipe2.h2d_bytes_frames < pipe2.h2d_bytes / 3        # 375 x 1242 x 3 bytes vs 288 x 1280 x 3 floats per frame
 
 
 def test_device_input_pipeline_matches_host():

@@ -63,6 +63,7 @@ __global__ void __launch_bounds__(CN_THREADS) cn_decode_nms_kernel(
     int n = ncand[b];
     if (t == 0) o_ncand[b] = n;
     if (n > cap) { if (t == 0) o_count[b] = -1; return; }
+    { int n2 = 2; while (n2 < n) n2 <<= 1; cap_pow2 = n2 < cap_pow2 ? n2 : cap_pow2; }      // sort only the occupied power of two (block-uniform)
     for (int i = t; i < cap_pow2; i += CN_THREADS) skey[i] = (i < n) ? keys[(long long)b * cap + i] : ~0ull;
     __syncthreads();
     for (int k = 2; k <= cap_pow2; k <<= 1)
@@ -221,6 +222,7 @@ __global__ void __launch_bounds__(CN_THREADS) km3d_decode_nms_kernel(
     for (int j = 0; j < KM_J; ++j) overflow = overflow || hp_ncand[b * KM_J + j] > hp_cap;
     if (overflow) { if (t == 0) o_count[b] = -1; return; }      // fixed-capacity candidate lists overflowed: reported, never silently truncated
     // ---- detection peaks: sort, keep the best K -----------------------------------------------------------------------------
+    { int n2 = 2; while (n2 < n) n2 <<= 1; cap_pow2 = n2 < cap_pow2 ? n2 : cap_pow2; }      // sort only the occupied power of two (block-uniform)
     for (int i = t; i < cap_pow2; i += CN_THREADS) skey[i] = (i < n) ? keys[(long long)b * cap + i] : ~0ull;
     __syncthreads();
     bitonic_sort_u64(skey, cap_pow2, t, CN_THREADS);
@@ -230,9 +232,12 @@ __global__ void __launch_bounds__(CN_THREADS) km3d_decode_nms_kernel(
     // ---- keypoint heat-map peaks per joint: best K of those above 0.1, with their sub-pixel offsets ---------------------------
     for (int j = 0; j < KM_J; ++j) {
         int nj = min(hp_ncand[b * KM_J + j], hp_cap);
-        for (int i = t; i < hp_cap_pow2; i += CN_THREADS) skey[i] = (i < nj) ? hp_keys[((long long)b * KM_J + j) * hp_cap + i] : ~0ull;
+        int hp2 = 2; while (hp2 < nj) hp2 <<= 1;
+        hp2 = hp2 < hp_cap_pow2 ? hp2 : hp_cap_pow2;
+        __syncthreads();                                     // the previous joint's readers of skey are done
+        for (int i = t; i < hp2; i += CN_THREADS) skey[i] = (i < nj) ? hp_keys[((long long)b * KM_J + j) * hp_cap + i] : ~0ull;
         __syncthreads();
-        bitonic_sort_u64(skey, hp_cap_pow2, t, CN_THREADS);
+        bitonic_sort_u64(skey, hp2, t, CN_THREADS);
         int m = min(nj, K);
         if (t < m) {
             unsigned long long key = skey[t];

@@ -90,13 +90,14 @@ __global__ void __launch_bounds__(DCN_THREADS) deform_im2col_kernel(const DcnPar
             float4 v3 = (flags & 4) ? ldg4(xb + (long long)(base + p.W) * p.x_cs) : make_float4(0.f, 0.f, 0.f, 0.f);
             float4 v4 = (flags & 8) ? ldg4(xb + (long long)(base + p.W + 1) * p.x_cs) : make_float4(0.f, 0.f, 0.f, 0.f);
             float w1 = s_w[pl][k][0], w2 = s_w[pl][k][1], w3 = s_w[pl][k][2], w4 = s_w[pl][k][3];
-            acc.x = w1 * v1.x + w2 * v2.x + w3 * v3.x + w4 * v4.x;
-            acc.y = w1 * v1.y + w2 * v2.y + w3 * v3.y + w4 * v4.y;
-            acc.z = w1 * v1.z + w2 * v2.z + w3 * v3.z + w4 * v4.z;
-            acc.w = w1 * v1.w + w2 * v2.w + w3 * v3.w + w4 * v4.w;
+            // explicit operation order (shared with dcn_fused.cu, whose columns must have the same bits): ((w1 v1 + w2 v2) + w3 v3) + w4 v4 as an fma chain
+            acc.x = fmaf(w4, v4.x, fmaf(w3, v3.x, fmaf(w2, v2.x, __fmul_rn(w1, v1.x))));
+            acc.y = fmaf(w4, v4.y, fmaf(w3, v3.y, fmaf(w2, v2.y, __fmul_rn(w1, v1.y))));
+            acc.z = fmaf(w4, v4.z, fmaf(w3, v3.z, fmaf(w2, v2.z, __fmul_rn(w1, v1.z))));
+            acc.w = fmaf(w4, v4.w, fmaf(w3, v3.w, fmaf(w2, v2.w, __fmul_rn(w1, v1.w))));
         }
         float m = s_m[pl][k];
-        acc.x *= m; acc.y *= m; acc.z *= m; acc.w *= m;
+        acc.x = __fmul_rn(acc.x, m); acc.y = __fmul_rn(acc.y, m); acc.z = __fmul_rn(acc.z, m); acc.w = __fmul_rn(acc.w, m);
         long long o = pix * p.col_cs + (long long)k * p.C + c;
         if (p.col) *reinterpret_cast<float4*>(p.col + o) = acc;
         if (p.col_h16_hi) {     // hi = rn16(v), lo = rn16(v - hi): identical to vd3d_split_h16_nhwc on the fp32 columns

@@ -23,6 +23,16 @@ from .base import synth_load
 from .dla import DLAP, DLARunner, DLASegUpsampleP, DLAUpRunner
 
 
+def _peak_capacity(n_cells: int) -> int:
+    """Capacity of a heat-map peak list: a 3x3 local maximum rules out its 8 neighbours, so a map of n cells has at most ~n / 4 peaks;
+    power of two in [1024, 8192] (the library's limit: more peaks than that are reported as an overflow, never truncated).  The decode
+    kernels sort only the occupied part of a list, so a generous capacity costs memory, not time."""
+    cap = 1024
+    while cap < min(8192, (n_cells + 3) // 4):
+        cap <<= 1
+    return cap
+
+
 class KM3DCoreP(M.Holder):
     """keys of KM3DCore (R/detectors/KM3D_core.py:10-50) for the DLA backbone."""
 
@@ -181,16 +191,17 @@ class MonoFlex(_CenterNetBase):
         if missing:
             raise Vd3dError(f"MonoFlex head_dict lacks {missing}")
         B, dev = out.B, out.t.device
-        key = (B, str(dev))
+        cap = _peak_capacity(self.num_classes * out.H * out.W)
+        key = (B, str(dev), cap)
         if key not in self._decoders:
             d = E.DecodeNms(B, 128, dev)
-            d.ws = torch.empty(int(_lib.load().vd3d_monoflex_decode_workspace(B, 4096)), dtype=torch.uint8, device=dev)
+            d.ws = torch.empty(int(_lib.load().vd3d_monoflex_decode_workspace(B, cap)), dtype=torch.uint8, device=dev)
             self._decoders[key] = d
         dec = self._decoders[key]
         call("vd3d_monoflex_decode", out.ptr, B, out.H, out.W, self.num_classes, out.cs, off["hm"], off["bbox2d"], off["hps"], off["rot"],
              off["dim"], off["reg"], off["depth"], off["depth_uncertainty"], off["corner_uncertainty"], P2.data_ptr(),
              float(self.test_cfg.get("score_thr", 0.1)), float(self.test_cfg.get("nms_iou_thr", 0.5)), self.topk,
-             float(self.uncertainty_range[0]), float(self.uncertainty_range[1]), float(W), float(H), 4096, dec.ws.data_ptr(), dec.cap,
+             float(self.uncertainty_range[0]), float(self.uncertainty_range[1]), float(W), float(H), cap, dec.ws.data_ptr(), dec.cap,
              dec.scores.data_ptr(), dec.boxes.data_ptr(), dec.cls.data_ptr(), dec.anchor.data_ptr(), dec.count.data_ptr(),
              dec.ncand.data_ptr(), E._stream())
         self._last_decoder = dec
@@ -223,15 +234,16 @@ class KM3D(_CenterNetBase):
         if self.bbox_head.head_dict["hps"] != 18 or self.bbox_head.head_dict["hm_hp"] != 9:
             raise Vd3dError("KM3D decode expects 9 keypoints (hps = 18, hm_hp = 9)")
         B, dev = out.B, out.t.device
-        key = (B, str(dev))
+        cap, hp_cap = _peak_capacity(self.num_classes * out.H * out.W), _peak_capacity(out.H * out.W)
+        key = (B, str(dev), cap, hp_cap)
         if key not in self._decoders:
             d = E.DecodeNms(B, 128, dev)
-            d.ws = torch.empty(int(_lib.load().vd3d_km3d_decode_workspace(B, 4096, 1024)), dtype=torch.uint8, device=dev)
+            d.ws = torch.empty(int(_lib.load().vd3d_km3d_decode_workspace(B, cap, hp_cap)), dtype=torch.uint8, device=dev)
             self._decoders[key] = d
         dec = self._decoders[key]
         call("vd3d_km3d_decode", out.ptr, B, out.H, out.W, self.num_classes, out.cs, off["hm"], off["wh"], off["hps"], off["rot"], off["dim"],
              off["prob"], off["reg"], off["hm_hp"], off["hp_offset"], P2.data_ptr(), float(self.test_cfg.get("score_thr", 0.1)),
-             float(self.test_cfg.get("nms_iou_thr", 0.5)), self.topk, float(W), float(H), 4096, 1024, dec.ws.data_ptr(), dec.cap,
+             float(self.test_cfg.get("nms_iou_thr", 0.5)), self.topk, float(W), float(H), cap, hp_cap, dec.ws.data_ptr(), dec.cap,
              dec.scores.data_ptr(), dec.boxes.data_ptr(), dec.cls.data_ptr(), dec.anchor.data_ptr(), dec.count.data_ptr(),
              dec.ncand.data_ptr(), E._stream())
         self._last_decoder = dec

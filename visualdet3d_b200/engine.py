@@ -350,7 +350,7 @@ class DeformConvLayer:
         ob = torch.zeros(n_pad, dtype=off_weight.dtype)
         ob[:n_off] = off_bias.detach().cpu()
         self.n_off_pad = n_pad
-        self.off_conv = ConvLayer(ow, ob, None, stride=stride, pad=pad, dil=1, relu=False, device=device)   # conv_offset has dilation 1
+        self.off_conv = ConvLayer(ow, ob, None, stride=stride, pad=pad, dil=dil, relu=False, device=device)   # conv_offset shares stride / padding / dilation (deform_conv.py:441-449)
         w1 = weight.detach().cpu().permute(0, 2, 3, 1).reshape(Cout, K * C, 1, 1)
         self.main = ConvLayer(w1, bias, bn, relu=relu, device=device)
 
@@ -365,6 +365,19 @@ class DeformConvLayer:
         Ho, Wo = self.out_hw(x.H, x.W)
         K = self.KH * self.KW
         om = self.off_conv(x, arena.act(name + ".om", (B, Ho, Wo, self.n_off_pad), dev))
+        need_f32(x, "deformable gather")
+        if self.fused_ok():
+            # gather -> shared-memory operand -> tcgen05 GEMM in ONE kernel: the column tensor never exists (csrc/dcn_fused.cu)
+            m = self.main
+            oh, ol = out.h16_ptrs
+            out.f32 = True
+            if res is not None:
+                need_f32(res, "deformable conv residual")
+            call("vd3d_deform_conv_fused", x.ptr, B, x.H, x.W, x.C, x.cs, x.co, om.ptr, om.cs, 0, 2 * K * self.dg, 1, 1,
+                 self.KH, self.KW, self.stride, self.pad, self.dil, m.w_hi.data_ptr(), m.w_lo.data_ptr(), m.out_scale, m.b.data_ptr(),
+                 res.ptr if res is not None else None, res.cs if res is not None else 0, res.co if res is not None else 0,
+                 out.ptr, oh, ol, m.Cout, out.cs, out.co, 1 if m.relu else 0, _stream())
+            return out
         cols = arena.act("dcn.cols", (B, Ho, Wo, K * self.C), dev, lo=self.main.engine != "simt")     # one buffer per shape, shared by all DCN layers
         if cols.h16:      # the fp16-split GEMM reads only the planes: the gather writes them directly, the fp32 columns are never stored
             ch, cl = cols.h16_ptrs
@@ -376,6 +389,12 @@ class DeformConvLayer:
                  om.ptr, om.cs, 2 * K * self.dg, 1, self.KH, self.KW, self.stride, self.pad, self.dil, self.dg,
                  cols.ptr, cols.lo_ptr, cols.cs, _stream())
         return self.main(cols, out, res=res)
+
+    def fused_ok(self) -> bool:
+        """the fused gather + GEMM kernel takes this layer (VD3D_DCN_FUSED=0 forces the im2col-planes + 1x1-conv path, kept for A/B and tests)"""
+        import os
+        return (self.main.engine == "tc16" and os.environ.get("VD3D_DCN_FUSED", "1") != "0" and os.environ.get("VD3D_TC_PERSIST", "1") != "0"
+                and self.KH * self.KW <= 9 and self.dg == 1 and self.C % 64 == 0)
 
 
 class DwConvLayer:
