@@ -515,6 +515,9 @@ conv2d_tcp_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                 const uint64_t off = (uint64_t)((k * 32) >> 4);       // one MMA K-step = 16 fp16 = 32 bytes inside the swizzle row
                 if (p.dbg & 1) {
                     if (CG == 2) umma_f16_2sm(d_tmem, dA + off, dB + off, idesc, acc0); else umma_f16(d_tmem, dA + off, dB + off, idesc, acc0);
+                } else if (p.two_pass) {
+                    if (CG == 2) { umma_f16_2sm(d_tmem, dA + off, dBlo + off, idesc, acc0); umma_f16_2sm(d_tmem, dA + off, dB + off, idesc, 1); }
+                    else { umma_f16(d_tmem, dA + off, dBlo + off, idesc, acc0); umma_f16(d_tmem, dA + off, dB + off, idesc, 1); }
                 } else if (CG == 2) {
                     umma_f16_2sm(d_tmem, dAlo + off, dB + off, idesc, acc0);      // small terms first, then the main product
                     umma_f16_2sm(d_tmem, dA + off, dBlo + off, idesc, 1);
@@ -763,7 +766,10 @@ conv2d_tcph_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const uint64_t off = (uint64_t)((k * 32) >> 4);
-                        if (CG == 2) {
+                        if (p.two_pass) {
+                            if (CG == 2) { umma_f16_2sm(d_tmem, dA + off, dBlo + off, idesc, first ? 0u : 1u); umma_f16_2sm(d_tmem, dA + off, dB + off, idesc, 1); }
+                            else { umma_f16(d_tmem, dA + off, dBlo + off, idesc, first ? 0u : 1u); umma_f16(d_tmem, dA + off, dB + off, idesc, 1); }
+                        } else if (CG == 2) {
                             umma_f16_2sm(d_tmem, dAlo + off, dB + off, idesc, first ? 0u : 1u);
                             umma_f16_2sm(d_tmem, dA + off, dBlo + off, idesc, 1);
                             umma_f16_2sm(d_tmem, dA + off, dB + off, idesc, 1);
@@ -1017,7 +1023,9 @@ static int conv2d_tc_launch(int f16, const void* in, const void* in_lo, int B, i
                             const void* res_h16_hi = nullptr, const void* res_h16_lo = nullptr) {
     VD3D_REQUIRE(in && w_hi && (out || out_h16_hi), "conv2d_tc: null pointer");
     VD3D_REQUIRE(!(res && res_h16_hi) && (!res_h16_hi == !res_h16_lo), "conv2d_tc: the residual is either an fp32 tensor or an fp16 (hi, lo) plane pair");
-    VD3D_REQUIRE(passes == 1 || passes == 3, "conv2d_tc: passes must be 1 or 3");
+    const int two_pass = (f16 && passes == 2) ? 1 : 0;        // error-budget experiments: 3-pass machinery with the A_lo * W_hi product dropped
+    if (two_pass) passes = 3;
+    VD3D_REQUIRE(passes == 1 || passes == 3, "conv2d_tc: passes must be 1, 3 (or 2 with the fp16-split engine)");
     VD3D_REQUIRE(passes == 1 || (in_lo && w_lo), "conv2d_tc: 3-pass mode needs the lo tensors");
     const int esize = f16 ? 2 : 4, bk = 128 / esize;
     VD3D_REQUIRE(f16 ? (Cin % 8 == 0) : (Cin % bk == 0), "conv2d_tc: Cin must be a multiple of %d (got %d)", f16 ? 8 : bk, Cin);
@@ -1075,6 +1083,7 @@ static int conv2d_tc_launch(int f16, const void* in, const void* in_lo, int B, i
     p.out_cs = out_cs; p.out_co = out_co; p.res_cs = res_cs; p.res_co = res_co; p.relu = relu;
     p.bias = bias; p.res = res; p.out = out; p.out_lo = out_lo; p.out_h16_hi = out_h16_hi; p.out_h16_lo = out_h16_lo;
     p.res_h16_hi = res_h16_hi; p.res_h16_lo = res_h16_lo;
+    p.two_pass = two_pass;
     p.range_flag = out_h16_hi ? fp16_range_flag() : nullptr;
     // instruction descriptor (cute::UMMA::InstrDescriptor): D = f32 (1 @4), A/B format @7/@10 (tf32 = 2, f16 = 0), K-major, N>>3 @17, M>>4 @24
     const uint32_t fmt = f16 ? 0u : 2u;

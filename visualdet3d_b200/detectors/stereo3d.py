@@ -89,7 +89,7 @@ class ResNetRunner:
 
         def want_f32(stage_idx, last_block, out_layer):
             """fp32 copy of a block output: needed only if it is a returned map whose consumers read fp32 (or planes mode is off)"""
-            if not plm or out_layer.engine != "tc16":
+            if not E.planes_only_ok(out_layer):
                 return True
             if last_block and stage_idx in self.p.out_indices:
                 return True if f32_outputs is None else bool(f32_outputs[n_ret])
@@ -109,7 +109,7 @@ class ResNetRunner:
                     c1, c2 = d["c1"], d["c2"]
                     Ho, Wo = c1.out_hw(x.H, x.W)
                     fresh = feed(c1, x, fresh)
-                    t = c1(x, arena.act(name + ".t", (B, Ho, Wo, c1.Cout), dev, lo=True), f32_out=not (plm and c2.engine == "tc16"))
+                    t = c1(x, arena.act(name + ".t", (B, Ho, Wo, c1.Cout), dev, lo=True), f32_out=not (E.planes_only_ok(c1) and c2.engine == "tc16"))
                     feed(c2, t, c1.engine == "simt")
                     r = x if "ds" not in d else d["ds"](x, arena.act(name + ".r", (B, Ho, Wo, c2.Cout), dev))
                     x = c2(t, arena.act(name + ".o", (B, Ho, Wo, c2.Cout), dev, lo=True), res=r, f32_out=want_f32(i, j == len(blocks) - 1, c2))
@@ -117,10 +117,10 @@ class ResNetRunner:
                 else:
                     c1, c2, c3 = d["c1"], d["c2"], d["c3"]
                     fresh = feed(c1, x, fresh)
-                    t1 = c1(x, arena.act(name + ".t1", (B, x.H, x.W, c1.Cout), dev, lo=True), f32_out=not (plm and c2.engine == "tc16"))
+                    t1 = c1(x, arena.act(name + ".t1", (B, x.H, x.W, c1.Cout), dev, lo=True), f32_out=not (E.planes_only_ok(c1) and c2.engine == "tc16"))
                     Ho, Wo = c2.out_hw(x.H, x.W)
                     feed(c2, t1, c1.engine == "simt")
-                    t2 = c2(t1, arena.act(name + ".t2", (B, Ho, Wo, c2.Cout), dev, lo=True), f32_out=not (plm and c3.engine == "tc16"))
+                    t2 = c2(t1, arena.act(name + ".t2", (B, Ho, Wo, c2.Cout), dev, lo=True), f32_out=not (E.planes_only_ok(c2) and c3.engine == "tc16"))
                     feed(c3, t2, c2.engine == "simt")
                     if "ds" in d:
                         fresh = feed(d["ds"], x, fresh)

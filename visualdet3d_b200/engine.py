@@ -99,6 +99,14 @@ def planes_mode_ok() -> bool:
     return conv_engine_default() == "tc16" and os.environ.get("VD3D_TC_PERSIST", "1") != "0" and os.environ.get("VD3D_PLANES", "1") != "0"
 
 
+def planes_only_ok(layer) -> bool:
+    """this tensor-core layer may write its output as planes only (no fp32 copy): planes mode on and the tile not wider than
+    VD3D_PLANES_MAXC columns (default 160: the widest epilogue variant, 16 x 8 accumulator groups per thread, has no registers to spare
+    for the planes form and runs slower with it)"""
+    import os
+    return planes_mode_ok() and layer.engine == "tc16" and layer.Cout <= int(os.environ.get("VD3D_PLANES_MAXC", "160"))
+
+
 class Arena:
     """Named, shape-keyed device buffers: allocated once, pointer-stable across forwards (CUDA-graph friendly)."""
 
@@ -214,6 +222,7 @@ class ConvLayer:
             hi, lo = fp16_split(wk.reshape(Cout, KH * KW * cin64) * (2.0 ** k))
             self.w_hi, self.w_lo = hi.to(device), lo.to(device)
             self.bn_tile = 0          # 0 = the library's policy for the engine in use (vd3d_tc_pick_bn_persistent / vd3d_tc_pick_bn)
+            self.passes = 3           # 2 = error-budget experiments (tools/error_budget.py): drop the A_lo * W_hi product
         else:
             wk = w.permute(0, 2, 3, 1).reshape(Cout, KH * KW * cin_p).contiguous().float()
             hi, lo = tf32_split(wk)
@@ -234,7 +243,7 @@ class ConvLayer:
         Ho, Wo = self.out_hw(x.H, x.W)
         assert (out.H, out.W) == (Ho, Wo), ((out.H, out.W), (Ho, Wo))
         r = self.relu if relu is None else relu
-        if self.engine != "tc16" or not out.h16:
+        if self.engine != "tc16" or not out.h16 or getattr(self, "passes", 3) != 3:
             f32_out = True
         out.f32 = f32_out
         if self.engine != "tc16" and res is not None:
@@ -254,6 +263,8 @@ class ConvLayer:
             xh, xl = x.h16_ptrs
             oh, ol = out.h16_ptrs
             res_planes = res is not None and not res.f32
+            if res_planes and self.passes != 3:
+                raise _lib.Vd3dError("the 2-pass experiment mode needs VD3D_PLANES=0 (fp32 residuals)")
             if not f32_out or res_planes:
                 if res_planes and not res.h16:
                     raise _lib.Vd3dError("conv residual: neither an fp32 tensor nor fp16 planes are valid")
@@ -267,7 +278,7 @@ class ConvLayer:
             call("vd3d_conv2d_tc16", xh, xl, x.B, x.H, x.W, x.C, x.cs, x.co, self.w_hi.data_ptr(), self.w_lo.data_ptr(), self.out_scale,
                  self.b.data_ptr(), self.KH, self.KW, self.pad, self.dil, self.stride,
                  res.ptr if res is not None else None, res.cs if res is not None else 0, res.co if res is not None else 0,
-                 out.ptr, oh, ol, self.Cout, out.cs, out.co, 1 if r else 0, 3, self.bn_tile, _stream())
+                 out.ptr, oh, ol, self.Cout, out.cs, out.co, 1 if r else 0, self.passes, self.bn_tile, _stream())
             return out
         passes = 3 if self.engine == "tc" else 1
         if passes == 3 and x.lo_ptr is None:
