@@ -274,7 +274,7 @@ int vd3d_deform_im2col_nhwc(const float* x, int B, int H, int W, int C, int x_cs
 int vd3d_deform_im2col_h16(const float* x, int B, int H, int W, int C, int x_cs, int x_co,
                            const float* off, int off_cs, int off_co,
                            const float* msk, int msk_cs, int msk_co, int mask_sigmoid,
-                           int KH, int KW, int stride, int pad, int dil, int deform_groups,
+                           int KH, int KW, int stride, int pad, int dil, int deform_groups, int k_order,
                            float* col, void* col_hi16, void* col_lo16, int col_cs, void* stream);
 
 /* ---- Ground-Aware Convolution sampling (LookGround.forward, R/lib/look_ground.py:24-71) ---------------------------
@@ -293,10 +293,14 @@ int vd3d_look_ground_sample(const float* x, int B, int H, int W, int C, int x_cs
  * has_mask, the modulation (msk_co + k; mask_sigmoid applies the sigmoid of ModulatedDeformConvPack.forward); weights: the fp16 (hi, lo)
  * [Cout][KH*KW*C] matrix of vd3d_conv2d_tc16 (k = tap*C + c) with its power-of-two out_scale; epilogue (bias, residual, ReLU, fp32 output and
  * optional fp16 planes) as vd3d_conv2d_tc16.  One deformable group, KH*KW <= 9, C % 64 == 0.  Bit-identical to vd3d_deform_im2col_h16 followed
- * by vd3d_conv2d_tc16 (same K order, same gather arithmetic). */
+ * by vd3d_conv2d_tc16 (same K order, same gather arithmetic).
+ * k_order: order of the K dimension of the weight matrix: 0 = tap * C + c; 1 = (chunk * KH*KW + tap) * 64 + c % 64 (64-channel chunk outermost).
+ * With k_order = 1 and a 3x3 / stride 1 / pad 1 / dilation 1 layer the STAGED kernel runs: the input neighbourhood of every 8 x 16 tile (12 x 20
+ * pixels x 64 channels, fp32) is brought into shared memory by TMA once per (tile, chunk), zero-filled outside the image, and the nine taps gather
+ * from shared memory (corners farther than the staged halo fall back to global loads).  VD3D_DCN_STAGED=0 selects the global-gather kernel. */
 int vd3d_deform_conv_fused(const float* x, int B, int H, int W, int C, int x_cs, int x_co,
                            const float* om, int om_cs, int off_co, int msk_co, int has_mask, int mask_sigmoid,
-                           int KH, int KW, int stride, int pad, int dil,
+                           int KH, int KW, int stride, int pad, int dil, int k_order,
                            const void* w_hi, const void* w_lo, float out_scale, const float* bias,
                            const float* res, int res_cs, int res_co,
                            float* out, void* out_hi16, void* out_lo16, int Cout, int out_cs, int out_co, int relu, void* stream);

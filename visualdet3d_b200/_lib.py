@@ -62,8 +62,8 @@ _SIGS = {
     "vd3d_psm_cosine_h16": (I, [P, P, P, P, c_longlong, I, I, I, I, I, P, I, I, P]),
     "vd3d_split_lo_nhwc": (I, [P, P, c_longlong, I, I, I, P]),
     "vd3d_deform_im2col_nhwc": (I, [P, I, I, I, I, I, I, P, I, I, P, I, I, I, I, I, I, I, I, I, P, P, I, P]),
-    "vd3d_deform_im2col_h16": (I, [P, I, I, I, I, I, I, P, I, I, P, I, I, I, I, I, I, I, I, I, P, P, P, I, P]),
-    "vd3d_deform_conv_fused": (I, [P, I, I, I, I, I, I, P, I, I, I, I, I, I, I, I, I, I, P, P, F, P, P, I, I, P, P, P, I, I, I, I, P]),
+    "vd3d_deform_im2col_h16": (I, [P, I, I, I, I, I, I, P, I, I, P, I, I, I, I, I, I, I, I, I, I, P, P, P, I, P]),
+    "vd3d_deform_conv_fused": (I, [P, I, I, I, I, I, I, P, I, I, I, I, I, I, I, I, I, I, I, P, P, F, P, P, I, I, P, P, P, I, I, I, I, P]),
     "vd3d_deform_col2im_nhwc": (I, [P, I, I, I, I, I, I, P, I, I, P, I, I, I, I, I, I, I, I, P, I, P, I, I, P, I, I, P, I, I, P]),
     "vd3d_boxes_overlap_bev": (I, [P, I, P, I, P, P]),
     "vd3d_boxes_iou_bev": (I, [P, I, P, I, P, P]),

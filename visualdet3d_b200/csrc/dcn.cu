@@ -23,6 +23,7 @@ struct DcnParams {
     float* col; float* col_lo; int col_cs;          // [B*Ho*Wo][col_cs], channels [0, KH*KW*C)
     __half* col_h16_hi; __half* col_h16_lo;         // optional fp16 (hi, lo) planes of the columns (same pitch): what the fp16-split GEMM reads
     int* range_flag;                                // fp16-range guard (common.cuh)
+    int k_order;                                    // column order: 0 = tap * C + c (the reference's `columns` transposed), 1 = (chunk64 * K + tap) * 64 + c % 64
 };
 
 constexpr int DCN_PIX = 32;       // pixels per CTA
@@ -98,7 +99,7 @@ __global__ void __launch_bounds__(DCN_THREADS) deform_im2col_kernel(const DcnPar
         }
         float m = s_m[pl][k];
         acc.x = __fmul_rn(acc.x, m); acc.y = __fmul_rn(acc.y, m); acc.z = __fmul_rn(acc.z, m); acc.w = __fmul_rn(acc.w, m);
-        long long o = pix * p.col_cs + (long long)k * p.C + c;
+        long long o = pix * p.col_cs + (p.k_order ? (long long)((c >> 6) * K + k) * 64 + (c & 63) : (long long)k * p.C + c);
         if (p.col) *reinterpret_cast<float4*>(p.col + o) = acc;
         if (p.col_h16_hi) {     // hi = rn16(v), lo = rn16(v - hi): identical to vd3d_split_h16_nhwc on the fp32 columns
             note_fp16_range(amax4(0.f, acc), p.range_flag);
@@ -131,7 +132,7 @@ static int deform_im2col_launch(const float* x, int B, int H, int W, int C, int 
                                 const float* off, int off_cs, int off_co,
                                 const float* msk, int msk_cs, int msk_co, int mask_sigmoid,
                                 int KH, int KW, int stride, int pad, int dil, int deform_groups,
-                                float* col, float* col_lo, void* col_hi16, void* col_lo16, int col_cs, void* stream) {
+                                float* col, float* col_lo, void* col_hi16, void* col_lo16, int col_cs, void* stream, int k_order = 0) {
     VD3D_REQUIRE(x && off && (col || col_hi16), "deform_im2col: null pointer");
     VD3D_REQUIRE(!col_hi16 || col_lo16, "deform_im2col: fp16 planes come in (hi, lo) pairs");
     VD3D_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && KH > 0 && KW > 0 && KH * KW <= DCN_MAXK, "deform_im2col: bad shape (<= 49 taps)");
@@ -146,6 +147,8 @@ static int deform_im2col_launch(const float* x, int B, int H, int W, int C, int 
     VD3D_REQUIRE(p.Ho > 0 && p.Wo > 0, "deform_im2col: empty output");
     p.col = col; p.col_lo = col_lo; p.col_cs = col_cs; p.col_h16_hi = (__half*)col_hi16; p.col_h16_lo = (__half*)col_lo16;
     p.range_flag = col_hi16 ? fp16_range_flag() : nullptr;
+    VD3D_REQUIRE(k_order == 0 || (k_order == 1 && C % 64 == 0 && deform_groups == 1), "deform_im2col: the chunk-major column order needs C % 64 == 0 and one deformable group");
+    p.k_order = k_order;
     long long npix = (long long)B * p.Ho * p.Wo;
     dim3 grid(cdiv(npix, DCN_PIX), deform_groups);
     deform_im2col_kernel<<<grid, DCN_THREADS, 0, (cudaStream_t)stream>>>(p);
@@ -166,9 +169,9 @@ extern "C" int vd3d_deform_im2col_nhwc(const float* x, int B, int H, int W, int 
 extern "C" int vd3d_deform_im2col_h16(const float* x, int B, int H, int W, int C, int x_cs, int x_co,
                                       const float* off, int off_cs, int off_co,
                                       const float* msk, int msk_cs, int msk_co, int mask_sigmoid,
-                                      int KH, int KW, int stride, int pad, int dil, int deform_groups,
+                                      int KH, int KW, int stride, int pad, int dil, int deform_groups, int k_order,
                                       float* col, void* col_hi16, void* col_lo16, int col_cs, void* stream) {
     VD3D_REQUIRE(col_hi16 && col_lo16, "deform_im2col_h16: null pointer");
     return deform_im2col_launch(x, B, H, W, C, x_cs, x_co, off, off_cs, off_co, msk, msk_cs, msk_co, mask_sigmoid, KH, KW, stride, pad, dil, deform_groups,
-                                col, nullptr, col_hi16, col_lo16, col_cs, stream);
+                                col, nullptr, col_hi16, col_lo16, col_cs, stream, k_order);
 }

@@ -232,13 +232,267 @@ deform_conv_fused_kernel(const __grid_constant__ CUtensorMap mapWhi, const __gri
     }
 }
 
+// ----------------------------------------------------------------------------------------------------------------
+// Staged form (stride 1, dilation 1: every deformable layer of the DLA up-sampling path and of the Yolo3D head).
+// The gather warps of the kernel above read the four bilinear corners of every (pixel, tap) from global memory: 36 loads per output
+// value whose latency eight warps cannot hide (measured: 340 us for 64 -> 64 at 96 x 320 x 8, the gather is the whole kernel).  Here the
+// input neighbourhood of the tile is STAGED IN SHARED MEMORY by TMA, once per (tile, 64-channel chunk):
+//   region = rows [h0 - 2, h0 + 10) x columns [w0 - 2, w0 + 18) x 64 channels of x (fp32, 61,440 B; out-of-image pixels are zero-filled by
+//   the TMA unit, which is exactly the reference's "corner outside the image contributes zero" rule), double-buffered;
+//   the nine taps of the chunk then gather from shared memory (a corner that falls outside the staged region -- an offset beyond
+//   +-1 pixel around the regular tap position -- is read from global memory instead: correct for any offset, fast for small ones).
+// K order: 64-channel chunk outermost, taps inside (k = (chunk * 9 + tap) * 64 + c): the weight matrix and the unfused A/B path
+// (vd3d_deform_im2col_h16 with k_order = 1) use the same order, so both still produce identical bits.
+// Shared memory: 2 operand stages (48 KB) + 2 regions (60 KB) + 2 per-tap sample tables (3.5 KB) = 223 KB.
+// ----------------------------------------------------------------------------------------------------------------
+constexpr int DFS_HALO = 2;
+constexpr int DFS_RH = TC_TH + 2 * DFS_HALO, DFS_RW = TC_TW + 2 * DFS_HALO;       // 12 x 20 pixels
+constexpr uint32_t DFS_REGION_BYTES = DFS_RH * DFS_RW * 64 * 4;                   // 61,440
+constexpr int DFS_STAGES = 2;
+
+struct DfSample2 { int hl, wl_flags; float w1, w2, w3, w4, m; };                  // wl in the low 16 bits (biased by 16384), validity bits 16..20
+
+template <int NG16>
+__global__ void __launch_bounds__(DF_THREADS, 1)
+deform_conv_fused_staged_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapWhi,
+                                const __grid_constant__ CUtensorMap mapWlo, const TcParams p, const DfParams q) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t a_bytes = 128u * 128u;
+    const uint32_t b_bytes = (uint32_t)p.BN * 128u;
+    const uint32_t stage_bytes = q.stage_bytes;
+    uint8_t* regions = smem + (size_t)DFS_STAGES * stage_bytes;
+    DfSample2* samp = reinterpret_cast<DfSample2*>(regions + 2 * DFS_REGION_BYTES);          // [2][128]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(samp) + 2 * 128 * sizeof(DfSample2));
+    uint64_t* fullA = bars;                        // [2]  gather warps -> MMA (8 arrivals)
+    uint64_t* fullB = fullA + DFS_STAGES;          // [2]  weight TMA -> MMA
+    uint64_t* empty = fullB + DFS_STAGES;          // [2]  MMA -> producers
+    uint64_t* fullR = empty + DFS_STAGES;          // [2]  region TMA -> gather warps
+    uint64_t* emptyR = fullR + 2;                  // [2]  gather warps -> region producer (8 arrivals)
+    uint64_t* tmem_full = emptyR + 2;              // [4]
+    uint64_t* tmem_empty = tmem_full + 4;          // [4]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int KB = q.K * q.cchunks;
+    const int NC = (KB + p.chunk - 1) / p.chunk;
+    const int mt_units = p.m_tiles;
+    const int units = mt_units * p.n_tiles;
+    const int u0 = (int)blockIdx.x, ustep = (int)gridDim.x;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < DFS_STAGES; ++s) { mbar_init(&fullA[s], DF_GATHER_WARPS); mbar_init(&fullB[s], 1); mbar_init(&empty[s], 1); }
+        for (int r = 0; r < 2; ++r) { mbar_init(&fullR[r], 1); mbar_init(&emptyR[r], DF_GATHER_WARPS); }
+        for (int i = 0; i < 4; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = __reduce_or_sync(0xffffffffu, *tmem_slot);
+
+    if (warp == 0) {
+        // ================= TMA producer: input regions (one (tile, chunk) ahead) and weight blocks =================
+        const int my_units = (units - u0 + ustep - 1) / ustep;
+        const int total_r = my_units * q.cchunks;                   // regions this CTA will stage
+        auto issue_region = [&](int ir) {
+            const int ul = ir / q.cchunks, ch = ir - ul * q.cchunks;
+            int mu, nt;
+            unit_tile(p, u0 + ul * ustep, mt_units, mu, nt);
+            int mt = mu;
+            const int tw = mt % p.tiles_w; mt /= p.tiles_w;
+            const int th = mt % p.tiles_h; const int b = mt / p.tiles_h;
+            const int r = ir & 1;
+            mbar_wait(&emptyR[r], ((ir >> 1) & 1) ^ 1);
+            if (elect_one()) {
+                mbar_expect_tx(&fullR[r], DFS_REGION_BYTES);
+                tma_load_4d(regions + (size_t)r * DFS_REGION_BYTES, &mapX, &fullR[r], ch * 64, tw * TC_TW - DFS_HALO, th * TC_TH - DFS_HALO, b);
+            }
+            __syncwarp();
+        };
+        int it = 0;
+        if (total_r > 0) issue_region(0);
+        for (int ir = 0; ir < total_r; ++ir) {
+            if (ir + 1 < total_r) issue_region(ir + 1);
+            const int ul = ir / q.cchunks, ch = ir - ul * q.cchunks;
+            const int n0 = unit_nt(p, u0 + ul * ustep, mt_units) * p.BN;
+            for (int t = 0; t < q.K; ++t, ++it) {
+                const int s = it % DFS_STAGES, ph = (it / DFS_STAGES) & 1;
+                mbar_wait(&empty[s], ph ^ 1);
+                if (elect_one()) {
+                    uint8_t* st = smem + (size_t)s * stage_bytes + 2 * a_bytes;
+                    mbar_expect_tx(&fullB[s], 2u * b_bytes);
+                    const int kcol = (ch * q.K + t) * 64;
+                    tma_load_2d(st, &mapWhi, &fullB[s], kcol, n0);
+                    tma_load_2d(st + b_bytes, &mapWlo, &fullB[s], kcol, n0);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (elect_one()) {
+            int it = 0, cc = 0;
+            for (int u = u0; u < units; u += ustep) {
+                const int nvalid = min(p.BN, p.cout_pad - unit_nt(p, u, mt_units) * p.BN);
+                const uint32_t idesc = (p.idesc & ~(0x3Fu << 17)) | ((uint32_t)(nvalid >> 3) << 17);
+                for (int kb = 0; kb < KB; ++kb, ++it) {
+                    const int ci = kb / p.chunk;
+                    const int buf = (cc + ci) % p.nbuf;
+                    const bool first_in_chunk = kb - ci * p.chunk == 0;
+                    if (first_in_chunk) {
+                        mbar_wait(&tmem_empty[buf], (((cc + ci) / p.nbuf) & 1) ^ 1);
+                        tc_fence_after();
+                    }
+                    const int s = it % DFS_STAGES, ph = (it / DFS_STAGES) & 1;
+                    mbar_wait(&fullB[s], ph);
+                    mbar_wait(&fullA[s], ph);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.BN);
+                    const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+                    const uint64_t dA = make_sdesc(sa), dAlo = make_sdesc(sa + a_bytes);
+                    const uint64_t dB = make_sdesc(sa + 2 * a_bytes), dBlo = make_sdesc(sa + 2 * a_bytes + b_bytes);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint64_t off = (uint64_t)((k * 32) >> 4);
+                        umma_f16(d_tmem, dAlo + off, dB + off, idesc, (first_in_chunk && k == 0) ? 0u : 1u);
+                        umma_f16(d_tmem, dA + off, dBlo + off, idesc, 1);
+                        umma_f16(d_tmem, dA + off, dB + off, idesc, 1);
+                    }
+                    umma_commit(&empty[s]);
+                    if (kb - ci * p.chunk == p.chunk - 1 || kb == KB - 1) umma_commit(&tmem_full[buf]);
+                }
+                cc += NC;
+            }
+        }
+        __syncwarp();
+    } else if (warp < 10) {
+        tcp_epilogue<NG16, 1, 0>(p, tmem_base, tmem_full, tmem_empty, warp, lane, 0u, NC, u0, ustep, units, mt_units);
+        tc_fence_before();
+    } else {
+        // ================= gather warps (256 threads) =================
+        const int gt = (int)threadIdx.x - 320;
+        const int j = gt & 7;
+        const int m0 = gt >> 3;
+        int it = 0, ir = 0;
+        for (int u = u0; u < units; u += ustep) {
+            int mu, nt;
+            unit_tile(p, u, mt_units, mu, nt);
+            int mt = mu;
+            const int tw = mt % p.tiles_w; mt /= p.tiles_w;
+            const int th = mt % p.tiles_h; const int b = mt / p.tiles_h;
+            const int rh0 = th * TC_TH - DFS_HALO, rw0 = tw * TC_TW - DFS_HALO;           // image coordinates of region pixel (0, 0)
+            const float* xb = q.x + ((long long)b * q.H * q.W) * q.x_cs + q.x_co;
+            for (int ch = 0; ch < q.cchunks; ++ch, ++ir) {
+                const int rr = ir & 1;
+                mbar_wait(&fullR[rr], (ir >> 1) & 1);
+                const float* reg = reinterpret_cast<const float*>(regions + (size_t)rr * DFS_REGION_BYTES) + j * 8;
+                const int c = ch * 64 + j * 8;
+                for (int tap = 0; tap < q.K; ++tap, ++it) {
+                    // ---- sample table of this tap: one entry per pixel of the tile (threads 0..127 of the gather group) ----
+                    DfSample2* tb = samp + (it & 1) * 128;
+                    if (gt < 128) {
+                        const int m = gt;
+                        const int ho = th * TC_TH + m / TC_TW, wo = tw * TC_TW + m % TC_TW;
+                        DfSample2 sm;
+                        sm.hl = 0; sm.wl_flags = 0; sm.w1 = sm.w2 = sm.w3 = sm.w4 = 0.f; sm.m = 1.f;
+                        if (ho < p.Ho && wo < p.Wo) {
+                            const long long pix = ((long long)b * p.Ho + ho) * p.Wo + wo;
+                            const int kh = tap / q.KW, kw = tap - kh * q.KW;
+                            const float* op = q.om + pix * q.om_cs + q.off_co + 2 * tap;
+                            const float dh = __ldg(op), dw = __ldg(op + 1);
+                            if (q.has_mask) {
+                                float mv = __ldg(q.om + pix * q.om_cs + q.msk_co + tap);
+                                if (q.mask_sigmoid) mv = __fdiv_rn(1.0f, 1.0f + expf(-mv));
+                                sm.m = mv;
+                            }
+                            const float h = (float)(ho * q.stride - q.pad + kh * q.dil) + dh;
+                            const float w = (float)(wo * q.stride - q.pad + kw * q.dil) + dw;
+                            if (h > -1.f && w > -1.f && h < (float)q.H && w < (float)q.W) {
+                                const int hl = (int)floorf(h), wl = (int)floorf(w);
+                                const float lh = h - (float)hl, lw = w - (float)wl, hh = 1.f - lh, hw = 1.f - lw;
+                                int flags = 16;
+                                if (hl >= 0 && wl >= 0) flags |= 1;
+                                if (hl >= 0 && wl + 1 <= q.W - 1) flags |= 2;
+                                if (hl + 1 <= q.H - 1 && wl >= 0) flags |= 4;
+                                if (hl + 1 <= q.H - 1 && wl + 1 <= q.W - 1) flags |= 8;
+                                sm.hl = hl; sm.wl_flags = (wl + 16384) | (flags << 16);
+                                sm.w1 = hh * hw; sm.w2 = hh * lw; sm.w3 = lh * hw; sm.w4 = lh * lw;
+                            }
+                        }
+                        tb[m] = sm;
+                    }
+                    asm volatile("bar.sync 1, 256;" ::: "memory");                 // table visible; also: everyone is past the table of tap - 2
+                    const int s = it % DFS_STAGES, ph = (it / DFS_STAGES) & 1;
+                    mbar_wait(&empty[s], ph ^ 1);
+                    uint8_t* sa = smem + (size_t)s * stage_bytes;
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const int m = m0 + 32 * r;
+                        const DfSample2 sm = tb[m];
+                        float a[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) a[e] = 0.f;
+                        const int flags = sm.wl_flags >> 16;
+                        if (flags & 16) {
+                            const int hl = sm.hl, wl = (sm.wl_flags & 0xFFFF) - 16384;
+                            const int hr = hl - rh0, wr = wl - rw0;                        // region coordinates of the top-left corner
+                            float4 v[4][2];
+#pragma unroll
+                            for (int cn = 0; cn < 4; ++cn) {
+                                const int dy = cn >> 1, dx = cn & 1;
+                                if (flags & (1 << cn)) {
+                                    const int y = hr + dy, x = wr + dx;
+                                    if ((unsigned)y < (unsigned)DFS_RH && (unsigned)x < (unsigned)DFS_RW) {
+                                        const float4* sp = reinterpret_cast<const float4*>(reg + (y * DFS_RW + x) * 64);
+                                        v[cn][0] = sp[0]; v[cn][1] = sp[1];
+                                    } else {                                                // far sample: straight from global memory
+                                        const float* gp = xb + ((long long)(hl + dy) * q.W + (wl + dx)) * q.x_cs + c;
+                                        v[cn][0] = ldg4(gp); v[cn][1] = ldg4(gp + 4);
+                                    }
+                                } else {
+                                    v[cn][0] = make_float4(0.f, 0.f, 0.f, 0.f); v[cn][1] = v[cn][0];
+                                }
+                            }
+#define VD3D_DF_MIX(o, hf, f) a[o] = __fmul_rn(fmaf(sm.w4, v[3][hf].f, fmaf(sm.w3, v[2][hf].f, fmaf(sm.w2, v[1][hf].f, __fmul_rn(sm.w1, v[0][hf].f)))), sm.m)
+                            VD3D_DF_MIX(0, 0, x); VD3D_DF_MIX(1, 0, y); VD3D_DF_MIX(2, 0, z); VD3D_DF_MIX(3, 0, w);
+                            VD3D_DF_MIX(4, 1, x); VD3D_DF_MIX(5, 1, y); VD3D_DF_MIX(6, 1, z); VD3D_DF_MIX(7, 1, w);
+#undef VD3D_DF_MIX
+                        }
+                        uint2 h0, l0, h1, l1;
+                        split4(a, h0, l0);
+                        split4(a + 4, h1, l1);
+                        const uint32_t off = (uint32_t)(m >> 3) * 1024u + (uint32_t)(m & 7) * 128u + (uint32_t)((j ^ (m & 7)) * 16);
+                        *reinterpret_cast<uint4*>(sa + off) = make_uint4(h0.x, h0.y, h1.x, h1.y);
+                        *reinterpret_cast<uint4*>(sa + a_bytes + off) = make_uint4(l0.x, l0.y, l1.x, l1.y);
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&fullA[s])) : "memory");
+                }
+                __syncwarp();                                                              // every lane is done reading the region
+                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&emptyR[rr])) : "memory");
+            }
+        }
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+    }
+}
+
 }  // namespace vd3d
 
 using namespace vd3d;
 
 extern "C" int vd3d_deform_conv_fused(const float* x, int B, int H, int W, int C, int x_cs, int x_co,
                                       const float* om, int om_cs, int off_co, int msk_co, int has_mask, int mask_sigmoid,
-                                      int KH, int KW, int stride, int pad, int dil,
+                                      int KH, int KW, int stride, int pad, int dil, int k_order,
                                       const void* w_hi, const void* w_lo, float out_scale, const float* bias,
                                       const float* res, int res_cs, int res_co,
                                       float* out, void* out_hi16, void* out_lo16, int Cout, int out_cs, int out_co, int relu, void* stream) {
@@ -274,23 +528,46 @@ extern "C" int vd3d_deform_conv_fused(const float* x, int B, int H, int W, int C
     q.om = om; q.om_cs = om_cs; q.off_co = off_co; q.msk_co = msk_co; q.has_mask = has_mask; q.mask_sigmoid = mask_sigmoid;
     q.KW = KW; q.stride = stride; q.pad = pad; q.dil = dil; q.K = KH * KW; q.cchunks = C / 64;
     q.stage_bytes = 2u * 128u * 128u + 2u * (uint32_t)BN * 128u;
+    CUtensorMap mWhi, mWlo;
+    int rc;
+    if ((rc = make_map_wgt(&mWhi, w_hi, Cout, KH * KW * C, BN, 2))) return rc;
+    if ((rc = make_map_wgt(&mWlo, w_lo, Cout, KH * KW * C, BN, 2))) return rc;
+    const int units = p.m_tiles * p.n_tiles;
+    const int grid = units < kNumSMs ? units : kNumSMs;
+    static bool attr_set = false;
+    if (!attr_set) {
+        VD3D_CUDA(cudaFuncSetAttribute(deform_conv_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        VD3D_CUDA(cudaFuncSetAttribute(deform_conv_fused_staged_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    const char* es = getenv("VD3D_DCN_STAGED");
+    const bool staged = k_order == 1 && stride == 1 && dil == 1 && pad == 1 && KH == 3 && KW == 3 && !(es && atoi(es) == 0);
+    if (staged) {
+        // input regions through TMA: fp32 NHWC, box {64 c, 20 w, 12 h, 1 b}, no swizzle, zero fill outside the image
+        EncodeTiledFn enc = get_encode();
+        VD3D_REQUIRE(enc, "deform_conv_fused: cuTensorMapEncodeTiled unavailable");
+        CUtensorMap mX;
+        cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+        cuuint64_t strides[3] = {(cuuint64_t)x_cs * 4, (cuuint64_t)W * x_cs * 4, (cuuint64_t)H * W * x_cs * 4};
+        cuuint32_t box[4] = {64, (cuuint32_t)DFS_RW, (cuuint32_t)DFS_RH, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult cr = enc(&mX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)(x + x_co), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        VD3D_REQUIRE(cr == CUDA_SUCCESS, "deform_conv_fused: cuTensorMapEncodeTiled(input regions) failed: %d", (int)cr);
+        q.stages = DFS_STAGES;
+        const size_t smem = (size_t)DFS_STAGES * q.stage_bytes + 2 * (size_t)DFS_REGION_BYTES + 2 * 128 * sizeof(DfSample2) + 32 * sizeof(uint64_t) + 1024;
+        VD3D_REQUIRE(smem <= 227 * 1024, "deform_conv_fused: shared-memory budget exceeded");
+        deform_conv_fused_staged_kernel<2><<<grid, DF_THREADS, smem, (cudaStream_t)stream>>>(mX, mWhi, mWlo, p, q);
+        VD3D_CHECK_LAUNCH("deform_conv_fused_staged");
+        return VD3D_OK;
+    }
+    VD3D_REQUIRE(k_order == 0 || C == 64, "deform_conv_fused: the chunk-major K order needs the staged kernel (3x3, stride 1, pad 1, dilation 1)");
     const size_t fixed = sizeof(DfSample) * 128 * DF_MAXK + 32 * sizeof(uint64_t) + 1024;
     int stages = (int)((227 * 1024 - fixed) / q.stage_bytes);
     if (stages > 6) stages = 6;
     VD3D_REQUIRE(stages >= 2, "deform_conv_fused: tile too large for shared memory");
     q.stages = stages;
     const size_t smem = (size_t)stages * q.stage_bytes + fixed;
-    CUtensorMap mWhi, mWlo;
-    int rc;
-    if ((rc = make_map_wgt(&mWhi, w_hi, Cout, KH * KW * C, BN, 2))) return rc;
-    if ((rc = make_map_wgt(&mWlo, w_lo, Cout, KH * KW * C, BN, 2))) return rc;
-    static bool attr_set = false;
-    if (!attr_set) {
-        VD3D_CUDA(cudaFuncSetAttribute(deform_conv_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set = true;
-    }
-    const int units = p.m_tiles * p.n_tiles;
-    const int grid = units < kNumSMs ? units : kNumSMs;
     deform_conv_fused_kernel<2><<<grid, DF_THREADS, smem, (cudaStream_t)stream>>>(mWhi, mWlo, p, q);
     VD3D_CHECK_LAUNCH("deform_conv_fused");
     return VD3D_OK;

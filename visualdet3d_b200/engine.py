@@ -362,7 +362,14 @@ class DeformConvLayer:
         ob[:n_off] = off_bias.detach().cpu()
         self.n_off_pad = n_pad
         self.off_conv = ConvLayer(ow, ob, None, stride=stride, pad=pad, dil=dil, relu=False, device=device)   # conv_offset shares stride / padding / dilation (deform_conv.py:441-449)
-        w1 = weight.detach().cpu().permute(0, 2, 3, 1).reshape(Cout, K * C, 1, 1)
+        # K order of the GEMM: tap-major (k = tap * C + c) in general; 64-channel chunk outermost (k = (chunk * K + tap) * 64 + c % 64) when the
+        # staged fused kernel can take the layer (it stages one chunk of the input neighbourhood in shared memory and runs the nine taps on it)
+        self.k_order = 1 if (C % 64 == 0 and deform_groups == 1 and KH == 3 and KW == 3 and stride == 1 and pad == 1 and dil == 1
+                             and conv_engine_default() == "tc16" and str(device).startswith("cuda")) else 0
+        wt = weight.detach().cpu().permute(0, 2, 3, 1).reshape(Cout, K, C)
+        if self.k_order:
+            wt = wt.reshape(Cout, K, C // 64, 64).permute(0, 2, 1, 3)
+        w1 = wt.reshape(Cout, K * C, 1, 1)
         self.main = ConvLayer(w1, bias, bn, relu=relu, device=device)
 
     def out_hw(self, H, W):
@@ -385,7 +392,7 @@ class DeformConvLayer:
             if res is not None:
                 need_f32(res, "deformable conv residual")
             call("vd3d_deform_conv_fused", x.ptr, B, x.H, x.W, x.C, x.cs, x.co, om.ptr, om.cs, 0, 2 * K * self.dg, 1, 1,
-                 self.KH, self.KW, self.stride, self.pad, self.dil, m.w_hi.data_ptr(), m.w_lo.data_ptr(), m.out_scale, m.b.data_ptr(),
+                 self.KH, self.KW, self.stride, self.pad, self.dil, self.k_order, m.w_hi.data_ptr(), m.w_lo.data_ptr(), m.out_scale, m.b.data_ptr(),
                  res.ptr if res is not None else None, res.cs if res is not None else 0, res.co if res is not None else 0,
                  out.ptr, oh, ol, m.Cout, out.cs, out.co, 1 if m.relu else 0, _stream())
             return out
@@ -393,9 +400,11 @@ class DeformConvLayer:
         if cols.h16:      # the fp16-split GEMM reads only the planes: the gather writes them directly, the fp32 columns are never stored
             ch, cl = cols.h16_ptrs
             call("vd3d_deform_im2col_h16", x.ptr, B, x.H, x.W, x.C, x.cs, x.co, om.ptr, om.cs, 0,
-                 om.ptr, om.cs, 2 * K * self.dg, 1, self.KH, self.KW, self.stride, self.pad, self.dil, self.dg,
+                 om.ptr, om.cs, 2 * K * self.dg, 1, self.KH, self.KW, self.stride, self.pad, self.dil, self.dg, self.k_order,
                  cols.ptr if CHECK_LO else None, ch, cl, cols.cs, _stream())
         else:
+            if self.k_order:
+                raise _lib.Vd3dError("DeformConvLayer: the chunk-major K order is only produced by the fp16-plane gather (engine tc16)")
             call("vd3d_deform_im2col_nhwc", x.ptr, B, x.H, x.W, x.C, x.cs, x.co, om.ptr, om.cs, 0,
                  om.ptr, om.cs, 2 * K * self.dg, 1, self.KH, self.KW, self.stride, self.pad, self.dil, self.dg,
                  cols.ptr, cols.lo_ptr, cols.cs, _stream())
