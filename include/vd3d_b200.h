@@ -103,6 +103,13 @@ int vd3d_image_to_h16_rows(const float* img_nchw, int B, int C, int H, int W, vo
 int vd3d_conv2d_tc16_stem(const void* in_hi, const void* in_lo, int B, int H, int W, int Wp, int KH, int KW, int stride, int pad, int win,
                           const void* w_hi, const void* w_lo, float out_scale, const float* bias,
                           float* out, void* out_hi16, void* out_lo16, int Cout, int out_cs, int out_co, int relu, void* stream);
+/* Stem conv + BN + ReLU + MaxPool2d(kernel 3, stride 2, padding 1) in ONE kernel (R/backbones/resnet.py:186-189): same inputs as
+ * vd3d_conv2d_tc16_stem; the conv output is never written: every 8 x 16 tile is pooled in shared memory by the epilogue and only the pooled
+ * tensor pool_out NHWC [B][(Ho + 1) / 2][(Wo + 1) / 2][pool_cs] (channels [pool_co, pool_co + 64)) goes to HBM (pooled positions whose window
+ * straddles two tiles are combined with atomicMax on the bit pattern: exact because of the ReLU).  Cout == 64. */
+int vd3d_conv2d_tc16_stem_pool(const void* in_hi, const void* in_lo, int B, int H, int W, int Wp, int KH, int KW, int stride, int pad, int win,
+                               const void* w_hi, const void* w_lo, float out_scale, const float* bias,
+                               float* pool_out, int Cout, int pool_cs, int pool_co, void* stream);
 /* Diagnostics: when set, CTA 0 of every persistent tensor-core conv writes clock64 stamps per k-block into a [5][n] int64 device
  * buffer (0 stage free / 1 loads issued / 2 MMA thread waits / 3 stage landed / 4 MMAs issued); NULL disables (tools/trace_conv.py). */
 void vd3d_tc_set_trace(void* dev_i64, int n);

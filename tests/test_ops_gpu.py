@@ -474,6 +474,35 @@ def test_stem_tensor_core_vs_fp64(shape, mode, win, monkeypatch):
     assert float(out.t[..., :4].min()) == 7.0 and float(out.t[..., 68:].min()) == 7.0
 
 
+@pytest.mark.parametrize("shape", [(2, 3, 64, 96), (3, 3, 70, 154), (1, 3, 34, 30), (2, 3, 96, 320), (16, 3, 96, 160)])
+def test_stem_with_fused_maxpool_is_bit_identical(shape):
+    """conv1 + BN + ReLU + MaxPool2d(3, 2, 1) (R/backbones/resnet.py:186-189) in one kernel -- every 8 x 16 conv tile pooled in shared memory by the
+    epilogue, windows that straddle tiles combined with atomicMax on the (non-negative) bit pattern -- against the stem kernel followed by the
+    max-pool kernel: bit for bit (max is exact), including odd conv output sizes, partial tiles and more tiles than SMs; repeated calls agree
+    (the border positions are re-zeroed by every launch); the pooled tensor respects its channel slice."""
+    E = _E()
+    B, C, H, W = shape
+    g = torch.Generator().manual_seed(sum(shape))
+    x = (torch.randn(B, C, H, W, generator=g) * 2.0).cuda()
+    w = torch.randn(64, C, 7, 7, generator=g) / np.sqrt(C * 49)
+    bn = dict(weight=torch.rand(64, generator=g) + 0.5, bias=torch.randn(64, generator=g) * 0.3,
+              running_mean=torch.randn(64, generator=g) * 0.1, running_var=torch.rand(64, generator=g) + 0.5)
+    layer = E.StemLayer(w, bn, stride=2, pad=3, relu=True, device="cuda")
+    Hs, Ws = layer.out_hw(H, W)
+    Hp, Wp = (Hs - 1) // 2 + 1, (Ws - 1) // 2 + 1
+    arena = E.Arena("h16")
+    full = layer(x, E.Act(torch.empty(B, Hs, Ws, 64, device="cuda")), arena, "a")
+    want = E.maxpool3x3s2(full, E.Act(torch.empty(B, Hp, Wp, 64, device="cuda")))
+    assert torch.equal(want.to_nchw(), F.max_pool2d(full.to_nchw(), 3, 2, 1))
+    got = E.Act(torch.full((B, Hp, Wp, 64 + 8), 7.0, device="cuda"), 4, 64)
+    for _ in range(2):
+        layer(x, got, arena, "b", pool=True)
+        torch.cuda.synchronize()
+        assert torch.equal(got.t[..., 4:68], want.t), float((got.t[..., 4:68] - want.t).abs().max())
+    assert float(got.t[..., :4].min()) == 7.0 and float(got.t[..., 68:].min()) == 7.0
+    assert float(want.t.min()) >= 0.0 and float((want.t == 0).float().mean()) < 0.9
+
+
 @pytest.mark.parametrize("shape", [(2, 64, 6, 80, 24), (1, 128, 5, 37, 12), (3, 64, 3, 50, 32), (1, 64, 2, 20, 4), (2, 192, 4, 64, 8)])
 def test_psm_cosine_tensor_core_vs_oracle(shape):
     """tensor-core PSMCosine (flat 128-pixel tiles x 160-pixel window, band extracted in the epilogue) against the oracle;

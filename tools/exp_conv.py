@@ -19,6 +19,7 @@ x = E.split_lo(E.Act(torch.randn(B, H, W, Cin, generator=g).cuda(), 0, None, pla
 res = E.split_lo(E.Act(torch.randn(B, H, W, Cout, generator=g).cuda(), 0, None, planes(Cout)))
 res_p = E.Act(res.t, 0, None, res.lo, f32=False)
 out = E.Act(torch.zeros(B, H, W, Cout, device="cuda"), 0, None, planes(Cout))
+MK = "planes" if Cout <= 160 else "f32"      # mode of the knock-out runs (the widest epilogue variant has no planes form worth timing)
 flush = torch.empty(64 * 1024 * 1024, device="cuda")          # 256 MB: evicts the L2 between repetitions
 
 
@@ -54,14 +55,19 @@ def run(label, env, mode):
 
 for mode in ("f32", "planes", "nores"):
     run("default", {}, mode)
-run("no input-halo reuse / no resident weights (generic kernel)", {"VD3D_TC_PHALO": 0, "VD3D_TC_WRES": 0}, "planes")
-run("generic kernel, CTA pairs", {"VD3D_TC_PHALO": 0, "VD3D_TC_WRES": 0, "VD3D_TC_CG": 2}, "planes")
-run("halo kernel always, no resident weights", {"VD3D_TC_PHALO": 1, "VD3D_TC_WRES": 0}, "planes")
+for l2 in (0, 28, 44, 64):
+    run(f"L2-aware tile order, block = {l2} MB", {"VD3D_TC_L2MB": l2}, "f32")
+run("no input-halo reuse / no resident weights (generic kernel)", {"VD3D_TC_PHALO": 0, "VD3D_TC_WRES": 0}, MK)
+run("generic kernel, CTA pairs", {"VD3D_TC_PHALO": 0, "VD3D_TC_WRES": 0, "VD3D_TC_CG": 2}, MK)
+run("halo kernel always, no resident weights", {"VD3D_TC_PHALO": 1, "VD3D_TC_WRES": 0}, MK)
 for dbg, lab in ((16, "knock-out: no epilogue output"), (32, "knock-out: no residual loads"), (48, "knock-out: no output, no residual"),
                  (2, "knock-out: no lo-plane loads"), (1, "knock-out: one MMA per k-step"), (51, "knock-out: 1 MMA, no lo loads, no output, no residual")):
-    run(lab, {"VD3D_TC_DEBUG": dbg}, "planes")
-    run(lab + " (generic kernel)", {"VD3D_TC_DEBUG": dbg, "VD3D_TC_PHALO": 0, "VD3D_TC_WRES": 0}, "planes")
+    run(lab, {"VD3D_TC_DEBUG": dbg}, MK)
+    run(lab + " (generic kernel)", {"VD3D_TC_DEBUG": dbg, "VD3D_TC_PHALO": 0, "VD3D_TC_WRES": 0}, MK)
+for dbg, lab in ((64, "knock-out: 1/12 of the MMAs (first K step, one pass), all loads"), (66, "knock-out: 1/12 of the MMAs, no lo loads"),
+                 (114, "knock-out: 1/12 MMAs, no lo loads, no output, no residual")):
+    run(lab, {"VD3D_TC_DEBUG": dbg}, MK)
 for ch in (2, 9, 36):
-    run(f"chunk = {ch} k-blocks per promotion", {"VD3D_TC_CHUNK": ch}, "planes")
+    run(f"chunk = {ch} k-blocks per promotion", {"VD3D_TC_CHUNK": ch}, MK)
 for nb in (2, 3):
-    run(f"TMEM buffers = {nb}", {"VD3D_TC_NBUF": nb}, "planes")
+    run(f"TMEM buffers = {nb}", {"VD3D_TC_NBUF": nb}, MK)

@@ -373,6 +373,116 @@ conv2d_tc_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
     }
 }
 
+
+// ----------------------------------------------------------------------------------------------------------------
+// Epilogue with the 3x3 / stride-2 / pad-1 max-pool fused in (ResNet stem: conv7x7 s2 + BN + ReLU -> MaxPool2d(3, 2, 1), resnet.py:186-189).
+// The stem output (64 ch at 1/2 resolution: 503 MB at batch 16 x 384 x 1280) is by far the largest tensor of the backbone and its only consumer is
+// the pool: here it never leaves the SM.  Per 8 x 16 tile: promote the accumulator chunks as usual, apply scale / bias / ReLU, park the 128 x 64
+// values in a shared-memory tile, then produce the pooled pixels whose 3x3 window touches the tile: 5 x 9 positions.  Positions whose window lies
+// entirely inside the tile (3 of 4 pooled rows, 7 of 8 pooled columns) are written with plain stores; the others are shared with the neighbouring
+// tile(s) and combined with atomicMax on the integer bit pattern -- exact and order-independent because ReLU makes every value >= +0 (the target
+// rows / columns are zeroed by pool_border_zero_kernel before the launch).  max() is exact, so the result equals maxpool(stem) bit for bit.
+// ----------------------------------------------------------------------------------------------------------------
+constexpr int POOL_LD = 68;          // floats per staged pixel row (64 + 4: conflict-free float4 rows)
+
+__device__ __forceinline__ void tcp_epilogue_pool(const TcParams& p, uint8_t* smem_base, uint32_t tmem_base, uint64_t* tmem_full, uint64_t* tmem_empty,
+                                                  int warp, int lane, int NC, int u0, int ustep, int units, int mt_units) {
+    const int e = warp - 2, q = warp & 3, half = e >> 2;
+    const int cb = half * 32;                                        // BN = 64: each thread owns 32 accumulator columns of one pixel
+    float* tile = reinterpret_cast<float*>(smem_base + p.pool_smem_off);
+    const uint32_t te_local = smem_u32(&tmem_empty[0]);
+    const float osc = p.out_scale;
+    const int et = e * 32 + lane;                                    // 0..255 among the epilogue threads
+    int cc = 0;
+    for (int u = u0; u < units; u += ustep) {
+        float acc[2][16];
+#pragma unroll
+        for (int g = 0; g < 2; ++g)
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[g][i] = 0.f;
+        for (int ci = 0; ci < NC; ++ci, ++cc) {
+            const int buf = cc % p.nbuf, use = cc / p.nbuf;
+            mbar_wait(&tmem_full[buf], use & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+                uint32_t v[16];
+                tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.BN + cb + g * 16), v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) acc[g][i] += __uint_as_float(v[i]);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(te_local + (uint32_t)buf * 8u) : "memory");
+        }
+        int mu, nt;
+        unit_tile(p, u, mt_units, mu, nt);
+        int mt = mu;
+        const int tw = mt % p.tiles_w; mt /= p.tiles_w;
+        const int th = mt % p.tiles_h; const int b = mt / p.tiles_h;
+        const int r = q * 32 + lane;
+        // ---- scale / bias / ReLU, parked in the shared-memory tile ----
+        asm volatile("bar.sync 2, 256;" ::: "memory");               // the previous tile has been pooled by everyone
+        {
+            float* tp = tile + r * POOL_LD + cb;
+#pragma unroll
+            for (int g = 0; g < 2; ++g)
+#pragma unroll
+                for (int i = 0; i < 16; i += 4) {
+                    const int n = cb + g * 16 + i;
+                    const float4 bb = p.bias ? ldg4(p.bias + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    float4 a;
+                    a.x = fmaxf(acc[g][i] * osc + bb.x, 0.f); a.y = fmaxf(acc[g][i + 1] * osc + bb.y, 0.f);
+                    a.z = fmaxf(acc[g][i + 2] * osc + bb.z, 0.f); a.w = fmaxf(acc[g][i + 3] * osc + bb.w, 0.f);
+                    *reinterpret_cast<float4*>(tp + g * 16 + i) = a;
+                }
+        }
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        // ---- pooled positions touched by this tile: rows i0 .. i0 + 4, columns j0 .. j0 + 8 ----
+        const int h0 = th * TC_TH, w0 = tw * TC_TW, i0 = th * (TC_TH / 2), j0 = tw * (TC_TW / 2);
+        for (int item = et; item < 45 * 16; item += 256) {
+            const int cq = item & 15, pp = item >> 4;
+            const int pi = pp / 9, pj = pp - pi * 9;
+            const int i = i0 + pi, j = j0 + pj;
+            if (i >= p.pool_H || j >= p.pool_W) continue;
+            // window rows / columns in tile coordinates, clipped to the tile and to the conv output
+            int r_lo = 2 * pi - 1, r_hi = 2 * pi + 1, c_lo = 2 * pj - 1, c_hi = 2 * pj + 1;
+            const int r_max = min(TC_TH - 1, p.Ho - 1 - h0), c_max = min(TC_TW - 1, p.Wo - 1 - w0);
+            // complete: every window row / column that exists in the conv output lies inside this tile
+            const bool complete = (r_lo >= 0 || h0 + r_lo < 0) && (2 * pi <= r_max || h0 + 2 * pi > p.Ho - 1) && (r_hi <= r_max || h0 + r_hi > p.Ho - 1) &&
+                                  (c_lo >= 0 || w0 + c_lo < 0) && (2 * pj <= c_max || w0 + 2 * pj > p.Wo - 1) && (c_hi <= c_max || w0 + c_hi > p.Wo - 1);
+            r_lo = max(r_lo, 0); c_lo = max(c_lo, 0); r_hi = min(r_hi, r_max); c_hi = min(c_hi, c_max);
+            if (r_lo > r_hi || c_lo > c_hi) continue;
+            float4 m = make_float4(0.f, 0.f, 0.f, 0.f);             // values are >= 0 after the ReLU
+            for (int rr = r_lo; rr <= r_hi; ++rr)
+                for (int c2 = c_lo; c2 <= c_hi; ++c2) {
+                    const float4 v = *reinterpret_cast<const float4*>(tile + (rr * TC_TW + c2) * POOL_LD + cq * 4);
+                    m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+                }
+            float* op = p.pool_out + (((long long)b * p.pool_H + i) * p.pool_W + j) * p.pool_cs + p.pool_co + cq * 4;
+            if (complete) *reinterpret_cast<float4*>(op) = m;
+            else {
+                int* ip = reinterpret_cast<int*>(op);
+                atomicMax(ip, __float_as_int(m.x)); atomicMax(ip + 1, __float_as_int(m.y));
+                atomicMax(ip + 2, __float_as_int(m.z)); atomicMax(ip + 3, __float_as_int(m.w));
+            }
+        }
+    }
+}
+
+// zero the pooled positions that receive atomicMax contributions from more than one tile (rows i % 4 == 0, columns j % 8 == 0)
+__global__ void pool_border_zero_kernel(float* __restrict__ out, int B, int Hp, int Wp, int C4, int cs, int co) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)B * Hp * Wp * C4;
+    if (idx >= total) return;
+    const int c4 = (int)(idx % C4); long long r = idx / C4;
+    const int j = (int)(r % Wp); r /= Wp;
+    const int i = (int)(r % Hp);
+    if ((i & 3) != 0 && (j & 7) != 0) return;
+    *reinterpret_cast<float4*>(out + (idx / C4) * cs + co + 4 * c4) = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
 // ----------------------------------------------------------------------------------------------------------------
 // Persistent kernel (fp16 hi/lo operands; the default engine).
 //
@@ -579,7 +689,12 @@ conv2d_tcp_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         }
         __syncwarp();
     } else {
-        tcp_epilogue<NG16, CG, PL>(p, tmem_base, tmem_full, tmem_empty, warp, lane, rank, NC, u0, ustep, units, mt_units);
+        if constexpr (NG16 == 2 && CG == 1 && PL == 0) {
+            if (p.pool_out) tcp_epilogue_pool(p, smem, tmem_base, tmem_full, tmem_empty, warp, lane, NC, u0, ustep, units, mt_units);
+            else tcp_epilogue<NG16, CG, PL>(p, tmem_base, tmem_full, tmem_empty, warp, lane, rank, NC, u0, ustep, units, mt_units);
+        } else {
+            tcp_epilogue<NG16, CG, PL>(p, tmem_base, tmem_full, tmem_empty, warp, lane, rank, NC, u0, ustep, units, mt_units);
+        }
         tc_fence_before();
     }
     __syncthreads();
@@ -674,12 +789,13 @@ conv2d_tcph_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
                     const int c0 = ch * 64;
                     if (CG == 2) {
                         const uint32_t lbar = mapa_shared(smem_u32(&fullA[s]), 0);
-                        if (rank == 0) mbar_expect_tx(&fullA[s], 2u * TCPH_ITEM);
+                        const bool lo_too = !(p.dbg & 2);
+                        if (rank == 0) mbar_expect_tx(&fullA[s], lo_too ? 2u * TCPH_ITEM : (uint32_t)TCPH_ITEM);
                         for (int r = 0; r < 10; ++r)
                             for (int g = 0; g < 2; ++g) {
                                 const uint32_t off = (uint32_t)r * 2560u + (uint32_t)g * 1280u;
                                 tma_load_4d_2sm(st + off, &mapA, lbar, c0, w0 - 1 + 8 * g, h0 - 1 + r, b);
-                                tma_load_4d_2sm(st + TCPH_PLANE + off, &mapAlo, lbar, c0, w0 - 1 + 8 * g, h0 - 1 + r, b);
+                                if (lo_too) tma_load_4d_2sm(st + TCPH_PLANE + off, &mapAlo, lbar, c0, w0 - 1 + 8 * g, h0 - 1 + r, b);
                             }
                     } else {
                         mbar_expect_tx(&fullA[s], TCPH_ITEM);
@@ -723,9 +839,10 @@ conv2d_tcph_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
                     uint8_t* st = smemB + (size_t)s * b_stage;
                     if (CG == 2) {
                         const uint32_t lbar = mapa_shared(smem_u32(&fullB[s]), 0);
-                        if (rank == 0) mbar_expect_tx(&fullB[s], 2u * b_stage);
+                        const bool lo_too = !(p.dbg & 2);
+                        if (rank == 0) mbar_expect_tx(&fullB[s], lo_too ? 2u * b_stage : b_stage);
                         tma_load_2d_2sm(st, &mapWhi, lbar, kcol, n0);
-                        tma_load_2d_2sm(st + b_bytes, &mapWlo, lbar, kcol, n0);
+                        if (lo_too) tma_load_2d_2sm(st + b_bytes, &mapWlo, lbar, kcol, n0);
                     } else {
                         mbar_expect_tx(&fullB[s], b_stage);
                         tma_load_2d(st, &mapWhi, &fullB[s], kcol, n0);
@@ -766,7 +883,13 @@ conv2d_tcph_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const uint64_t off = (uint64_t)((k * 32) >> 4);
-                        if (p.two_pass) {
+                        if (p.dbg & 1) {          // timing experiment: one MMA per K step
+                            if (CG == 2) umma_f16_2sm(d_tmem, dA + off, dB + off, idesc, first ? 0u : 1u); else umma_f16(d_tmem, dA + off, dB + off, idesc, first ? 0u : 1u);
+                        } else if (p.dbg & 64) {   // timing experiment: only the first K step of every k-block (1/4 of the MMAs, same loads)
+                            if (k == 0) {
+                                if (CG == 2) umma_f16_2sm(d_tmem, dA + off, dB + off, idesc, first ? 0u : 1u); else umma_f16(d_tmem, dA + off, dB + off, idesc, first ? 0u : 1u);
+                            }
+                        } else if (p.two_pass) {
                             if (CG == 2) { umma_f16_2sm(d_tmem, dA + off, dBlo + off, idesc, first ? 0u : 1u); umma_f16_2sm(d_tmem, dA + off, dB + off, idesc, 1); }
                             else { umma_f16(d_tmem, dA + off, dBlo + off, idesc, first ? 0u : 1u); umma_f16(d_tmem, dA + off, dB + off, idesc, 1); }
                         } else if (CG == 2) {
@@ -913,12 +1036,16 @@ static int tcp_launch(TcParams& p, const CUtensorMap& mA, const CUtensorMap& mAl
     tcp_set_accumulators(p);
     if (p.rowb == 0) p.rowb = 128;
     const size_t stage_bytes = 2 * (size_t)128 * p.rowb + 2 * (size_t)(BN / CG) * p.rowb;
-    int stages = (int)((227 * 1024 - 1024 - 512) / stage_bytes);
+    const size_t pool_bytes = p.pool_out ? (size_t)128 * POOL_LD * sizeof(float) : 0;
+    VD3D_REQUIRE(!p.pool_out || (BN == 64 && CG == 1 && p.relu && !p.res && !p.res_h16_hi), "conv2d_tc: the fused max-pool needs a 64-column single-CTA tile with ReLU and no residual");
+    int stages = (int)((227 * 1024 - 1024 - 512 - pool_bytes) / stage_bytes);
     if (stages > 8) stages = 8;
     VD3D_REQUIRE(stages >= 2, "conv2d_tc: tile too large for shared memory");
     p.stages = stages;
     if (CG == 2) p.idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
-    const size_t smem = stages * stage_bytes + (2 * stages + 10) * sizeof(uint64_t) + 1024;
+    const size_t bar_bytes = ((2 * stages + 10) * sizeof(uint64_t) + 15) / 16 * 16;
+    p.pool_smem_off = (uint32_t)(stages * stage_bytes + bar_bytes);
+    const size_t smem = stages * stage_bytes + bar_bytes + pool_bytes + 1024;
     static bool pattr_set = false;
     if (!pattr_set) {
 #define VD3D_TCP_ATTR(NG, C) VD3D_CUDA(cudaFuncSetAttribute(conv2d_tcp_kernel<NG, C, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
@@ -1059,10 +1186,10 @@ static int conv2d_tc_launch(int f16, const void* in, const void* in_lo, int B, i
     p.m_tiles = p.tiles_w * p.tiles_h * B; p.n_tiles = cdiv(p.cout_pad, BN);
     {
         // L2-aware tile order (unit_tile): M blocks whose activation slab (hi + lo planes of the block's input pixels, all channels) is about
-        // VD3D_TC_L2MB megabytes (default 28: a block plus one N tile of weights stays inside the share of the 126 MB L2 that survives the
-        // streaming of the rest); only when there is more than one N tile (otherwise A is read once anyway).  0 disables.
+        // VD3D_TC_L2MB megabytes (default 44 = two blocks for the 1408-wide layers; measured with ncu: 550 -> 450 MB of DRAM reads per launch,
+        // same duration: the layers are not DRAM-bound); only when there is more than one N tile (otherwise A is read once anyway).  0 disables.
         const char* e = getenv("VD3D_TC_L2MB");
-        const double l2mb = e ? atof(e) : 28.0;
+        const double l2mb = e ? atof(e) : 44.0;
         p.mblock = 0;
         if (f16 && p.n_tiles > 1 && l2mb > 0) {
             const double a_bytes_per_tile = 128.0 * stride * stride * (double)p.cin_pad * 4.0;      // input pixels behind one 128-pixel output tile, 2 fp16 planes
@@ -1263,10 +1390,34 @@ extern "C" int vd3d_stem_row_pitch(int W, int KW, int stride, int pad) {
     return (need + 1) / 2 * 2;
 }
 
+static int stem_launch(const void* in_hi, const void* in_lo, int B, int H, int W, int Wp, int KH, int KW, int stride, int pad, int win,
+                       const void* w_hi, const void* w_lo, float out_scale, const float* bias,
+                       float* out, void* out_hi16, void* out_lo16, int Cout, int out_cs, int out_co, int relu, void* stream,
+                       float* pool_out, int pool_cs, int pool_co);
+
 extern "C" int vd3d_conv2d_tc16_stem(const void* in_hi, const void* in_lo, int B, int H, int W, int Wp, int KH, int KW, int stride, int pad, int win,
                                      const void* w_hi, const void* w_lo, float out_scale, const float* bias,
                                      float* out, void* out_hi16, void* out_lo16, int Cout, int out_cs, int out_co, int relu, void* stream) {
-    VD3D_REQUIRE(in_hi && in_lo && w_hi && w_lo && out, "conv2d_tc16_stem: null pointer");
+    VD3D_REQUIRE(out, "conv2d_tc16_stem: null pointer");
+    return stem_launch(in_hi, in_lo, B, H, W, Wp, KH, KW, stride, pad, win, w_hi, w_lo, out_scale, bias, out, out_hi16, out_lo16, Cout, out_cs, out_co, relu, stream,
+                       nullptr, 0, 0);
+}
+
+// stem conv + BN + ReLU + MaxPool2d(3, 2, 1) in one kernel: pool_out = NHWC [B][Hp][Wp'][pool_cs], Hp = (Ho + 1) / 2, Wp' = (Wo + 1) / 2; the conv
+// output itself is never written (vd3d_conv2d_tc16_stem_pool in include/vd3d_b200.h)
+extern "C" int vd3d_conv2d_tc16_stem_pool(const void* in_hi, const void* in_lo, int B, int H, int W, int Wp, int KH, int KW, int stride, int pad, int win,
+                                          const void* w_hi, const void* w_lo, float out_scale, const float* bias,
+                                          float* pool_out, int Cout, int pool_cs, int pool_co, void* stream) {
+    VD3D_REQUIRE(pool_out && Cout == 64 && pool_cs % 4 == 0 && pool_co % 4 == 0 && ((uintptr_t)pool_out & 15) == 0, "conv2d_tc16_stem_pool: 64 output channels, 16-byte aligned pooled tensor");
+    return stem_launch(in_hi, in_lo, B, H, W, Wp, KH, KW, stride, pad, win, w_hi, w_lo, out_scale, bias, nullptr, nullptr, nullptr, Cout, pool_cs, pool_co, 1, stream,
+                       pool_out, pool_cs, pool_co);
+}
+
+static int stem_launch(const void* in_hi, const void* in_lo, int B, int H, int W, int Wp, int KH, int KW, int stride, int pad, int win,
+                       const void* w_hi, const void* w_lo, float out_scale, const float* bias,
+                       float* out, void* out_hi16, void* out_lo16, int Cout, int out_cs, int out_co, int relu, void* stream,
+                       float* pool_out, int pool_cs, int pool_co) {
+    VD3D_REQUIRE(in_hi && in_lo && w_hi && w_lo && (out || pool_out), "conv2d_tc16_stem: null pointer");
     VD3D_REQUIRE((win == 64 || win == 32) && KW >= 1 && KW * 4 <= win && KH >= 1 && stride >= 2 && stride <= 4 && stride % 2 == 0,
                  "conv2d_tc16_stem: window of 32 or 64 elements >= 4 * KW and an even stride are required (got KW=%d win=%d stride=%d)", KW, win, stride);
     VD3D_REQUIRE(Wp == vd3d_stem_row_pitch(W, KW, stride, pad), "conv2d_tc16_stem: row pitch %d != vd3d_stem_row_pitch() = %d", Wp, vd3d_stem_row_pitch(W, KW, stride, pad));
@@ -1295,7 +1446,14 @@ extern "C" int vd3d_conv2d_tc16_stem(const void* in_hi, const void* in_lo, int B
     p.chunk = 4;
     int persist, cg_env;
     tc_env(persist, cg_env);
-    const int CG = (cg_env == 2 || (cg_env == 0 && BN > 128)) ? 2 : 1;
+    const int CG = pool_out ? 1 : ((cg_env == 2 || (cg_env == 0 && BN > 128)) ? 2 : 1);
+    if (pool_out) {
+        p.pool_out = pool_out; p.pool_cs = pool_cs; p.pool_co = pool_co;
+        p.pool_H = (p.Ho + 2 - 3) / 2 + 1; p.pool_W = (p.Wo + 2 - 3) / 2 + 1;
+        const long long total = (long long)B * p.pool_H * p.pool_W * (Cout / 4);
+        pool_border_zero_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(pool_out, B, p.pool_H, p.pool_W, Cout / 4, pool_cs, pool_co);
+        VD3D_CHECK_LAUNCH("pool_border_zero");
+    }
     EncodeTiledFn enc = get_encode();
     if (!enc) { set_error("conv2d_tc16_stem: cuTensorMapEncodeTiled unavailable"); return VD3D_ECUDA; }
     CUtensorMap mA, mAlo, mWhi, mWlo;

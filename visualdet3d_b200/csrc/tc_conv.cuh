@@ -24,6 +24,10 @@ struct TcParams {
     int tiles_w, tiles_h;
     int stride_w, pad_w;     // W-direction stride / padding (the H direction uses stride / pad); equal to them for ordinary convs
     int m_tiles, n_tiles;    // persistent kernel: tile counts along M (B * tiles_h * tiles_w) and N
+    // fused 3x3 / stride-2 / pad-1 max-pool of the (ReLU) output (the ResNet stem, resnet.py:186-189): when pool_out != nullptr the epilogue of
+    // conv2d_tcp_kernel<2, 1, 0> does not write the conv output at all; it pools every tile in shared memory and writes the pooled tensor
+    float* pool_out; int pool_cs, pool_co, pool_H, pool_W;
+    uint32_t pool_smem_off;  // byte offset of the [128][68] fp32 staging tile in dynamic shared memory
     int two_pass;            // error-budget experiments (vd3d_conv2d_tc16 passes = 2): drop the A_lo * W_hi product (activations then carry 11 significant bits)
     int mblock;              // persistent kernels: scheduling units (tiles / tile pairs) per M block of the L2-aware tile order (0: one block)
     int rowb;                // bytes per operand row in shared memory = K bytes per k-block: 128 (64 channels, SWIZZLE_128B) or 64 (32, SWIZZLE_64B)

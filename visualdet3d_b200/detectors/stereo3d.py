@@ -67,7 +67,15 @@ class ResNetRunner:
         _, _, H, W = parts[0].shape
         B = sum(int(p.shape[0]) for p in parts)
         Hs, Ws = self.stem.out_hw(H, W)
-        if self.stem_tc is not None:
+        Hp, Wp = (Hs + 2 - 3) // 2 + 1, (Ws + 2 - 3) // 2 + 1
+        import os
+        fuse_pool = (self.stem_tc is not None and -1 not in self.p.out_indices and os.environ.get("VD3D_STEM_POOL", "1") != "0"
+                     and os.environ.get("VD3D_TC_PERSIST", "1") != "0" and os.environ.get("VD3D_TC_CG", "0") != "2")
+        x = None
+        if fuse_pool:
+            # stem conv + BN + ReLU + max-pool in ONE kernel (the 64-channel half-resolution stem output never reaches HBM)
+            pooled = self.stem_tc(parts, arena.act(tag + ".pool", (B, Hp, Wp, 64), dev, lo=True), arena, tag, pool=True)
+        elif self.stem_tc is not None:
             x = self.stem_tc(parts, arena.act(tag + ".stem", (B, Hs, Ws, 64), dev), arena, tag)
         else:
             x0 = arena.act(tag + ".in4", (B, H, W, 4), dev, zero=True)
@@ -76,13 +84,12 @@ class ResNetRunner:
                 E.nchw_to_nhwc(p, x0.batch(b0, b0 + int(p.shape[0])))
                 b0 += int(p.shape[0])
             x = self.stem(x0, arena.act(tag + ".stem", (B, Hs, Ws, 64), dev))
-        Hp, Wp = (Hs + 2 - 3) // 2 + 1, (Ws + 2 - 3) // 2 + 1
         outs = []
         self.out_lo_stale = []             # per returned feature map: True if its tensor-core companion is not up to date
         if -1 in self.p.out_indices:
             outs.append(x)
             self.out_lo_stale.append(True)
-        x = E.maxpool3x3s2(x, arena.act(tag + ".pool", (B, Hp, Wp, 64), dev, lo=True))
+        x = pooled if fuse_pool else E.maxpool3x3s2(x, arena.act(tag + ".pool", (B, Hp, Wp, 64), dev, lo=True))
         fresh = True                       # x.lo is stale (x was written by a non-tensor-core kernel)
         plm = E.planes_mode_ok()
         n_ret = len(outs)                  # index of the next returned feature map

@@ -317,7 +317,7 @@ class StemLayer:
     def out_hw(self, H, W):
         return (H + 2 * self.pad - self.KH) // self.stride + 1, (W + 2 * self.pad - self.KW) // self.stride + 1
 
-    def __call__(self, img_nchw, out: Act, arena: "Arena", name: str):
+    def __call__(self, img_nchw, out: Act, arena: "Arena", name: str, pool: bool = False):
         """`img_nchw`: one [B, C, H, W] tensor, or a list of such tensors that together form the batch (the stereo plan passes
         [left, right]: each part is converted straight into its batch range of the row planes, no concatenated copy exists)."""
         parts = list(img_nchw) if isinstance(img_nchw, (list, tuple)) else [img_nchw]
@@ -328,6 +328,8 @@ class StemLayer:
         B = sum(int(p.shape[0]) for p in parts)
         assert all(tuple(p.shape[1:]) == (C, H, W) for p in parts)
         assert C == self.Cin and out.C == self.Cout and out.B == B
+        import os
+        pool = pool and os.environ.get("VD3D_STEM_POOL", "1") != "0"
         Wp = int(_lib.load().vd3d_stem_row_pitch(W, self.KW, self.stride, self.pad))
         planes = arena.get(name + ".rows#h16", (2, B, H, Wp, 4), parts[0].device, dtype=torch.float16, zero=True)   # borders stay zero
         b0 = 0
@@ -336,6 +338,14 @@ class StemLayer:
             call("vd3d_image_to_h16_rows", p.data_ptr(), nb, C, H, W, planes[0, b0:b0 + nb].data_ptr(), planes[1, b0:b0 + nb].data_ptr(),
                  Wp, self.pad, _stream())
             b0 += nb
+        if pool:
+            # conv + BN + ReLU + MaxPool2d(3, 2, 1) in one kernel: `out` is the POOLED tensor, the conv output is never written
+            Hs, Ws = self.out_hw(H, W)
+            assert self.relu and self.Cout == 64 and (out.H, out.W) == ((Hs - 1) // 2 + 1, (Ws - 1) // 2 + 1), "fused stem pool: 64 channels, ReLU, pooled shape"
+            call("vd3d_conv2d_tc16_stem_pool", planes[0].data_ptr(), planes[1].data_ptr(), B, H, W, Wp, self.KH, self.KW, self.stride, self.pad, self.win,
+                 self.w_hi.data_ptr(), self.w_lo.data_ptr(), self.out_scale, self.b.data_ptr(), out.ptr, self.Cout, out.cs, out.co, _stream())
+            out.f32 = True
+            return out
         oh, ol = out.h16_ptrs
         call("vd3d_conv2d_tc16_stem", planes[0].data_ptr(), planes[1].data_ptr(), B, H, W, Wp, self.KH, self.KW, self.stride, self.pad, self.win,
              self.w_hi.data_ptr(), self.w_lo.data_ptr(), self.out_scale, self.b.data_ptr(), out.ptr, oh, ol, self.Cout, out.cs, out.co,
