@@ -718,6 +718,7 @@ conv2d_tcp_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
 // ----------------------------------------------------------------------------------------------------------------
 constexpr int TCPH_THREADS = 352;            // warps: 0 = A producer, 1 = MMA, 2..9 = epilogue, 10 = W producer
 constexpr int TCPH_PLANE = 25600;
+constexpr int TCPH_XPLANE = 18 * 10 * 128;   // x-major item: 18 columns x 10 rows x 128 B (fits in the same plane slot)
 constexpr int TCPH_ITEM = 2 * TCPH_PLANE;
 
 template <int NG16, int CG, int PL>
@@ -787,7 +788,22 @@ conv2d_tcph_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
                     mbar_wait(&emptyA[s], ph ^ 1);
                     uint8_t* st = smemA + (size_t)s * TCPH_ITEM;
                     const int c0 = ch * 64;
-                    if (CG == 2) {
+                    if (p.m_xmajor) {
+                        // x-major item: ONE box {64 c, 10 h, 18 w} per plane (the tensor map lists h before w), written as [18 x][10 rows][128 B]:
+                        // 2 TMA operations of 23 KB per (tile, chunk) instead of 40 of 1.25 KB
+                        const bool lo_too = !(p.dbg & 2);
+                        const uint32_t bytes = lo_too ? 2u * TCPH_XPLANE : (uint32_t)TCPH_XPLANE;
+                        if (CG == 2) {
+                            const uint32_t lbar = mapa_shared(smem_u32(&fullA[s]), 0);
+                            if (rank == 0) mbar_expect_tx(&fullA[s], 2u * bytes);
+                            tma_load_4d_2sm(st, &mapA, lbar, c0, h0 - 1, w0 - 1, b);
+                            if (lo_too) tma_load_4d_2sm(st + TCPH_PLANE, &mapAlo, lbar, c0, h0 - 1, w0 - 1, b);
+                        } else {
+                            mbar_expect_tx(&fullA[s], bytes);
+                            tma_load_4d(st, &mapA, &fullA[s], c0, h0 - 1, w0 - 1, b);
+                            if (lo_too) tma_load_4d(st + TCPH_PLANE, &mapAlo, &fullA[s], c0, h0 - 1, w0 - 1, b);
+                        }
+                    } else if (CG == 2) {
                         const uint32_t lbar = mapa_shared(smem_u32(&fullA[s]), 0);
                         const bool lo_too = !(p.dbg & 2);
                         if (rank == 0) mbar_expect_tx(&fullA[s], lo_too ? 2u * TCPH_ITEM : (uint32_t)TCPH_ITEM);
@@ -876,7 +892,8 @@ conv2d_tcph_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
                     if (!p.w_res) mbar_wait(&fullB[sb], (itb / p.h_sb) & 1);
                     tc_fence_after();
                     const int ky = t / 3, kx = t - ky * 3;
-                    const uint32_t a0 = smem_u32(smemA + (size_t)sa * TCPH_ITEM) + (uint32_t)ky * 2560u + (uint32_t)kx * 128u;
+                    const uint32_t a0 = smem_u32(smemA + (size_t)sa * TCPH_ITEM) +
+                                        (p.m_xmajor ? (uint32_t)kx * 1280u + (uint32_t)ky * 128u : (uint32_t)ky * 2560u + (uint32_t)kx * 128u);
                     const uint32_t b0 = smem_u32(smemB + (size_t)sb * b_stage);
                     const uint64_t dA = make_sdesc(a0, 1280), dAlo = make_sdesc(a0 + TCPH_PLANE, 1280);
                     const uint64_t dB = make_sdesc(b0), dBlo = make_sdesc(b0 + b_bytes);
@@ -963,6 +980,22 @@ __global__ void split_h16_kernel(const float* __restrict__ in, __half* __restric
 // ----------------------------------------------------------------------------------------------------------------
 // `stride` > 1: TMA traversal stride (elementStrides) on W and H, so the box holds every stride-th pixel: a strided conv
 // reads exactly the 16 x 8 input pixels its 128 outputs need for one tap, densely packed in shared memory.
+// activation map with the H dimension listed before W (box {64 c, box_h rows, box_w columns, 1}): the box lands in shared memory as
+// [column][row][64 c], which gives the halo kernel's x-major item one uniform 1280-byte stride between its 8-pixel groups
+static int make_map_act_hw(CUtensorMap* m, const void* base_v, int B, int H, int W, int C, int cs, int co, int box_h, int box_w) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { set_error("conv2d_tc: cuTensorMapEncodeTiled unavailable"); return VD3D_ECUDA; }
+    const char* base = (const char*)base_v + (size_t)co * 2;
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)H, (cuuint64_t)W, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)W * cs * 2, (cuuint64_t)cs * 2, (cuuint64_t)H * W * cs * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)box_h, (cuuint32_t)box_w, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("conv2d_tc: cuTensorMapEncodeTiled(activation, h-major box) failed: %d", (int)r); return VD3D_ECUDA; }
+    return VD3D_OK;
+}
+
 static int make_map_act(CUtensorMap* m, const void* base_v, int B, int H, int W, int C, int cs, int co, int esize = 4,
                         int box_w = TC_TW, int box_h = TC_TH, int stride = 1) {
     EncodeTiledFn enc = get_encode();
@@ -1248,6 +1281,12 @@ static int conv2d_tc_launch(int f16, const void* in, const void* in_lo, int B, i
         const int phalo = eh ? atoi(eh) : 2;
         const bool halo_fits = 227 * 1024 - 1024 - 512 - 2 * (size_t)TCPH_ITEM >= 2 * (2 * (size_t)(BN / CG) * 128);
         if ((phalo == 1 || (phalo == 2 && CG == 2)) && halo_fits && s1_3x3) {
+            const char* exm = getenv("VD3D_TC_XMAJOR");
+            if (!(exm && atoi(exm) == 0) && make_map_act_hw(&mA, in, B, H, W, Cin, in_cs, in_co, 10, 18) == VD3D_OK &&
+                make_map_act_hw(&mAlo, in_lo, B, H, W, Cin, in_cs, in_co, 10, 18) == VD3D_OK) {
+                p.m_xmajor = 1;          // x-major halo item: 2 TMA operations per (tile, chunk)
+                return tcph_launch(p, mA, mAlo, mWhi, mWlo, CG, stream);
+            }
             if ((rc = make_map_act(&mA, in, B, H, W, Cin, in_cs, in_co, 2, 10, 1))) return rc;
             if ((rc = make_map_act(&mAlo, in_lo, B, H, W, Cin, in_cs, in_co, 2, 10, 1))) return rc;
             return tcph_launch(p, mA, mAlo, mWhi, mWlo, CG, stream);

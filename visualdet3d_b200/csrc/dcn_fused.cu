@@ -38,6 +38,7 @@ struct DfParams {
     int cchunks;                                    // C / 64
     int stages;
     uint32_t stage_bytes;
+    int dbg;                                        // timing knock-outs (VD3D_DF_DEBUG; results wrong): 1 no corner loads, 2 no offset / mask loads, 4 no operand stores, 8 one MMA per k-block
 };
 
 struct DfSample { int base_flags; float w1, w2, w3, w4, m; };      // base + W + 1 in bits 0..25, validity bits 26..30 (bit 30 = tap inside)
@@ -356,6 +357,8 @@ deform_conv_fused_staged_kernel(const __grid_constant__ CUtensorMap mapX, const 
                     const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
                     const uint64_t dA = make_sdesc(sa), dAlo = make_sdesc(sa + a_bytes);
                     const uint64_t dB = make_sdesc(sa + 2 * a_bytes), dBlo = make_sdesc(sa + 2 * a_bytes + b_bytes);
+                    if (q.dbg & 8) umma_f16(d_tmem, dA, dB, idesc, first_in_chunk ? 0u : 1u);
+                    else
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const uint64_t off = (uint64_t)((k * 32) >> 4);
@@ -404,8 +407,9 @@ deform_conv_fused_staged_kernel(const __grid_constant__ CUtensorMap mapX, const 
                             const long long pix = ((long long)b * p.Ho + ho) * p.Wo + wo;
                             const int kh = tap / q.KW, kw = tap - kh * q.KW;
                             const float* op = q.om + pix * q.om_cs + q.off_co + 2 * tap;
-                            const float dh = __ldg(op), dw = __ldg(op + 1);
-                            if (q.has_mask) {
+                            float dh = 0.25f, dw = 0.25f;
+                            if (!(q.dbg & 2)) { dh = __ldg(op); dw = __ldg(op + 1); }
+                            if (q.has_mask && !(q.dbg & 2)) {
                                 float mv = __ldg(q.om + pix * q.om_cs + q.msk_co + tap);
                                 if (q.mask_sigmoid) mv = __fdiv_rn(1.0f, 1.0f + expf(-mv));
                                 sm.m = mv;
@@ -420,6 +424,7 @@ deform_conv_fused_staged_kernel(const __grid_constant__ CUtensorMap mapX, const 
                                 if (hl >= 0 && wl + 1 <= q.W - 1) flags |= 2;
                                 if (hl + 1 <= q.H - 1 && wl >= 0) flags |= 4;
                                 if (hl + 1 <= q.H - 1 && wl + 1 <= q.W - 1) flags |= 8;
+                                if (q.dbg & 1) flags = 0;
                                 sm.hl = hl; sm.wl_flags = (wl + 16384) | (flags << 16);
                                 sm.w1 = hh * hw; sm.w2 = hh * lw; sm.w3 = lh * hw; sm.w4 = lh * lw;
                             }
@@ -467,8 +472,10 @@ deform_conv_fused_staged_kernel(const __grid_constant__ CUtensorMap mapX, const 
                         split4(a, h0, l0);
                         split4(a + 4, h1, l1);
                         const uint32_t off = (uint32_t)(m >> 3) * 1024u + (uint32_t)(m & 7) * 128u + (uint32_t)((j ^ (m & 7)) * 16);
-                        *reinterpret_cast<uint4*>(sa + off) = make_uint4(h0.x, h0.y, h1.x, h1.y);
-                        *reinterpret_cast<uint4*>(sa + a_bytes + off) = make_uint4(l0.x, l0.y, l1.x, l1.y);
+                        if (!(q.dbg & 4)) {
+                            *reinterpret_cast<uint4*>(sa + off) = make_uint4(h0.x, h0.y, h1.x, h1.y);
+                            *reinterpret_cast<uint4*>(sa + a_bytes + off) = make_uint4(l0.x, l0.y, l1.x, l1.y);
+                        }
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
@@ -523,6 +530,7 @@ extern "C" int vd3d_deform_conv_fused(const float* x, int B, int H, int W, int C
     p.idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     { const char* e = getenv("VD3D_TC_CHUNK"); p.chunk = e ? atoi(e) : 4; if (p.chunk < 1) p.chunk = 1; }
     { const char* e = getenv("VD3D_TC_DEBUG"); p.dbg = e ? atoi(e) : 0; }
+    { const char* e = getenv("VD3D_DF_DEBUG"); q.dbg = e ? atoi(e) : 0; }
     tcp_set_accumulators(p);
     q.x = x; q.H = H; q.W = W; q.C = C; q.x_cs = x_cs; q.x_co = x_co;
     q.om = om; q.om_cs = om_cs; q.off_co = off_co; q.msk_co = msk_co; q.has_mask = has_mask; q.mask_sigmoid = mask_sigmoid;

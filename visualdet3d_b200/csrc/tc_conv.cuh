@@ -28,6 +28,7 @@ struct TcParams {
     // conv2d_tcp_kernel<2, 1, 0> does not write the conv output at all; it pools every tile in shared memory and writes the pooled tensor
     float* pool_out; int pool_cs, pool_co, pool_H, pool_W;
     uint32_t pool_smem_off;  // byte offset of the [128][68] fp32 staging tile in dynamic shared memory
+    int m_xmajor;            // pixel order inside the 8 x 16 output tile: 0: m = row * 16 + x (TMA tap boxes), 1: m = x * 8 + row (x-major halo item, see conv2d_tcph_kernel)
     int two_pass;            // error-budget experiments (vd3d_conv2d_tc16 passes = 2): drop the A_lo * W_hi product (activations then carry 11 significant bits)
     int mblock;              // persistent kernels: scheduling units (tiles / tile pairs) per M block of the L2-aware tile order (0: one block)
     int rowb;                // bytes per operand row in shared memory = K bytes per k-block: 128 (64 channels, SWIZZLE_128B) or 64 (32, SWIZZLE_64B)
@@ -172,7 +173,7 @@ __device__ __forceinline__ void tcp_epilogue(const TcParams& p, uint32_t tmem_ba
         const int tw = mt % p.tiles_w; mt /= p.tiles_w;
         const int th = mt % p.tiles_h; const int b = mt / p.tiles_h;
         const int r = q * 32 + lane;
-        const int ho = th * TC_TH + r / TC_TW, wo = tw * TC_TW + r % TC_TW;
+        const int ho = th * TC_TH + (p.m_xmajor ? (r & (TC_TH - 1)) : r / TC_TW), wo = tw * TC_TW + (p.m_xmajor ? r / TC_TH : r % TC_TW);
         if (live && ho < p.Ho && wo < p.Wo && !(p.dbg & 16)) {
             const long long pix = ((long long)b * p.Ho + ho) * p.Wo + wo;
             float* op = (PL == 0 || p.out) ? p.out + pix * p.out_cs + p.out_co : nullptr;           // nullptr (PL = 1 only): planes-only output, no fp32 copy is written

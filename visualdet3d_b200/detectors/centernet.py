@@ -155,8 +155,10 @@ class _CenterNetBase(nn.Module):
         tc_out = all(l.engine == "tc16" for (l, _, _, _) in pl["outs"].values())
         # the stem output (9 x 256 channels at 1/4 resolution: the largest tensor of the network) feeds only the 1x1 output convs: with
         # those on the tensor cores it is written as fp16 planes only (no fp32 copy: 2.3 GB less HBM traffic per batch-8 step at 384x1280)
-        stem = pl["stem"](feat, ar.act("heads.stem", (B, feat.H, feat.W, pl["stem"].Cout), dev, lo=tc_out),
-                          f32_out=not (tc_out and E.planes_mode_ok()))
+        planes_only = tc_out and E.planes_mode_ok()
+        if planes_only:
+            pl["stem"].bn_tile = 128          # 128-column tiles: the planes-only epilogue variant of the wider tiles runs out of registers (measured 1.7x slower)
+        stem = pl["stem"](feat, ar.act("heads.stem", (B, feat.H, feat.W, pl["stem"].Cout), dev, lo=tc_out), f32_out=not planes_only)
         out = ar.act("heads.out", (B, feat.H, feat.W, pl["out_channels"]), dev)
         for n in pl["names"]:
             layer, cin_off, cout_off, n_pad = pl["outs"][n]
