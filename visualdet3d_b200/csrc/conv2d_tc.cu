@@ -1102,7 +1102,7 @@ static int tcp_launch(TcParams& p, const CUtensorMap& mA, const CUtensorMap& mAl
     cfg.attrs = attr; cfg.numAttrs = 1;
     const int ng = (BN + 31) / 32;
     cudaError_t le;
-    const bool pl = p.out == nullptr || p.res_h16_hi != nullptr;
+    const bool pl = (p.out == nullptr && p.pool_out == nullptr) || p.res_h16_hi != nullptr;      // (the fused-pool epilogue lives in the <2, 1, 0> instance)
 #define VD3D_TCP_LAUNCH(NG, C) le = pl ? cudaLaunchKernelEx(&cfg, conv2d_tcp_kernel<NG, C, 1>, mA, mAlo, mWhi, mWlo, p) \
                                        : cudaLaunchKernelEx(&cfg, conv2d_tcp_kernel<NG, C, 0>, mA, mAlo, mWhi, mWlo, p)
     if (CG == 2) {
