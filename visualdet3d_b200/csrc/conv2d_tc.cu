@@ -609,6 +609,7 @@ conv2d_tcp_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             // (issue is blocking and the queue is shallow: anything between the last MMA of g and the first of g+1 is a bubble).
             const int my_units = (units - u0 + ustep - 1) / ustep;           // tiles of this CTA (>= 1: the grid never exceeds the tile count)
             const long long total = (long long)my_units * KB;
+            const int mma_mode = (p.dbg & 1) ? 1 : (p.two_pass ? 3 : 0);      // 0 = production
             int s = 0, ph = 0, cc = 0;
             auto stage_desc = [&](int st, uint64_t& dA, uint64_t& dAlo, uint64_t& dB, uint64_t& dBlo) {
                 const uint32_t sa = smem_u32(smem + (size_t)st * stage_bytes);
@@ -623,10 +624,10 @@ conv2d_tcp_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             };
             auto issue = [&](uint32_t d_tmem, uint32_t idesc, uint64_t dA, uint64_t dAlo, uint64_t dB, uint64_t dBlo, int k, uint32_t acc0) {
                 const uint64_t off = (uint64_t)((k * 32) >> 4);       // one MMA K-step = 16 fp16 = 32 bytes inside the swizzle row
-                if (p.dbg & 1) {
-                    if (CG == 2) umma_f16_2sm(d_tmem, dA + off, dB + off, idesc, acc0); else umma_f16(d_tmem, dA + off, dB + off, idesc, acc0);
-                } else if (p.two_pass) {
-                    if (CG == 2) { umma_f16_2sm(d_tmem, dA + off, dBlo + off, idesc, acc0); umma_f16_2sm(d_tmem, dA + off, dB + off, idesc, 1); }
+                if (mma_mode != 0) {          // experiments (results differ): 1 = one MMA per K step, 3 = two passes
+                    if (mma_mode == 1) {
+                        if (CG == 2) umma_f16_2sm(d_tmem, dA + off, dB + off, idesc, acc0); else umma_f16(d_tmem, dA + off, dB + off, idesc, acc0);
+                    } else if (CG == 2) { umma_f16_2sm(d_tmem, dA + off, dBlo + off, idesc, acc0); umma_f16_2sm(d_tmem, dA + off, dB + off, idesc, 1); }
                     else { umma_f16(d_tmem, dA + off, dBlo + off, idesc, acc0); umma_f16(d_tmem, dA + off, dB + off, idesc, 1); }
                 } else if (CG == 2) {
                     umma_f16_2sm(d_tmem, dAlo + off, dB + off, idesc, acc0);      // small terms first, then the main product
@@ -872,6 +873,7 @@ conv2d_tcph_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
         if (rank == 0 && elect_one()) {
             // ================= MMA issuer (leader CTA, one elected lane) =================
             int ita = 0, itb = 0, cc = 0;
+            const int mma_mode = (p.dbg & 1) ? 1 : ((p.dbg & 64) ? 2 : (p.two_pass ? 3 : 0));      // 0 = production (hoisted: the issue loop tests one register)
             if (p.w_res) { mbar_wait(&fullB[0], 0); tc_fence_after(); }
             for (int u = u0; u < units; u += ustep) {
                 const int nvalid = min(p.BN, p.cout_pad - unit_nt(p, u, mt_units) * p.BN);
@@ -897,28 +899,36 @@ conv2d_tcph_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
                     const uint32_t b0 = smem_u32(smemB + (size_t)sb * b_stage);
                     const uint64_t dA = make_sdesc(a0, 1280), dAlo = make_sdesc(a0 + TCPH_PLANE, 1280);
                     const uint64_t dB = make_sdesc(b0), dBlo = make_sdesc(b0 + b_bytes);
+                    if (mma_mode == 0) {
+                        // the production path: three back-to-back MMAs per K step, nothing else in the issue loop
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const uint64_t off = (uint64_t)((k * 32) >> 4);
-                        if (p.dbg & 1) {          // timing experiment: one MMA per K step
-                            if (CG == 2) umma_f16_2sm(d_tmem, dA + off, dB + off, idesc, first ? 0u : 1u); else umma_f16(d_tmem, dA + off, dB + off, idesc, first ? 0u : 1u);
-                        } else if (p.dbg & 64) {   // timing experiment: only the first K step of every k-block (1/4 of the MMAs, same loads)
-                            if (k == 0) {
-                                if (CG == 2) umma_f16_2sm(d_tmem, dA + off, dB + off, idesc, first ? 0u : 1u); else umma_f16(d_tmem, dA + off, dB + off, idesc, first ? 0u : 1u);
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t off = (uint64_t)((k * 32) >> 4);
+                            if (CG == 2) {
+                                umma_f16_2sm(d_tmem, dAlo + off, dB + off, idesc, first ? 0u : 1u);
+                                umma_f16_2sm(d_tmem, dA + off, dBlo + off, idesc, 1);
+                                umma_f16_2sm(d_tmem, dA + off, dB + off, idesc, 1);
+                            } else {
+                                umma_f16(d_tmem, dAlo + off, dB + off, idesc, first ? 0u : 1u);
+                                umma_f16(d_tmem, dA + off, dBlo + off, idesc, 1);
+                                umma_f16(d_tmem, dA + off, dB + off, idesc, 1);
                             }
-                        } else if (p.two_pass) {
-                            if (CG == 2) { umma_f16_2sm(d_tmem, dA + off, dBlo + off, idesc, first ? 0u : 1u); umma_f16_2sm(d_tmem, dA + off, dB + off, idesc, 1); }
-                            else { umma_f16(d_tmem, dA + off, dBlo + off, idesc, first ? 0u : 1u); umma_f16(d_tmem, dA + off, dB + off, idesc, 1); }
-                        } else if (CG == 2) {
-                            umma_f16_2sm(d_tmem, dAlo + off, dB + off, idesc, first ? 0u : 1u);
-                            umma_f16_2sm(d_tmem, dA + off, dBlo + off, idesc, 1);
-                            umma_f16_2sm(d_tmem, dA + off, dB + off, idesc, 1);
-                        } else {
-                            umma_f16(d_tmem, dAlo + off, dB + off, idesc, first ? 0u : 1u);
-                            umma_f16(d_tmem, dA + off, dBlo + off, idesc, 1);
-                            umma_f16(d_tmem, dA + off, dB + off, idesc, 1);
+                            first = false;
                         }
-                        first = false;
+                    } else {
+                        // experiments (results differ): 1 = one MMA per K step, 2 = only the first K step, 3 = two passes (A_lo * W_hi dropped)
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t off = (uint64_t)((k * 32) >> 4);
+                            const uint32_t acc = first ? 0u : 1u;
+                            if (mma_mode == 2 && k != 0) continue;
+                            if (mma_mode == 3) {
+                                if (CG == 2) { umma_f16_2sm(d_tmem, dA + off, dBlo + off, idesc, acc); umma_f16_2sm(d_tmem, dA + off, dB + off, idesc, 1); }
+                                else { umma_f16(d_tmem, dA + off, dBlo + off, idesc, acc); umma_f16(d_tmem, dA + off, dB + off, idesc, 1); }
+                            } else {
+                                if (CG == 2) umma_f16_2sm(d_tmem, dA + off, dB + off, idesc, acc); else umma_f16(d_tmem, dA + off, dB + off, idesc, acc);
+                            }
+                            first = false;
+                        }
                     }
                     if (!p.w_res) { if (CG == 2) umma_commit_2sm(&emptyB[sb]); else umma_commit(&emptyB[sb]); }
                     if (t == 8) { if (CG == 2) umma_commit_2sm(&emptyA[sa]); else umma_commit(&emptyA[sa]); }

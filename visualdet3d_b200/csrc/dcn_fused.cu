@@ -234,22 +234,28 @@ deform_conv_fused_kernel(const __grid_constant__ CUtensorMap mapWhi, const __gri
 }
 
 // ----------------------------------------------------------------------------------------------------------------
-// Staged form (stride 1, dilation 1: every deformable layer of the DLA up-sampling path and of the Yolo3D head).
+// Staged form (3x3, stride 1, pad 1, dilation 1: every deformable layer of the DLA up-sampling path and of the Yolo3D head).
 // The gather warps of the kernel above read the four bilinear corners of every (pixel, tap) from global memory: 36 loads per output
-// value whose latency eight warps cannot hide (measured: 340 us for 64 -> 64 at 96 x 320 x 8, the gather is the whole kernel).  Here the
-// input neighbourhood of the tile is STAGED IN SHARED MEMORY by TMA, once per (tile, 64-channel chunk):
+// value whose latency eight warps cannot hide.  Here the input neighbourhood of the tile is STAGED IN SHARED MEMORY by TMA, once per
+// (tile, 64-channel chunk):
 //   region = rows [h0 - 2, h0 + 10) x columns [w0 - 2, w0 + 18) x 64 channels of x (fp32, 61,440 B; out-of-image pixels are zero-filled by
-//   the TMA unit, which is exactly the reference's "corner outside the image contributes zero" rule), double-buffered;
+//   the TMA unit, which is exactly the reference's "corner outside the image contributes zero" rule);
 //   the nine taps of the chunk then gather from shared memory (a corner that falls outside the staged region -- an offset beyond
 //   +-1 pixel around the regular tap position -- is read from global memory instead: correct for any offset, fast for small ones).
+// The sampling table (position, validity, 4 weights, mask of every (pixel, tap)) is computed once per tile for all nine taps.
+// Weights run through their own 4-deep TMA ring (16 KB blocks), the gathered operand through a 2-deep ring: measured with the shared
+// 2-deep ring of the first version, every k-block paid the full latency of its weight load (1.9k clk of a 3.0k clk k-block period).
+// Each gather thread owns channels [4j, 4j + 4) and [32 + 4j, 32 + 4j + 4) of four pixels: its two 16-byte shared-memory reads per corner
+// are conflict-free (8 lanes = 128 contiguous bytes).
 // K order: 64-channel chunk outermost, taps inside (k = (chunk * 9 + tap) * 64 + c): the weight matrix and the unfused A/B path
 // (vd3d_deform_im2col_h16 with k_order = 1) use the same order, so both still produce identical bits.
-// Shared memory: 2 operand stages (48 KB) + 2 regions (60 KB) + 2 per-tap sample tables (3.5 KB) = 223 KB.
+// Shared memory: A ring 2 x 32 KB + W ring 4 x 16 KB + region 60 KB + sample table 31.5 KB = 221 KB.
 // ----------------------------------------------------------------------------------------------------------------
 constexpr int DFS_HALO = 2;
 constexpr int DFS_RH = TC_TH + 2 * DFS_HALO, DFS_RW = TC_TW + 2 * DFS_HALO;       // 12 x 20 pixels
 constexpr uint32_t DFS_REGION_BYTES = DFS_RH * DFS_RW * 64 * 4;                   // 61,440
-constexpr int DFS_STAGES = 2;
+constexpr int DFS_A_STAGES = 2, DFS_W_STAGES = 4;
+constexpr uint32_t DFS_A_STAGE = 2u * 128u * 128u;                                 // A hi | A lo
 
 struct DfSample2 { int hl, wl_flags; float w1, w2, w3, w4, m; };                  // wl in the low 16 bits (biased by 16384), validity bits 16..20
 
@@ -261,16 +267,19 @@ deform_conv_fused_staged_kernel(const __grid_constant__ CUtensorMap mapX, const 
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t a_bytes = 128u * 128u;
     const uint32_t b_bytes = (uint32_t)p.BN * 128u;
-    const uint32_t stage_bytes = q.stage_bytes;
-    uint8_t* regions = smem + (size_t)DFS_STAGES * stage_bytes;
-    DfSample2* samp = reinterpret_cast<DfSample2*>(regions + 2 * DFS_REGION_BYTES);          // [2][128]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(samp) + 2 * 128 * sizeof(DfSample2));
+    const uint32_t w_stage = 2u * b_bytes;
+    uint8_t* smemA = smem;
+    uint8_t* smemW = smemA + (size_t)DFS_A_STAGES * DFS_A_STAGE;
+    uint8_t* region = smemW + (size_t)DFS_W_STAGES * w_stage;
+    DfSample2* samp = reinterpret_cast<DfSample2*>(region + DFS_REGION_BYTES);               // [K taps][128 pixels]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(samp) + (size_t)DF_MAXK * 128 * sizeof(DfSample2));
     uint64_t* fullA = bars;                        // [2]  gather warps -> MMA (8 arrivals)
-    uint64_t* fullB = fullA + DFS_STAGES;          // [2]  weight TMA -> MMA
-    uint64_t* empty = fullB + DFS_STAGES;          // [2]  MMA -> producers
-    uint64_t* fullR = empty + DFS_STAGES;          // [2]  region TMA -> gather warps
-    uint64_t* emptyR = fullR + 2;                  // [2]  gather warps -> region producer (8 arrivals)
-    uint64_t* tmem_full = emptyR + 2;              // [4]
+    uint64_t* emptyA = fullA + DFS_A_STAGES;       // [2]  MMA -> gather warps
+    uint64_t* fullW = emptyA + DFS_A_STAGES;       // [4]  weight TMA -> MMA
+    uint64_t* emptyW = fullW + DFS_W_STAGES;       // [4]  MMA -> weight producer
+    uint64_t* fullR = emptyW + DFS_W_STAGES;       // [1]  region TMA -> gather warps
+    uint64_t* emptyR = fullR + 1;                  // [1]  gather warps -> region producer (8 arrivals)
+    uint64_t* tmem_full = emptyR + 1;              // [4]
     uint64_t* tmem_empty = tmem_full + 4;          // [4]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 4);
 
@@ -282,8 +291,9 @@ deform_conv_fused_staged_kernel(const __grid_constant__ CUtensorMap mapX, const 
     const int u0 = (int)blockIdx.x, ustep = (int)gridDim.x;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < DFS_STAGES; ++s) { mbar_init(&fullA[s], DF_GATHER_WARPS); mbar_init(&fullB[s], 1); mbar_init(&empty[s], 1); }
-        for (int r = 0; r < 2; ++r) { mbar_init(&fullR[r], 1); mbar_init(&emptyR[r], DF_GATHER_WARPS); }
+        for (int s = 0; s < DFS_A_STAGES; ++s) { mbar_init(&fullA[s], DF_GATHER_WARPS); mbar_init(&emptyA[s], 1); }
+        for (int s = 0; s < DFS_W_STAGES; ++s) { mbar_init(&fullW[s], 1); mbar_init(&emptyW[s], 1); }
+        mbar_init(fullR, 1); mbar_init(emptyR, DF_GATHER_WARPS);
         for (int i = 0; i < 4; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -297,41 +307,34 @@ deform_conv_fused_staged_kernel(const __grid_constant__ CUtensorMap mapX, const 
     const uint32_t tmem_base = __reduce_or_sync(0xffffffffu, *tmem_slot);
 
     if (warp == 0) {
-        // ================= TMA producer: input regions (one (tile, chunk) ahead) and weight blocks =================
-        const int my_units = (units - u0 + ustep - 1) / ustep;
-        const int total_r = my_units * q.cchunks;                   // regions this CTA will stage
-        auto issue_region = [&](int ir) {
-            const int ul = ir / q.cchunks, ch = ir - ul * q.cchunks;
+        // ================= TMA producer: the input region of every (tile, chunk), then its nine weight blocks =================
+        int itw = 0, ir = 0;
+        for (int u = u0; u < units; u += ustep) {
             int mu, nt;
-            unit_tile(p, u0 + ul * ustep, mt_units, mu, nt);
+            unit_tile(p, u, mt_units, mu, nt);
             int mt = mu;
             const int tw = mt % p.tiles_w; mt /= p.tiles_w;
             const int th = mt % p.tiles_h; const int b = mt / p.tiles_h;
-            const int r = ir & 1;
-            mbar_wait(&emptyR[r], ((ir >> 1) & 1) ^ 1);
-            if (elect_one()) {
-                mbar_expect_tx(&fullR[r], DFS_REGION_BYTES);
-                tma_load_4d(regions + (size_t)r * DFS_REGION_BYTES, &mapX, &fullR[r], ch * 64, tw * TC_TW - DFS_HALO, th * TC_TH - DFS_HALO, b);
-            }
-            __syncwarp();
-        };
-        int it = 0;
-        if (total_r > 0) issue_region(0);
-        for (int ir = 0; ir < total_r; ++ir) {
-            if (ir + 1 < total_r) issue_region(ir + 1);
-            const int ul = ir / q.cchunks, ch = ir - ul * q.cchunks;
-            const int n0 = unit_nt(p, u0 + ul * ustep, mt_units) * p.BN;
-            for (int t = 0; t < q.K; ++t, ++it) {
-                const int s = it % DFS_STAGES, ph = (it / DFS_STAGES) & 1;
-                mbar_wait(&empty[s], ph ^ 1);
+            const int n0 = nt * p.BN;
+            for (int ch = 0; ch < q.cchunks; ++ch, ++ir) {
+                mbar_wait(emptyR, (ir & 1) ^ 1);                     // the gather warps are done with the previous region
                 if (elect_one()) {
-                    uint8_t* st = smem + (size_t)s * stage_bytes + 2 * a_bytes;
-                    mbar_expect_tx(&fullB[s], 2u * b_bytes);
-                    const int kcol = (ch * q.K + t) * 64;
-                    tma_load_2d(st, &mapWhi, &fullB[s], kcol, n0);
-                    tma_load_2d(st + b_bytes, &mapWlo, &fullB[s], kcol, n0);
+                    mbar_expect_tx(fullR, DFS_REGION_BYTES);
+                    tma_load_4d(region, &mapX, fullR, ch * 64, tw * TC_TW - DFS_HALO, th * TC_TH - DFS_HALO, b);
                 }
                 __syncwarp();
+                for (int t = 0; t < q.K; ++t, ++itw) {
+                    const int s = itw % DFS_W_STAGES, ph = (itw / DFS_W_STAGES) & 1;
+                    mbar_wait(&emptyW[s], ph ^ 1);
+                    if (elect_one()) {
+                        uint8_t* st = smemW + (size_t)s * w_stage;
+                        mbar_expect_tx(&fullW[s], w_stage);
+                        const int kcol = (ch * q.K + t) * 64;
+                        tma_load_2d(st, &mapWhi, &fullW[s], kcol, n0);
+                        tma_load_2d(st + b_bytes, &mapWlo, &fullW[s], kcol, n0);
+                    }
+                    __syncwarp();
+                }
             }
         }
     } else if (warp == 1) {
@@ -349,14 +352,15 @@ deform_conv_fused_staged_kernel(const __grid_constant__ CUtensorMap mapX, const 
                         mbar_wait(&tmem_empty[buf], (((cc + ci) / p.nbuf) & 1) ^ 1);
                         tc_fence_after();
                     }
-                    const int s = it % DFS_STAGES, ph = (it / DFS_STAGES) & 1;
-                    mbar_wait(&fullB[s], ph);
-                    mbar_wait(&fullA[s], ph);
+                    const int sa = it % DFS_A_STAGES, pa = (it / DFS_A_STAGES) & 1;
+                    const int sw = it % DFS_W_STAGES, pw = (it / DFS_W_STAGES) & 1;
+                    mbar_wait(&fullW[sw], pw);
+                    mbar_wait(&fullA[sa], pa);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.BN);
-                    const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
-                    const uint64_t dA = make_sdesc(sa), dAlo = make_sdesc(sa + a_bytes);
-                    const uint64_t dB = make_sdesc(sa + 2 * a_bytes), dBlo = make_sdesc(sa + 2 * a_bytes + b_bytes);
+                    const uint32_t aa = smem_u32(smemA + (size_t)sa * DFS_A_STAGE), ww = smem_u32(smemW + (size_t)sw * w_stage);
+                    const uint64_t dA = make_sdesc(aa), dAlo = make_sdesc(aa + a_bytes);
+                    const uint64_t dB = make_sdesc(ww), dBlo = make_sdesc(ww + b_bytes);
                     if (q.dbg & 8) umma_f16(d_tmem, dA, dB, idesc, first_in_chunk ? 0u : 1u);
                     else
 #pragma unroll
@@ -366,7 +370,8 @@ deform_conv_fused_staged_kernel(const __grid_constant__ CUtensorMap mapX, const 
                         umma_f16(d_tmem, dA + off, dBlo + off, idesc, 1);
                         umma_f16(d_tmem, dA + off, dB + off, idesc, 1);
                     }
-                    umma_commit(&empty[s]);
+                    umma_commit(&emptyA[sa]);
+                    umma_commit(&emptyW[sw]);
                     if (kb - ci * p.chunk == p.chunk - 1 || kb == KB - 1) umma_commit(&tmem_full[buf]);
                 }
                 cc += NC;
@@ -379,8 +384,8 @@ deform_conv_fused_staged_kernel(const __grid_constant__ CUtensorMap mapX, const 
     } else {
         // ================= gather warps (256 threads) =================
         const int gt = (int)threadIdx.x - 320;
-        const int j = gt & 7;
-        const int m0 = gt >> 3;
+        const int j = gt & 7;                             // channel groups [4j, 4j + 4) and [32 + 4j, 32 + 4j + 4) of the chunk
+        const int m0 = gt >> 3;                           // pixels m0, m0 + 32, m0 + 64, m0 + 96 of the tile
         int it = 0, ir = 0;
         for (int u = u0; u < units; u += ustep) {
             int mu, nt;
@@ -390,51 +395,51 @@ deform_conv_fused_staged_kernel(const __grid_constant__ CUtensorMap mapX, const 
             const int th = mt % p.tiles_h; const int b = mt / p.tiles_h;
             const int rh0 = th * TC_TH - DFS_HALO, rw0 = tw * TC_TW - DFS_HALO;           // image coordinates of region pixel (0, 0)
             const float* xb = q.x + ((long long)b * q.H * q.W) * q.x_cs + q.x_co;
-            for (int ch = 0; ch < q.cchunks; ++ch, ++ir) {
-                const int rr = ir & 1;
-                mbar_wait(&fullR[rr], (ir >> 1) & 1);
-                const float* reg = reinterpret_cast<const float*>(regions + (size_t)rr * DFS_REGION_BYTES) + j * 8;
-                const int c = ch * 64 + j * 8;
-                for (int tap = 0; tap < q.K; ++tap, ++it) {
-                    // ---- sample table of this tap: one entry per pixel of the tile (threads 0..127 of the gather group) ----
-                    DfSample2* tb = samp + (it & 1) * 128;
-                    if (gt < 128) {
-                        const int m = gt;
-                        const int ho = th * TC_TH + m / TC_TW, wo = tw * TC_TW + m % TC_TW;
-                        DfSample2 sm;
-                        sm.hl = 0; sm.wl_flags = 0; sm.w1 = sm.w2 = sm.w3 = sm.w4 = 0.f; sm.m = 1.f;
-                        if (ho < p.Ho && wo < p.Wo) {
-                            const long long pix = ((long long)b * p.Ho + ho) * p.Wo + wo;
-                            const int kh = tap / q.KW, kw = tap - kh * q.KW;
-                            const float* op = q.om + pix * q.om_cs + q.off_co + 2 * tap;
-                            float dh = 0.25f, dw = 0.25f;
-                            if (!(q.dbg & 2)) { dh = __ldg(op); dw = __ldg(op + 1); }
-                            if (q.has_mask && !(q.dbg & 2)) {
-                                float mv = __ldg(q.om + pix * q.om_cs + q.msk_co + tap);
-                                if (q.mask_sigmoid) mv = __fdiv_rn(1.0f, 1.0f + expf(-mv));
-                                sm.m = mv;
-                            }
-                            const float h = (float)(ho * q.stride - q.pad + kh * q.dil) + dh;
-                            const float w = (float)(wo * q.stride - q.pad + kw * q.dil) + dw;
-                            if (h > -1.f && w > -1.f && h < (float)q.H && w < (float)q.W) {
-                                const int hl = (int)floorf(h), wl = (int)floorf(w);
-                                const float lh = h - (float)hl, lw = w - (float)wl, hh = 1.f - lh, hw = 1.f - lw;
-                                int flags = 16;
-                                if (hl >= 0 && wl >= 0) flags |= 1;
-                                if (hl >= 0 && wl + 1 <= q.W - 1) flags |= 2;
-                                if (hl + 1 <= q.H - 1 && wl >= 0) flags |= 4;
-                                if (hl + 1 <= q.H - 1 && wl + 1 <= q.W - 1) flags |= 8;
-                                if (q.dbg & 1) flags = 0;
-                                sm.hl = hl; sm.wl_flags = (wl + 16384) | (flags << 16);
-                                sm.w1 = hh * hw; sm.w2 = hh * lw; sm.w3 = lh * hw; sm.w4 = lh * lw;
-                            }
-                        }
-                        tb[m] = sm;
+            // ---- sampling table of the tile, all taps: entry [tap][pixel] ----
+            asm volatile("bar.sync 1, 256;" ::: "memory");         // every gather thread is done with the previous tile's table
+            for (int i = gt; i < 128 * q.K; i += 256) {
+                const int tap = i >> 7, m = i & 127;
+                const int ho = th * TC_TH + m / TC_TW, wo = tw * TC_TW + m % TC_TW;
+                DfSample2 sm;
+                sm.hl = 0; sm.wl_flags = 0; sm.w1 = sm.w2 = sm.w3 = sm.w4 = 0.f; sm.m = 1.f;
+                if (ho < p.Ho && wo < p.Wo) {
+                    const long long pix = ((long long)b * p.Ho + ho) * p.Wo + wo;
+                    const int kh = tap / q.KW, kw = tap - kh * q.KW;
+                    const float* op = q.om + pix * q.om_cs + q.off_co + 2 * tap;
+                    float dh = 0.25f, dw = 0.25f;
+                    if (!(q.dbg & 2)) { dh = __ldg(op); dw = __ldg(op + 1); }
+                    if (q.has_mask && !(q.dbg & 2)) {
+                        float mv = __ldg(q.om + pix * q.om_cs + q.msk_co + tap);
+                        if (q.mask_sigmoid) mv = __fdiv_rn(1.0f, 1.0f + expf(-mv));
+                        sm.m = mv;
                     }
-                    asm volatile("bar.sync 1, 256;" ::: "memory");                 // table visible; also: everyone is past the table of tap - 2
-                    const int s = it % DFS_STAGES, ph = (it / DFS_STAGES) & 1;
-                    mbar_wait(&empty[s], ph ^ 1);
-                    uint8_t* sa = smem + (size_t)s * stage_bytes;
+                    const float h = (float)(ho * q.stride - q.pad + kh * q.dil) + dh;
+                    const float w = (float)(wo * q.stride - q.pad + kw * q.dil) + dw;
+                    if (h > -1.f && w > -1.f && h < (float)q.H && w < (float)q.W) {
+                        const int hl = (int)floorf(h), wl = (int)floorf(w);
+                        const float lh = h - (float)hl, lw = w - (float)wl, hh = 1.f - lh, hw = 1.f - lw;
+                        int flags = 16;
+                        if (hl >= 0 && wl >= 0) flags |= 1;
+                        if (hl >= 0 && wl + 1 <= q.W - 1) flags |= 2;
+                        if (hl + 1 <= q.H - 1 && wl >= 0) flags |= 4;
+                        if (hl + 1 <= q.H - 1 && wl + 1 <= q.W - 1) flags |= 8;
+                        if (q.dbg & 1) flags = 0;
+                        sm.hl = hl; sm.wl_flags = (wl + 16384) | (flags << 16);
+                        sm.w1 = hh * hw; sm.w2 = hh * lw; sm.w3 = lh * hw; sm.w4 = lh * lw;
+                    }
+                }
+                samp[i] = sm;
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            for (int ch = 0; ch < q.cchunks; ++ch, ++ir) {
+                mbar_wait(fullR, ir & 1);
+                const float* reg = reinterpret_cast<const float*>(region) + j * 4;
+                const int c = ch * 64 + j * 4;
+                for (int tap = 0; tap < q.K; ++tap, ++it) {
+                    const DfSample2* tb = samp + tap * 128;
+                    const int s = it % DFS_A_STAGES, ph = (it / DFS_A_STAGES) & 1;
+                    mbar_wait(&emptyA[s], ph ^ 1);
+                    uint8_t* sa = smemA + (size_t)s * DFS_A_STAGE;
 #pragma unroll
                     for (int r = 0; r < 4; ++r) {
                         const int m = m0 + 32 * r;
@@ -453,11 +458,11 @@ deform_conv_fused_staged_kernel(const __grid_constant__ CUtensorMap mapX, const 
                                 if (flags & (1 << cn)) {
                                     const int y = hr + dy, x = wr + dx;
                                     if ((unsigned)y < (unsigned)DFS_RH && (unsigned)x < (unsigned)DFS_RW) {
-                                        const float4* sp = reinterpret_cast<const float4*>(reg + (y * DFS_RW + x) * 64);
-                                        v[cn][0] = sp[0]; v[cn][1] = sp[1];
+                                        const float* sp = reg + (y * DFS_RW + x) * 64;
+                                        v[cn][0] = *reinterpret_cast<const float4*>(sp); v[cn][1] = *reinterpret_cast<const float4*>(sp + 32);
                                     } else {                                                // far sample: straight from global memory
                                         const float* gp = xb + ((long long)(hl + dy) * q.W + (wl + dx)) * q.x_cs + c;
-                                        v[cn][0] = ldg4(gp); v[cn][1] = ldg4(gp + 4);
+                                        v[cn][0] = ldg4(gp); v[cn][1] = ldg4(gp + 32);
                                     }
                                 } else {
                                     v[cn][0] = make_float4(0.f, 0.f, 0.f, 0.f); v[cn][1] = v[cn][0];
@@ -469,12 +474,13 @@ deform_conv_fused_staged_kernel(const __grid_constant__ CUtensorMap mapX, const 
 #undef VD3D_DF_MIX
                         }
                         uint2 h0, l0, h1, l1;
-                        split4(a, h0, l0);
-                        split4(a + 4, h1, l1);
-                        const uint32_t off = (uint32_t)(m >> 3) * 1024u + (uint32_t)(m & 7) * 128u + (uint32_t)((j ^ (m & 7)) * 16);
+                        split4(a, h0, l0);                                                   // channels 4j .. 4j + 3      -> 16-byte chunk j / 2, half j % 2
+                        split4(a + 4, h1, l1);                                               // channels 32 + 4j .. + 3   -> chunk 4 + j / 2
                         if (!(q.dbg & 4)) {
-                            *reinterpret_cast<uint4*>(sa + off) = make_uint4(h0.x, h0.y, h1.x, h1.y);
-                            *reinterpret_cast<uint4*>(sa + a_bytes + off) = make_uint4(l0.x, l0.y, l1.x, l1.y);
+                            const uint32_t row = (uint32_t)(m >> 3) * 1024u + (uint32_t)(m & 7) * 128u, sub = (uint32_t)(j & 1) * 8u;
+                            const uint32_t o0 = row + (uint32_t)(((j >> 1) ^ (m & 7)) * 16) + sub, o1 = row + (uint32_t)(((4 + (j >> 1)) ^ (m & 7)) * 16) + sub;
+                            *reinterpret_cast<uint2*>(sa + o0) = h0; *reinterpret_cast<uint2*>(sa + o1) = h1;
+                            *reinterpret_cast<uint2*>(sa + a_bytes + o0) = l0; *reinterpret_cast<uint2*>(sa + a_bytes + o1) = l1;
                         }
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -482,7 +488,7 @@ deform_conv_fused_staged_kernel(const __grid_constant__ CUtensorMap mapX, const 
                     if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&fullA[s])) : "memory");
                 }
                 __syncwarp();                                                              // every lane is done reading the region
-                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&emptyR[rr])) : "memory");
+                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(emptyR)) : "memory");
             }
         }
     }
@@ -562,8 +568,9 @@ extern "C" int vd3d_deform_conv_fused(const float* x, int B, int H, int W, int C
         CUresult cr = enc(&mX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)(x + x_co), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         VD3D_REQUIRE(cr == CUDA_SUCCESS, "deform_conv_fused: cuTensorMapEncodeTiled(input regions) failed: %d", (int)cr);
-        q.stages = DFS_STAGES;
-        const size_t smem = (size_t)DFS_STAGES * q.stage_bytes + 2 * (size_t)DFS_REGION_BYTES + 2 * 128 * sizeof(DfSample2) + 32 * sizeof(uint64_t) + 1024;
+        q.stages = DFS_A_STAGES;
+        const size_t smem = (size_t)DFS_A_STAGES * DFS_A_STAGE + (size_t)DFS_W_STAGES * 2 * BN * 128 + (size_t)DFS_REGION_BYTES +
+                            (size_t)DF_MAXK * 128 * sizeof(DfSample2) + 32 * sizeof(uint64_t) + 1024;
         VD3D_REQUIRE(smem <= 227 * 1024, "deform_conv_fused: shared-memory budget exceeded");
         deform_conv_fused_staged_kernel<2><<<grid, DF_THREADS, smem, (cudaStream_t)stream>>>(mX, mWhi, mWlo, p, q);
         VD3D_CHECK_LAUNCH("deform_conv_fused_staged");
