@@ -441,7 +441,11 @@ def main():
         barrier()
         launches = _lib.launch_count()
         ms_dev = e0.elapsed_time(e1)
-        psm_ms = [a.elapsed_time(b) for a, b in det.profile_events] if stereo else []
+        situ = {}
+        if stereo:
+            for nm, a, b in det.profile_events:
+                situ.setdefault(nm, []).append(a.elapsed_time(b))
+        psm_ms = situ.get("psm4", [])
         det.profile_events = None
         clocks = sampler.stop()
         if E_overflow():
@@ -526,6 +530,10 @@ def main():
                            # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at B = 8 from the committed `ncu --set full` capture
                            "traffic": (PSM4_NCU_TRAFFIC_B8 if (B == 8 and tc) else None),
                            "traffic_source": "ncu --set full, one launch, profiles/r01_ncu_psm_cosine_tc.txt"}
+        # the other cost-volume kernels, timed in situ the same way (SURVEY.md 8(d) algorithmic bytes per pair x batch)
+        alg = {"psm8": 4 * (H // 8) * (W // 8) * (2 * 128 + 24) * B, "concat_volume": (2 * 8 * (H // 16) * (W // 16) * 4 + 16 * 12 * (H // 16) * (W // 16) * 4) * B}
+        out["cost_volume_in_situ"] = {k: {"avg_launch_ms": statistics.mean(v), "algorithmic_bytes": alg[k], "GB_per_s": alg[k] / 1e9 / (statistics.mean(v) / 1e3),
+                                          "frac_of_hbm_peak": alg[k] / 1e9 / (statistics.mean(v) / 1e3) / peak} for k, v in situ.items() if k in alg and v}
     if not args.no_cpu_baseline and world == 1:          # the CPU arm is timed on rank 0 at N = 1 only (the driver runs --impl reference for every N)
         out["cpu_baseline"] = cpu_baseline_subprocess(args.config, B)
     print(json.dumps(out))

@@ -86,6 +86,25 @@ class Anchor3DDetector(nn.Module):
         if self.stage_hook is not None:
             self.stage_hook(name, value)
 
+    def _timed(self, name: str):
+        """Context manager: CUDA events around a kernel IN SITU when `profile_events` is a list (bench.py sets it for the timed region; the
+        events are recorded on the current stream, nothing synchronises); a no-op otherwise."""
+        det = self
+
+        class _T:
+            def __enter__(self_t):
+                if det.profile_events is not None:
+                    self_t.e0 = torch.cuda.Event(enable_timing=True)
+                    self_t.e0.record()
+
+            def __exit__(self_t, *a):
+                if det.profile_events is not None:
+                    e1 = torch.cuda.Event(enable_timing=True)
+                    e1.record()
+                    det.profile_events.append((name, self_t.e0, e1))
+                return False
+        return _T()
+
     def _anchor_table(self, H, W, dev) -> AnchorTable:
         key = (H, W, str(dev))
         if key not in self._anchor_tables:

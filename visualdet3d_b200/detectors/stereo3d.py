@@ -257,16 +257,12 @@ class Stereo3D(Anchor3DDetector):
         def cost_volume_early(f: E.Act, lo_stale: bool) -> bool:
             """PSMCosine of a scale, launched the moment the backbone has produced its features (they are still in L2)."""
             if f.H == h4:
-                if self.profile_events is not None:          # bench.py: CUDA events around the dominant cost-volume kernel
-                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    e0.record()
-                refreshed = E.psm_cosine_stereo(f, B, D4, G4.slice(0, D4), planes_fresh=not lo_stale)
-                if self.profile_events is not None:
-                    e1.record()
-                    self.profile_events.append((e0, e1))
+                with self._timed("psm4"):                    # bench.py: CUDA events around the dominant cost-volume kernel, in situ
+                    refreshed = E.psm_cosine_stereo(f, B, D4, G4.slice(0, D4), planes_fresh=not lo_stale)
                 return lo_stale and not refreshed
             if f.H == h8:
-                refreshed = E.psm_cosine_stereo(f, B, D8, G8.slice(3 * D4, D8), planes_fresh=not lo_stale)
+                with self._timed("psm8"):
+                    refreshed = E.psm_cosine_stereo(f, B, D8, G8.slice(3 * D4, D8), planes_fresh=not lo_stale)
                 return lo_stale and not refreshed
             return lo_stale
 
@@ -305,9 +301,10 @@ class Stereo3D(Anchor3DDetector):
         lr = pl["cv2_down"](f16, ar.act("cv2.lr", (2 * B, h16, w16, Fv), dev))
         mid = ar.get("cv2.mid", (B, D16, h16, w16, Fv), dev)
         vol16 = G16.slice(3 * c8, Fv * D16)
-        call("vd3d_concat_volume_conv3d", lr.batch(0, B).ptr, lr.batch(B, 2 * B).ptr, B, h16, w16, Fv, D16,
-             pl["cv2_w1"].data_ptr(), pl["cv2_b1"].data_ptr(), pl["cv2_w2"].data_ptr(), pl["cv2_b2"].data_ptr(),
-             mid.data_ptr(), vol16.ptr, vol16.cs, vol16.co, E._stream())
+        with self._timed("concat_volume"):
+            call("vd3d_concat_volume_conv3d", lr.batch(0, B).ptr, lr.batch(B, 2 * B).ptr, B, h16, w16, Fv, D16,
+                 pl["cv2_w1"].data_ptr(), pl["cv2_b1"].data_ptr(), pl["cv2_w2"].data_ptr(), pl["cv2_b2"].data_ptr(),
+                 mid.data_ptr(), vol16.ptr, vol16.cs, vol16.co, E._stream())
         self._hook("vol16", vol16)
         pl["g16"].run(G16)                     # x = G16[0:384]: split_lo covers the SIMT-written parts
         cf = f16.C
