@@ -179,6 +179,43 @@ def test_streamed_pipeline_mono_with_post_opt_geometry_and_frames():
     assert pipe2.h2d_bytes_frames < pipe2.h2d_bytes / 3        # 375 x 1242 x 3 bytes vs 288 x 1280 x 3 floats per frame
 
 
+def test_graphed_step_replays_the_eager_step_bit_for_bit():
+    """graphs.GraphedStep: forward .. NMS + yaw post-optimisation + geometry + record block captured into one CUDA graph; replays over
+    refilled static buffers give exactly the record block of the eager launches, and a parameter change drops the stale graph."""
+    from visualdet3d_b200 import synth, parallel
+    from visualdet3d_b200.detectors import build_synthetic_mono3d
+    from visualdet3d_b200.graphs import GraphedStep
+    det, sd, cfg, _ = build_synthetic_mono3d("Yolo3D", seed=0)
+    det = det.cuda().eval()
+    det.post_optimization = True
+    B, H, W, kmax = 2, 96, 320, 256
+    img = torch.empty(B, 3, H, W, device="cuda")
+    P2 = torch.empty(B, 3, 4, device="cuda")
+    oP = torch.empty(B, 3, 4, device="cuda")
+    rec = torch.empty(B, 1 + kmax * parallel.REC_GEO, device="cuda")
+    step = GraphedStep(det, [img], P2, rec, kmax, geometry=True, original_P=oP)
+    ndet = 0
+    for it in range(5):
+        x, p = synth.synth_mono_inputs(B, H, W, seed=30 + it)
+        img.copy_(x), P2.copy_(p), oP.copy_(p)
+        with torch.no_grad():
+            step()
+            got = rec.clone()
+            dec = det.launch(img, P2)                         # the eager step on the same inputs
+            dec.post_forward(P2, oP)
+            want = parallel.pack_records_device(dec, kmax, geometry=True).clone()
+        torch.cuda.synchronize()
+        assert torch.equal(got, want), it
+        ndet += int(want[:, 0].sum())
+        if it == 2:
+            assert step.graph is not None and step.replays >= 1 and step.launches_per_replay > 10
+            with torch.no_grad():
+                next(det.parameters()).mul_(1.0)              # bumps the parameter version: the plan is rebuilt and the graph dropped
+        if it == 3:
+            assert step.graph is None
+    assert step.graph is not None and ndet > 0
+
+
 def test_device_input_pipeline_matches_host():
     """vd3d_preprocess (batched CUDA form, frames of two different sizes in one batch) vs vd3d_preprocess_host on the same frames."""
     import os

@@ -19,7 +19,10 @@ def num(r, k, scale=1.0):
     i = C[k]
     if i is None or i >= len(r) or r[i] in ("", "n/a"):
         return float("nan")
-    v = float(r[i].replace(",", ""))
+    try:
+        v = float(r[i].replace(",", ""))
+    except ValueError:
+        return float("nan")
     u = units[i]
     if u in ("nsecond", "ns"):
         v /= 1e3

@@ -28,7 +28,9 @@ from . import _lib, parallel
 
 class StreamedInference:
     def __init__(self, detector, batch: int, height: int, width: int, kmax: int = 512, world: int = 1, depth: int = 2,
-                 geometry: bool = False, frame_hw: Optional[Sequence[int]] = None, crop_top: int = 0, group=None):
+                 geometry: bool = False, frame_hw: Optional[Sequence[int]] = None, crop_top: int = 0, group=None, graphs: bool = True):
+        """`graphs`: replay the forward (.. NMS, post-optimisation, geometry, record block) of every staging slot as ONE CUDA graph from the
+        slot's second batch on (`graphs.GraphedStep`; the launches and results are those of the eager step)."""
         n_img = getattr(detector, "N_IMAGES", None)
         if n_img not in (1, 2) or not hasattr(detector, "launch"):
             raise TypeError(f"StreamedInference needs a B200 detector with `launch` and N_IMAGES (got {type(detector).__name__})")
@@ -53,6 +55,8 @@ class StreamedInference:
         self.h2d_bytes = 4 * (n_img * batch * 3 * height * width + batch * 12)
         self.d2h_bytes = 4 * world * batch * self.rec_width
         self.last_geometry: Optional[list] = None
+        self.graphs = bool(graphs)
+        self._steps = {}                           # (slot, input form, original_P given) -> graphs.GraphedStep
         # uint8 frame staging (submit_frames)
         self.frame_hw, self.crop_top = (tuple(int(v) for v in frame_hw) if frame_hw is not None else None), int(crop_top)
         if self.frame_hw is not None:
@@ -151,12 +155,16 @@ class StreamedInference:
 
     def _run(self, i: int, k: int, images, P2, original_P) -> int:
         cur = torch.cuda.current_stream(self.dev)
+        from .graphs import GraphedStep
+        key = (k, original_P is not None)
+        if key not in self._steps:
+            self._steps[key] = GraphedStep(self.det, images, P2, self.dev_rec[k], self.kmax, geometry=self.geometry, original_P=original_P,
+                                           enabled=self.graphs)
         with torch.no_grad():
-            dec = self.det.launch(*images, P2)      # backbone .. NMS (+ the yaw post-optimisation when the detector's test_cfg asks for it)
-            if self.geometry:
-                dec.post_forward(P2, original_P)
+            # backbone .. NMS (+ the yaw post-optimisation when the detector's test_cfg asks for it) [+ geometry] + the record block
+            self._steps[key]()
+        rec = self.dev_rec[k]
         self.ev_free[k].record(cur)
-        rec = parallel.pack_records_device(dec, self.kmax, geometry=self.geometry, out=self.dev_rec[k])
         if self.world > 1:
             # the single collective of the path, on a side stream: the next forward does not wait for the slowest rank's records
             self.ev_packed[k].record(cur)
