@@ -1,6 +1,8 @@
-python -m pytest tests/test_zz_next_rows_gpu.py tests/test_stereo3d_gpu.py tests/test_mono3d_gpu.py -m gpu -q -x --tb=short -p no:cacheprovider -k "graph or pipeline or streamed" > gpurun_out/r2_tests11.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/r2_tests11.log
-python tools/exp_chunk.py > gpurun_out/r2_exp_chunk.log 2>&1; cat gpurun_out/r2_exp_chunk.log | cut -c1-400
-for c in gac monoflex yolo3d; do python bench.py --config $c --steps 20 --warmup 4 --no-cpu-baseline > gpurun_out/r2_bench11_$c.json 2> gpurun_out/r2_bench11_$c.err; python -c "
-import json;d=json.load(open('gpurun_out/r2_bench11_$c.json'));print('$c',d['value'],d['e2e']['value'],d['gpu_launches'])"; tail -2 gpurun_out/r2_bench11_$c.err; done
-python bench.py --steps 10 --warmup 4 --no-cpu-baseline > gpurun_out/r2_bench11.json 2> gpurun_out/r2_bench11.err;  python -c "
-import json;d=json.load(open('gpurun_out/r2_bench11.json'));print('stereo',d['value'],d['e2e']['value'],d['gpu_launches'])"; tail -2 gpurun_out/r2_bench11.err
+for v in default 512 300 0; do
+  if [ $v = default ]; then unset VD3D_TC_PHALO_MAXC; else export VD3D_TC_PHALO_MAXC=$v; fi
+  python bench.py --steps 20 --warmup 4 --no-cpu-baseline > gpurun_out/r2_bench12_$v.json 2> gpurun_out/r2_bench12_$v.err; python -c "
+import json;d=json.load(open('gpurun_out/r2_bench12_$v.json'));print('PHALO_MAXC=$v',d['value'],d['e2e']['value'],d['clocks']['sm_mhz'])"; tail -2 gpurun_out/r2_bench12_$v.err
+done
+unset VD3D_TC_PHALO_MAXC
+python bench.py --steps 20 --warmup 4 --no-cpu-baseline > gpurun_out/r2_bench12_again.json 2>/dev/null; python -c "
+import json;d=json.load(open('gpurun_out/r2_bench12_again.json'));print('default again',d['value'],d['e2e']['value'],d['clocks']['sm_mhz'])"

@@ -1290,7 +1290,10 @@ static int conv2d_tc_launch(int f16, const void* in, const void* in_lo, int B, i
         const char* eh = getenv("VD3D_TC_PHALO");
         const int phalo = eh ? atoi(eh) : 2;
         const bool halo_fits = 227 * 1024 - 1024 - 512 - 2 * (size_t)TCPH_ITEM >= 2 * (2 * (size_t)(BN / CG) * 128);
-        if ((phalo == 1 || (phalo == 2 && CG == 2)) && halo_fits && s1_3x3) {
+        // VD3D_TC_PHALO_MAXC: widest input (channels) that still takes the halo kernel (experiments; default: no limit)
+        const char* ehc = getenv("VD3D_TC_PHALO_MAXC");
+        const bool halo_width_ok = !ehc || Cin <= atoi(ehc);
+        if ((phalo == 1 || (phalo == 2 && CG == 2)) && halo_fits && s1_3x3 && halo_width_ok) {
             const char* exm = getenv("VD3D_TC_XMAJOR");
             if (!(exm && atoi(exm) == 0) && make_map_act_hw(&mA, in, B, H, W, Cin, in_cs, in_co, 10, 18) == VD3D_OK &&
                 make_map_act_hw(&mAlo, in_lo, B, H, W, Cin, in_cs, in_co, 10, 18) == VD3D_OK) {
