@@ -444,13 +444,16 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record()
+        e_fwd = torch.cuda.Event(enable_timing=True)
         for i in range(args.steps):
             step_device(i)
+        e_fwd.record()                            # this rank's own forwards are done (per_rank.forward_ms_per_step: shows a slow GPU)
         drain()                                   # the last all-gathers are inside the timed region
         e1.record()
         barrier()
         launches = _lib.launch_count() + graph_launches() - g0          # kernels launched directly + kernels inside the replayed graphs
         ms_dev = e0.elapsed_time(e1)
+        ms_fwd = e0.elapsed_time(e_fwd)
         situ = {}
         if stereo:
             for nm, a, b in det.profile_events:
@@ -494,7 +497,7 @@ def main():
     t = torch.tensor([ms_dev, ms_e2e, ms_e2e_f32], device=dev, dtype=torch.float64)
     per_rank = None
     if world > 1:
-        mine = {"rank": rank, "ms_per_step": ms_dev / args.steps, "e2e_ms_per_step": ms_e2e / args.steps, "sm_mhz": clocks.get("sm_mhz"),
+        mine = {"rank": rank, "ms_per_step": ms_dev / args.steps, "forward_ms_per_step": ms_fwd / args.steps, "e2e_ms_per_step": ms_e2e / args.steps, "sm_mhz": clocks.get("sm_mhz"),
                 "sm_min_mhz": clocks.get("sm_min_mhz"), "power_w": clocks.get("power_w"), "reasons": clocks.get("reasons"), "numa_cores": numa_cores}
         per_rank = [None] * world
         dist.all_gather_object(per_rank, mine)

@@ -110,6 +110,17 @@ int vd3d_conv2d_tc16_stem(const void* in_hi, const void* in_lo, int B, int H, in
 int vd3d_conv2d_tc16_stem_pool(const void* in_hi, const void* in_lo, int B, int H, int W, int Wp, int KH, int KW, int stride, int pad, int win,
                                const void* w_hi, const void* w_lo, float out_scale, const float* bias,
                                float* pool_out, int Cout, int pool_cs, int pool_co, void* stream);
+/* The ResNet stem as one persistent kernel (csrc/stem_pool.cu): conv 7x7 / stride 2 / pad 3 (<= 4 -> 64 channels) + folded BN + ReLU +
+ * MaxPool2d(3, 2, 1) (R/networks/backbones/resnet.py:120-122,186-189).  Replaces vd3d_conv2d_tc16_stem_pool: no window re-reads (the UMMA
+ * descriptor walks the overlapping 8-pixel windows inside one staged image row), no atomics, pooled tensor written as fp32 (`out`, may be
+ * NULL) and / or fp16 (hi, lo) planes (may be NULL) NHWC [B][Hq][Wq][out_cs], channels [out_co, out_co + 64).
+ * in_hi / in_lo: row planes [B][H][Wp][4] made by vd3d_image_to_h16_rows with xoff = vd3d_stem_pool_xoff() and Wp = vd3d_stem_pool_row_pitch(W)
+ * (the buffer must be zero outside the image columns); w_hi / w_lo: the [64][7 * 32] matrices of the 32-element-window stem.
+ * Results are bit-identical to vd3d_conv2d_tc16_stem + vd3d_maxpool3x3s2_nhwc. */
+int vd3d_stem_pool_row_pitch(int W);
+int vd3d_stem_pool_xoff(void);
+int vd3d_stem_pool_fused(const void* in_hi, const void* in_lo, int B, int H, int W, int Wp, const void* w_hi, const void* w_lo, float out_scale,
+                         const float* bias, float* out, void* out_hi16, void* out_lo16, int out_cs, int out_co, void* stream);
 /* Diagnostics: when set, CTA 0 of every persistent tensor-core conv writes clock64 stamps per k-block into a [5][n] int64 device
  * buffer (0 stage free / 1 loads issued / 2 MMA thread waits / 3 stage landed / 4 MMAs issued); NULL disables (tools/trace_conv.py). */
 void vd3d_tc_set_trace(void* dev_i64, int n);

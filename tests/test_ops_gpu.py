@@ -503,6 +503,42 @@ def test_stem_with_fused_maxpool_is_bit_identical(shape):
     assert float(want.t.min()) >= 0.0 and float((want.t == 0).float().mean()) < 0.9
 
 
+@pytest.mark.parametrize("shape", [(2, 3, 64, 96), (3, 3, 70, 154), (1, 3, 34, 30), (2, 3, 96, 320), (16, 3, 96, 160), (2, 3, 384, 1280), (1, 3, 75, 515), (5, 3, 21, 1010)])
+@pytest.mark.parametrize("f32_out", [True, False])
+def test_stem_row_strip_kernel_is_bit_identical(shape, f32_out):
+    """csrc/stem_pool.cu (conv1 + BN + ReLU + MaxPool2d(3, 2, 1) as one row-strip kernel: overlapping windows through a no-swizzle UMMA
+    descriptor, max-pool in registers, pooled tensor as fp16 planes [+ fp32]) against the stem kernel followed by the max-pool kernel: bit for
+    bit, for one and several strips / row segments, odd conv and pooled sizes, image rows above / below the image, a channel slice, repeated calls."""
+    E = _E()
+    B, C, H, W = shape
+    g = torch.Generator().manual_seed(sum(shape))
+    x = (torch.randn(B, C, H, W, generator=g) * 2.0).cuda()
+    w = torch.randn(64, C, 7, 7, generator=g) / np.sqrt(C * 49)
+    bn = dict(weight=torch.rand(64, generator=g) + 0.5, bias=torch.randn(64, generator=g) * 0.3,
+              running_mean=torch.randn(64, generator=g) * 0.1, running_var=torch.rand(64, generator=g) + 0.5)
+    layer = E.StemLayer(w, bn, stride=2, pad=3, relu=True, device="cuda")
+    assert layer.row_kernel_ok()
+    Hs, Ws = layer.out_hw(H, W)
+    Hp, Wp = (Hs - 1) // 2 + 1, (Ws - 1) // 2 + 1
+    arena = E.Arena("h16")
+    full = layer(x, E.Act(torch.empty(B, Hs, Ws, 64, device="cuda")), arena, "a")
+    want = E.maxpool3x3s2(full, E.Act(torch.empty(B, Hp, Wp, 64, device="cuda")))
+    wh = want.t.half()
+    wl = (want.t - wh.float()).half()
+    got = E.Act(torch.full((B, Hp, Wp, 64 + 16), 7.0, device="cuda"), 8, 64, torch.full((2, B, Hp, Wp, 64 + 16), 3.0, device="cuda", dtype=torch.float16))
+    for _ in range(2):
+        r = layer(x, got, arena, "b", pool=True, f32_out=f32_out)
+        torch.cuda.synchronize()
+        assert layer.wrote_planes and r.f32 == f32_out
+        assert torch.equal(got.lo[0][..., 8:72], wh) and torch.equal(got.lo[1][..., 8:72], wl), float((got.lo[0][..., 8:72].float() - wh.float()).abs().max())
+        if f32_out:
+            assert torch.equal(got.t[..., 8:72], want.t), float((got.t[..., 8:72] - want.t).abs().max())
+        else:
+            assert float(got.t.min()) == 7.0 and float(got.t.max()) == 7.0
+    assert float(got.t[..., :8].min()) == 7.0 and float(got.t[..., 72:].min()) == 7.0
+    assert float(got.lo[..., :8].float().min()) == 3.0 and float(got.lo[..., 72:].float().max()) == 3.0
+
+
 @pytest.mark.parametrize("shape", [(2, 64, 6, 80, 24), (1, 128, 5, 37, 12), (3, 64, 3, 50, 32), (1, 64, 2, 20, 4), (2, 192, 4, 64, 8)])
 def test_psm_cosine_tensor_core_vs_oracle(shape):
     """tensor-core PSMCosine (flat 128-pixel tiles x 160-pixel window, band extracted in the epilogue) against the oracle;

@@ -59,6 +59,9 @@ _SIGS = {
     "vd3d_image_to_h16_rows": (I, [P, I, I, I, I, P, P, I, I, P]),
     "vd3d_conv2d_tc16_stem": (I, [P, P, I, I, I, I, I, I, I, I, I, P, P, F, P, P, P, P, I, I, I, I, P]),
     "vd3d_conv2d_tc16_stem_pool": (I, [P, P, I, I, I, I, I, I, I, I, I, P, P, F, P, P, I, I, I, P]),
+    "vd3d_stem_pool_row_pitch": (I, [I]),
+    "vd3d_stem_pool_xoff": (I, []),
+    "vd3d_stem_pool_fused": (I, [P, P, I, I, I, I, P, P, F, P, P, P, P, I, I, P]),
     "vd3d_split_h16_nhwc": (I, [P, P, P, c_longlong, I, I, I, P]),
     "vd3d_psm_cosine_h16": (I, [P, P, P, P, c_longlong, I, I, I, I, I, P, I, I, P]),
     "vd3d_split_lo_nhwc": (I, [P, P, c_longlong, I, I, I, P]),

@@ -74,7 +74,8 @@ class ResNetRunner:
         x = None
         if fuse_pool:
             # stem conv + BN + ReLU + max-pool in ONE kernel (the 64-channel half-resolution stem output never reaches HBM)
-            pooled = self.stem_tc(parts, arena.act(tag + ".pool", (B, Hp, Wp, 64), dev, lo=True), arena, tag, pool=True)
+            # (row-strip kernel: the pooled tensor is written as the fp16 planes layer 1 reads; its fp32 copy only when planes mode is off)
+            pooled = self.stem_tc(parts, arena.act(tag + ".pool", (B, Hp, Wp, 64), dev, lo=True), arena, tag, pool=True, f32_out=not E.planes_mode_ok())
         elif self.stem_tc is not None:
             x = self.stem_tc(parts, arena.act(tag + ".stem", (B, Hs, Ws, 64), dev), arena, tag)
         else:
@@ -90,7 +91,7 @@ class ResNetRunner:
             outs.append(x)
             self.out_lo_stale.append(True)
         x = pooled if fuse_pool else E.maxpool3x3s2(x, arena.act(tag + ".pool", (B, Hp, Wp, 64), dev, lo=True))
-        fresh = True                       # x.lo is stale (x was written by a non-tensor-core kernel)
+        fresh = not (fuse_pool and getattr(self.stem_tc, "wrote_planes", False))     # True: x.lo is stale (x was written by a kernel that does not write the planes)
         plm = E.planes_mode_ok()
         n_ret = len(outs)                  # index of the next returned feature map
 

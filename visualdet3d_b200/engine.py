@@ -317,7 +317,13 @@ class StemLayer:
     def out_hw(self, H, W):
         return (H + 2 * self.pad - self.KH) // self.stride + 1, (W + 2 * self.pad - self.KW) // self.stride + 1
 
-    def __call__(self, img_nchw, out: Act, arena: "Arena", name: str, pool: bool = False):
+    def row_kernel_ok(self) -> bool:
+        """the row-strip stem + pool kernel (csrc/stem_pool.cu) covers this layer: 7x7 / 2 / 3, 64 outputs, ReLU, 32-element windows (VD3D_STEM_ROWS=0: off)"""
+        import os
+        return (self.KH, self.KW, self.stride, self.pad, self.Cout, self.win) == (7, 7, 2, 3, 64, 32) and self.relu and \
+            os.environ.get("VD3D_STEM_ROWS", "1") != "0"
+
+    def __call__(self, img_nchw, out: Act, arena: "Arena", name: str, pool: bool = False, f32_out: bool = True):
         """`img_nchw`: one [B, C, H, W] tensor, or a list of such tensors that together form the batch (the stereo plan passes
         [left, right]: each part is converted straight into its batch range of the row planes, no concatenated copy exists)."""
         parts = list(img_nchw) if isinstance(img_nchw, (list, tuple)) else [img_nchw]
@@ -330,6 +336,27 @@ class StemLayer:
         assert C == self.Cin and out.C == self.Cout and out.B == B
         import os
         pool = pool and os.environ.get("VD3D_STEM_POOL", "1") != "0"
+        if pool and self.row_kernel_ok() and out.h16:
+            # conv + BN + ReLU + MaxPool2d(3, 2, 1) as the row-strip kernel (csrc/stem_pool.cu): `out` is the POOLED tensor, written as fp16 planes
+            # (the layer-1 convs and their plane residual read nothing else) and as fp32 only when `f32_out` asks for it
+            Hs, Ws = self.out_hw(H, W)
+            assert (out.H, out.W) == ((Hs - 1) // 2 + 1, (Ws - 1) // 2 + 1) and out.h16, "fused stem: pooled shape, fp16 planes"
+            lib = _lib.load()
+            Wp, xoff = int(lib.vd3d_stem_pool_row_pitch(W)), int(lib.vd3d_stem_pool_xoff())
+            planes = arena.get(name + ".rows5#h16", (2, B, H, Wp, 4), parts[0].device, dtype=torch.float16, zero=True)   # borders stay zero
+            b0 = 0
+            for p in parts:
+                nb = int(p.shape[0])
+                call("vd3d_image_to_h16_rows", p.data_ptr(), nb, C, H, W, planes[0, b0:b0 + nb].data_ptr(), planes[1, b0:b0 + nb].data_ptr(),
+                     Wp, xoff, _stream())
+                b0 += nb
+            oh, ol = out.h16_ptrs
+            call("vd3d_stem_pool_fused", planes[0].data_ptr(), planes[1].data_ptr(), B, H, W, Wp, self.w_hi.data_ptr(), self.w_lo.data_ptr(), self.out_scale,
+                 self.b.data_ptr(), out.ptr if f32_out else None, oh, ol, out.cs, out.co, _stream())
+            out.f32 = bool(f32_out)
+            self.wrote_planes = True
+            return out
+        self.wrote_planes = False
         Wp = int(_lib.load().vd3d_stem_row_pitch(W, self.KW, self.stride, self.pad))
         planes = arena.get(name + ".rows#h16", (2, B, H, Wp, 4), parts[0].device, dtype=torch.float16, zero=True)   # borders stay zero
         b0 = 0
