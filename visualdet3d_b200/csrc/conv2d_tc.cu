@@ -544,6 +544,8 @@ conv2d_tcp_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     // REDUX puts the (identical) value in a uniform register: the MMA issue loop then needs no per-instruction lane-broadcast of the
     // accumulator address (measured: ~90 -> ~25 clk of issue time per tcgen05.mma)
     const uint32_t tmem_base = __reduce_or_sync(0xffffffffu, *tmem_slot);
+    pdl_launch_dependents();
+    pdl_wait();                            // (PDL launches only) the producer of the activations / residual has completed
 
     if (warp == 0) {
         {
@@ -771,6 +773,8 @@ conv2d_tcph_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     if (CG == 2) cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = __reduce_or_sync(0xffffffffu, *tmem_slot);      // uniform register (see conv2d_tcp_kernel)
+    pdl_launch_dependents();
+    pdl_wait();
 
     if (warp == 0) {
         if (elect_one()) {
@@ -1106,10 +1110,12 @@ static int tcp_launch(TcParams& p, const CUtensorMap& mA, const CUtensorMap& mAl
     cfg.blockDim = dim3(TCP_THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = (cudaStream_t)stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = (unsigned)CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
     const int ng = (BN + 31) / 32;
     cudaError_t le;
     const bool pl = (p.out == nullptr && p.pool_out == nullptr) || p.res_h16_hi != nullptr;      // (the fused-pool epilogue lives in the <2, 1, 0> instance)
@@ -1132,10 +1138,17 @@ static int tcph_launch(TcParams& p, const CUtensorMap& mA, const CUtensorMap& mA
     { const char* e = getenv("VD3D_TC_DEBUG"); p.dbg = e ? atoi(e) : 0; }
     tcp_set_accumulators(p);
     const size_t b_stage = 2 * (size_t)(BN / CG) * 128;
-    p.h_sa = 2;
-    const size_t budget = 227 * 1024 - 1024 - 512 - (size_t)p.h_sa * TCPH_ITEM;
     const int KBtot = 9 * (p.cin_pad / 64);
+    p.h_sa = 2;
+    {
+        // input-halo stages: VD3D_TC_HSA=3 adds a third one when the resident weights leave room for it (64 -> 64 layers: 72 KB of weights + 3 x 50 KB)
+        const char* e = getenv("VD3D_TC_HSA");
+        const int want = e ? atoi(e) : 2;      // measured (same box, alternating): 3 stages 746 / 746 pairs/s against 748 / 758 with 2, layer 1 183 us against 169: no gain, kept as a switch
+        if (want >= 3 && p.n_tiles == 1 && (size_t)KBtot * b_stage + 3 * (size_t)TCPH_ITEM + (2 * 3 + 2 * KBtot + 10) * sizeof(uint64_t) + 1024 <= (size_t)227 * 1024) p.h_sa = 3;
+    }
+    const size_t budget = 227 * 1024 - 1024 - 512 - (size_t)p.h_sa * TCPH_ITEM;
     p.w_res = (p.n_tiles == 1 && (size_t)KBtot * b_stage <= budget) ? 1 : 0;
+    if (!p.w_res && p.h_sa == 3) p.h_sa = 2;
     p.h_sb = p.w_res ? KBtot : (int)(budget / b_stage);
     if (!p.w_res && p.h_sb > 8) p.h_sb = 8;
     VD3D_REQUIRE(p.h_sb >= 2, "conv2d_tc: halo tile too large for shared memory");
@@ -1158,10 +1171,12 @@ static int tcph_launch(TcParams& p, const CUtensorMap& mA, const CUtensorMap& mA
     cfg.blockDim = dim3(TCPH_THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = (cudaStream_t)stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = (unsigned)CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
     const int ng = (BN + 31) / 32;
     cudaError_t le;
     const bool pl = p.out == nullptr || p.res_h16_hi != nullptr;

@@ -12,9 +12,9 @@
 //   * a CTA walks DOWN a strip of 128 conv columns: consecutive conv rows share 5 of their 7 image rows, so the producer streams two new
 //     image rows per conv row (1-D bulk copies into a ring of 8 row pairs; out-of-image rows are zero-filled by the producer warp).
 //     The weights (7 filter rows x [64][32] fp16 hi | lo, 56 KB) are loaded once per CTA.
-//   * the max-pool happens in registers: thread (column x) keeps the running column-wise maximum of the horizontal 3-maxima (neighbour
-//     columns by warp shuffle, the one column across a warp boundary through 2 KB of shared memory) and writes a pooled row after every
-//     second conv row.  Strips overlap by 2 conv columns (63 pooled columns per 128-column strip) and row segments by one conv row, so every
+//   * the max-pool happens in registers: thread (column x) keeps the running maximum of its column over the conv rows of the open pooled row;
+//     after every second conv row the horizontal 3-max of these column maxima (neighbour columns by warp shuffle, the one column across a warp
+//     boundary through 2 KB of shared memory) is the pooled row, and it is written.  Strips overlap by 2 conv columns (63 pooled columns per 128-column strip) and row segments by one conv row, so every
 //     3 x 3 window is complete inside one CTA: no atomics, no border pre-zeroing, deterministic.
 //   * the pooled tensor is written as the fp16 (hi, lo) planes layer 1 reads (and as fp32 only when asked): the separate max-pool kernel,
 //     split kernel and the 126 MB stem output of the unfused path do not exist.
@@ -103,6 +103,8 @@ stem_pool_kernel(const __grid_constant__ CUtensorMap mapWhi, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = __reduce_or_sync(0xffffffffu, *tmem_slot);
+    pdl_launch_dependents();
+    pdl_wait();
 
     if (warp == 0) {
         // ================= producer: the weights once, then two image rows per conv row =================
@@ -215,10 +217,12 @@ stem_pool_kernel(const __grid_constant__ CUtensorMap mapWhi, const __grid_consta
             const int jl = (x - 1) >> 1;                               // pooled column inside the strip (x odd)
             const int j = SP_CENTERS * strip + jl;
             const bool centre = (x & 1) && jl < SP_CENTERS && j < q.Wq;
+            // run[k] = column-wise maximum of the conv rows of the pooled row that is open (vertical max first: the horizontal 3-max, its
+            // shuffles and the cross-warp exchange are then needed only once per pooled row, on the maximum of the three conv rows)
             float run[32];
 #pragma unroll
             for (int k = 0; k < 32; ++k) run[k] = 0.f;
-            for (int t = 0; t < T; ++t, ++tile) {
+            for (int t = 0; t < T; ++t) {
                 float acc[32];
 #pragma unroll
                 for (int k = 0; k < 32; ++k) acc[k] = 0.f;
@@ -227,14 +231,10 @@ stem_pool_kernel(const __grid_constant__ CUtensorMap mapWhi, const __grid_consta
                     const int buf = cc & 3;
                     mbar_wait(&tmem_full[buf], (cc >> 2) & 1);
                     tc_fence_after();
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(buf * 64 + cb), v);
 #pragma unroll
-                    for (int g = 0; g < 2; ++g) {
-                        uint32_t v[16];
-                        tmem_ld16(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(buf * 64 + cb + g * 16), v);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) acc[g * 16 + i] += __uint_as_float(v[i]);
-                    }
+                    for (int i = 0; i < 32; ++i) acc[i] += __uint_as_float(v[i]);
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(te + (uint32_t)buf * 8u) : "memory");
@@ -249,24 +249,6 @@ stem_pool_kernel(const __grid_constant__ CUtensorMap mapWhi, const __grid_consta
                     acc[k + 2] = ok ? fmaxf(acc[k + 2] * osc + bb.z, 0.f) : 0.f;
                     acc[k + 3] = ok ? fmaxf(acc[k + 3] * osc + bb.w, 0.f) : 0.f;
                 }
-                // horizontal 3-max: left / right neighbours by shuffle; column 32 (q + 1) .. for lane 31 through shared memory
-                float* ed = edge + (((tile & 1) * 2 + half) * 4) * 32;
-                if (lane == 0) {
-#pragma unroll
-                    for (int k = 0; k < 32; k += 4) *reinterpret_cast<float4*>(ed + qd * 32 + k) = make_float4(acc[k], acc[k + 1], acc[k + 2], acc[k + 3]);
-                }
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-                const bool last_lane = lane == 31;
-                const float* en = ed + ((qd + 1) & 3) * 32;
-                const bool wrap = qd == 3;                                 // column 128 does not exist (and column 127 is no centre)
-#pragma unroll
-                for (int k = 0; k < 32; ++k) {
-                    const float lf = __shfl_up_sync(0xffffffffu, acc[k], 1);
-                    float rt = __shfl_down_sync(0xffffffffu, acc[k], 1);
-                    if (last_lane) rt = wrap ? 0.f : en[k];
-                    const float h = fmaxf(fmaxf(lf, acc[k]), rt);          // (lane 0's `lf` is its own value: lane 0 is never a centre)
-                    acc[k] = h;
-                }
                 if (t == 0) {
 #pragma unroll
                     for (int k = 0; k < 32; ++k) run[k] = acc[k];
@@ -274,16 +256,36 @@ stem_pool_kernel(const __grid_constant__ CUtensorMap mapWhi, const __grid_consta
 #pragma unroll
                     for (int k = 0; k < 32; ++k) run[k] = fmaxf(run[k], acc[k]);
                 } else {
-                    // conv row 2i + 1 closes pooled row i = i0 + t / 2 - 1
+                    // conv row 2i + 1 closes pooled row i = i0 + t / 2 - 1: column maxima of its three conv rows, then the horizontal 3-max
                     const int i = i0 + (t >> 1) - 1;
-                    if (centre && !(q.dbg & 16)) {
-                        const long long pix = ((long long)b * q.Hq + i) * q.Wq + j;
-                        const long long o = pix * q.out_cs + q.out_co + cb;
 #pragma unroll
-                        for (int k = 0; k < 32; k += 8) {
-                            float a[8];
+                    for (int k = 0; k < 32; ++k) run[k] = fmaxf(run[k], acc[k]);
+                    float* ed = edge + (((tile & 1) * 2 + half) * 4) * 32;
+                    ++tile;
+                    if (lane == 0) {                                       // column 32 (qd + 1) of the strip is lane 31's right neighbour
 #pragma unroll
-                            for (int m = 0; m < 8; ++m) { a[m] = fmaxf(run[k + m], acc[k + m]); amax = fmaxf(amax, a[m]); }
+                        for (int k = 0; k < 32; k += 4) *reinterpret_cast<float4*>(ed + qd * 32 + k) = make_float4(run[k], run[k + 1], run[k + 2], run[k + 3]);
+                    }
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    const bool last_lane = lane == 31;
+                    const float* en = ed + ((qd + 1) & 3) * 32;
+                    const bool wrap = qd == 3;                             // column 128 does not exist (and column 127 is no centre)
+                    const long long pix = ((long long)b * q.Hq + i) * q.Wq + j;
+                    const long long o = pix * q.out_cs + q.out_co + cb;
+                    const bool wr = centre && !(q.dbg & 16);
+#pragma unroll
+                    for (int k = 0; k < 32; k += 8) {
+                        float a[8];
+#pragma unroll
+                        for (int m = 0; m < 8; ++m) {
+                            const float lf = __shfl_up_sync(0xffffffffu, run[k + m], 1);      // (lane 0 gets its own value back: lane 0 is never a centre)
+                            float rt = __shfl_down_sync(0xffffffffu, run[k + m], 1);
+                            if (last_lane) rt = wrap ? 0.f : en[k + m];
+                            a[m] = fmaxf(fmaxf(lf, run[k + m]), rt);
+                        }
+                        if (wr) {
+#pragma unroll
+                            for (int m = 0; m < 8; ++m) amax = fmaxf(amax, a[m]);
                             if (q.out) {
                                 *reinterpret_cast<float4*>(q.out + o + k) = make_float4(a[0], a[1], a[2], a[3]);
                                 *reinterpret_cast<float4*>(q.out + o + k + 4) = make_float4(a[4], a[5], a[6], a[7]);
@@ -298,7 +300,7 @@ stem_pool_kernel(const __grid_constant__ CUtensorMap mapWhi, const __grid_consta
                         }
                     }
 #pragma unroll
-                    for (int k = 0; k < 32; ++k) run[k] = acc[k];
+                    for (int k = 0; k < 32; ++k) run[k] = acc[k];          // conv row 2i + 1 is also the first row of pooled row i + 1
                 }
             }
         }
@@ -376,7 +378,15 @@ extern "C" int vd3d_stem_pool_fused(const void* in_hi, const void* in_lo, int B,
     }
     const int units = B * q.nstrips * q.nseg;
     const int grid = units < kNumSMs ? units : kNumSMs;
-    stem_pool_kernel<<<grid, SP_THREADS, smem, (cudaStream_t)stream>>>(mWhi, mWlo, q);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(SP_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    const cudaError_t le = cudaLaunchKernelEx(&cfg, stem_pool_kernel, mWhi, mWlo, q);
+    if (le != cudaSuccess) { set_error("stem_pool_fused: launch failed: %s", cudaGetErrorString(le)); return VD3D_ECUDA; }
     VD3D_CHECK_LAUNCH("stem_pool_fused");
     return VD3D_OK;
 }

@@ -86,6 +86,11 @@ __device__ __forceinline__ bool elect_one() {
         "}\n" : "=r"(pred));
     return pred != 0;
 }
+// Programmatic dependent launch (VD3D_PDL=1): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may become resident while its
+// predecessor is still draining; everything it does before pdl_wait() (barrier init, TMEM allocation) overlaps the predecessor's tail, and
+// pdl_wait() returns when the predecessor has completed and its writes are visible.  Both are no-ops in an ordinary launch.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 

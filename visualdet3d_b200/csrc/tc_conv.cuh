@@ -278,6 +278,13 @@ __device__ __forceinline__ void tcp_epilogue(const TcParams& p, uint32_t tmem_ba
     note_fp16_range(amax, p.range_flag);
 }
 
+// VD3D_PDL=1: the persistent tensor-core kernels are launched as programmatic dependents of their predecessor in the stream (pdl_wait() in the kernels)
+inline bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("VD3D_PDL"); v = (e && atoi(e) != 0) ? 1 : 0; }
+    return v == 1;
+}
+
 inline int make_map_wgt(CUtensorMap* m, const void* base, int Cout, int K, int BN, int esize = 4, int rowb = 128) {
     EncodeTiledFn enc = get_encode();
     if (!enc) { set_error("conv2d_tc: cuTensorMapEncodeTiled unavailable"); return VD3D_ECUDA; }
