@@ -121,6 +121,18 @@ int vd3d_stem_pool_row_pitch(int W);
 int vd3d_stem_pool_xoff(void);
 int vd3d_stem_pool_fused(const void* in_hi, const void* in_lo, int B, int H, int W, int Wp, const void* w_hi, const void* w_lo, float out_scale,
                          const float* bias, float* out, void* out_hi16, void* out_lo16, int out_cs, int out_co, void* stream);
+/* Few-channel convolutions on the tensor cores as row-strip kernels (csrc/row_conv.cu): the DLA-34 front end (base_layer 7x7 3 -> 16, level0 3x3
+ * 16 -> 16, level1 3x3 / 2 16 -> 32; R/networks/backbones/dla.py:246-262), i.e. the layers with Cin < 32 that vd3d_conv2d_tc16 does not take.
+ * Input: fp16 (hi, lo) ROW PLANES [B][H][Wp][pc] (pc = 4, 8 or 16 channels per pixel, image column x at pixel xoff + x, xoff >= pad, zero outside the
+ * image columns; Wp >= vd3d_row_conv_pitch(...)); weights [N][KH * KS * 16] fp16 (hi, lo), k = ky * KS * 16 + kx * pc + c, KS = 2 if KW * pc <= 32 else 4,
+ * scaled by a power of two undone by out_scale; N = 16 or 32.  Output: NHWC [B][Ho][out_W][out_cs] channels [out_co, out_co + N) as fp32 (may be NULL)
+ * and / or fp16 (hi, lo) planes (may be NULL), image column x at out_xoff + x (so the output can be the next row conv's input planes).
+ * vd3d_image_to_h16_rows_c: NCHW float image -> row planes with cpad = 4 or 8 channels per pixel. */
+int vd3d_row_conv_pitch(int W, int pc, int KW, int S, int P, int xoff);
+int vd3d_image_to_h16_rows_c(const float* img, int B, int C, int H, int W, void* hi16, void* lo16, int Wp, int xoff, int cpad, void* stream);
+int vd3d_row_conv(const void* in_hi, const void* in_lo, int B, int H, int W, int Wp, int xoff, int pc, int KH, int KW, int S, int P,
+                  const void* w_hi, const void* w_lo, float out_scale, const float* bias, int relu, int N,
+                  float* out, void* out_hi16, void* out_lo16, int out_W, int out_xoff, int out_cs, int out_co, void* stream);
 /* Diagnostics: when set, CTA 0 of every persistent tensor-core conv writes clock64 stamps per k-block into a [5][n] int64 device
  * buffer (0 stage free / 1 loads issued / 2 MMA thread waits / 3 stage landed / 4 MMAs issued); NULL disables (tools/trace_conv.py). */
 void vd3d_tc_set_trace(void* dev_i64, int n);

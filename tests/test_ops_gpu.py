@@ -539,6 +539,68 @@ def test_stem_row_strip_kernel_is_bit_identical(shape, f32_out):
     assert float(got.lo[..., :8].float().min()) == 3.0 and float(got.lo[..., 72:].float().max()) == 3.0
 
 
+ROW_CONV_CASES = [
+    # B, Cin, pc, H, W, Cout, k, stride, pad
+    (2, 3, 8, 40, 150, 16, 7, 1, 3),        # DLA base_layer: 7x7, image as 8-channel planes
+    (1, 3, 8, 96, 320, 16, 7, 1, 3),
+    (2, 16, 16, 33, 141, 16, 3, 1, 1),      # level0: 16-channel planes, every second operand row is an output column
+    (1, 16, 16, 64, 640, 16, 3, 1, 1),
+    (2, 16, 16, 33, 141, 32, 3, 2, 1),      # level1: stride 2, every fourth operand row
+    (3, 16, 16, 96, 320, 32, 3, 2, 1),
+    (1, 3, 8, 384, 1280, 16, 7, 1, 3),      # full size: 10 strips, several row segments
+]
+
+
+@pytest.mark.parametrize("case", ROW_CONV_CASES)
+def test_row_conv_vs_fp64(case):
+    """csrc/row_conv.cu (few-channel convs as row-strip tcgen05 kernels: overlapping windows through a no-swizzle UMMA descriptor on fp16 (hi, lo)
+    row planes) against an fp64 convolution of the same fp32 inputs: < 2e-5 (the bound of the fp16-split engine), fp32 output and planes, output
+    written at a column offset of a wider, zero-bordered buffer (the next row conv's input form), neighbouring channels untouched."""
+    E = _E()
+    B, Cin, pc, H, W, Cout, k, s, p = case
+    g = torch.Generator().manual_seed(sum(case))
+    x = torch.randn(B, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, k, k, generator=g) / np.sqrt(Cin * k * k)
+    bn = dict(weight=torch.rand(Cout, generator=g) + 0.5, bias=torch.randn(Cout, generator=g) * 0.3,
+              running_mean=torch.randn(Cout, generator=g) * 0.1, running_var=torch.rand(Cout, generator=g) + 0.5)
+    layer = E.RowConvLayer(w, bn, stride=s, pad=p, relu=True, pc_in=pc, device="cuda")
+    xoff = p + (2 if pc == 4 else 1)
+    Wp = layer.in_pitch(W, xoff)
+    planes = torch.zeros(2, B, H, Wp, pc, dtype=torch.float16, device="cuda")
+    if Cin <= 4 and pc in (4, 8):
+        xin = E.image_to_row_planes(x.cuda(), planes, xoff)
+    else:
+        xh = x.half()
+        xl = (x - xh.float()).half()
+        planes[0, :, :, xoff:xoff + W, :Cin] = xh.permute(0, 2, 3, 1).cuda()
+        planes[1, :, :, xoff:xoff + W, :Cin] = xl.permute(0, 2, 3, 1).cuda()
+        xin = E.RowPlanes(planes, W, xoff)
+    xq = (planes[0].float() + planes[1].float())[:, :, xoff:xoff + W, :Cin].permute(0, 3, 1, 2).double().cpu()      # what the kernel sees (22 significant bits)
+    assert float((xq - x.double()).abs().max()) < 1e-6
+    wf, bf = E.fold_bn(w, None, bn)
+    ref = F.relu(F.conv2d(xq, wf.double(), bf.double(), stride=s, padding=p)).float()
+    Ho, Wo = layer.out_hw(H, W)
+    oW, oxo, cs, co = Wo + 5, 2, Cout + 16, 8
+    of = torch.full((B, Ho, oW, cs), 7.0, device="cuda")
+    op = torch.full((2, B, Ho, oW, cs), 3.0, device="cuda", dtype=torch.float16)
+    for _ in range(2):
+        layer(xin, op, of, out_xoff=oxo, out_co=co)
+    torch.cuda.synchronize()
+    got = of[:, :, oxo:oxo + Wo, co:co + Cout].permute(0, 3, 1, 2).cpu()
+    err = float((got - ref).abs().max())
+    print(case, "max|err|", err)
+    assert err < 2e-5, err
+    gp = (op[0].float() + op[1].float())[:, :, oxo:oxo + Wo, co:co + Cout].permute(0, 3, 1, 2).cpu()
+    assert float((gp - got).abs().max()) < 2e-6 and torch.equal(op[0][:, :, oxo:oxo + Wo, co:co + Cout], of[:, :, oxo:oxo + Wo, co:co + Cout].half())
+    assert float(of[..., :co].min()) == 7.0 and float(of[..., co + Cout:].min()) == 7.0 and float(of[:, :, :oxo].min()) == 7.0 and float(of[:, :, oxo + Wo:].min()) == 7.0
+    assert float(op[..., :co].float().min()) == 3.0 and float(op[:, :, :, :oxo].float().max()) == 3.0 and float(op[:, :, :, oxo + Wo:].float().min()) == 3.0
+    # planes-only output gives the same planes
+    op2 = torch.full_like(op, 3.0)
+    layer(xin, op2, None, out_xoff=oxo, out_co=co)
+    torch.cuda.synchronize()
+    assert torch.equal(op2, op)
+
+
 @pytest.mark.parametrize("shape", [(2, 64, 6, 80, 24), (1, 128, 5, 37, 12), (3, 64, 3, 50, 32), (1, 64, 2, 20, 4), (2, 192, 4, 64, 8)])
 def test_psm_cosine_tensor_core_vs_oracle(shape):
     """tensor-core PSMCosine (flat 128-pixel tiles x 160-pixel window, band extracted in the epilogue) against the oracle;

@@ -62,6 +62,9 @@ _SIGS = {
     "vd3d_stem_pool_row_pitch": (I, [I]),
     "vd3d_stem_pool_xoff": (I, []),
     "vd3d_stem_pool_fused": (I, [P, P, I, I, I, I, P, P, F, P, P, P, P, I, I, P]),
+    "vd3d_row_conv_pitch": (I, [I, I, I, I, I, I]),
+    "vd3d_image_to_h16_rows_c": (I, [P, I, I, I, I, P, P, I, I, I, P]),
+    "vd3d_row_conv": (I, [P, P, I, I, I, I, I, I, I, I, I, I, P, P, F, P, I, I, P, P, P, I, I, I, I, P]),
     "vd3d_split_h16_nhwc": (I, [P, P, P, c_longlong, I, I, I, P]),
     "vd3d_psm_cosine_h16": (I, [P, P, P, P, c_longlong, I, I, I, I, I, P, I, I, P]),
     "vd3d_split_lo_nhwc": (I, [P, P, c_longlong, I, I, I, P]),

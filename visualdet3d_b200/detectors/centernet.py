@@ -108,7 +108,7 @@ class _CenterNetBase(nn.Module):
         ver = (self._param_version(), str(dev))
         if self._plan is not None and not force and ver == self._plan_version:
             return self._plan
-        pl = dict(dla=DLARunner(self.core.backbone, dev), up=DLAUpRunner(self.core.deconv_layers, dev))
+        pl = dict(dla=DLARunner(self.core.backbone, dev, first_used_level=self.core.deconv_layers.first_level), up=DLAUpRunner(self.core.deconv_layers, dev))
         hl = self.bbox_head.head_layers
         names = list(hl.keys())
         # one stem conv for all heads: weights / biases concatenated along Cout

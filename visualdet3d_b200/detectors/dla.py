@@ -233,16 +233,55 @@ class _TreeRun:
 class DLARunner:
     """DLA.forward (dla.py:317-326): returns the list of level outputs selected by out_indices (plain Acts, lo stale)."""
 
-    def __init__(self, p: DLAP, dev):
+    def __init__(self, p: DLAP, dev, first_used_level: int = 0):
+        """first_used_level: lowest level output the caller reads (DLASegUpsample: first_level); levels below it need not exist as activations"""
         self.p = p
         self.base = E.ConvLayer(p.base_layer[0].weight, None, E.bn_dict(p.base_layer[1]), pad=3, relu=True, device=dev, cin_pad=4)
         self.l0 = E.ConvLayer(p.level0[0].weight, None, E.bn_dict(p.level0[1]), pad=1, relu=True, device=dev)
         self.l1 = E.ConvLayer(p.level1[0].weight, None, E.bn_dict(p.level1[1]), stride=2, pad=1, relu=True, device=dev)
         self.trees = [_TreeRun(getattr(p, f"level{i}"), dev) for i in range(2, 6)]
+        # the three full-resolution layers (Cin < 32: exact-fp32 SIMT kernel in the generic engine, 2.8 ms of a 13 ms MonoFlex step at 384x1280) as
+        # row-strip tensor-core kernels on fp16 row planes (csrc/row_conv.cu); VD3D_ROWCONV=0 restores the SIMT path
+        import os
+        self.rc = None
+        if (E.conv_engine_default() == "tc16" and os.environ.get("VD3D_ROWCONV", "1") != "0" and -1 not in p.out_indices and first_used_level >= 2
+                and tuple(p.base_layer[0].weight.shape) == (16, 3, 7, 7) and tuple(p.level0[0].weight.shape) == (16, 16, 3, 3)
+                and tuple(p.level1[0].weight.shape) == (32, 16, 3, 3)):
+            self.rc = (E.RowConvLayer(p.base_layer[0].weight, E.bn_dict(p.base_layer[1]), stride=1, pad=3, relu=True, pc_in=8, device=dev),
+                       E.RowConvLayer(p.level0[0].weight, E.bn_dict(p.level0[1]), stride=1, pad=1, relu=True, pc_in=16, device=dev),
+                       E.RowConvLayer(p.level1[0].weight, E.bn_dict(p.level1[1]), stride=2, pad=1, relu=True, pc_in=16, device=dev))
+
+    def _front_rows(self, img: torch.Tensor, ar: E.Arena, tag: str) -> E.Act:
+        """base_layer -> level0 -> level1 on row planes: image -> 8-channel planes -> 16-channel planes (written straight into the zero-bordered
+        input form of the next layer) -> the ordinary NHWC activation (fp32 + planes) of level1"""
+        base, l0, l1 = self.rc
+        dev = img.device
+        B, _, H, W = img.shape
+        f16 = torch.float16
+        p0 = E.image_to_row_planes(img, ar.get(tag + ".img#rows", (2, B, H, base.in_pitch(W, 4), 8), dev, dtype=f16, zero=True), 4)
+        r1 = ar.get(tag + ".base#rows", (2, B, H, l0.in_pitch(W, 2), 16), dev, dtype=f16, zero=True)
+        base(p0, r1, None, out_xoff=2)
+        r2 = ar.get(tag + ".l0#rows", (2, B, H, l1.in_pitch(W, 2), 16), dev, dtype=f16, zero=True)
+        l0(E.RowPlanes(r1, W, 2), r2, None, out_xoff=2)
+        H1, W1 = l1.out_hw(H, W)
+        x = ar.act(tag + ".l1", (B, H1, W1, 32), dev, lo=True)
+        assert x.h16
+        l1(E.RowPlanes(r2, W, 2), x.lo, x.t)
+        return x
 
     def run(self, img: torch.Tensor, ar: E.Arena, tag: str = "dla") -> List[E.Act]:
         dev = img.device
         B, _, H, W = img.shape
+        if self.rc is not None and ar.lo_form == "h16":
+            x = self._front_rows(img, ar, tag)
+            # level 0 / 1 outputs exist only as row planes: DLAUp starts at first_level >= 2 (dla_utils.py:106-112) and never reads them; their list
+            # slots (the up-sampling path indexes the list by level) hold None
+            ys = [None for i in (0, 1) if i in self.p.out_indices]
+            for i, tr in enumerate(self.trees):
+                x = tr.run(x, ar, f"{tag}.lv{i + 2}")
+                if i + 2 in self.p.out_indices:
+                    ys.append(x)
+            return ys
         x0 = ar.act(tag + ".in4", (B, H, W, 4), dev, zero=True)
         E.nchw_to_nhwc(img, x0)
         ys = []

@@ -380,6 +380,79 @@ class StemLayer:
         return out
 
 
+class RowPlanes:
+    """fp16 (hi, lo) ROW PLANES of a few-channel NHWC tensor, the input form of `RowConvLayer`: t = [2, B, H, Wp, PC] (zero outside the image
+    columns), image column x at pixel xoff + x of the padded row."""
+
+    def __init__(self, t: torch.Tensor, W: int, xoff: int):
+        assert t.dtype == torch.float16 and t.dim() == 5 and t.shape[0] == 2 and t.is_contiguous()
+        self.t, self.W, self.xoff = t, int(W), int(xoff)
+
+    B = property(lambda s: s.t.shape[1])
+    H = property(lambda s: s.t.shape[2])
+    Wp = property(lambda s: s.t.shape[3])
+    pc = property(lambda s: s.t.shape[4])
+
+
+class RowConvLayer:
+    """Few-channel KHxKW conv + folded BN [+ ReLU] on the tensor cores as a row-strip kernel (csrc/row_conv.cu): the DLA-34 front end
+    (base_layer 7x7 3 -> 16, level0 3x3 16 -> 16, level1 3x3 / 2 16 -> 32, R/networks/backbones/dla.py:246-262), which the generic engine leaves to the
+    exact-fp32 SIMT kernel because Cin < 32.  `pc_in` = channels per pixel of the input planes (8 for the image, else Cin)."""
+
+    def __init__(self, weight, bn=None, stride=1, pad=0, relu=True, pc_in: Optional[int] = None, device="cuda"):
+        w, b = fold_bn(weight, None, bn)
+        Cout, Cin, KH, KW = w.shape
+        pc = int(pc_in or Cin)
+        assert Cout in (16, 32) and pc in (4, 8, 16) and Cin <= pc and KW * pc * 2 <= 128 and KH <= 7 and stride in (1, 2)
+        self.Cin, self.Cout, self.KH, self.KW, self.stride, self.pad, self.relu, self.pc = Cin, Cout, KH, KW, stride, pad, relu, pc
+        self.KS = 2 if KW * pc * 2 <= 64 else 4
+        wk = torch.zeros(Cout, KH, self.KS * 16, dtype=torch.float64)
+        wk[:, :, :KW * pc].view(Cout, KH, KW, pc)[..., :Cin] = w.permute(0, 2, 3, 1)
+        wmax = float(wk.abs().max())
+        k = int(np.floor(np.log2(16384.0 / wmax))) if wmax > 0 else 0
+        k = max(-24, min(24, k))
+        self.out_scale = float(2.0 ** (-k))
+        hi, lo = fp16_split(wk.reshape(Cout, KH * self.KS * 16) * (2.0 ** k))
+        self.w_hi, self.w_lo = hi.to(device), lo.to(device)
+        self.b = b.float().to(device)
+        self.engine = "tc16"
+
+    def out_hw(self, H, W):
+        return (H + 2 * self.pad - self.KH) // self.stride + 1, (W + 2 * self.pad - self.KW) // self.stride + 1
+
+    def in_pitch(self, W: int, xoff: int) -> int:
+        """row pitch (pixels) the INPUT planes of this layer need for W image columns with `xoff` zero pixels in front of every row"""
+        v = int(_lib.load().vd3d_row_conv_pitch(W, self.pc, self.KW, self.stride, self.pad, xoff))
+        if v <= 0:
+            raise _lib.Vd3dError("RowConvLayer: unsupported geometry")
+        return v
+
+    def __call__(self, x: RowPlanes, out_planes: Optional[torch.Tensor] = None, out_f32: Optional[torch.Tensor] = None, out_xoff: int = 0, out_co: int = 0):
+        """out_planes: [2, B, Ho, out_W, cs] fp16 and / or out_f32: [B, Ho, out_W, cs] fp32 (same out_W / cs); image column x lands at out_xoff + x."""
+        assert x.pc == self.pc and (out_planes is not None or out_f32 is not None)
+        Ho, Wo = self.out_hw(x.H, x.W)
+        ref = out_f32 if out_f32 is not None else out_planes[0]
+        assert tuple(ref.shape[:2]) == (x.B, Ho) and ref.shape[2] >= Wo + out_xoff and ref.is_contiguous()
+        if out_planes is not None and out_f32 is not None:
+            assert tuple(out_planes.shape[1:]) == tuple(out_f32.shape)
+        call("vd3d_row_conv", x.t[0].data_ptr(), x.t[1].data_ptr(), x.B, x.H, x.W, x.Wp, x.xoff, self.pc, self.KH, self.KW, self.stride, self.pad,
+             self.w_hi.data_ptr(), self.w_lo.data_ptr(), self.out_scale, self.b.data_ptr(), 1 if self.relu else 0, self.Cout,
+             out_f32.data_ptr() if out_f32 is not None else None,
+             out_planes[0].data_ptr() if out_planes is not None else None, out_planes[1].data_ptr() if out_planes is not None else None,
+             int(ref.shape[2]), out_xoff, int(ref.shape[3]), out_co, _stream())
+        return Ho, Wo
+
+
+def image_to_row_planes(img: torch.Tensor, planes: torch.Tensor, xoff: int):
+    """NCHW float image -> fp16 (hi, lo) row planes [2, B, H, Wp, 4 | 8] (channels beyond C zero), image column x at xoff + x."""
+    _require_cuda(img, "image")
+    B, C, H, W = img.shape
+    assert planes.dtype == torch.float16 and tuple(planes.shape[:3]) == (2, B, H) and planes.shape[4] in (4, 8) and planes.shape[3] >= W + xoff
+    img = img.contiguous().float()
+    call("vd3d_image_to_h16_rows_c", img.data_ptr(), B, C, H, W, planes[0].data_ptr(), planes[1].data_ptr(), int(planes.shape[3]), xoff, int(planes.shape[4]), _stream())
+    return RowPlanes(planes, W, xoff)
+
+
 class DeformConvLayer:
     """ModulatedDeformConvPack (R/lib/ops/dcn/deform_conv.py:408-466) [+ folded BN] [+ ReLU] on NHWC activations:
     3x3 offset/mask conv (conv engine) -> deformable im2col with the mask sigmoid fused -> ONE tcgen05 1x1 GEMM over
