@@ -102,6 +102,17 @@ def test_against_reference_fixture(mf, tag):
             np.testing.assert_array_equal(res[b][2].cpu().numpy().reshape(-1), fx[f"cls_{b}"].reshape(-1))
 
 
+def test_lo_companions_are_fresh_everywhere(mf, monkeypatch):
+    """VD3D_CHECK_LO: in front of every tensor-core conv of the DLA / DLAUp / head plan the fp16 (hi, lo) planes must equal the split of the fp32 tensor:
+    the plan skips the split pass for views whose producer wrote the planes itself (`Act.lo_fresh`), and splits only the copied children of a Root concat."""
+    from visualdet3d_b200 import synth, engine
+    det = mf[0]
+    monkeypatch.setattr(engine, "CHECK_LO", True)
+    img, P2 = synth.synth_mono_inputs(2, 96, 320, seed=6)
+    with torch.no_grad():
+        det.forward_batch(img.cuda(), P2.cuda())
+
+
 def test_batch8_384x1280_all_images_vs_oracle(mf):
     """BASELINE configs[3] shape (DLA-34 + DCNv2, batch 8, 384x1280): determinism, batch invariance, and EVERY image of the
     batch against the oracle."""

@@ -151,7 +151,7 @@ class _CenterNetBase(nn.Module):
         self._hook("features", feat)
         dev = images.device
         if pl["stem"].engine != "simt":
-            E.split_lo(feat)
+            E.split_lo_if_stale(feat)
         tc_out = all(l.engine == "tc16" for (l, _, _, _) in pl["outs"].values())
         # the stem output (9 x 256 channels at 1/4 resolution: the largest tensor of the network) feeds only the 1x1 output convs: with
         # those on the tensor cores it is written as fp16 planes only (no fp32 copy: 2.3 GB less HBM traffic per batch-8 step at 384x1280)

@@ -169,7 +169,7 @@ class _BlockRun:
         """x may have a stale lo (refreshed here if needed); `out` gets relu(bn2(conv2(relu(bn1(conv1 x)))) + residual)."""
         B, dev = x.B, x.t.device
         if _tc(self.c1):
-            E.split_lo(x)
+            E.split_lo_if_stale(x)
         Ho, Wo = self.c1.out_hw(x.H, x.W)
         t = self.c1(x, ar.act(name + ".t", (B, Ho, Wo, self.c1.Cout), dev, lo=_tc(self.c2)))
         if _tc(self.c2) and not _tc(self.c1):
@@ -206,7 +206,7 @@ class _TreeRun:
         if p.levels == 1:
             if self.project is not None:
                 if _tc(self.project):
-                    E.split_lo(bottom)
+                    E.split_lo_if_stale(bottom)
                 res = self.project(bottom, ar.act(name + ".res", (B, bottom.H, bottom.W, p.cout), dev))
             else:
                 res = bottom
@@ -221,7 +221,11 @@ class _TreeRun:
                 E.copy_channels(ch, cat.slice(co, ch.C))
                 co += ch.C
             if _tc(self.root):
-                E.split_lo(cat)
+                if x1.lo_fresh and x2.lo_fresh:       # both block outputs came from tensor-core convs: only the copied children lack their planes
+                    if co > 2 * p.cout:
+                        E.split_lo(cat.slice(2 * p.cout, co - 2 * p.cout))
+                else:
+                    E.split_lo(cat)
             out = ar.act(name + ".out", (B, Ho, Wo, p.cout), dev, lo=True)
             return self.root(cat, out, res=x2 if self.root_residual else None)
         # levels > 1: the reference also evaluates project(bottom) here but never uses it (Tree.forward overwrites `residual`)
@@ -267,6 +271,7 @@ class DLARunner:
         x = ar.act(tag + ".l1", (B, H1, W1, 32), dev, lo=True)
         assert x.h16
         l1(E.RowPlanes(r2, W, 2), x.lo, x.t)
+        x.lo_fresh = True
         return x
 
     def run(self, img: torch.Tensor, ar: E.Arena, tag: str = "dla") -> List[E.Act]:
@@ -313,7 +318,7 @@ class _DeformRun:
 
     def run(self, x: E.Act, out: E.Act, ar: E.Arena, name: str) -> E.Act:
         if _tc(self.layer.off_conv):
-            E.split_lo(x)
+            E.split_lo_if_stale(x)
         return self.layer(x, out, ar, name)
 
 

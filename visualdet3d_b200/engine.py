@@ -40,6 +40,7 @@ class Act:
         # False: the fp32 tensor was NOT written by the producer (planes-only output of a tensor-core conv whose consumers are all
         # tensor-core convs / plane residuals): the fp16 (hi, lo) planes are the tensor, `t` only carries the shape
         self.f32 = f32
+        self.lo_fresh = False      # True once a kernel that writes the companion together with the tensor (tensor-core conv, fused DCN, row conv) produced THIS view
         self.C = (t.shape[3] - co) if C is None else C
         assert 0 <= co and co + self.C <= t.shape[3]
         assert lo is None or (lo.dtype == torch.float32 and lo.shape == t.shape) or \
@@ -274,11 +275,13 @@ class ConvLayer:
                      res.ptr if (res is not None and not res_planes) else None, rh, rl,
                      res.cs if res is not None else 0, res.co if res is not None else 0,
                      out.ptr if f32_out else None, oh, ol, self.Cout, out.cs, out.co, 1 if r else 0, self.bn_tile, _stream())
+                out.lo_fresh = oh is not None
                 return out
             call("vd3d_conv2d_tc16", xh, xl, x.B, x.H, x.W, x.C, x.cs, x.co, self.w_hi.data_ptr(), self.w_lo.data_ptr(), self.out_scale,
                  self.b.data_ptr(), self.KH, self.KW, self.pad, self.dil, self.stride,
                  res.ptr if res is not None else None, res.cs if res is not None else 0, res.co if res is not None else 0,
                  out.ptr, oh, ol, self.Cout, out.cs, out.co, 1 if r else 0, self.passes, self.bn_tile, _stream())
+            out.lo_fresh = oh is not None
             return out
         passes = 3 if self.engine == "tc" else 1
         if passes == 3 and x.lo_ptr is None:
@@ -505,6 +508,7 @@ class DeformConvLayer:
                  self.KH, self.KW, self.stride, self.pad, self.dil, self.k_order, m.w_hi.data_ptr(), m.w_lo.data_ptr(), m.out_scale, m.b.data_ptr(),
                  res.ptr if res is not None else None, res.cs if res is not None else 0, res.co if res is not None else 0,
                  out.ptr, oh, ol, m.Cout, out.cs, out.co, 1 if m.relu else 0, _stream())
+            out.lo_fresh = oh is not None
             return out
         cols = arena.act("dcn.cols", (B, Ho, Wo, K * self.C), dev, lo=self.main.engine != "simt")     # one buffer per shape, shared by all DCN layers
         if cols.h16:      # the fp16-split GEMM reads only the planes: the gather writes them directly, the fp32 columns are never stored
@@ -563,7 +567,20 @@ def split_lo(x: Act) -> Act:
         call("vd3d_split_h16_nhwc", x.ptr, h, l, x.B * x.H * x.W, x.C, x.cs, x.co, _stream())
     else:
         call("vd3d_split_lo_nhwc", x.ptr, x.lo_ptr, x.B * x.H * x.W, x.C, x.cs, x.co, _stream())
+    x.lo_fresh = True
     return x
+
+
+def split_lo_if_stale(x: Act) -> Act:
+    """`split_lo` unless the producer of this view wrote the companion itself (`Act.lo_fresh`: set by the fp16-split tensor-core convs, the fused
+    deformable conv and the row convs on their OUTPUT view; every other view, slice or later writer starts / stays stale)."""
+    if x.lo is None:
+        return x
+    if x.lo_fresh:
+        if CHECK_LO:
+            check_lo(x)
+        return x
+    return split_lo(x)
 
 
 def check_lo(x: Act):
