@@ -32,7 +32,7 @@ class Act:
       * float16, shape [2, B, H, W, cs]: planes hi = rn16(t) and lo = rn16(t - hi) ("tc16" engine, the default).
     The tcgen05 conv engine consumes and produces these; other producers leave them stale and the plan calls `split_lo`
     before a tensor-core consumer."""
-    __slots__ = ("t", "co", "C", "lo", "f32")
+    __slots__ = ("t", "co", "C", "lo", "f32", "lo_fresh")
 
     def __init__(self, t: torch.Tensor, co: int = 0, C: Optional[int] = None, lo: Optional[torch.Tensor] = None, f32: bool = True):
         assert t.dim() == 4 and t.dtype == torch.float32 and t.is_contiguous()
