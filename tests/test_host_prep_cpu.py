@@ -117,3 +117,17 @@ def test_anchor_config_is_honoured_or_refused(tmp_path):
     cfg["head"]["read_precompute_anchor"] = False
     with pytest.raises(ValueError):
         Stereo3D(cfg)
+
+
+def test_act_views_and_freshness_flag():
+    """engine.Act bookkeeping runs without a GPU: slices are new views that start stale (`lo_fresh` False) whatever the parent's state"""
+    import torch
+    from visualdet3d_b200 import engine as E
+    t = torch.zeros(2, 3, 4, 16)
+    a = E.Act(t, 0, None, torch.zeros(2, 2, 3, 4, 16, dtype=torch.float16))
+    assert a.h16 and a.f32 and not a.lo_fresh and (a.B, a.H, a.W, a.C, a.cs) == (2, 3, 4, 16, 16)
+    a.lo_fresh = True
+    s = a.slice(8, 8)
+    assert (s.co, s.C) == (8, 8) and s.lo is a.lo and not s.lo_fresh
+    rp = E.RowPlanes(torch.zeros(2, 1, 4, 12, 8, dtype=torch.float16), W=8, xoff=4)
+    assert (rp.B, rp.H, rp.Wp, rp.pc) == (1, 4, 12, 8)

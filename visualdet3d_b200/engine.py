@@ -203,7 +203,8 @@ class ConvLayer:
         on_gpu = str(device).startswith("cuda")
         if eng == "tc16":      # fp16-split engine: any stride <= 4, Cin % 8 (zero-filled up to the 64-channel k-block), Cout % 4;
             # below 32 input channels the 64-channel k-block is mostly padding and the SIMT engine is faster
-            eligible = on_gpu and stride <= 4 and cin_p % 8 == 0 and cin_p >= 32 and Cout % 4 == 0 and Cout >= 16
+            import os
+            eligible = on_gpu and stride <= 4 and cin_p % 8 == 0 and cin_p >= int(os.environ.get("VD3D_TC_MINC", "32")) and Cout % 4 == 0 and Cout >= 16
         else:
             eligible = on_gpu and stride == 1 and cin_p % 32 == 0 and Cout % 16 == 0
         self.engine = eng if (eng in ("tc", "tc1", "tc16") and eligible) else "simt"
