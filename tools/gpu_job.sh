@@ -1,4 +1,7 @@
-for v in 32 24 32 24 8; do VD3D_TC_MINC=$v timeout 300 python bench.py --steps 20 --warmup 4 --no-cpu-baseline > gpurun_out/r2_bench23_$v.json 2> gpurun_out/r2_bench23_$v.err; python -c "
-import json;d=json.load(open('gpurun_out/r2_bench23_$v.json'));print('MINC=$v',d['value'],d['e2e']['value'],d['clocks']['sm_mhz'])"; tail -1 gpurun_out/r2_bench23_$v.err | cut -c1-200; done
-VD3D_TC_MINC=24 timeout 600 python -m pytest tests/test_stereo3d_gpu.py -m gpu -q -x --tb=short -p no:cacheprovider > gpurun_out/r2_tests23.log 2>&1; echo "pytest MINC=24 rc=$?"; tail -3 gpurun_out/r2_tests23.log | cut -c1-300
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2_launches23.csv python bench.py --profile-mode --steps 1 --warmup 3 > gpurun_out/r2_prof23.log 2>&1; tail -1 gpurun_out/r2_prof23.log
+timeout 300 python tools/exp_bottleneck.py 10 > gpurun_out/r2_exp_bottleneck3.log 2>&1; grep "default tile policy\|bn_tile = 64" gpurun_out/r2_exp_bottleneck3.log | cut -c1-150
+run() { env "$@" timeout 300 python bench.py --config $CFG --steps 20 --warmup 4 --no-cpu-baseline > gpurun_out/r2_b27.json 2> gpurun_out/r2_b27.err; python -c "
+import json;d=json.load(open('gpurun_out/r2_b27.json'));print('$CFG $*',d['value'],d['e2e']['value'],d['clocks']['sm_mhz'])"; tail -1 gpurun_out/r2_b27.err | cut -c1-200; }
+CFG=gac; run A=0; run VD3D_TC_SHORTK=0; run VD3D_TC_SHORTK_RES=0; run A=0; run VD3D_TC_SHORTK=0; run VD3D_TC_SHORTK_RES=0
+CFG=monoflex; run A=0; run VD3D_TC_SHORTK_RES=0
+CFG=stereo; run A=0; run VD3D_TC_SHORTK_RES=0
+timeout 600 python -m pytest tests/test_mono3d_gpu.py -m gpu -q -x --tb=short -p no:cacheprovider > gpurun_out/r2_tests27.log 2>&1; echo "pytest mono3d rc=$?"; tail -3 gpurun_out/r2_tests27.log | cut -c1-300

@@ -11,7 +11,7 @@ import re
 from ctypes import c_char_p, c_double, c_float, c_int, c_longlong, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvd3d_b200.so")
+LIB_PATH = os.environ.get("VD3D_LIB") or os.path.join(_HERE, "libvd3d_b200.so")      # VD3D_LIB: A/B timing against another build of the same ABI
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "vd3d_b200.h")
 
 _lib = None

@@ -1226,6 +1226,16 @@ static int conv2d_tc_launch(int f16, const void* in, const void* in_lo, int B, i
         if (f16 && passes == 3 && persist != 0) {
             const int Ho_ = (H + 2 * pad - dil * (KH - 1) - 1) / stride + 1, Wo_ = (W + 2 * pad - dil * (KW - 1) - 1) / stride + 1;
             BN = pick_bn_cost(Cout, cdiv(Wo_, TC_TW) * cdiv(Ho_, TC_TH) * B);
+            // short-K layers (the 1x1 expansion convs of the ResNet bottlenecks: 4 k-blocks, wide output, residual): a tile's MMAs are over before its
+            // epilogue has fetched the first residual columns, so the step is the epilogue's chain of global round trips.  64-column tiles take the
+            // prefetching epilogue variant (residual requested before the accumulation, tcp_epilogue PRE) and put twice as many CTAs on the output:
+            // measured on 256 -> 1024 at 11520 pixels: 93 us (256-column pairs) -> 78 (128) -> 76 (64) (profiles/r02_exp_bottleneck_r101.txt)
+            const char* esk = getenv("VD3D_TC_SHORTK");
+            const int shortk = esk ? atoi(esk) : 8;
+            const int kb_total = KH * KW * ((Cin + 63) / 64);
+            const char* esr = getenv("VD3D_TC_SHORTK_RES");          // 1 (default): only layers with a residual; 0: every short-K layer
+            const bool need_res = !(esr && atoi(esr) == 0);
+            if (shortk > 0 && kb_total <= shortk && BN > 64 && Cout % 64 == 0 && (!need_res || res || res_h16_hi)) BN = 64;
         } else BN = vd3d_tc_pick_bn(Cout);
     }
     const bool use_p = f16 && passes == 3 && persist != 0;
