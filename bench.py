@@ -335,9 +335,19 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # stdout carries exactly one JSON line: NCCL's own "NCCL version ..." banner (printed to stdout at NCCL_DEBUG=VERSION / INFO) is kept off it
-        os.environ["NCCL_DEBUG"] = os.environ.get("VD3D_NCCL_DEBUG", "WARN")
-        dist.init_process_group("nccl", device_id=dev)
+        # stdout carries exactly one JSON line: the "NCCL version ..." banner the library prints to stdout when the first communicator is created
+        # is sent to stderr instead (file-descriptor level: the print comes from C code)
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     args.warmup = max(args.warmup, 4)            # >= 3 by contract; 4 so that both record buffers have had their eager step and their graph capture
     metric, unit, H, W, defB, text = CONFIGS[args.config]
     B = args.batch or defB

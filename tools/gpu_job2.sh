@@ -1,4 +1,6 @@
-python -m pytest tests/test_nccl_gpu.py -m gpu -q -s --tb=short -p no:cacheprovider > gpurun_out/r2_tests_nccl.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/r2_tests_nccl.log
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 20 --warmup 3 > gpurun_out/r2_bench_n2.json 2> gpurun_out/r2_bench_n2.err; echo "bench rc=$?"; tail -c 2500 gpurun_out/r2_bench_n2.json; tail -3 gpurun_out/r2_bench_n2.err
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29534 bench.py --gpus 2 --config gac --steps 10 --warmup 3 > gpurun_out/r2_bench_gac_n2.json 2> gpurun_out/r2_bench_gac_n2.err; echo "bench gac rc=$?"; tail -c 600 gpurun_out/r2_bench_gac_n2.json
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29535 bench.py --impl reference --gpus 2 --steps 3 --warmup 1 2>/dev/null | tail -c 400
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 20 --warmup 4 > gpurun_out/r2_bench_n2c.json 2> gpurun_out/r2_bench_n2c.err; echo "bench rc=$?"; python -c "
+import json
+for l in open('gpurun_out/r2_bench_n2c.json'):
+    if l.startswith('{'):
+        d=json.loads(l); print('n2',d['value'],d['e2e']['value'],d['gather_verified'])
+    else: print('EXTRA STDOUT LINE:',l[:80])"; grep -c "NCCL version" gpurun_out/r2_bench_n2c.err
