@@ -348,6 +348,7 @@ def main():
             sys.stdout.flush()
             os.dup2(saved, 1)
             os.close(saved)
+    warmup_requested = args.warmup
     args.warmup = max(args.warmup, 4)            # >= 3 by contract; 4 so that both record buffers have had their eager step and their graph capture
     metric, unit, H, W, defB, text = CONFIGS[args.config]
     B = args.batch or defB
@@ -521,12 +522,13 @@ def main():
     value = total / (ms_dev / 1e3)
     peak, peak_kind = measured_peaks()
     out = {
-        "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": warmup_requested,
         "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": text.format(B=B) + ", random-init seeded weights", "name": args.config,
                    "global_batch": B * world, "parallelism": f"dp{world}",
                    "l2": "activations + weights of one step exceed the 126 MB L2 several times over; no explicit flush",
+                   "warmup_steps_run": args.warmup,
                    "conv_engine": os.environ.get("VD3D_CONV_ENGINE", "default"),
                    "cuda_graphs": ("one graph per record buffer / staging slot (graphs.GraphedStep); the stereo device-resident leg stays eager for the "
                                    "in-situ event timing of its cost-volume kernels" if use_graphs else "off"),
