@@ -131,3 +131,33 @@ def test_host_side_tile_and_layout_helpers():
     # the null-pointer / bad-argument paths return an error code and a message instead of launching anything
     assert lib.vd3d_conv2d_tc16_stem(None, None, 1, 8, 8, 16, 7, 7, 2, 3, 32, None, None, 1.0, None, None, None, None, 64, 64, 0, 1, None) != 0
     assert b"null pointer" in lib.vd3d_last_error()
+
+
+def test_row_strip_host_helpers():
+    """Pure host entries of the row-strip kernels (no GPU): padded row pitches of the fp16 row planes, and the argument checks that run before any launch."""
+    from visualdet3d_b200 import _lib
+    lib = _lib.load()
+    # stem + pool: 5 leading zero pixels; 63 pooled columns (126 conv columns, 252 pixels, 2016 bytes) per strip, the last strip stages 264 pixels
+    assert lib.vd3d_stem_pool_xoff() == 5
+    for W in (30, 96, 320, 515, 1010, 1280):
+        Wo = (W + 6 - 7) // 2 + 1
+        Wq = (Wo - 1) // 2 + 1
+        nstrips = (Wq + 62) // 63
+        Wp = lib.vd3d_stem_pool_row_pitch(W)
+        assert Wp % 2 == 0 and Wp >= W + 5 and Wp >= 252 * (nstrips - 1) + 264
+    assert lib.vd3d_stem_pool_row_pitch(1280) == 252 * 5 + 264
+    # row convs: 128 operand rows of 16 bytes per strip = 2048 bytes of input columns, + the filter row of the last operand row
+    for (W, pc, KW, S, P, xoff) in ((1280, 8, 7, 1, 3, 4), (1280, 16, 3, 1, 1, 2), (1280, 16, 3, 2, 1, 2), (141, 16, 3, 2, 1, 2), (150, 8, 7, 1, 3, 4)):
+        Wp = lib.vd3d_row_conv_pitch(W, pc, KW, S, P, xoff)
+        pxb, Wo = pc * 2, (W + 2 * P - KW) // S + 1
+        RS = S * pxb // 16
+        nstrips = (Wo + 128 // RS - 1) // (128 // RS)
+        KS = 2 if KW * pxb <= 64 else 4
+        assert Wp % 4 == 0 and Wp >= W + xoff and Wp * pxb >= (xoff - P) * pxb + 2048 * (nstrips - 1) + 127 * 16 + KS * 32
+    assert lib.vd3d_row_conv_pitch(1280, 12, 3, 1, 1, 2) < 0          # 24-byte pixels: not a whole number of 16-byte operand rows
+    assert lib.vd3d_row_conv_pitch(1280, 16, 3, 1, 1, 0) < 0          # fewer leading zero pixels than the padding
+    assert lib.vd3d_row_conv_pitch(1280, 16, 5, 1, 2, 2) < 0          # filter row wider than one 128-byte weight row
+    assert lib.vd3d_row_conv(None, None, 1, 8, 8, 16, 2, 16, 3, 3, 1, 1, None, None, 1.0, None, 1, 16, None, None, None, 8, 0, 16, 0, None) != 0
+    assert b"null pointer" in lib.vd3d_last_error()
+    assert lib.vd3d_stem_pool_fused(None, None, 1, 8, 8, 16, None, None, 1.0, None, None, None, None, 64, 0, None) != 0
+    assert b"null pointer" in lib.vd3d_last_error()
