@@ -556,7 +556,7 @@ def main():
                            "frac": (achieved / peak) if achieved else None, "avg_launch_ms": psm_avg_ms, "algorithmic_bytes_per_launch": psm_bytes,
                            # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at B = 8 from the committed `ncu --set full` capture
                            "traffic": (PSM4_NCU_TRAFFIC_B8 if (B == 8 and tc) else None),
-                           "traffic_source": "ncu --set full, one launch, profiles/r01_ncu_psm_cosine_tc.txt"}
+                           "traffic_source": "ncu --set full, one launch, profiles/r01_ncu_psm_cosine_tc.txt (round 2 re-capture, profiles/r02_ncu_misc.txt row 10: 125.9 MB read + 11.3 MB written)"}
         # the other cost-volume kernels, timed in situ the same way (SURVEY.md 8(d) algorithmic bytes per pair x batch)
         alg = {"psm8": 4 * (H // 8) * (W // 8) * (2 * 128 + 24) * B, "concat_volume": (2 * 8 * (H // 16) * (W // 16) * 4 + 16 * 12 * (H // 16) * (W // 16) * 4) * B}
         out["cost_volume_in_situ"] = {k: {"avg_launch_ms": statistics.mean(v), "algorithmic_bytes": alg[k], "GB_per_s": alg[k] / 1e9 / (statistics.mean(v) / 1e3),
